@@ -1,0 +1,177 @@
+"""Host mirror of GPclust/MOHGP.py (class MOHGP): a hierarchical mixture of Gaussian processes.
+
+Same constructor, attributes and methods as the reference; the arithmetic of do_computations /
+bound / vb_grad_natgrad (MOHGP.py:70-90, :124-135, :137-153) runs in the sm_100a kernels:
+
+    S pass (gpc_step_stats)      softmax, phi_hat, H, ybark = phi^T Y                MOHGP.py:76
+    gpc_mohgp_cluster            C_k = I + phi_hat_k A, jitchol, Lambda_inv, muk     MOHGP.py:79-90
+    gpc_mohgp_finalize           bound                                                MOHGP.py:124-135
+    G pass (gpc_natgrad)         Mahalanobis terms as one GEMM, natural gradient      MOHGP.py:137-153
+
+Y may be a numpy array or a CUDA tensor (N x D; N = the rows this rank holds).  The dead N x D x D
+`YYT` of MOHGP.py:52 is not materialised.
+"""
+import numpy as np
+
+from . import _cabi
+from ._cabi import lib, check, ptr
+from .collapsed_mixture import CollapsedMixture
+from .kern import cov_to_device
+
+
+class MOHGP(CollapsedMixture):
+    def __init__(self, X, kernF, kernY, Y, K=2, alpha=1.0, prior_Z="symmetric", name="MOHGP", phi_init=None, group=None):
+        torch = _cabi.require_cuda()
+        N, self.D = Y.shape
+        self.X = np.asarray(X, dtype=np.float64)
+        assert self.X.shape[0] == self.D, "input data don't match observations"
+
+        CollapsedMixture.__init__(self, N, K, prior_Z, alpha, name, phi_init=phi_init, group=group)
+
+        self.kernF = kernF
+        self.kernY = kernY
+
+        # features: F = Y, padded to Npad x DP
+        DP = _cabi.padded_d(self.D)
+        if isinstance(Y, torch.Tensor):
+            Yd = Y.to(device=self.device, dtype=torch.float64).contiguous()
+            self._Y_host = None
+        else:
+            self._Y_host = _cabi.f64(Y)
+            Yd = torch.from_numpy(self._Y_host).to(self.device)
+        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)
+        check(lib.gpc_pad_rows(ptr(Yd), N, self.D, DP, ptr(F), self._stream()), "gpc_pad_rows")
+        self.kernel_launches += 1
+        del Yd
+        self._X_dev = torch.from_numpy(self.X).to(self.device)
+        D = self.D
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        self._Sf, self._Sy = z(D, D), z(D, D)
+        self._Ly, self._Ly_inv, self._Sy_inv, self._A = z(D, D), z(D, D), z(D, D), z(D, D)
+        self._Sy_logdet, self._const = z(1), z(1)
+        self._YTY = z(D, D)
+        self._set_features(F, DP)
+
+        # Computations that can be done outside the optimisation loop (MOHGP.py:52-53)
+        self._compute_YTY()
+        # initialize kernels (MOHGP.py:47-49) and the first do_computations (MOHGP.py:55)
+        self.parameters_changed()
+
+    @property
+    def Y(self):
+        if self._Y_host is None:
+            self._Y_host = self._F[:self.N, :self.D].cpu().numpy()
+        return self._Y_host
+
+    def _alloc_model(self):
+        torch = self.torch
+        D, K = self.D, self._KP
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        self._muk_t = z(K, D)
+        self._Syi_ybark_t = z(K, D)
+        self._Lambda_inv = z(K, D, D)
+        self._C_chols_dev = z(K, D, D)
+
+    def _compute_YTY(self):
+        torch = self.torch
+        DP = self._DP
+        grid = min(self._grid, self._Npad // 32)
+        part = torch.zeros(grid * DP * DP, dtype=torch.float64, device=self.device)
+        full = torch.zeros(DP * DP, dtype=torch.float64, device=self.device)
+        check(lib.gpc_gram_partials(ptr(self._F), self._Npad, DP, ptr(part), grid, self._stream()), "gpc_gram_partials")
+        check(lib.gpc_reduce_partials(ptr(part), grid, DP * DP, ptr(full), self._stream()), "gpc_reduce_partials")
+        self.kernel_launches += 2
+        self._allreduce(full)
+        self._YTY.copy_(full.view(DP, DP)[:self.D, :self.D])
+
+    def parameters_changed(self):
+        """MOHGP.py:58-67: refresh the kernel matrices and their factorisation, then recompute.
+        (update_kern_grads, MOHGP.py:92-122, belongs to the hyper-parameter 'next' row.)"""
+        D = self.D
+        self._Sf.copy_(cov_to_device(self.kernF, self.X, self._X_dev))
+        self._Sy.copy_(cov_to_device(self.kernY, self.X, self._X_dev))
+        check(lib.gpc_mohgp_setup(ptr(self._Sf), ptr(self._Sy), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._A),
+                                  ptr(self._Sy_logdet), self._info_ptr(), D, self._stream()), "gpc_mohgp_setup")
+        check(lib.gpc_mohgp_const(ptr(self._YTY), ptr(self._Sy_inv), ptr(self._Sy_logdet), float(self.N_total), D, ptr(self._const),
+                                  self._stream()), "gpc_mohgp_const")
+        self.kernel_launches += 4
+        _, _, _, failed = self._readback()
+        if failed:
+            raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+        self.do_computations()
+
+    def _launch_cluster(self):
+        check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),
+                                    ptr(self._Wt), ptr(self._muk_t), ptr(self._per_k), ptr(self._Syi_ybark_t), ptr(self._Lambda_inv),
+                                    ptr(self._C_chols_dev), self._info_ptr(), self.K, self.D, self._KP, self._DP, self._stream()),
+              "gpc_mohgp_cluster")
+        self.kernel_launches += 1
+
+    def _launch_finalize(self):
+        check(lib.gpc_mohgp_finalize(ptr(self._stats), ptr(self._per_k), ptr(self._const), ptr(self._bias), ptr(self._ctrl),
+                                     ptr(self._mixgrad), float(self.alpha), _cabi.PRIOR[self.prior_Z], self.K, self._KP, self._DP,
+                                     self._stream()), "gpc_mohgp_finalize")
+        self.kernel_launches += 1
+
+    # ---- reference attributes (copied from the device on access)
+    def _np(self, t):
+        return t.cpu().numpy()
+
+    Sf = property(lambda self: self._np(self._Sf))
+    Sy = property(lambda self: self._np(self._Sy))
+    Sy_inv = property(lambda self: self._np(self._Sy_inv))
+    Sy_chol = property(lambda self: self._np(self._Ly))
+    Sy_chol_inv = property(lambda self: self._np(self._Ly_inv))
+    Sy_logdet = property(lambda self: float(self._Sy_logdet.cpu()[0]))
+    YTY = property(lambda self: self._np(self._YTY))
+
+    @property
+    def ybark(self):  # D x K (MOHGP.py:76)
+        self._ensure_state()
+        T = self._stats[:self._KP * self._DP].view(self._KP, self._DP)
+        return self._np(T[:self.K, :self.D]).T.copy()
+
+    @property
+    def muk(self):  # D x K (MOHGP.py:90)
+        self._ensure_state()
+        return self._np(self._muk_t[:self.K]).T.copy()
+
+    @property
+    def Syi_ybark(self):  # D x K (MOHGP.py:88)
+        self._ensure_state()
+        return self._np(self._Syi_ybark_t[:self.K]).T.copy()
+
+    @property
+    def Lambda_inv(self):  # K x D x D (MOHGP.py:85)
+        self._ensure_state()
+        return self._np(self._Lambda_inv[:self.K])
+
+    @property
+    def _C_chols(self):  # list of K lower factors (MOHGP.py:82)
+        self._ensure_state()
+        return list(self._np(self._C_chols_dev[:self.K]))
+
+    @property
+    def log_det_diff(self):  # MOHGP.py:83
+        self._ensure_state()
+        return self._np(self._per_k[:self.K, 0])
+
+    @property
+    def Syi_ybarkybarkT_Syi(self):  # K x D x D (MOHGP.py:89)
+        s = self.Syi_ybark.T
+        return s[:, None, :] * s[:, :, None]
+
+    def predict_components(self, Xnew):
+        """The predictive density under each component (MOHGP.py:156-174); small host algebra on the
+        device-computed posterior (K x D x D), not part of the VB iteration."""
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        Sy_chol_inv, Sf, Sy_inv = self.Sy_chol_inv, self.Sf, self.Sy_inv
+        from scipy.linalg import solve_triangular
+        tmp = [solve_triangular(L, Sy_chol_inv, lower=True) for L in self._C_chols]
+        B_invs = [ph * np.dot(t.T, t) for ph, t in zip(self.phi_hat, tmp)]
+        kx = self.kernF.K(self.X, Xnew)
+        kxx = self.kernF.K(Xnew) + self.kernY.K(Xnew)
+        tmp = [np.eye(self.D) - np.dot(Bi, Sf) for Bi in B_invs]
+        mu = [kx.T.dot(t).dot(Sy_inv).dot(yb) for t, yb in zip(tmp, self.ybark.T)]
+        var = [kxx - kx.T.dot(Bi).dot(kx) for Bi in B_invs]
+        return mu, var

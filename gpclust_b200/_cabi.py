@@ -1,0 +1,123 @@
+"""ctypes binding of include/gpclust_b200.h -- the only way the host code reaches the GPU.
+
+There is no CPU fallback: if the library is missing the import raises, and every compute call
+requires a CUDA device (the launchers return a negative cudaError otherwise, which `check` raises).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libgpclust_b200.so")
+
+GPC_ROW_TILE = 64
+GPC_EINVAL = 2
+GPC_INFO_NOT_PD = 1
+PRIOR = {"symmetric": 0, "DP": 1}
+BETA = {"zero": 0, "HS": 1, "PR": 2, "FR": 3}
+KERN = {"rbf": 0, "matern32": 1, "matern52": 2, "bias": 3, "white": 4}
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_d = ctypes.c_double
+
+# name -> argtypes; mirrors include/gpclust_b200.h one to one (tests/test_cabi.py checks both sides)
+PROTOTYPES = {
+    "gpc_abi_version": [],
+    "gpc_padded_k": [_i],
+    "gpc_padded_d": [_i],
+    "gpc_padded_rows": [_ll],
+    "gpc_stats_len": [_i, _i],
+    "gpc_default_grid": [_i],
+    "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_reduce_partials": [_p, _i, _i, _p, _p],
+    "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
+    "gpc_mohgp_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "gpc_mohgp_finalize": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p],
+    "gpc_mog_features": [_p, _p, _ll, _i, _i, _p, _p],
+    "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],
+    "gpc_mog_finalize": [_p, _p, _p, _p, _p, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i, _p],
+    "gpc_kern_fill": [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _d, _p, _p],
+    "gpc_softmax_rows": [_p, _ll, _i, _i, _p, _p, _i, _p, _i, _p],
+    "gpc_multiple_mahalanobis": [_p, _p, _p, _ll, _i, _i, _p, _p],
+    "gpc_multiple_pdinv": [_p, _i, _i, _p, _p, _p, _p],
+    "gpc_gram_partials": [_p, _ll, _i, _p, _i, _p],
+    "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],
+    "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
+}
+_RESTYPE = {"gpc_padded_rows": _ll}
+
+
+class GpclustLibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise GpclustLibraryError(
+            "gpclust_b200: %s is missing -- build it with `python -m gpclust_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise GpclustLibraryError("gpclust_b200: symbol %s missing from %s (stale build?)" % (name, LIB_PATH))
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, _i)
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    """0 -> ok; GPC_EINVAL -> ValueError; negative -> CUDA error (no device, launch failure, ...)."""
+    if rc == 0:
+        return
+    if rc == GPC_EINVAL:
+        raise ValueError("gpclust_b200: invalid argument in %s" % what)
+    raise GpclustLibraryError("gpclust_b200: %s failed with CUDA error %d (is a B200 / CUDA device present?)" % (what, -rc))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def padded_k(K):
+    kp = lib.gpc_padded_k(int(K))
+    if kp < 0:
+        raise ValueError("gpclust_b200: K=%d is outside the supported range 1..64" % K)
+    return kp
+
+
+def padded_d(D):
+    dp = lib.gpc_padded_d(int(D))
+    if dp < 0:
+        raise ValueError("gpclust_b200: feature dimension %d is outside the supported range 1..64" % D)
+    return dp
+
+
+def padded_rows(N):
+    return int(lib.gpc_padded_rows(int(N)))
+
+
+def as_c_array(values, ctype):
+    values = list(values)
+    return (ctype * len(values))(*values)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise GpclustLibraryError("gpclust_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback.")
+    return torch
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

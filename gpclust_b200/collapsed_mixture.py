@@ -1,0 +1,418 @@
+"""Host mirror of GPclust/collapsed_mixture.py (class CollapsedMixture) with the variational state
+resident in HBM.
+
+What lives where
+  device (torch CUDA float64 tensors, row-major, padded -- include/gpclust_b200.h "Layout"):
+      logits phi_ (three rotating buffers: accepted / previous accepted / trial), natural gradient
+      (current / previous), search direction, the feature rows F, per-CTA partials, the reduced
+      statistics [T | phi_hat | H], per-cluster posterior outputs, the control block that is read
+      back once per bound evaluation.
+  host: loop control, K bookkeeping, the merge/split search (collapsed_mixture.py:96-205).
+
+Reference attributes (`phi`, `phi_`, `phi_hat`, `H`, `Hgrad`, ...) are properties that copy from the
+device on access.  Rows ("series") may be sharded over ranks of a torch.distributed process group:
+every rank holds a contiguous block of rows, the statistics vector and the three dot products are
+all-reduced; everything K- or D-sized is replicated.
+"""
+import ctypes
+import sys
+
+import numpy as np
+from numpy.linalg import LinAlgError
+
+from . import _cabi
+from ._cabi import lib, check, ptr
+from .collapsed_vb import CollapsedVB
+
+# control block layout (doubles)
+_C_BOUND, _C_MIX, _C_H, _C_SQ, _C_NUM, _C_DEN, _C_BETA, _C_INFO = 0, 1, 2, 3, 4, 5, 6, 8
+_CTRL_LEN = 16
+
+
+class CollapsedMixture(CollapsedVB):
+    """collapsed_mixture.py:15-205.  N is the number of rows held by THIS rank."""
+
+    def __init__(self, N, K, prior_Z="symmetric", alpha=1.0, name="col_mix", phi_init=None, group=None):
+        CollapsedVB.__init__(self, name)
+        self.torch = _cabi.require_cuda()
+        torch = self.torch
+        self.N, self.K = int(N), int(K)
+        assert prior_Z in ["symmetric", "DP"]
+        self.prior_Z = prior_Z
+        self.alpha = alpha
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._grid = lib.gpc_default_grid(self.device.index)
+        if self._grid <= 0:
+            check(self._grid or -1, "gpc_default_grid")
+
+        # row sharding (one process per GPU); a single process is world 1
+        self._dist = None
+        self._group = group
+        self._world, self._rank = 1, 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._dist = dist
+                self._world = dist.get_world_size(group)
+                self._rank = dist.get_rank(group)
+        except ImportError:
+            pass
+        self._row_start, self.N_total = self._row_partition(self.N)
+
+        self._Npad = _cabi.padded_rows(self.N)
+        self._F = None          # Npad x DP features, set by the subclass
+        self._DP = None
+        self._kbuf_K = None
+        self._ctrl = torch.zeros(_CTRL_LEN, dtype=torch.float64, device=self.device)
+        self._ctrl_host = torch.zeros(_CTRL_LEN, dtype=torch.float64).pin_memory()
+        self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._gpart = torch.zeros(self._grid * 4, dtype=torch.float64, device=self.device)
+        self._state_valid = False
+        self._bound_value = None
+        self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
+
+        # random initial conditions for the vb parameters (collapsed_mixture.py:41): the legacy global
+        # numpy stream, drawn for ALL rows so that a sharded run starts from the same point
+        if phi_init is None:
+            phi_init = self._draw_rows(self.K)
+        self._alloc_k(self.K)
+        self._upload_logits(phi_init)
+
+    # ------------------------------------------------------------------ sharding helpers
+    def _is_root(self):
+        return self._rank == 0
+
+    def _row_partition(self, n_local):
+        if self._world == 1:
+            return 0, int(n_local)
+        t = self.torch.zeros(self._world, dtype=self.torch.int64, device=self.device)
+        t[self._rank] = n_local
+        self._dist.all_reduce(t, group=self._group)
+        counts = t.cpu().numpy()
+        return int(counts[:self._rank].sum()), int(counts.sum())
+
+    def _draw_rows(self, K):
+        if self._world == 1:
+            return np.random.randn(self.N, K)
+        full = np.random.randn(self.N_total, K)  # same stream on every rank
+        return full[self._row_start:self._row_start + self.N].copy()
+
+    def _allreduce(self, t):
+        if self._world > 1:
+            self._dist.all_reduce(t, group=self._group)
+
+    # ------------------------------------------------------------------ device buffers
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _alloc_k(self, K):
+        torch = self.torch
+        KP = _cabi.padded_k(K)
+        if self._kbuf_K is not None and KP == self._KP:
+            self._kbuf_K = K
+            return
+        self._KP = KP
+        self._kbuf_K = K
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        self._xbuf = [z(self._Npad, KP) for _ in range(3)]
+        self._xi, self._xprev, self._xtrial = 0, None, 1
+        self._ngbuf = [z(self._Npad, KP) for _ in range(2)]
+        self._ngi = 0
+        self._sd = z(self._Npad, KP)
+        self._bias = z(KP)
+        self._per_k = z(KP, 4)
+        self._mixgrad = z(KP)
+        self._alloc_kd()
+
+    def _alloc_kd(self):
+        """Buffers whose size depends on both KP and DP (needs the features to be known)."""
+        if self._DP is None:
+            return
+        torch = self.torch
+        KP, DP = self._KP, self._DP
+        self._stats_len = lib.gpc_stats_len(KP, DP)
+        self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
+        self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
+        self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
+        self._alloc_model()
+
+    def _alloc_model(self):
+        """Subclass hook: per-cluster output buffers (K x D x D ...)."""
+
+    def _set_features(self, F, DP):
+        self._F, self._DP = F, DP
+        self._alloc_kd()
+
+    def _upload_logits(self, x):
+        """x: numpy (N*K,) / (N,K) or a CUDA tensor of that shape -> padded current buffer; CG history reset."""
+        torch = self.torch
+        K = self.K
+        if K != self._kbuf_K:
+            self._alloc_k(K)
+        if isinstance(x, torch.Tensor):
+            src = x.to(device=self.device, dtype=torch.float64).reshape(self.N, K).contiguous()
+        else:
+            src = torch.from_numpy(_cabi.f64(np.asarray(x).reshape(self.N, K))).to(self.device)
+        cur = self._xbuf[self._xi]
+        check(lib.gpc_pad_rows(ptr(src), self.N, K, self._KP, ptr(cur), self._stream()), "gpc_pad_rows")
+        self.kernel_launches += 1
+        self._xprev = None
+        self._xtrial = (self._xi + 1) % 3
+        self._state_valid = False
+        self._cache = {}
+
+    # ------------------------------------------------------------------ reference API: parameters
+    def set_vb_param(self, phi_):
+        """collapsed_mixture.py:49-61: accept the flattened variational parameters and recompute."""
+        self._upload_logits(phi_)
+        self.do_computations()
+
+    def get_vb_param(self):
+        return self.phi_.flatten()  # collapsed_mixture.py:63-64
+
+    def _unpad(self, buf):
+        out = self.torch.empty((self.N, self.K), dtype=self.torch.float64, device=self.device)
+        check(lib.gpc_unpad_rows(ptr(buf), self.N, self.K, self._KP, ptr(out), self._stream()), "gpc_unpad_rows")
+        self.kernel_launches += 1
+        return out
+
+    @property
+    def phi_(self):
+        return self._unpad(self._xbuf[self._xi]).cpu().numpy()
+
+    @phi_.setter
+    def phi_(self, value):
+        value = np.asarray(value)
+        self.K = value.shape[1] if value.ndim == 2 else self.K
+        self._upload_logits(value)
+
+    def phi_device(self):
+        """N x K responsibilities as a CUDA tensor (no host copy)."""
+        return self._softmax_readout()[0]
+
+    def _softmax_readout(self):
+        if "softmax" not in self._cache:
+            torch = self.torch
+            phi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
+            logphi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
+            grid = min(self._grid * 4, (self.N + 7) // 8)
+            hpart = torch.zeros(grid, dtype=torch.float64, device=self.device)
+            check(lib.gpc_softmax_rows(ptr(self._xbuf[self._xi]), self.N, self.K, self._KP, ptr(phi), ptr(logphi), self.K, ptr(hpart), grid,
+                                       self._stream()), "gpc_softmax_rows")
+            self.kernel_launches += 1
+            self._cache["softmax"] = (phi, logphi, hpart)
+        return self._cache["softmax"]
+
+    @property
+    def phi(self):
+        return self._softmax_readout()[0].cpu().numpy()
+
+    @property
+    def Hgrad(self):
+        return (-self._softmax_readout()[1]).cpu().numpy()  # collapsed_mixture.py:56
+
+    def _ensure_state(self):
+        if not self._state_valid:
+            self.do_computations()
+
+    @property
+    def phi_hat(self):
+        self._ensure_state()
+        o = self._KP * self._DP
+        return self._stats[o:o + self.K].cpu().numpy()
+
+    @property
+    def H(self):
+        self._ensure_state()
+        return float(self._ctrl_host[_C_H])
+
+    @property
+    def phi_tilde_plus_hat(self):
+        return self.phi_hat[::-1].cumsum()[::-1]  # collapsed_mixture.py:58
+
+    @property
+    def phi_tilde(self):
+        return self.phi_tilde_plus_hat - self.phi_hat  # collapsed_mixture.py:59
+
+    def mixing_prop_bound(self):
+        """collapsed_mixture.py:66-78, evaluated by the finalize kernel."""
+        self._ensure_state()
+        return float(self._ctrl_host[_C_MIX])
+
+    def mixing_prop_bound_grad(self):
+        """collapsed_mixture.py:80-94, evaluated by the finalize kernel."""
+        self._ensure_state()
+        return self._mixgrad[:self.K].cpu().numpy()
+
+    def bound(self):
+        self._ensure_state()
+        return self._bound_value
+
+    # ------------------------------------------------------------------ device passes
+    def _launch_cluster(self):
+        raise NotImplementedError
+
+    def _launch_finalize(self):
+        raise NotImplementedError
+
+    def _s_pass(self, x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old):
+        check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(self._ctrl[_C_SQ:]),
+                                 float(sq_old), ptr(self._ctrl[_C_BETA:]), ptr(self._spart), float(step), _cabi.BETA[beta_mode], self.N,
+                                 self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_step_stats")
+        check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+        self.kernel_launches += 2
+        self._allreduce(self._stats)
+        self._launch_cluster()
+        self._launch_finalize()
+
+    def _readback(self):
+        """One small D2H copy per bound evaluation: bound, mix, H, the CG dots, beta, the not-PD flag."""
+        self._ctrl_host.copy_(self._ctrl, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        h = self._ctrl_host
+        info = int(h.view(self.torch.int32)[2 * _C_INFO])
+        return float(h[_C_BOUND]), float(h[_C_SQ]), float(h[_C_BETA]), info != 0
+
+    def _info_ptr(self):
+        return ptr(self._ctrl[_C_INFO:])
+
+    def do_computations(self):
+        """Statistics, per-cluster posterior and bound at the current logits (MOHGP.py:70-90 / MOG.py:52-61).
+        Raises numpy.linalg.LinAlgError when a per-cluster factorisation fails (GPy jitchol semantics)."""
+        self._s_pass(self._xbuf[self._xi], None, None, None, None, "zero", 0.0, 0.0)
+        bound, _, _, failed = self._readback()
+        self._cache = {}
+        if failed:
+            self._state_valid = False
+            raise LinAlgError("not positive definite, even with jitter.")
+        self._bound_value = bound
+        self._state_valid = True
+
+    # ---- CG hooks (collapsed_vb.py:152-193 on the device)
+    def _cg_gradient(self, with_old):
+        self._ensure_state()
+        have_old = with_old and self._xprev is not None
+        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._Wt), ptr(self._bias),
+                              ptr(self._xbuf[self._xprev]) if have_old else None, ptr(self._ngbuf[1 - self._ngi]) if have_old else None,
+                              ptr(self._ngbuf[self._ngi]), None, ptr(self._gpart), ptr(self._counter), ptr(self._ctrl[_C_SQ:]), self.N,
+                              self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_natgrad")
+        self.kernel_launches += 1
+        if self._world > 1:
+            self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
+
+    def _cg_trial(self, beta_mode, step_length, sq_old):
+        mode = "zero" if beta_mode == "steepest_retry" else beta_mode
+        self._s_pass(self._xbuf[self._xi], self._ngbuf[self._ngi], self._sd, self._sd, self._xbuf[self._xtrial], mode, step_length, sq_old)
+        bound, sq, beta, failed = self._readback()
+        self._cache = {}
+        self._trial_failed = failed
+        self._trial_bound = bound
+        return bound, sq, beta, failed
+
+    def _cg_restore(self):
+        """collapsed_vb.py:189-190: set_vb_param(phi_old); bound = self.bound()."""
+        self.do_computations()
+        self._xbuf[self._xtrial].copy_(self._xbuf[self._xi])
+        self._trial_bound = self._bound_value
+        self._trial_failed = False
+        return self._bound_value
+
+    def _cg_accept(self):
+        free = self._xprev if self._xprev is not None else 3 - self._xi - self._xtrial
+        self._xprev, self._xi, self._xtrial = self._xi, self._xtrial, free
+        self._ngi = 1 - self._ngi
+        self._bound_value = self._trial_bound
+        self._state_valid = not self._trial_failed
+        self._cache = {}
+
+    def vb_grad_natgrad(self):
+        """Flattened (grad, natgrad) as numpy arrays -- the reference's return convention
+        (MOHGP.py:137-153, MOG.py:72-84).  Does not disturb the optimiser's device state."""
+        self._ensure_state()
+        torch = self.torch
+        ng = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
+        gr = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
+        dots = torch.zeros(4, dtype=torch.float64, device=self.device)
+        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None, ptr(ng), ptr(gr),
+                              ptr(self._gpart), ptr(self._counter), ptr(dots), self.N, self.K, self._KP, self._DP, self._grid,
+                              self._stream()), "gpc_natgrad")
+        self.kernel_launches += 1
+        return self._unpad(gr).cpu().numpy().flatten(), self._unpad(ng).cpu().numpy().flatten()
+
+    # ------------------------------------------------------------------ merge / split search (host control)
+    def reorder(self):
+        """collapsed_mixture.py:96-103: re-order the clusters so that the biggest one is first (DP only)."""
+        if self.prior_Z == "DP":
+            i = np.argsort(self.phi_hat)[::-1]
+            self.set_vb_param(self.phi_[:, i])
+
+    def remove_empty_clusters(self, threshold=1e-6):
+        """collapsed_mixture.py:105-110."""
+        i = self.phi_hat > threshold
+        phi_ = self.phi_[:, i]
+        self.K = int(i.sum())
+        self.set_vb_param(phi_)
+
+    def try_split(self, indexK=None, threshold=0.9, verbose=True, maxiter=100, optimize_params=None):
+        """collapsed_mixture.py:112-189 (single-rank: the row gather / scatter is done on the host copy)."""
+        if self._world > 1:
+            raise NotImplementedError("try_split over sharded rows is a 'next' row (SURVEY.md section 8 f-1)")
+        if indexK is None:
+            indexK = np.random.multinomial(1, self.phi_hat / self.N).argmax()
+        if indexK > (self.K - 1):
+            return False  # index exceed no. of clusters
+        elif self.phi_hat[indexK] < 1:
+            return False  # no data to split
+        phi = self.phi
+        if np.sum(phi[:, indexK] > threshold) < 2:
+            return False  # only one data point
+        if verbose:
+            print("\nattempting to split cluster ", indexK)
+
+        bound_old = self.bound()
+        phi_old = self.get_vb_param().copy()
+        old_K = self.K
+
+        # re-initalize
+        logits = phi_old.reshape(self.N, old_K)
+        logits = np.hstack((logits, logits.min(1)[:, None]))
+        indexN = np.nonzero(phi[:, indexK] > threshold)[0]
+        special = np.random.permutation(indexN)[0]
+        logits[indexN, -1] = logits[indexN, indexK].copy()
+        logits[special, -1] = np.max(logits[special]) + 10
+        self.K = old_K + 1
+        self.set_vb_param(logits)
+
+        self.optimize(maxiter=maxiter, verbose=verbose)
+        self.remove_empty_clusters()
+        bound_new = self.bound()
+
+        bound_increase = bound_new - bound_old
+        if bound_increase < 1e-3:
+            self.K = old_K
+            self.set_vb_param(phi_old)
+            if verbose:
+                print("split failed, bound changed by: ", bound_increase, "(K=%s)" % self.K)
+            return False
+        if verbose:
+            print("split suceeded, bound changed by: ", bound_increase, ",", self.K - old_K, " new clusters", "(K=%s)" % self.K)
+            print("optimizing new split to convergence:")
+        self.last_split_increase = bound_increase
+        if optimize_params:
+            self.optimize(**optimize_params)
+        else:
+            self.optimize(maxiter=5000, verbose=verbose)
+        return True
+
+    def systematic_splits(self, verbose=True):
+        """collapsed_mixture.py:191-195."""
+        for kk in range(self.K):
+            self.recursive_splits(kk, verbose=verbose)
+
+    def recursive_splits(self, k=0, verbose=True, optimize_params=None):
+        """collapsed_mixture.py:197-205."""
+        success = self.try_split(k, verbose=verbose, optimize_params=optimize_params)
+        if success:
+            if not k == (self.K - 1):
+                self.recursive_splits(self.K - 1, verbose=verbose, optimize_params=optimize_params)
+            self.recursive_splits(k, verbose=verbose, optimize_params=optimize_params)

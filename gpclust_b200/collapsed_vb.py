@@ -1,0 +1,137 @@
+"""Host mirror of GPclust/collapsed_vb.py (class CollapsedVB): the Riemannian conjugate natural-gradient
+loop.  Control flow, iteration accounting, messages and termination follow collapsed_vb.py:143-193 and
+:228-303 line for line; the N*K-long vector algebra of :152-172 is NOT done on the host -- it is
+delegated to four device hooks that the mixture layer implements with the fused sm_100a passes:
+
+    _cg_gradient(with_old)                G pass at the accepted point (natgrad + the three CG dots)
+    _cg_trial(beta_mode, step, sq_old)    S pass: search direction, trial point, stats, bound
+                                          -> (bound, squareNorm, beta, failed)
+    _cg_accept() / _cg_restore()          buffer rotation / fall back to the accepted point
+
+GPy is not a dependency: the model base class here is a plain object.  Kernel hyper-parameter
+optimisation (collapsed_vb.py:313-323 -> GPy Model.optimize) is a documented "next" row; with no free
+parameters `optimize_parameters()` returns 0. exactly like the reference (:322-323).
+"""
+import sys
+import warnings
+
+import numpy as np
+from numpy.linalg import LinAlgError
+
+
+class LinAlgWarning(Warning):
+    pass
+
+
+class CollapsedVB(object):
+    def __init__(self, name):
+        self.name = name
+        self.hyperparam_interval = 50  # collapsed_vb.py:29
+        self.default_method = "HS"
+        self.hyperparam_opt_args = {"max_iters": 20, "messages": 1, "clear_after_finish": True}
+
+    # ---- template methods (collapsed_vb.py:41-54)
+    def randomize(self):
+        self.set_vb_param(np.random.randn(self.get_vb_param().size))  # collapsed_vb.py:37-39
+
+    def get_vb_param(self):
+        raise NotImplementedError
+
+    def set_vb_param(self, x):
+        raise NotImplementedError
+
+    def bound(self):
+        raise NotImplementedError
+
+    def vb_grad_natgrad(self):
+        raise NotImplementedError
+
+    def log_likelihood(self):
+        return self.bound()  # collapsed_vb.py:56-61
+
+    @property
+    def optimizer_array(self):
+        return np.zeros(0)
+
+    def optimize_parameters(self):
+        """collapsed_vb.py:313-323. No free (kernel) parameters are exposed by this build => 0."""
+        return 0.0
+
+    # ---- device hooks
+    def _cg_gradient(self, with_old):
+        raise NotImplementedError
+
+    def _cg_trial(self, beta_mode, step_length, sq_old):
+        raise NotImplementedError
+
+    def _cg_accept(self):
+        raise NotImplementedError
+
+    def _cg_restore(self):
+        raise NotImplementedError
+
+    def _is_root(self):
+        return True
+
+    def optimize(self, method="HS", maxiter=500, ftol=1e-6, gtol=1e-6, step_length=1.0, callback=None, verbose=True):
+        """Conjugate natural-gradient ascent on the variational parameters; collapsed_vb.py:63-310."""
+        assert method in ["FR", "PR", "HS", "steepest"], "invalid conjugate gradient method specified."
+        say = verbose and self._is_root()
+        iteration = 0
+        bound_old = self.bound()
+        squareNorm_old = 0.0
+        self.optimize_trace = []
+        while True:
+            if callback is not None:
+                callback()
+
+            # collapsed_vb.py:152-167 -- gradient at the accepted point, beta, search direction
+            first = not iteration
+            self._cg_gradient(with_old=not first)
+            beta_mode = "zero" if (method == "steepest" or first) else method
+
+            # collapsed_vb.py:170-176 -- try a conjugate step
+            bound, squareNorm, beta, failed = self._cg_trial(beta_mode, step_length, squareNorm_old)
+            if failed:
+                bound = bound_old - 1
+            iteration += 1
+
+            # collapsed_vb.py:182-193 -- revert to steepest (== VBEM) if the bound fell
+            if bound < bound_old:
+                bound, _, _, failed = self._cg_trial("steepest_retry", step_length, squareNorm_old)
+                if failed:
+                    warnings.warn("Caught LinalgError in setting variational parameters, trying to continue with old parameter settings",
+                                  LinAlgWarning)
+                    bound = self._cg_restore()
+                iteration += 1
+            self._cg_accept()
+
+            self.optimize_trace.append((iteration, bound, squareNorm, beta))
+            if say:
+                sys.stdout.write("\riteration " + str(iteration) + " bound=" + str(bound) + " grad=" + str(squareNorm) + ", beta=" + str(beta) + "\n")
+                sys.stdout.flush()
+
+            # collapsed_vb.py:229-291
+            if np.abs(bound - bound_old) <= ftol:
+                if say:
+                    print("vb converged (ftol)")
+                if self.optimize_parameters() < 1e-1:
+                    break
+            if squareNorm <= gtol:
+                if say:
+                    print("vb converged (gtol)")
+                if self.optimize_parameters() < 1e-1:
+                    break
+            if iteration >= maxiter:
+                if say:
+                    print("maxiter exceeded")
+                break
+
+            squareNorm_old = squareNorm  # collapsed_vb.py:294-297 (the vectors stay on the device)
+            if (iteration > 1) and not (iteration % self.hyperparam_interval):
+                self.optimize_parameters()  # collapsed_vb.py:300-301
+            bound_old = bound
+        return iteration
+
+
+__all__ = ["CollapsedVB", "LinAlgError", "LinAlgWarning"]

@@ -1,0 +1,307 @@
+// gpclust_b200 -- C-ABI launchers (see include/gpclust_b200.h for the contract and the reference
+// lines each entry point replaces).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include "../../include/gpclust_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "gpc_cluster_kernels.cuh"
+#include "gpc_common.cuh"
+#include "gpc_util_kernels.cuh"
+#include "gpc_vb_kernels.cuh"
+
+using namespace gpc;
+
+namespace {
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
+inline int launch_rc() { return cuda_rc(cudaGetLastError()); }
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+size_t natgrad_smem(int KP, int DP) {
+  const VbSmemLayout L(DP);
+  return sizeof(double) * ((size_t)kStages * L.stage_doubles + (size_t)KP * L.f_stride + KP + GPC_CONSUMER_WARPS * 4) +
+         sizeof(uint64_t) * 2 * kStages;
+}
+size_t step_stats_smem(int KP, int DP) {
+  const VbSmemLayout L(DP);
+  return sizeof(double) * ((size_t)kStages * L.stage_doubles + 2 * (size_t)GPC_ROW_TILE * (KP + 4) + GPC_CONSUMER_WARPS * (KP + 1)) +
+         sizeof(uint64_t) * 2 * kStages;
+}
+
+template <int KP>
+int launch_natgrad(const NatgradArgs &a, int grid, cudaStream_t st) {
+  const size_t smem = natgrad_smem(KP, a.DP);
+  cudaError_t e = cudaFuncSetAttribute(k_natgrad<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  k_natgrad<KP><<<grid, GPC_THREADS, smem, st>>>(a);
+  return launch_rc();
+}
+template <int KP>
+int launch_step_stats(const StepStatsArgs &a, int grid, cudaStream_t st) {
+  const size_t smem = step_stats_smem(KP, a.DP);
+  cudaError_t e = cudaFuncSetAttribute(k_step_stats<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  k_step_stats<KP><<<grid, GPC_THREADS, smem, st>>>(a);
+  return launch_rc();
+}
+
+bool geometry_ok(long long N, int K, int KP, int DP, int grid) {
+  return N >= 1 && K >= 1 && K <= KP && KP == gpc_padded_k(K) && DP >= 8 && DP <= GPC_MAX_DP && (DP % 8) == 0 && grid >= 1 &&
+         gpc_padded_rows(N) / GPC_ROW_TILE < 0x7fffffffLL;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpc_abi_version(void) { return 1; }
+
+int gpc_padded_k(int K) {
+  if (K < 1 || K > GPC_MAX_KP) return -1;
+  int kp = 8;
+  while (kp < K) kp *= 2;
+  return kp;
+}
+int gpc_padded_d(int D) {
+  if (D < 1 || D > GPC_MAX_DP) return -1;
+  return (D + 7) / 8 * 8;
+}
+long long gpc_padded_rows(long long N) { return (N + GPC_ROW_TILE - 1) / GPC_ROW_TILE * GPC_ROW_TILE; }
+int gpc_stats_len(int KP, int DP) { return KP * DP + KP + 1; }
+
+int gpc_default_grid(int device) {
+  int sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return cuda_rc(e);
+  return sms;
+}
+
+int gpc_natgrad(const double *F, const double *x, const double *Wt, const double *bias, const double *x_old, const double *ng_old,
+                double *ng_out, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
+                int DP, int grid, void *stream) {
+  if (!F || !x || !Wt || !bias || !ng_out || !partials || !counter || !dots) return GPC_EINVAL;
+  if ((x_old == nullptr) != (ng_old == nullptr)) return GPC_EINVAL;
+  if (!geometry_ok(N, K, KP, DP, grid)) return GPC_EINVAL;
+  NatgradArgs a;
+  a.F = F;
+  a.x = x;
+  a.Wt = Wt;
+  a.bias = bias;
+  a.x_old = x_old;
+  a.ng_old = ng_old;
+  a.ng_out = ng_out;
+  a.grad_out = grad_out;
+  a.partials = partials;
+  a.counter = counter;
+  a.dots_out = dots;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_tiles = (int)(gpc_padded_rows(N) / GPC_ROW_TILE);
+  if (N > 0x7fffffffLL) return GPC_EINVAL;
+  if (grid > a.num_tiles) grid = a.num_tiles;
+  cudaStream_t st = as_stream(stream);
+  switch (KP) {
+    case 8: return launch_natgrad<8>(a, grid, st);
+    case 16: return launch_natgrad<16>(a, grid, st);
+    case 32: return launch_natgrad<32>(a, grid, st);
+    case 64: return launch_natgrad<64>(a, grid, st);
+  }
+  return GPC_EINVAL;
+}
+
+int gpc_step_stats(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
+                   const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
+                   int K, int KP, int DP, int grid, void *stream) {
+  if (!F || !x_base || !partials) return GPC_EINVAL;
+  if (ng && !x_new) return GPC_EINVAL;
+  if (beta_mode != GPC_BETA_ZERO && (!dots || !ng)) return GPC_EINVAL;
+  if (beta_mode < GPC_BETA_ZERO || beta_mode > GPC_BETA_FR) return GPC_EINVAL;
+  if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
+  StepStatsArgs a;
+  a.F = F;
+  a.x_base = x_base;
+  a.ng = ng;
+  a.sd_old = sd_old;
+  a.sd_new = sd_new;
+  a.x_new = x_new;
+  a.dots = dots;
+  a.sq_old = sq_old;
+  a.beta_out = beta_out;
+  a.partials = partials;
+  a.step = step;
+  a.beta_mode = beta_mode;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_tiles = (int)(gpc_padded_rows(N) / GPC_ROW_TILE);
+  // NOTE: every CTA of the launch grid writes one partial block, so the grid is NOT clamped here:
+  // CTAs without a tile write zeros.
+  cudaStream_t st = as_stream(stream);
+  switch (KP) {
+    case 8: return launch_step_stats<8>(a, grid, st);
+    case 16: return launch_step_stats<16>(a, grid, st);
+    case 32: return launch_step_stats<32>(a, grid, st);
+    case 64: return launch_step_stats<64>(a, grid, st);
+  }
+  return GPC_EINVAL;
+}
+
+int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
+  if (!partials || !out || num_parts < 1 || len < 1) return GPC_EINVAL;
+  k_reduce_partials<<<(len + 127) / 128, 128, 0, as_stream(stream)>>>(partials, num_parts, len, out);
+  return launch_rc();
+}
+
+int gpc_mohgp_setup(const double *Sf, const double *Sy, double *Ly, double *Ly_inv, double *Sy_inv, double *A, double *Sy_logdet,
+                    int *info, int D, void *stream) {
+  if (!Sf || !Sy || !Ly || !Ly_inv || !Sy_inv || !A || !Sy_logdet || !info || D < 1 || D > GPC_MAX_DP) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const size_t smem = sizeof(double) * 3 * (size_t)D * (D + 1);
+  e = cudaFuncSetAttribute(k_mohgp_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MohgpSetupArgs a{Sf, Sy, Ly, Ly_inv, Sy_inv, A, Sy_logdet, info, D};
+  k_mohgp_setup<<<1, kClusterThreads, smem, st>>>(a);
+  return launch_rc();
+}
+
+__global__ void k_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_logdet, double n_total, int D, double *out) {
+  __shared__ double red_s[32];
+  double v = 0.0;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) v += YTY[e] * Sy_inv[e];
+  v = block_sum(v, red_s);
+  if (threadIdx.x == 0) *out = -0.5 * (n_total * D * log(2.0 * M_PI) + n_total * (*Sy_logdet) + v);
+}
+
+int gpc_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_logdet, double n_total, int D, double *const_term,
+                    void *stream) {
+  if (!YTY || !Sy_inv || !Sy_logdet || !const_term || D < 1) return GPC_EINVAL;
+  k_mohgp_const<<<1, 256, 0, as_stream(stream)>>>(YTY, Sy_inv, Sy_logdet, n_total, D, const_term);
+  return launch_rc();
+}
+
+int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Sy, const double *Sy_inv, const double *Sf,
+                      double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
+                      int K, int D, int KP, int DP, void *stream) {
+  if (!stats || !A || !Ly || !Sy || !Sy_inv || !Sf || !Wt || !muk_t || !per_k || !info) return GPC_EINVAL;
+  if (K < 1 || K > KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const size_t smem = sizeof(double) * (3 * (size_t)D * (D + 1) + 2 * D + 32);
+  e = cudaFuncSetAttribute(k_mohgp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MohgpClusterArgs a{stats, A, Ly, Sy, Sy_inv, Sf, Wt, muk_t, per_k, Syi_ybark_t, Lambda_inv, C_chols, info, K, D, KP, DP};
+  k_mohgp_cluster<<<KP, kClusterThreads, smem, st>>>(a);
+  return launch_rc();
+}
+
+int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
+                       double *mixgrad_out, double alpha, int prior, int K, int KP, int DP, void *stream) {
+  if (!stats || !per_k || !const_term || !bias || !scalars || K < 1 || K > KP || KP > kMaxMixK) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  MohgpFinalizeArgs a{stats, per_k, bias, scalars, mixgrad_out, 0.0, const_term, alpha, prior, K, KP, DP};
+  k_mohgp_finalize<<<1, kClusterThreads, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream) {
+  if (!X || !centre || !F || N < 1 || D < 1 || D * (D + 1) / 2 + D > DP) return GPC_EINVAL;
+  const long long total = gpc_padded_rows(N) * DP;
+  k_mog_features<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, centre, (int)N, (int)gpc_padded_rows(N), D, DP, F);
+  return launch_rc();
+}
+
+int gpc_mog_cluster(const double *stats, const double *m0c, const double *S0, double *Wt, double *per_k, double *mun_c, double *Sns,
+                    double *Sns_inv, int *info, double k0, double v0, int K, int D, int KP, int DP, void *stream) {
+  if (!stats || !m0c || !S0 || !Wt || !per_k || !mun_c || !Sns || !Sns_inv || !info) return GPC_EINVAL;
+  if (K < 1 || K > KP || D < 1 || D > kMogMaxD || D * (D + 1) / 2 + D > DP) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MogClusterArgs a{stats, m0c, S0, Wt, per_k, mun_c, Sns, Sns_inv, info, k0, v0, K, D, KP, DP};
+  k_mog_cluster<<<(KP + 31) / 32, 32, 0, st>>>(a);
+  return launch_rc();
+}
+
+int gpc_mog_finalize(const double *stats, const double *per_k, double *bias, double *scalars, double *mixgrad_out, double n_total,
+                     double k0, double v0, double S0_halflogdet, double alpha, int prior, int K, int KP, int DP, int D, void *stream) {
+  if (!stats || !per_k || !bias || !scalars || K < 1 || K > KP || KP > kMaxMixK) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  MogFinalizeArgs a{stats, per_k, bias, scalars, mixgrad_out, n_total, k0, v0, S0_halflogdet, alpha, prior, K, KP, DP, D};
+  k_mog_finalize<<<1, kClusterThreads, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_kern_fill(const double *X, const double *X2, int n, int m, int q, int nparts, const int *kinds, const double *variances,
+                  const double *lengthscales, double diag_add, double *out, void *stream) {
+  if (!X || !out || n < 1 || m < 1 || q < 1 || nparts < 1 || nparts > kMaxKernParts || !kinds || !variances || !lengthscales)
+    return GPC_EINVAL;
+  if (!X2 && m != n) return GPC_EINVAL;
+  KernSpec spec;
+  spec.nparts = nparts;
+  for (int p = 0; p < kMaxKernParts; ++p) {
+    spec.kind[p] = p < nparts ? kinds[p] : 0;
+    spec.variance[p] = p < nparts ? variances[p] : 0.0;
+    spec.lengthscale[p] = p < nparts ? lengthscales[p] : 1.0;
+    if (p < nparts && (kinds[p] < GPC_KERN_RBF || kinds[p] > GPC_KERN_WHITE)) return GPC_EINVAL;
+  }
+  const long long total = (long long)n * m;
+  k_kern_fill<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, X2, n, m, q, spec, diag_add, out);
+  return launch_rc();
+}
+
+int gpc_softmax_rows(const double *x, long long N, int K, int ldx, double *phi, double *logphi, int ldo, double *Hpart, int grid,
+                     void *stream) {
+  if (!x || N < 1 || K < 1 || ldx < K || ((phi || logphi) && ldo < K) || grid < 1 || N > 0x7fffffffLL) return GPC_EINVAL;
+  k_softmax_rows<<<grid, kSoftmaxWarps * 32, 0, as_stream(stream)>>>(x, (int)N, K, ldx, phi, logphi, ldo, Hpart);
+  return launch_rc();
+}
+
+int gpc_multiple_mahalanobis(const double *X1, const double *X2, const double *L, long long N1, int N2, int D, double *out,
+                             void *stream) {
+  if (!X1 || !X2 || !L || !out || N1 < 1 || N2 < 1 || D < 1 || D > kMahaMaxD) return GPC_EINVAL;
+  const size_t smem = sizeof(double) * (size_t)D * D;
+  cudaError_t e = cudaFuncSetAttribute(k_mahalanobis_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const long long pairs = N1 * N2;
+  k_mahalanobis_pairs<<<(unsigned)((pairs + 127) / 128), 128, smem, as_stream(stream)>>>(X1, X2, L, (int)N1, N2, D, out);
+  return launch_rc();
+}
+
+int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, int *info, void *stream) {
+  if (!A || !inv || !hld || !info || D < 1 || D > GPC_MAX_DP || K < 1) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  const size_t smem = sizeof(double) * ((size_t)D * D + 2 * (size_t)D * (D + 1));
+  e = cudaFuncSetAttribute(k_batched_pdinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  k_batched_pdinv<<<K, kClusterThreads, smem, st>>>(A, D, K, inv, hld, info);
+  return launch_rc();
+}
+
+int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream) {
+  if (!F || !partials || Npad < kGramRows || (Npad % kGramRows) || DP < 8 || DP > GPC_MAX_DP || grid < 1) return GPC_EINVAL;
+  k_gram_partials<<<grid, 256, sizeof(double) * kGramRows * DP, as_stream(stream)>>>(F, (int)Npad, DP, partials);
+  return launch_rc();
+}
+
+int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, void *stream) {
+  if (!src || !dst || N < 1 || D < 1 || DP < D) return GPC_EINVAL;
+  const long long total = gpc_padded_rows(N) * DP;
+  k_pad_rows<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, (int)N, D, (int)gpc_padded_rows(N), DP, dst);
+  return launch_rc();
+}
+
+int gpc_unpad_rows(const double *src, long long N, int K, int ld, double *dst, void *stream) {
+  if (!src || !dst || N < 1 || K < 1 || ld < K) return GPC_EINVAL;
+  const long long total = N * K;
+  k_unpad_rows<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, (int)N, K, ld, dst);
+  return launch_rc();
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+// gpclust_b200 -- per-cluster posterior kernels (small D x D FP64 linear algebra in shared memory)
+// and the scalar "finalize" kernels that assemble the collapsed bound and the per-cluster gradient
+// constants.  These sit on the serial critical path between the two N-sized passes.
+//
+//   k_mohgp_cluster : MOHGP.py:79-90   (jitchol, dtrtrs, Lambda_inv, dpotrs, muk) + the per-cluster
+//                     pieces of MOHGP.py:129-135 and :146-147
+//   k_mog_cluster   : MOG.py:52-61 (+ np_utilities.py:6-22 multiple_pdinv) and the per-cluster pieces of
+//                     MOG.py:63-70, :79
+//   k_*_finalize    : collapsed_mixture.py:66-94 (mixing-proportion bound and gradient), bound assembly
+#pragma once
+#include "gpc_common.cuh"
+
+namespace gpc {
+
+constexpr int kClusterThreads = 256;
+// GPC_PRIOR_* and GPC_INFO_NOT_PD come from include/gpclust_b200.h
+
+// In-place lower Cholesky of the n x n matrix M (row stride ld) in shared memory, all threads of the
+// CTA.  Returns false when a pivot is not positive / not finite.  Strict upper triangle is left as is.
+__device__ inline bool chol_lower_smem(double *M, int n, int ld, int *flag_s) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  if (tid == 0) *flag_s = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      const double d = M[j * ld + j];
+      if (!(d > 0.0) || isinf(d)) *flag_s = 1;
+      else M[j * ld + j] = sqrt(d);
+    }
+    __syncthreads();
+    if (*flag_s) return false;
+    const double ljj = M[j * ld + j];
+    for (int i = j + 1 + tid; i < n; i += nth) M[i * ld + j] /= ljj;
+    __syncthreads();
+    const int m = n - j - 1;  // trailing size
+    for (int e = tid; e < m * m; e += nth) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) M[i * ld + k] -= M[i * ld + j] * M[k * ld + j];
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// x := (L L^T)^-1 x for one vector in shared memory, executed by warp 0 (other warps idle).
+// Column-oriented substitution; L lower, row stride ld.
+__device__ inline void potrs_vec_warp0(const double *L, int n, int ld, double *x) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    for (int i = 0; i < n; ++i) {  // forward: L y = x
+      __syncwarp();
+      const double xi = x[i] / L[i * ld + i];
+      __syncwarp();
+      if (lane == 0) x[i] = xi;
+      for (int m = i + 1 + lane; m < n; m += 32) x[m] -= L[m * ld + i] * xi;
+    }
+    for (int i = n - 1; i >= 0; --i) {  // backward: L^T z = y
+      __syncwarp();
+      const double xi = x[i] / L[i * ld + i];
+      __syncwarp();
+      if (lane == 0) x[i] = xi;
+      for (int m = lane; m < i; m += 32) x[m] -= L[i * ld + m] * xi;
+    }
+    __syncwarp();
+  }
+}
+
+__device__ inline double block_sum(double v, double *red_s) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red_s[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < nw; ++w) r += red_s[w];
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MohgpClusterArgs {
+  const double *stats;   // [ybark KP x DP | phi_hat KP | H], already summed over CTAs (and ranks)
+  const double *A;       // D x D : Ly^-1 Sf Ly^-T             (MOHGP.py:79)
+  const double *Ly;      // D x D : chol(Sy + 1e-6 I), lower   (MOHGP.py:49)
+  const double *Sy;      // D x D : un-jittered                (MOHGP.py:85)
+  const double *Sy_inv;  // D x D
+  const double *Sf;      // D x D
+  double *Wt;            // out KP x DP : Wt[k][:] = Sy^-1 mu_k (pad = 0)
+  double *muk_t;         // out K x D   : row k = mu_k
+  double *per_k;         // out KP x 4  : log_det_diff, s^T Lambda_inv s, tr(Lambda_inv Sy_inv), mu^T Sy^-1 mu
+  double *Syi_ybark_t;   // out K x D   : row k = Sy^-1 ybark_k  (nullable)
+  double *Lambda_inv;    // out K x D x D (nullable)
+  double *C_chols;       // out K x D x D (nullable)
+  int *info;
+  int K, D, KP, DP;
+};
+
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_cluster(const MohgpClusterArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, ld = D + 1, k = blockIdx.x, tid = threadIdx.x;
+  double *C = sm;              // D x ld : C_k, then its Cholesky factor, then Lambda_inv
+  double *T = C + D * ld;      // D x ld : L_k^-1 Ly^T
+  double *Ls = T + D * ld;     // D x ld : Ly
+  double *vec_s = Ls + D * ld; // D      : s_k, then w_k
+  double *mu_s = vec_s + D;    // D
+  double *red_s = mu_s + D;    // 32
+  __shared__ int flag_s;
+
+  if (k >= a.K) {  // pad clusters: zero weights so that the G pass sees finite numbers
+    for (int d = tid; d < a.DP; d += blockDim.x) a.Wt[(size_t)k * a.DP + d] = 0.0;
+    if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
+    return;
+  }
+  const double phi_hat = a.stats[(size_t)a.KP * a.DP + k];
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    Ls[i * ld + j] = a.Ly[e];
+  }
+
+  // jitchol semantics (GPy.util.linalg.jitchol): plain attempt, then mean(diag)*1e-6 * 10^i, i = 0..4
+  bool ok = false;
+  double diag_mean = 0.0;
+  for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+    double jitter = 0.0;
+    if (attempt > 0) {
+      jitter = diag_mean * 1e-6;
+      for (int q = 1; q < attempt; ++q) jitter *= 10.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < D * D; e += blockDim.x) {
+      const int i = e / D, j = e % D;
+      C[i * ld + j] = ((i == j) ? 1.0 + jitter : 0.0) + a.A[e] * phi_hat;  // MOHGP.py:80
+    }
+    __syncthreads();
+    if (attempt == 0) {
+      double dsum = 0.0, dmin = INFINITY;
+      for (int i = 0; i < D; ++i) {  // every thread, same order: identical result everywhere
+        dsum += C[i * ld + i];
+        dmin = fmin(dmin, C[i * ld + i]);
+      }
+      diag_mean = dsum / D;
+      if (!(dmin > 0.0)) break;  // "not pd: non-positive diagonal elements"
+    }
+    ok = chol_lower_smem(C, D, ld, &flag_s);
+    if (attempt > 0 && !isfinite(jitter)) break;
+  }
+  if (!ok) {
+    if (tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
+    for (int d = tid; d < a.DP; d += blockDim.x) a.Wt[(size_t)k * a.DP + d] = 0.0;
+    if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
+    return;
+  }
+  if (a.C_chols)
+    for (int e = tid; e < D * D; e += blockDim.x) {
+      const int i = e / D, j = e % D;
+      a.C_chols[(size_t)k * D * D + e] = (j <= i) ? C[i * ld + j] : 0.0;
+    }
+  double ldd = 0.0;
+  if (tid < 32) {
+    for (int i = tid; i < D; i += 32) ldd += log(C[i * ld + i]);
+    ldd = 2.0 * warp_sum(ldd);  // MOHGP.py:83
+  }
+
+  // T = L_k^-1 Ly^T  (MOHGP.py:84): 4 threads per right-hand-side column, split inner products
+  {
+    const int col = tid >> 2, q = tid & 3;
+    for (int cbase = 0; cbase < D; cbase += kClusterThreads / 4) {
+      const int j = cbase + col;
+      for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+        if (j < D)
+          for (int m = q; m < i; m += 4) acc += C[i * ld + m] * T[m * ld + j];
+        acc = quad_sum(acc);
+        if (j < D && q == 0) T[i * ld + j] = (((j >= i) ? Ls[j * ld + i] : 0.0) - acc) / C[i * ld + i];
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+
+  // Lambda_inv = (Sy - T^T T) / phi_hat   or Sf when phi_hat <= 1e-6   (MOHGP.py:85)
+  {
+    const bool tiny = !(phi_hat > 1e-6);
+    for (int e = tid; e < D * D; e += blockDim.x) {
+      const int i = e / D, j = e % D;
+      double v;
+      if (tiny) v = a.Sf[e];
+      else {
+        double tt = 0.0;
+        for (int m = 0; m < D; ++m) tt += T[m * ld + i] * T[m * ld + j];
+        v = (a.Sy[e] - tt) / phi_hat;
+      }
+      C[i * ld + j] = v;  // the Cholesky factor is no longer needed
+    }
+  }
+  // s_k = (Ly Ly^T)^-1 ybark_k   (MOHGP.py:88)
+  for (int d = tid; d < D; d += blockDim.x) vec_s[d] = a.stats[(size_t)k * a.DP + d];
+  __syncthreads();
+  potrs_vec_warp0(Ls, D, ld, vec_s);
+  __syncthreads();
+  if (a.Lambda_inv)
+    for (int e = tid; e < D * D; e += blockDim.x) a.Lambda_inv[(size_t)k * D * D + e] = C[(e / D) * ld + (e % D)];
+  if (a.Syi_ybark_t)
+    for (int d = tid; d < D; d += blockDim.x) a.Syi_ybark_t[(size_t)k * D + d] = vec_s[d];
+  // mu_k[j] = sum_i Lambda_inv[i][j] s[i]   (MOHGP.py:90)
+  for (int j = tid; j < D; j += blockDim.x) {
+    double v = 0.0;
+    for (int i = 0; i < D; ++i) v += C[i * ld + j] * vec_s[i];
+    mu_s[j] = v;
+    a.muk_t[(size_t)k * D + j] = v;
+  }
+  __syncthreads();
+  // quad = sum_ij s_i s_j Lambda_inv_ij (MOHGP.py:133) ; trace = sum_ij Lambda_inv_ij Sy_inv_ij (MOHGP.py:147)
+  double quad = 0.0, tr = 0.0;
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    const double l = C[i * ld + j];
+    quad += vec_s[i] * vec_s[j] * l;
+    tr += l * a.Sy_inv[e];
+  }
+  quad = block_sum(quad, red_s);
+  tr = block_sum(tr, red_s);
+  // w_k = (Ly Ly^T)^-1 mu_k : the GEMM form of multiple_mahalanobis(Y, muk.T, Sy_chol) (MOHGP.py:144)
+  __syncthreads();
+  for (int d = tid; d < D; d += blockDim.x) vec_s[d] = mu_s[d];
+  __syncthreads();
+  potrs_vec_warp0(Ls, D, ld, vec_s);
+  __syncthreads();
+  double m2 = 0.0;
+  for (int d = tid; d < D; d += blockDim.x) m2 += mu_s[d] * vec_s[d];
+  m2 = block_sum(m2, red_s);
+  for (int d = tid; d < a.DP; d += blockDim.x) a.Wt[(size_t)k * a.DP + d] = (d < D) ? vec_s[d] : 0.0;
+  if (tid == 0) {
+    a.per_k[k * 4 + 0] = ldd;
+    a.per_k[k * 4 + 1] = quad;
+    a.per_k[k * 4 + 2] = tr;
+    a.per_k[k * 4 + 3] = m2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mixing-proportion terms (collapsed_mixture.py:66-94).  Block-cooperative: the special functions are
+// evaluated one cluster per thread, the K-long sums / cumulative sums serially by thread 0 (same
+// left-to-right order as numpy's cumsum).  Writes mixgrad[0..K) (shared) and *mix_out (shared).
+constexpr int kMaxMixK = 512;
+struct MixScratch {
+  double a[kMaxMixK], b[kMaxMixK], c[kMaxMixK], da[kMaxMixK], db[kMaxMixK], dc[kMaxMixK];
+};
+
+__device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, int prior, MixScratch &w, double *mixgrad, double *mix_out) {
+  const int tid = threadIdx.x;
+  if (prior == GPC_PRIOR_SYMMETRIC) {
+    for (int k = tid; k < K; k += blockDim.x) {
+      const double v = alpha + phi_hat[k];
+      w.a[k] = lgamma(v);
+      mixgrad[k] = digamma_pos(v);  // collapsed_mixture.py:86
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // ln_dirichlet_C(alpha*1) - ln_dirichlet_C(alpha + phi_hat)   (np_utilities.py:67-69)
+      double sum_a = 0.0, sum_lg = 0.0;
+      for (int k = 0; k < K; ++k) {
+        sum_a += alpha + phi_hat[k];
+        sum_lg += w.a[k];
+      }
+      *mix_out = (lgamma(alpha * K) - K * lgamma(alpha)) - (lgamma(sum_a) - sum_lg);
+    }
+    __syncthreads();
+    return;
+  }
+  // truncated DP, collapsed_mixture.py:72-77 and :88-92
+  if (tid == 0) {
+    double tail = 0.0;  // phi_tilde_plus_hat[k] = sum_{j>=k} phi_hat[j]: the reference's reversed cumsum
+    for (int k = K - 1; k >= 0; --k) {
+      tail += phi_hat[k];
+      w.c[k] = tail;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) {
+    const double ph = phi_hat[k], tph = w.c[k], til = tph - ph;
+    w.a[k] = lgamma(1.0 + ph);
+    w.b[k] = lgamma(alpha + til);
+    w.da[k] = digamma_pos(ph + 1.0);
+    w.db[k] = digamma_pos(til + alpha);
+    w.dc[k] = digamma_pos(tph + alpha + 1.0);
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) w.c[k] = lgamma(alpha + 1.0 + w.c[k]);
+  __syncthreads();
+  if (tid == 0) {
+    double A = 0.0, B = 0.0, C = 0.0, cumB = 0.0, cumC = 0.0;
+    for (int k = 0; k < K; ++k) {
+      A += w.a[k];
+      B += w.b[k];
+      C += w.c[k];
+      cumC += w.dc[k];
+      mixgrad[k] = w.da[k] + cumB - cumC;  // the B term is shifted by one cluster (collapsed_mixture.py:90)
+      cumB += w.db[k];
+    }
+    *mix_out = A + B - C + K * (lgamma(1.0 + alpha) - lgamma(alpha));
+  }
+  __syncthreads();
+}
+
+struct MohgpFinalizeArgs {
+  const double *stats;  // [ybark | phi_hat | H]
+  const double *per_k;  // KP x 4
+  double *bias;         // out KP : mixgrad_k - 0.5*trace_k - 0.5*mu^T Sy^-1 mu   (MOHGP.py:146-148 + GEMM-form constant)
+  double *scalars;      // out: [0]=bound [1]=mixing_prop_bound [2]=H
+  double *mixgrad_out;  // out K (nullable): mixing_prop_bound_grad, collapsed_mixture.py:80-94
+  double n_total;       // N over all ranks
+  const double *const_term;  // device scalar: -0.5*(N*D*log(2pi) + N*Sy_logdet + sum(YTY*Sy_inv))   (MOHGP.py:129-132)
+  double alpha;
+  int prior, K, KP, DP;
+};
+
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_finalize(const MohgpFinalizeArgs a) {
+  __shared__ double mixgrad[kMaxMixK];
+  __shared__ MixScratch scratch;
+  __shared__ double mix_s;
+  const double *phi_hat = a.stats + (size_t)a.KP * a.DP;
+  mixing_terms(phi_hat, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
+  if (threadIdx.x == 0) {
+    const double H = phi_hat[a.KP];
+    const double mix = mix_s;
+    double ldd = 0.0, quad = 0.0;
+    for (int k = 0; k < a.K; ++k) {
+      ldd += a.per_k[k * 4 + 0];
+      quad += a.per_k[k * 4 + 1];
+    }
+    a.scalars[0] = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix + H;  // MOHGP.py:129-135
+    a.scalars[1] = mix;
+    a.scalars[2] = H;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.KP; k += blockDim.x)
+    a.bias[k] = (k < a.K) ? (mixgrad[k] - 0.5 * a.per_k[k * 4 + 2]) - 0.5 * a.per_k[k * 4 + 3] : 0.0;
+  if (a.mixgrad_out)
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) a.mixgrad_out[k] = mixgrad[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// MOG: features f = [x_i x_j (i <= j, row-major upper) | x_i], NF = D(D+1)/2 + D, computed from data
+// centred at `centre` (the posterior is translation invariant; centring limits cancellation).
+struct MogClusterArgs {
+  const double *stats;  // [T KP x DP | phi_hat KP | H] ; T[k][f] = sum_n phi_nk f_n
+  const double *m0c;    // D : prior mean, centred
+  const double *S0;     // D x D
+  double *Wt;           // out KP x DP
+  double *per_k;        // out KP x 4 : kN, vN, Sns_halflogdet, grad const (without mixgrad)
+  double *mun_c;        // out K x D (centred posterior means, row k)
+  double *Sns;          // out K x D x D
+  double *Sns_inv;      // out K x D x D
+  int *info;
+  double k0, v0;
+  int K, D, KP, DP;
+};
+
+constexpr int kMogMaxD = 10;
+
+__global__ void k_mog_cluster(const MogClusterArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.KP) return;
+  const int D = a.D;
+  if (k >= a.K) {
+    for (int d = 0; d < a.DP; ++d) a.Wt[(size_t)k * a.DP + d] = 0.0;
+    for (int q = 0; q < 4; ++q) a.per_k[k * 4 + q] = 0.0;
+    return;
+  }
+  const double *T = a.stats + (size_t)k * a.DP;
+  const double phi_hat = a.stats[(size_t)a.KP * a.DP + k];
+  const double kN = phi_hat + a.k0, vN = phi_hat + a.v0;  // MOG.py:54-55
+  const int NQ = D * (D + 1) / 2;
+  double mun[kMogMaxD], S[kMogMaxD][kMogMaxD], L[kMogMaxD][kMogMaxD], Si[kMogMaxD][kMogMaxD];
+  for (int i = 0; i < D; ++i) mun[i] = (a.k0 * a.m0c[i] + T[NQ + i]) / kN;  // MOG.py:58
+  {
+    int f = 0;
+    for (int i = 0; i < D; ++i)
+      for (int j = i; j < D; ++j, ++f) {
+        const double v = a.S0[i * D + j] + T[f] + a.k0 * a.m0c[i] * a.m0c[j] - kN * mun[i] * mun[j];  // MOG.py:60
+        S[i][j] = v;
+        S[j][i] = v;
+      }
+  }
+  // jitchol
+  bool ok = false;
+  double dsum = 0.0, dmin = INFINITY;
+  for (int i = 0; i < D; ++i) {
+    dsum += S[i][i];
+    dmin = fmin(dmin, S[i][i]);
+  }
+  double jitter = 0.0;
+  for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+    if (attempt == 1) {
+      if (!(dmin > 0.0)) break;
+      jitter = dsum / D * 1e-6;
+    } else if (attempt > 1) jitter *= 10.0;
+    ok = true;
+    for (int j = 0; j < D && ok; ++j) {
+      double d = S[j][j] + jitter;
+      for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m];
+      if (!(d > 0.0) || isinf(d)) {
+        ok = false;
+        break;
+      }
+      L[j][j] = sqrt(d);
+      for (int i = j + 1; i < D; ++i) {
+        double v = S[i][j];
+        for (int m = 0; m < j; ++m) v -= L[i][m] * L[j][m];
+        L[i][j] = v / L[j][j];
+      }
+    }
+  }
+  if (!ok) {
+    atomicOr(a.info, GPC_INFO_NOT_PD);
+    for (int d = 0; d < a.DP; ++d) a.Wt[(size_t)k * a.DP + d] = 0.0;
+    for (int q = 0; q < 4; ++q) a.per_k[k * 4 + q] = 0.0;
+    return;
+  }
+  double hld = 0.0;
+  for (int i = 0; i < D; ++i) hld += log(L[i][i]);  // np_utilities.py:19
+  // inverse from the factor (dpotri): Si = L^-T L^-1
+  double Li[kMogMaxD][kMogMaxD];
+  for (int j = 0; j < D; ++j) {
+    for (int i = 0; i < D; ++i) Li[i][j] = 0.0;
+    Li[j][j] = 1.0 / L[j][j];
+    for (int i = j + 1; i < D; ++i) {
+      double v = 0.0;
+      for (int m = j; m < i; ++m) v -= L[i][m] * Li[m][j];
+      Li[i][j] = v / L[i][i];
+    }
+  }
+  for (int i = 0; i < D; ++i)
+    for (int j = i; j < D; ++j) {
+      double v = 0.0;
+      for (int m = j; m < D; ++m) v += Li[m][i] * Li[m][j];
+      Si[i][j] = v;
+      Si[j][i] = v;
+    }
+  // gradient weights: -0.5*vN*(x-mu)^T Si (x-mu) expanded on the features   (MOG.py:74-79)
+  double Sm[kMogMaxD], mSm = 0.0;
+  for (int i = 0; i < D; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < D; ++j) v += Si[i][j] * mun[j];
+    Sm[i] = v;
+    mSm += v * mun[i];
+  }
+  {
+    double *w = a.Wt + (size_t)k * a.DP;
+    int f = 0;
+    for (int i = 0; i < D; ++i)
+      for (int j = i; j < D; ++j, ++f) w[f] = (i == j) ? -0.5 * vN * Si[i][i] : -vN * Si[i][j];
+    for (int i = 0; i < D; ++i) w[NQ + i] = vN * Sm[i];
+    for (int d = NQ + D; d < a.DP; ++d) w[d] = 0.0;
+  }
+  double dg = 0.0;
+  for (int d = 0; d < D; ++d) dg += digamma_pos((vN - d) / 2.0);
+  const double gconst = -0.5 * D / kN + 0.5 * dg - hld - 1.0;  // MOG.py:79 without mixing_prop_bound_grad
+  a.per_k[k * 4 + 0] = kN;
+  a.per_k[k * 4 + 1] = vN;
+  a.per_k[k * 4 + 2] = hld;
+  a.per_k[k * 4 + 3] = gconst - 0.5 * vN * mSm;
+  for (int i = 0; i < D; ++i) {
+    a.mun_c[(size_t)k * D + i] = mun[i];
+    for (int j = 0; j < D; ++j) {
+      a.Sns[(size_t)k * D * D + i * D + j] = S[i][j];
+      a.Sns_inv[(size_t)k * D * D + i * D + j] = Si[i][j];
+    }
+  }
+}
+
+struct MogFinalizeArgs {
+  const double *stats;
+  const double *per_k;
+  double *bias;     // out KP
+  double *scalars;  // [0]=bound [1]=mix [2]=H
+  double *mixgrad_out;  // nullable
+  double n_total, k0, v0, S0_halflogdet, alpha;
+  int prior, K, KP, DP, D;
+};
+
+__device__ inline double lngammad_dev(double v, int D) {  // np_utilities.py:62-64
+  double s = 0.0;
+  for (int d = 1; d <= D; ++d) s += lgamma((v + 1.0 - d) / 2.0);
+  return s;
+}
+
+__global__ void __launch_bounds__(kClusterThreads) k_mog_finalize(const MogFinalizeArgs a) {
+  __shared__ double mixgrad[kMaxMixK];
+  __shared__ MixScratch scratch;
+  __shared__ double mix_s;
+  const double *phi_hat = a.stats + (size_t)a.KP * a.DP;
+  mixing_terms(phi_hat, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
+  if (threadIdx.x == 0) {
+    const double H = phi_hat[a.KP];
+    const double mix = mix_s;
+    double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int k = 0; k < a.K; ++k) {
+      const double kN = a.per_k[k * 4 + 0], vN = a.per_k[k * 4 + 1], hld = a.per_k[k * 4 + 2];
+      t1 += log(kN / a.k0);
+      t2 += vN * hld;
+      t3 += lngammad_dev(vN, a.D);
+    }
+    // MOG.py:63-70
+    a.scalars[0] = -0.5 * a.D * t1 + a.K * a.v0 * a.S0_halflogdet - t2 + t3 - a.K * lngammad_dev(a.v0, a.D) + mix + H -
+                   0.5 * a.n_total * a.D * log(M_PI);
+    a.scalars[1] = mix;
+    a.scalars[2] = H;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.KP; k += blockDim.x) a.bias[k] = (k < a.K) ? a.per_k[k * 4 + 3] + mixgrad[k] : 0.0;
+  if (a.mixgrad_out)
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) a.mixgrad_out[k] = mixgrad[k];
+}
+
+}  // namespace gpc

@@ -1,0 +1,348 @@
+// gpclust_b200 -- setup / read-out kernels around the two N-sized passes (FP64, sm_100a).
+//
+//   k_kern_fill        : GPy covariance functions .K(X, X2)  (call sites MOHGP.py:47-48,61-62; OMGP.py:104,132)
+//   k_mog_features     : MOG feature rows [x_i x_j | x_i] that turn MOG.py:56-57,74-77 into the same
+//                        two GEMMs as MOHGP
+//   k_softmax_rows     : np_utilities.py:25-40 / utilities.py:61-102 -- materialises phi, log phi, H
+//   k_mahalanobis_pairs: utilities.py:147-170, per-pair forward substitution, same operation order
+//   k_gram_partials    : Y^T Y of MOHGP.py:53 (per-CTA partials, fixed-order reduction afterwards)
+//   k_mohgp_setup      : pdinv(Sy + 1e-6 I) and backsub_both_sides(Ly, Sf) of MOHGP.py:49,63,79
+//   k_batched_pdinv    : np_utilities.py:6-22 (multiple_pdinv)
+#pragma once
+#include "gpc_cluster_kernels.cuh"
+#include "gpc_common.cuh"
+
+namespace gpc {
+
+// ------------------------------------------------------------------------------------------------
+// GPC_KERN_* come from include/gpclust_b200.h
+constexpr int kMaxKernParts = 8;
+struct KernSpec {
+  int nparts;
+  int kind[kMaxKernParts];
+  double variance[kMaxKernParts];
+  double lengthscale[kMaxKernParts];
+};
+
+// out[i][j] = sum_parts k_p(x_i, x2_j).  r^2 is formed the way GPy's Stationary._unscaled_dist does:
+// -2 x.x2 + |x|^2 + |x2|^2, diagonal forced to zero when X2 is absent, clipped at zero.
+__global__ void k_kern_fill(const double *__restrict__ X, const double *__restrict__ X2, int n, int m, int q, const KernSpec spec,
+                            double diag_add, double *__restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n * m) return;
+  const int i = (int)(e / m), j = (int)(e % m);
+  const bool self = (X2 == nullptr);
+  const double *xi = X + (size_t)i * q;
+  const double *xj = (self ? X : X2) + (size_t)j * q;
+  double dot = 0.0, si = 0.0, sj = 0.0;
+  for (int c = 0; c < q; ++c) {
+    dot += xi[c] * xj[c];
+    si += xi[c] * xi[c];
+    sj += xj[c] * xj[c];
+  }
+  double r2 = -2.0 * dot + (si + sj);
+  if (self && i == j) r2 = 0.0;
+  r2 = fmax(r2, 0.0);
+  const double r_un = sqrt(r2);
+  double v = 0.0;
+  for (int p = 0; p < spec.nparts; ++p) {
+    const double var = spec.variance[p];
+    const double r = r_un / spec.lengthscale[p];
+    double kp;
+    switch (spec.kind[p]) {
+      case GPC_KERN_RBF: kp = var * exp(-0.5 * (r * r)); break;
+      case GPC_KERN_MATERN32: kp = var * (1.0 + sqrt(3.0) * r) * exp(-sqrt(3.0) * r); break;
+      case GPC_KERN_MATERN52: kp = var * (1.0 + sqrt(5.0) * r + 5.0 / 3.0 * (r * r)) * exp(-sqrt(5.0) * r); break;
+      case GPC_KERN_BIAS: kp = var; break;
+      default: kp = (self && i == j) ? var : 0.0; break;  // white
+    }
+    v = (p == 0) ? kp : v + kp;
+  }
+  if (self && i == j) v += diag_add;
+  out[e] = v;
+}
+
+// out[i] += var / (w[i] + eps)  on the diagonal of an n x n matrix (OMGP.py:105,135: diag(variance/(phi_i+1e-6)))
+__global__ void k_add_weighted_noise_diag(double *__restrict__ M, int n, const double *__restrict__ w, int w_stride, double variance, double eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[(size_t)i * n + i] += 1.0 / ((w[(size_t)i * w_stride] + eps) / variance);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MOG features: row n -> [ xc_i*xc_j (i<=j, row-major upper) | xc_i | 0 pad ], xc = x - centre.
+__global__ void k_mog_features(const double *__restrict__ X, const double *__restrict__ centre, int N, int Npad, int D, int DP,
+                               double *__restrict__ F) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)Npad * DP) return;
+  const int n = (int)(e / DP), f = (int)(e % DP);
+  const int NQ = D * (D + 1) / 2;
+  double v = 0.0;
+  if (n < N) {
+    if (f < NQ) {
+      int i = 0, rem = f;
+      while (rem >= D - i) {
+        rem -= D - i;
+        ++i;
+      }
+      const int j = i + rem;
+      v = (X[(size_t)n * D + i] - centre[i]) * (X[(size_t)n * D + j] - centre[j]);
+    } else if (f < NQ + D) {
+      const int i = f - NQ;
+      v = X[(size_t)n * D + i] - centre[i];
+    }
+  }
+  F[e] = v;
+}
+
+// Copy an N x D matrix into the padded Npad x DP feature layout (pad = 0).
+__global__ void k_pad_rows(const double *__restrict__ src, int N, int D, int Npad, int DP, double *__restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)Npad * DP) return;
+  const int n = (int)(e / DP), d = (int)(e % DP);
+  dst[e] = (n < N && d < D) ? src[(size_t)n * D + d] : 0.0;
+}
+// and back: padded Npad x ld -> contiguous N x K
+__global__ void k_unpad_rows(const double *__restrict__ src, int N, int K, int ld, double *__restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * K) return;
+  const int n = (int)(e / K), k = (int)(e % K);
+  dst[e] = src[(size_t)n * ld + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax read-out: one warp per row.  x has leading dimension ldx; phi / logphi (nullable) are
+// written with leading dimension ldo; Hpart[blockIdx.x] = sum over this CTA's rows of -sum_k phi log phi.
+constexpr int kSoftmaxWarps = 8;
+__global__ void __launch_bounds__(kSoftmaxWarps * 32) k_softmax_rows(const double *__restrict__ x, int N, int K, int ldx, double *__restrict__ phi,
+                                                                     double *__restrict__ logphi, int ldo, double *__restrict__ Hpart) {
+  __shared__ double red_s[kSoftmaxWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double hsum = 0.0;
+  for (long long row = (long long)blockIdx.x * kSoftmaxWarps + warp; row < N; row += (long long)gridDim.x * kSoftmaxWarps) {
+    const double *xr = x + (size_t)row * ldx;
+    double m = -INFINITY;
+    for (int k = lane; k < K; k += 32) m = fmax(m, xr[k]);
+    m = warp_max(m);
+    double s = 0.0;
+    for (int k = lane; k < K; k += 32) s += exp(xr[k] - m);
+    s = warp_sum(s);
+    const double lognorm = log(s);
+    double h = 0.0;
+    for (int k = lane; k < K; k += 32) {
+      const double lp0 = xr[k] - m;
+      const double p = exp(lp0) / s;
+      const double lp = lp0 - lognorm;
+      h -= p * lp;
+      if (phi) phi[(size_t)row * ldo + k] = p;
+      if (logphi) logphi[(size_t)row * ldo + k] = lp;
+    }
+    hsum += warp_sum(h);
+  }
+  if (lane == 0) red_s[warp] = hsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && Hpart) {
+    double v = 0.0;
+    for (int w = 0; w < kSoftmaxWarps; ++w) v += red_s[w];
+    Hpart[blockIdx.x] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pairwise Mahalanobis by forward substitution (the reference's own native kernel, utilities.py:147-170):
+// out[n][m] = | L^-1 (x1_n - x2_m) |^2.  One thread per pair, L staged in shared memory.
+constexpr int kMahaMaxD = 128;
+__global__ void __launch_bounds__(128) k_mahalanobis_pairs(const double *__restrict__ X1, const double *__restrict__ X2, const double *__restrict__ L,
+                                                           int N1, int N2, int D, double *__restrict__ out) {
+  extern __shared__ __align__(16) double Ls[];  // D x D
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) Ls[e] = L[e];
+  __syncthreads();
+  const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= (long long)N1 * N2) return;
+  const int n = (int)(pair / N2), m = (int)(pair % N2);
+  double t[kMahaMaxD];
+  double acc2 = 0.0;
+  for (int i = 0; i < D; ++i) {
+    double v = X1[(size_t)n * D + i] - X2[(size_t)m * D + i];
+    for (int j = 0; j < i; ++j) v -= Ls[i * D + j] * t[j];
+    v /= Ls[i * D + i];
+    t[i] = v;
+  }
+  for (int i = 0; i < D; ++i) acc2 += t[i] * t[i];
+  out[pair] = acc2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP)
+constexpr int kGramRows = 32;
+__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, double *__restrict__ partials) {
+  extern __shared__ __align__(16) double tile[];  // kGramRows x DP
+  const int tid = threadIdx.x;
+  const int nout = DP * DP;
+  // each thread owns outputs tid, tid+256, ... (at most 16 for DP = 64)
+  double acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+  const int num_tiles = Npad / kGramRows;
+  for (int tix = blockIdx.x; tix < num_tiles; tix += gridDim.x) {
+    __syncthreads();
+    const double *src = F + (size_t)tix * kGramRows * DP;
+    for (int e = tid; e < kGramRows * DP; e += blockDim.x) tile[e] = src[e];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int o = tid + q * 256;
+      if (o < nout) {
+        const int i = o / DP, j = o % DP;
+        double v = acc[q];
+        for (int r = 0; r < kGramRows; ++r) v += tile[r * DP + i] * tile[r * DP + j];
+        acc[q] = v;
+      }
+    }
+  }
+  double *part = partials + (size_t)blockIdx.x * nout;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int o = tid + q * 256;
+    if (o < nout) part[o] = acc[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lower-triangular inverse in shared memory: Li = L^-1, one column per thread (column-oriented).
+__device__ inline void tri_inverse_lower_smem(const double *L, int n, int ld, double *Li) {
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    for (int i = 0; i < j; ++i) Li[i * ld + j] = 0.0;
+    Li[j * ld + j] = 1.0 / L[j * ld + j];
+    for (int i = j + 1; i < n; ++i) {
+      double v = 0.0;
+      for (int m = j; m < i; ++m) v -= L[i * ld + m] * Li[m * ld + j];
+      Li[i * ld + j] = v / L[i * ld + i];
+    }
+  }
+  __syncthreads();
+}
+
+// jitchol (GPy.util.linalg.jitchol) of the n x n matrix `src` (global, row-major, + diag_add on the
+// diagonal) into shared memory M.  Returns false when not positive definite even with jitter.
+__device__ inline bool jitchol_smem(const double *src, double diag_add, int n, int ld, double *M, int *flag_s) {
+  bool ok = false;
+  double diag_mean = 0.0;
+  for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+    double jitter = 0.0;
+    if (attempt > 0) {
+      jitter = diag_mean * 1e-6;
+      for (int q = 1; q < attempt; ++q) jitter *= 10.0;
+      if (!isfinite(jitter)) break;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      M[i * ld + j] = src[e] + ((i == j) ? diag_add + jitter : 0.0);
+    }
+    __syncthreads();
+    if (attempt == 0) {
+      double dsum = 0.0, dmin = INFINITY;
+      for (int i = 0; i < n; ++i) {
+        dsum += M[i * ld + i];
+        dmin = fmin(dmin, M[i * ld + i]);
+      }
+      diag_mean = dsum / n;
+      ok = chol_lower_smem(M, n, ld, flag_s);
+      if (!ok && !(dmin > 0.0)) break;
+    } else {
+      ok = chol_lower_smem(M, n, ld, flag_s);
+    }
+  }
+  return ok;
+}
+
+struct MohgpSetupArgs {
+  const double *Sf;    // D x D
+  const double *Sy;    // D x D (un-jittered)
+  double *Ly;          // out D x D : chol(Sy + 1e-6 I), lower, strict upper zero   (Sy_chol)
+  double *Ly_inv;      // out D x D : Ly^-1                                          (Sy_chol_inv)
+  double *Sy_inv;      // out D x D : (Sy + 1e-6 I)^-1
+  double *A;           // out D x D : Ly^-1 Sf Ly^-T                                 (MOHGP.py:79)
+  double *Sy_logdet;   // out scalar
+  int *info;
+  int D;
+};
+
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_setup(const MohgpSetupArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, ld = D + 1, tid = threadIdx.x;
+  double *Lm = sm;            // factor
+  double *Li = Lm + D * ld;   // its inverse
+  double *W = Li + D * ld;    // work
+  __shared__ int flag_s;
+  if (!jitchol_smem(a.Sy, 1e-6, D, ld, Lm, &flag_s)) {
+    if (tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
+    return;
+  }
+  if (tid < 32) {
+    double ldd = 0.0;
+    for (int i = tid; i < D; i += 32) ldd += log(Lm[i * ld + i]);
+    ldd = 2.0 * warp_sum(ldd);
+    if (tid == 0) *a.Sy_logdet = ldd;
+  }
+  __syncthreads();
+  tri_inverse_lower_smem(Lm, D, ld, Li);
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    a.Ly[e] = (j <= i) ? Lm[i * ld + j] : 0.0;
+    a.Ly_inv[e] = (j <= i) ? Li[i * ld + j] : 0.0;
+    // Sy_inv = Li^T Li
+    double v = 0.0;
+    for (int m = (i > j ? i : j); m < D; ++m) v += Li[m * ld + i] * Li[m * ld + j];
+    a.Sy_inv[e] = v;
+  }
+  // W = Li Sf ; A = W Li^T
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    double v = 0.0;
+    for (int m = 0; m <= i; ++m) v += Li[i * ld + m] * a.Sf[m * D + j];
+    W[i * ld + j] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    double v = 0.0;
+    for (int m = 0; m <= j; ++m) v += W[i * ld + m] * Li[j * ld + m];
+    a.A[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multiple_pdinv (np_utilities.py:6-22): A is D x D x K with K LAST (stride K between matrix entries);
+// inv has the same layout; hld[k] = sum log diag chol.  One CTA per k.
+__global__ void __launch_bounds__(kClusterThreads) k_batched_pdinv(const double *__restrict__ A, int D, int K, double *__restrict__ inv,
+                                                                   double *__restrict__ hld, int *info) {
+  extern __shared__ __align__(16) double sm[];
+  const int ld = D + 1, k = blockIdx.x, tid = threadIdx.x;
+  double *G = sm;            // gathered matrix (contiguous D x D)
+  double *Lm = G + D * D;    // factor
+  double *Li = Lm + D * ld;  // inverse factor
+  __shared__ int flag_s;
+  for (int e = tid; e < D * D; e += blockDim.x) G[e] = A[(size_t)e * K + k];
+  __syncthreads();
+  if (!jitchol_smem(G, 0.0, D, ld, Lm, &flag_s)) {
+    if (tid == 0) atomicOr(info, GPC_INFO_NOT_PD);
+    return;
+  }
+  if (tid < 32) {
+    double s = 0.0;
+    for (int i = tid; i < D; i += 32) s += log(Lm[i * ld + i]);
+    s = warp_sum(s);
+    if (tid == 0) hld[k] = s;
+  }
+  __syncthreads();
+  tri_inverse_lower_smem(Lm, D, ld, Li);
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    double v = 0.0;
+    for (int m = (i > j ? i : j); m < D; ++m) v += Li[m * ld + i] * Li[m * ld + j];
+    inv[(size_t)e * K + k] = v;
+  }
+}
+
+}  // namespace gpc

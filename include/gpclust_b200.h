@@ -1,0 +1,141 @@
+/* gpclust_b200 -- C-ABI of the B200 (sm_100a) collapsed-VB hot path of GPclust.
+ *
+ * The reference (/root/reference/GPclust) is pure Python; its only backend seam is the L1 utility
+ * module pair utilities.py (scipy.weave inline C++) / np_utilities.py (numpy), bound at import time by
+ *   collapsed_mixture.py:6-10, MOHGP.py:9-12, MOG.py:6-9.
+ * The entry points below are what a ctypes binding in those modules (and in the template methods
+ * set_vb_param / do_computations / bound / vb_grad_natgrad, collapsed_vb.py:41-54) would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to IEEE double (row-major) unless stated otherwise;
+ *   - the caller owns every buffer; the library allocates nothing and keeps no global state;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it;
+ *   - return value: 0 = enqueued, GPC_EINVAL = bad argument, negative = -(cudaError_t);
+ *   - numerical failure (matrix not positive definite, the reference's LinAlgError raised by
+ *     GPy.util.linalg.jitchol) is reported asynchronously through an `int *info` device flag
+ *     (bit GPC_INFO_NOT_PD), which the host mirror turns into numpy.linalg.LinAlgError so that
+ *     collapsed_vb.py:174,187 keep their meaning.
+ *
+ * Layout of the N-sized arrays ("series" rows n, "cluster" columns k)
+ *   - logits / natural gradient / search direction: Npad x KP, Npad = roundup(N, GPC_ROW_TILE),
+ *     KP = gpc_padded_k(K) in {8,16,32,64}; pad rows and pad columns hold zeros;
+ *   - features F: Npad x DP, DP = gpc_padded_d(D) (multiple of 8, <= 64), pad zero.
+ *     MOHGP: F = Y.  MOG: F = [x_i x_j (i<=j) | x_i] of the centred data (gpc_mog_features).
+ *   - stats vector: [ T (KP x DP) | phi_hat (KP) | H (1) ],  T[k][f] = sum_n phi[n][k] F[n][f].
+ */
+#ifndef GPCLUST_B200_H
+#define GPCLUST_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPC_ROW_TILE 64
+#define GPC_EINVAL 2
+#define GPC_INFO_NOT_PD 1
+
+#define GPC_PRIOR_SYMMETRIC 0
+#define GPC_PRIOR_DP 1
+
+#define GPC_BETA_ZERO 0 /* steepest / first iteration  collapsed_vb.py:157-158 */
+#define GPC_BETA_HS 1   /* collapsed_vb.py:163-164 */
+#define GPC_BETA_PR 2   /* collapsed_vb.py:159-160 */
+#define GPC_BETA_FR 3   /* collapsed_vb.py:161-162 */
+
+#define GPC_KERN_RBF 0
+#define GPC_KERN_MATERN32 1
+#define GPC_KERN_MATERN52 2
+#define GPC_KERN_BIAS 3
+#define GPC_KERN_WHITE 4
+
+/* ---- library / geometry queries (host only, no GPU needed) ---------------------------------- */
+int gpc_abi_version(void);
+int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
+int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
+long long gpc_padded_rows(long long N);
+int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 1                                               */
+int gpc_default_grid(int device);  /* number of persistent CTAs (= SM count); <0 on CUDA error     */
+
+/* ---- G pass: natural gradient + conjugate-gradient dot products ------------------------------
+ * Replaces MOHGP.vb_grad_natgrad (MOHGP.py:137-153) / MOG.vb_grad_natgrad (MOG.py:72-84) including
+ * multiple_mahalanobis (utilities.py:108-172) and the dots of collapsed_vb.py:154,160-164.
+ *   a[n,k]   = F[n,:] . Wt[k,:] + bias[k] - x[n,k]
+ *   natgrad  = a - sum_k phi a ;  grad = natgrad * phi ;  phi = softmax_k(x)
+ *   dots[0] = natgrad.grad  dots[1] = (natgrad - ng_old).grad  dots[2] = (natgrad - ng_old).grad_old
+ * x_old / ng_old may both be NULL (first iteration): dots[1], dots[2] are then 0.
+ * grad_out may be NULL.  partials: grid*4 doubles.  counter: one zero-initialised unsigned int.     */
+int gpc_natgrad(const double *F, const double *x, const double *Wt, const double *bias, const double *x_old, const double *ng_old,
+                double *ng_out, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
+                int DP, int grid, void *stream);
+
+/* ---- S pass: conjugate step + softmax + sufficient statistics --------------------------------
+ * Replaces collapsed_vb.py:167,172 (searchDir, phi_old + step*searchDir) fused with
+ * CollapsedMixture.set_vb_param (collapsed_mixture.py:49-59: softmax, phi_hat, H) and the N-sized part
+ * of do_computations (MOHGP.py:76 ybark; MOG.py:56-57 Xsumk, Ck).
+ *   beta from dots (device) according to beta_mode, nan / negative -> 0 (collapsed_vb.py:165-166)
+ *   sd_new = ng + beta*sd_old ; x_new = x_base + step*sd_new ; stats of softmax(x_new)
+ * ng == NULL: "set" mode -- statistics of x_base itself, nothing is written but the partials.
+ * sd_new may alias sd_old.  partials: grid * gpc_stats_len doubles -> reduce with gpc_reduce_partials. */
+int gpc_step_stats(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
+                   const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
+                   int K, int KP, int DP, int grid, void *stream);
+
+/* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
+int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);
+
+/* ---- MOHGP per-cluster posterior (MOHGP.py:79-90) + bound (MOHGP.py:124-135) ------------------ */
+/* once per kernel-parameter change (MOHGP.py:47-49 / :61-63): Ly = chol(Sy+1e-6 I), Ly_inv, Sy_inv,
+ * A = Ly^-1 Sf Ly^-T, Sy_logdet.  D <= 64.                                                         */
+int gpc_mohgp_setup(const double *Sf, const double *Sy, double *Ly, double *Ly_inv, double *Sy_inv, double *A, double *Sy_logdet,
+                    int *info, int D, void *stream);
+/* const_term = -0.5*(n_total*D*log(2 pi) + n_total*Sy_logdet + sum(YTY o Sy_inv))  (MOHGP.py:129-132) */
+int gpc_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_logdet, double n_total, int D, double *const_term,
+                    void *stream);
+/* per cluster k (one CTA each): C_k = I + phi_hat_k A, jitchol, log_det_diff, Lambda_inv, s_k, mu_k,
+ * and the G-pass weights Wt[k,:] = Sy^-1 mu_k.  per_k: KP x 4 = [log_det_diff, s^T Lambda_inv s,
+ * tr(Lambda_inv Sy_inv), mu^T Sy^-1 mu].  Syi_ybark_t, Lambda_inv, C_chols may be NULL.  *info is
+ * cleared first.                                                                                     */
+int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Sy, const double *Sy_inv, const double *Sf,
+                      double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
+                      int K, int D, int KP, int DP, void *stream);
+/* mixing-proportion bound and gradient (collapsed_mixture.py:66-94), bound assembly, G-pass bias.
+ * scalars: [0] bound, [1] mixing_prop_bound, [2] H.  mixgrad_out (K doubles) may be NULL.             */
+int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
+                       double *mixgrad_out, double alpha, int prior, int K, int KP, int DP, void *stream);
+
+/* ---- MOG (MOG.py:34-84) ------------------------------------------------------------------------ */
+int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream);
+/* per_k: KP x 4 = [kN, vN, Sns_halflogdet, grad const].  mun_c: K x D (centred), Sns / Sns_inv: K x D x D.
+ * D <= 10.  *info is cleared first.                                                                   */
+int gpc_mog_cluster(const double *stats, const double *m0c, const double *S0, double *Wt, double *per_k, double *mun_c, double *Sns,
+                    double *Sns_inv, int *info, double k0, double v0, int K, int D, int KP, int DP, void *stream);
+int gpc_mog_finalize(const double *stats, const double *per_k, double *bias, double *scalars, double *mixgrad_out, double n_total,
+                     double k0, double v0, double S0_halflogdet, double alpha, int prior, int K, int KP, int DP, int D, void *stream);
+
+/* ---- covariance fills (GPy kern.K(X, X2); call sites MOHGP.py:47-48,61-62, OMGP.py:104,132) ---- */
+/* out (n x m) = sum_p k_p(X_i, X2_j) ; X2 == NULL -> X2 = X, m = n (White contributes, diagonal r = 0).
+ * kinds/variances/lengthscales: HOST arrays of nparts (<= 8) entries.  diag_add is added to the
+ * diagonal when X2 == NULL.                                                                          */
+int gpc_kern_fill(const double *X, const double *X2, int n, int m, int q, int nparts, const int *kinds, const double *variances,
+                  const double *lengthscales, double diag_add, double *out, void *stream);
+
+/* ---- the reference's L1 utilities, same meaning as np_utilities.py ---------------------------- */
+/* softmax (np_utilities.py:25-40): x is N x K with leading dimension ldx; phi / logphi (either may be
+ * NULL) get leading dimension ldo; Hpart must hold `grid` doubles, H = sum(Hpart) (gpc_reduce_partials). */
+int gpc_softmax_rows(const double *x, long long N, int K, int ldx, double *phi, double *logphi, int ldo, double *Hpart, int grid,
+                     void *stream);
+/* multiple_mahalanobis (utilities.py:108-172): out[n][m] = |L^-1 (X1_n - X2_m)|^2, D <= 128.         */
+int gpc_multiple_mahalanobis(const double *X1, const double *X2, const double *L, long long N1, int N2, int D, double *out,
+                             void *stream);
+/* multiple_pdinv (np_utilities.py:6-22): A, inv are D x D x K (K last); hld K doubles.  D <= 64.     */
+int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, int *info, void *stream);
+/* Y^T Y (MOHGP.py:53): partials grid x DP x DP, then gpc_reduce_partials(len = DP*DP).               */
+int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream);
+/* layout helpers: contiguous N x D  <->  padded Npad x ld                                             */
+int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, void *stream);
+int gpc_unpad_rows(const double *src, long long N, int K, int ld, double *dst, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,167 @@
+"""GPU parity of the MOHGP hot path (through the Python mirror -> C-ABI -> sm_100a kernels) against the
+CPU oracle on identical seeded inputs.  Tolerance (north_star): 1e-9 relative in FP64 for phi, bound and
+gradients -- arrays are compared in max-norm-relative terms; cluster assignments
+after convergence must be identical."""
+import io
+
+import numpy as np
+import pytest
+
+from helpers import mohgp_problem, oracle_kernels, product_kernels, relerr
+from oracle.vb_oracle import MOHGPOracle, mahalanobis_pairs_substitution, mahalanobis_whitened_gemm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _pair(N, D, K, prior_Z="symmetric", alpha=1.0, seed=0):
+    from gpclust_b200 import MOHGP
+    X, Y, _ = mohgp_problem(N, D, K, seed)
+    np.random.seed(seed + 1)
+    phi0 = np.random.randn(N, K)
+    kF, kY = oracle_kernels()
+    np.random.seed(seed + 1)
+    mo = MOHGPOracle(X, kF, kY, Y, K=K, prior_Z=prior_Z, alpha=alpha, mahalanobis=mahalanobis_whitened_gemm if N * K > 40000 else None)
+    pF, pY = product_kernels()
+    np.random.seed(seed + 1)
+    mp = MOHGP(X, pF, pY, Y, K=K, prior_Z=prior_Z, alpha=alpha)
+    assert np.array_equal(mp.phi_, phi0) and np.array_equal(mo.phi_, phi0)
+    return mo, mp
+
+
+SHAPES = [(400, 12, 5), (1000, 64, 64), (777, 56, 20), (64, 8, 2), (130, 3, 1), (5000, 33, 17), (300, 64, 9)]
+
+
+@pytest.mark.parametrize("N,D,K", SHAPES)
+@pytest.mark.parametrize("prior_Z", ["symmetric", "DP"])
+def test_state_bound_gradient(N, D, K, prior_Z):
+    mo, mp = _pair(N, D, K, prior_Z, alpha=1.0 if prior_Z == "symmetric" else 3.0)
+    assert relerr(mp.phi, mo.phi) < 1e-13
+    assert relerr(mp.Hgrad, mo.Hgrad) < 1e-13
+    assert relerr(mp.phi_hat, mo.phi_hat) < 1e-12
+    assert abs(mp.H - mo.H) < 1e-11 * abs(mo.H)
+    assert relerr(mp.Sf, mo.Sf) < 1e-14 and relerr(mp.Sy, mo.Sy) < 1e-14
+    assert relerr(mp.Sy_chol, mo.Sy_chol) < 1e-10
+    assert relerr(mp.Sy_inv, mo.Sy_inv) < 1e-8  # Sy is ill-conditioned; the inverse is compared loosely, its uses tightly
+    assert abs(mp.Sy_logdet - mo.Sy_logdet) < 1e-10 * abs(mo.Sy_logdet)
+    assert relerr(mp.YTY, mo.YTY) < 1e-12
+    assert relerr(mp.ybark, mo.ybark) < 1e-12
+    assert relerr(mp.log_det_diff, mo.log_det_diff) < TOL
+    assert relerr(mp.muk, mo.muk) < TOL
+    assert relerr(mp.Lambda_inv, mo.Lambda_inv) < 1e-7  # the reference's own formula is noisy here
+    assert abs(mp.mixing_prop_bound() - mo.mixing_prop_bound()) < 1e-11 * max(1.0, abs(mo.mixing_prop_bound()))
+    assert relerr(mp.mixing_prop_bound_grad(), mo.mixing_prop_bound_grad()) < 1e-13
+    assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
+    assert abs(mp.log_likelihood() - mo.bound()) < TOL * abs(mo.bound())
+    g_p, ng_p = mp.vb_grad_natgrad()
+    g_o, ng_o = mo.vb_grad_natgrad()
+    assert g_p.shape == (N * K,) and ng_p.shape == (N * K,)
+    assert relerr(ng_p, ng_o) < TOL
+    assert relerr(g_p, g_o) < TOL
+
+
+def test_gemm_form_equals_pairwise_substitution():
+    """The G pass evaluates the Mahalanobis terms as one GEMM; the reference forward-substitutes per pair
+    (utilities.py:147-170).  Same natural gradient to 1e-9 (the row-constant |L^-1 y|^2 is projected out)."""
+    mo, mp = _pair(300, 24, 6)
+    mo.mahalanobis = mahalanobis_pairs_substitution
+    g_o, ng_o = mo.vb_grad_natgrad()
+    g_p, ng_p = mp.vb_grad_natgrad()
+    assert relerr(ng_p, ng_o) < TOL and relerr(g_p, g_o) < TOL
+
+
+@pytest.mark.parametrize("method", ["HS", "PR", "FR", "steepest"])
+def test_optimize_trace(method):
+    N, D, K = 600, 16, 6
+    mo, mp = _pair(N, D, K, seed=3)
+    mo.out = io.StringIO()
+    mo.optimize(method=method, maxiter=40, verbose=False)
+    mp.optimize(method=method, maxiter=40, verbose=False)
+    to, tp = mo.trace, mp.optimize_trace
+    assert [r[0] for r in tp] == [r[0] for r in to]  # identical iteration accounting (incl. rejected steps)
+    for (it, b, sq, beta), (_, b0, sq0, beta0) in zip(tp, to):
+        assert abs(b - b0) < 1e-9 * abs(b0), (it, b, b0)
+        assert abs(sq - sq0) < 1e-6 * max(abs(sq0), 1e-12), (it, sq, sq0)
+    assert relerr(mp.phi, mo.phi) < 1e-6
+    assert np.array_equal(mp.phi.argmax(1), mo.phi.argmax(1))
+
+
+def test_converged_assignments_identical():
+    N, D, K = 2000, 32, 8
+    mo, mp = _pair(N, D, K, seed=5)
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=200, verbose=False)
+    it = mp.optimize(maxiter=200, verbose=False)
+    assert it == mo.trace[-1][0]
+    assert abs(mp.bound() - mo.bound()) < 1e-9 * abs(mo.bound())
+    assert np.array_equal(mp.phi.argmax(1), mo.phi.argmax(1))
+    # bound is monotone non-decreasing over accepted iterations
+    b = [r[1] for r in mp.optimize_trace]
+    assert all(b2 >= b1 - 1e-9 * abs(b1) for b1, b2 in zip(b, b[1:]))
+
+
+def test_set_get_roundtrip_and_randomize():
+    mo, mp = _pair(200, 10, 4)
+    x = mp.get_vb_param()
+    assert x.shape == (200 * 4,)
+    b = mp.bound()
+    mp.set_vb_param(x.copy())
+    assert mp.bound() == b  # bit-reproducible re-evaluation
+    assert np.array_equal(mp.get_vb_param(), x)
+    np.random.seed(11)
+    mp.randomize()
+    np.random.seed(11)
+    mo.randomize()
+    assert abs(mp.bound() - mo.bound()) < 1e-9 * abs(mo.bound())
+
+
+def test_tiny_phi_hat_guard():
+    """MOHGP.py:85: clusters with phi_hat <= 1e-6 take Lambda_inv = Sf."""
+    mo, mp = _pair(150, 8, 3)
+    x = mo.get_vb_param().reshape(150, 3).copy()
+    x[:, 2] = -60.0
+    mo.set_vb_param(x.flatten())
+    mp.set_vb_param(x.flatten())
+    assert mo.phi_hat[2] < 1e-6
+    assert relerr(mp.Lambda_inv[2], mo.Sf) < 1e-14
+    assert abs(mp.bound() - mo.bound()) < 1e-9 * abs(mo.bound())
+    g_p, ng_p = mp.vb_grad_natgrad()
+    g_o, ng_o = mo.vb_grad_natgrad()
+    assert relerr(ng_p, ng_o) < TOL
+
+
+def test_not_pd_raises_linalgerror():
+    from gpclust_b200 import MOHGP, kern
+    X, Y, _ = mohgp_problem(100, 8, 3)
+    with pytest.raises(np.linalg.LinAlgError):
+        MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.Bias(1, -1.0), Y, K=3)
+
+
+def test_matern_dp_drosophila_like():
+    """Config 1 stand-in: D=56 time points with replicated inputs, Matern52 kernels, DP prior, K=20."""
+    from gpclust_b200 import MOHGP, kern
+    from oracle import gpy_shim as G
+    import os
+    from helpers import GOLDEN
+    rows = [l.strip().split(",") for l in open(os.path.join(GOLDEN, "kalinka09_pdata.csv")).read().strip().split("\n")]
+    hours = np.array([float(r[2]) for r in rows if r[0] == "me"])  # melanogaster: 8 replicates x hours 2..20 (no header row)
+    assert hours.size == 56
+    X = hours[:56, None]
+    D = X.shape[0]
+    rng = np.random.RandomState(0)
+    kF, kY = G.Matern52(1, 1.0, 12.0), G.Matern52(1, 0.1, 12.0) + G.White(1, 0.05)
+    Sf, Sy = kF.K(X), kY.K(X)
+    K, N = 20, 500
+    means = np.linalg.cholesky(Sf + 1e-6 * np.eye(D)).dot(rng.randn(D, 6)).T
+    Y = means[rng.randint(0, 6, N)] + np.linalg.cholesky(Sy + 1e-8 * np.eye(D)).dot(rng.randn(D, N)).T
+    Y = (Y - Y.mean(1)[:, None]) / Y.std(1)[:, None]
+    np.random.seed(2)
+    mo = MOHGPOracle(X, kF, kY, Y, K=K, prior_Z="DP", alpha=1.0)
+    np.random.seed(2)
+    mp = MOHGP(X, kern.Matern52(1, 1.0, 12.0), kern.Matern52(1, 0.1, 12.0) + kern.White(1, 0.05), Y, K=K, prior_Z="DP", alpha=1.0)
+    assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=30, verbose=False)
+    mp.optimize(maxiter=30, verbose=False)
+    assert [r[0] for r in mp.optimize_trace] == [r[0] for r in mo.trace]
+    assert abs(mp.bound() - mo.bound()) < 1e-8 * abs(mo.bound())
