@@ -68,7 +68,7 @@ int gpc_padded_d(int D) {
   return (D + 7) / 8 * 8;
 }
 long long gpc_padded_rows(long long N) { return (N + GPC_ROW_TILE - 1) / GPC_ROW_TILE * GPC_ROW_TILE; }
-int gpc_stats_len(int KP, int DP) { return KP * DP + KP + 1; }
+int gpc_stats_len(int KP, int DP) { return KP * DP + KP + 2; }
 
 int gpc_default_grid(int device) {
   int sms = 0;

@@ -255,7 +255,7 @@ struct StepStatsArgs {
   double *x_new;         // trial logits (may be nullptr in "set" mode)
   const double *dots;    // [0]=sq [1]=num [2]=den of the G pass at x_base (device scalars, read when beta_mode != 0)
   double *beta_out;      // device scalar, written by CTA 0
-  double *partials;      // gridDim.x * stat_len, stat_len = KP*DP + KP + 1  ([ybark KPxDP | phi_hat KP | H])
+  double *partials;      // gridDim.x * stat_len, stat_len = KP*DP + KP + 2  ([T KPxDP | phi_hat KP | H | pad]; even => 16-B aligned blocks)
   double step;
   double sq_old;         // natgrad.grad of the previous iteration (PR / FR only; the host read it back already)
   int beta_mode;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
     }
 
     // ---- per-CTA partial statistics
-    double *part = a.partials + (size_t)blockIdx.x * (KP * a.DP + KP + 1);
+    double *part = a.partials + (size_t)blockIdx.x * (KP * a.DP + KP + 2);
 #pragma unroll
     for (int i = 0; i < DT_PER; ++i) {
       const int dt = dgrp + i * NGRP;
@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
       for (int w = 0; w < GPC_CONSUMER_WARPS; ++w) v += red_s[w * (KP + 1) + j];
       part[(size_t)KP * a.DP + j] = v;
     }
+    if (threadIdx.x == 0) part[(size_t)KP * a.DP + KP + 1] = 0.0;
   }
 }
 

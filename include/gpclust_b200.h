@@ -21,7 +21,7 @@
  *     KP = gpc_padded_k(K) in {8,16,32,64}; pad rows and pad columns hold zeros;
  *   - features F: Npad x DP, DP = gpc_padded_d(D) (multiple of 8, <= 64), pad zero.
  *     MOHGP: F = Y.  MOG: F = [x_i x_j (i<=j) | x_i] of the centred data (gpc_mog_features).
- *   - stats vector: [ T (KP x DP) | phi_hat (KP) | H (1) ],  T[k][f] = sum_n phi[n][k] F[n][f].
+ *   - stats vector: [ T (KP x DP) | phi_hat (KP) | H (1) | pad (1) ],  T[k][f] = sum_n phi[n][k] F[n][f].
  */
 #ifndef GPCLUST_B200_H
 #define GPCLUST_B200_H
@@ -53,7 +53,7 @@ int gpc_abi_version(void);
 int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
 int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
 long long gpc_padded_rows(long long N);
-int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 1                                               */
+int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 2 (one pad double keeps blocks 16-B aligned)    */
 int gpc_default_grid(int device);  /* number of persistent CTAs (= SM count); <0 on CUDA error     */
 
 /* ---- G pass: natural gradient + conjugate-gradient dot products ------------------------------
