@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- MOHGP VB iterations/sec (BASELINE.json metric), config 3: N=1M series, D=64 time points,
+K=64 clusters, FP64, method='HS', synthetic data (SURVEY.md section 8d recipe).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the collapsed-VB loop body (collapsed_vb.py:147-303): G pass (natural gradient +
+CG dots), S pass (search direction, trial point, softmax, statistics), per-cluster posterior, bound, and
+the host accept/reject decision on the bound read back from the device.  Rows are sharded over the ranks
+(strong scaling: N_total is fixed at 1M), statistics and dots are all-reduced over NCCL.
+
+The JSON line carries, besides the contract keys:
+  roofline      the dominant N-sized kernel (largest share of the step), HBM-bound: algorithmic bytes per
+                launch / mean CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  fp64_tensor   4*N*K*D flop per step / step time against the measured DMMA peak (profiles/fp64_peaks_r01.json)
+  cpu_baseline  the oracle port of the reference's native path (weave C kernels + numpy/LAPACK) on the
+                host cores, on a bounded row sample, scaled linearly in N
+  e2e           the same metric through the public API with HOST buffers: construct MOHGP from numpy Y and
+                numpy phi_ (H2D), optimize() for the same number of steps, read phi and the bound back (D2H)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_TOTAL, D, K = 1000000, 64, 64
+METRIC = "MOHGP VB iterations/sec (N=1M,D=64,K=64)"
+UNIT = "iterations/s"
+FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
+
+
+def synth(n_total, d, k, seed=0):
+    """SURVEY.md section 8(d) config 3 generator (host numpy, deterministic)."""
+    from oracle import gpy_shim as G
+    rng = np.random.RandomState(seed)
+    X = np.linspace(0, 10, d)[:, None]
+    Sf = G.RBF(1, 1.0, 2.0).K(X)
+    Sy = (G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)).K(X)
+    z = rng.randint(0, k, n_total)
+    means = (np.linalg.cholesky(Sf + 1e-8 * np.eye(d)).dot(rng.randn(d, k))).T
+    Y = means[z] + (np.linalg.cholesky(Sy).dot(rng.randn(d, n_total))).T
+    np.random.seed(0)
+    phi0 = np.random.randn(n_total, k)  # collapsed_mixture.py:41
+    return X, np.ascontiguousarray(Y), phi0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(object):
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().split("\n"):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_rate(X, Y, phi0, k, budget_s, passes=2):
+    """Oracle port of the reference's native path on the host cores: weave C kernels (oracle/weave_kernels.c,
+    OpenMP over rows as utilities.py:54,143) + numpy/LAPACK for everything else, host-vector CG loop.
+    Runs `passes` loop-body passes on a row sample sized for ~budget_s seconds; returns iterations/s scaled
+    linearly to N_TOTAL rows (every N-dependent term of the iteration is linear in N)."""
+    from oracle import native
+    from oracle.build import build_oracle, has_openmp
+    from oracle.vb_oracle import MOHGPOracle
+    from oracle import gpy_shim as G
+    build_oracle()
+    cores = os.cpu_count() if has_openmp() else 1
+
+    def run(n_rows):
+        kF = G.RBF(1, 1.0, 2.0)
+        kY = G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+        np.random.seed(0)
+        m = MOHGPOracle(X, kF, kY, Y[:n_rows], K=k, mahalanobis=native.multiple_mahalanobis)
+        m.softmax = native.softmax_weave
+        m.set_vb_param(phi0[:n_rows].flatten())
+        t0 = time.perf_counter()
+        m.iterate(passes, method="HS")
+        return (time.perf_counter() - t0) / passes
+
+    probe_rows = min(4000, Y.shape[0])
+    t_probe = run(probe_rows)
+    per_row = t_probe / probe_rows
+    rows = int(min(Y.shape[0], max(probe_rows, budget_s / passes / per_row)))
+    t_iter = run(rows) if rows > probe_rows else t_probe
+    rate = 1.0 / (t_iter * (N_TOTAL / float(rows)))
+    sample = "%d of %d rows, %d loop passes, %.2f s/pass on the sample, scaled linearly in N" % (rows, N_TOTAL, passes, t_iter)
+    return rate, cores, sample, t_iter
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be imported --
+    GPy / scipy.weave are absent).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, Y, phi0 = synth(min(N_TOTAL, 200000), D, K)  # the sample never needs more rows than this
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    budget = 150.0
+    per_step_budget = budget / (steps + warm)
+    t0 = time.perf_counter()
+    from oracle import native
+    from oracle.build import build_oracle, has_openmp
+    from oracle.vb_oracle import MOHGPOracle
+    from oracle import gpy_shim as G
+    build_oracle()
+    cores = os.cpu_count() if has_openmp() else 1
+    # calibrate the sample size so that (steps + warmup) passes fit the budget
+    probe = 2000
+    kF, kY = G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+
+    def make(n_rows):
+        m = MOHGPOracle(X, kF, kY, Y[:n_rows], K=K, mahalanobis=native.multiple_mahalanobis)
+        m.softmax = native.softmax_weave
+        m.set_vb_param(phi0[:n_rows].flatten())
+        return m
+    m = make(probe)
+    t1 = time.perf_counter()
+    m.iterate(1)
+    per_row = (time.perf_counter() - t1) / probe
+    rows = int(min(Y.shape[0], max(probe, per_step_budget / per_row)))
+    m = make(rows)
+    m.iterate(warm) if warm else None
+    t1 = time.perf_counter()
+    m.iterate(steps)
+    dt = time.perf_counter() - t1
+    t_step_full = dt / steps * (N_TOTAL / float(rows))
+    value = 1.0 / t_step_full
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": t_step_full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "MOHGP N=1M D=64 K=64 FP64 HS-CG (config 3)", "N": N_TOTAL, "D": D, "K": K, "method": "HS"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of %d rows per step, %.3f s/step on the sample, scaled linearly in N" % (rows, N_TOTAL, dt / steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gpclust_b200 import MOHGP, kern
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, Y, phi0 = synth(N_TOTAL, D, K)
+    lo = rank * N_TOTAL // world
+    hi = (rank + 1) * N_TOTAL // world
+    Y_loc, phi_loc = Y[lo:hi], phi0[lo:hi]
+    n_loc = hi - lo
+    kF = lambda: kern.RBF(1, 1.0, 2.0)
+    kY = lambda: kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    method = args.method
+
+    # ---------------- device-resident timing: K loop-body passes, state already in HBM
+    m = MOHGP(X, kF(), kY(), Y_loc, K=K, phi_init=phi_loc)
+    bound0 = m.bound()
+    state = {"bound_old": bound0, "sq_old": 0.0, "first": True, "rejected": 0}
+
+    def one_step():
+        b, sq, beta, evals = m._cg_iteration(state["first"], method, 1.0, state["bound_old"], state["sq_old"])
+        state["first"] = False
+        state["bound_old"], state["sq_old"] = b, sq
+        state["rejected"] += evals - 1
+        return b
+
+    for _ in range(warm):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    state["rejected"] = 0
+    launches0 = m.kernel_launches
+    m._kernel_events = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        last_bound = one_step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    launches = m.kernel_launches - launches0
+    kernel_ms = {name: float(np.mean([a.elapsed_time(b) for a, b in pairs])) for name, pairs in m._kernel_events.items()}
+    kernel_n = {name: len(pairs) for name, pairs in m._kernel_events.items()}
+    m._kernel_events = None
+    rejected = state["rejected"]
+    ms_per_step = elapsed_ms / steps
+    value = 1e3 / ms_per_step
+
+    # ---------------- end to end through the public API with host buffers
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    Y_pin, phi_pin = pin(Y_loc), pin(phi_loc)
+    del m
+    torch.cuda.empty_cache()
+    e2e_steps = steps
+
+    class _Stop(Exception):
+        pass
+
+    class _StopAfter(object):
+        def __init__(self, n):
+            self.n, self.c = n, 0
+
+        def __call__(self):
+            if self.c >= self.n:
+                raise _Stop()
+            self.c += 1
+
+    # optimize() has no "exactly n passes" argument: the callback (collapsed_vb.py:149-150) counts passes and
+    # stops the loop after e2e_steps of them; the model is then read back.
+    def e2e_run():
+        mm = MOHGP(X, kF(), kY(), Y_pin, K=K, phi_init=phi_pin)
+        try:
+            mm.optimize(method=method, maxiter=10 ** 9, ftol=-1.0, gtol=-1.0, verbose=False, callback=_StopAfter(e2e_steps))
+        except _Stop:
+            pass
+        phi = mm.phi
+        return mm.bound(), phi
+
+    e2e_run()  # warm-up (allocator, pinned staging)
+    barrier()
+    t0 = time.perf_counter()
+    b_e2e, phi_host = e2e_run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = e2e_steps / e2e_s
+    h2d = (n_loc * D * 8 + n_loc * K * 8) * world / float(e2e_steps)
+    d2h = (n_loc * K * 8) * world / float(e2e_steps) + 128.0 * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # algorithmic bytes per launch: G pass reads F, x, x_old, ng_old and writes ng;
+    # S pass reads F, x, ng, sd_old and writes sd, x_new  (steepest / FR drop the *_old reads)
+    with_old = method in ("HS", "PR")
+    g_bytes = n_loc * 8.0 * (D + K * (4 if with_old else 2))
+    s_bytes = n_loc * 8.0 * (D + K * (5 if method != "steepest" else 4))
+    alg = {"natgrad": g_bytes, "step_stats": s_bytes}
+    dom = max(("natgrad", "step_stats"), key=lambda n: kernel_ms.get(n, 0.0) * kernel_n.get(n, 0))
+    achieved = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    iter_bytes = g_bytes + s_bytes
+    tensor_tf = 4.0 * n_loc * K * D * world / (ms_per_step * 1e-3) / 1e12
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, cores, sample, _ = cpu_reference_rate(X, Y, phi0, K, budget_s=args.cpu_budget)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "MOHGP N=1M D=64 K=64 FP64 %s-CG (config 3)" % method, "N": N_TOTAL, "D": D, "K": K, "method": method,
+                   "rows_per_gpu": n_loc, "parallelism": "rows sharded x%d, NCCL allreduce of stats+dots" % world,
+                   "l2": "inputs larger than L2 (11 N x K arrays of %.0f MB per step)" % (n_loc * K * 8 / 1e6),
+                   "rejected_steps": rejected, "final_bound": last_bound},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "what": "MOHGP(X,kernF,kernY,Y_host,K,phi_init=host) + optimize(%d passes) + m.phi + m.bound(), host numpy in/out" % e2e_steps,
+                "bound": b_e2e},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_kind": peak_kind, "traffic": None, "alg_bytes_per_launch": alg[dom], "ms_per_launch": kernel_ms[dom],
+                     "iteration_hbm_frac": iter_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+        "kernels_ms": kernel_ms,
+        "fp64_tensor": {"achieved": tensor_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tensor_tf / FP64_DMMA_PEAK_TFLOPS,
+                        "flops_per_step": 4.0 * N_TOTAL * K * D},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--method", default="HS", choices=["HS", "PR", "FR", "steepest"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,25 @@ _C_BOUND, _C_MIX, _C_H, _C_SQ, _C_NUM, _C_DEN, _C_BETA, _C_INFO = 0, 1, 2, 3, 4,
 _CTRL_LEN = 16
 
 
+class _EventPair(object):
+    def __init__(self, owner, name):
+        self.owner, self.name = owner, name
+
+    def __enter__(self):
+        ev = self.owner._kernel_events
+        if ev is not None:
+            torch = self.owner.torch
+            self.pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.pair[0].record()
+
+    def __exit__(self, *exc):
+        ev = self.owner._kernel_events
+        if ev is not None:
+            self.pair[1].record()
+            ev.setdefault(self.name, []).append(self.pair)
+        return False
+
+
 class CollapsedMixture(CollapsedVB):
     """collapsed_mixture.py:15-205.  N is the number of rows held by THIS rank."""
 
@@ -70,6 +89,7 @@ class CollapsedMixture(CollapsedVB):
         self._state_valid = False
         self._bound_value = None
         self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
+        self._kernel_events = None  # bench.py: {"natgrad": [(start, end), ...], "step_stats": [...]} CUDA events
 
         # random initial conditions for the vb parameters (collapsed_mixture.py:41): the legacy global
         # numpy stream, drawn for ALL rows so that a sharded run starts from the same point
@@ -255,12 +275,25 @@ class CollapsedMixture(CollapsedVB):
     def _launch_finalize(self):
         raise NotImplementedError
 
+    def _timed(self, name):
+        """Context manager recording a CUDA-event pair around one launch on the current stream (bench only)."""
+        return _EventPair(self, name)
+
     def _s_pass(self, x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old):
+        with self._timed("step_stats"):
+            self._launch_step_stats(x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old)
+        with self._timed("posterior"):
+            self._launch_posterior()
+
+    def _launch_step_stats(self, x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old):
         check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(self._ctrl[_C_SQ:]),
                                  float(sq_old), ptr(self._ctrl[_C_BETA:]), ptr(self._spart), float(step), _cabi.BETA[beta_mode], self.N,
                                  self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_step_stats")
+        self.kernel_launches += 1
+
+    def _launch_posterior(self):
         check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
-        self.kernel_launches += 2
+        self.kernel_launches += 1
         self._allreduce(self._stats)
         self._launch_cluster()
         self._launch_finalize()
@@ -292,13 +325,17 @@ class CollapsedMixture(CollapsedVB):
     def _cg_gradient(self, with_old):
         self._ensure_state()
         have_old = with_old and self._xprev is not None
+        with self._timed("natgrad"):
+            self._launch_natgrad(have_old)
+        if self._world > 1:
+            self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
+
+    def _launch_natgrad(self, have_old):
         check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._Wt), ptr(self._bias),
                               ptr(self._xbuf[self._xprev]) if have_old else None, ptr(self._ngbuf[1 - self._ngi]) if have_old else None,
                               ptr(self._ngbuf[self._ngi]), None, ptr(self._gpart), ptr(self._counter), ptr(self._ctrl[_C_SQ:]), self.N,
                               self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_natgrad")
         self.kernel_launches += 1
-        if self._world > 1:
-            self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
 
     def _cg_trial(self, beta_mode, step_length, sq_old):
         mode = "zero" if beta_mode == "steepest_retry" else beta_mode

@@ -73,6 +73,29 @@ class CollapsedVB(object):
     def _is_root(self):
         return True
 
+    def _cg_iteration(self, first, method, step_length, bound_old, squareNorm_old):
+        """One pass of the loop body collapsed_vb.py:152-193 -> (bound, squareNorm, beta, bound evaluations)."""
+        # :152-167 -- gradient at the accepted point, beta, search direction (HS / PR need the previous point)
+        self._cg_gradient(with_old=(not first) and method in ("HS", "PR"))
+        beta_mode = "zero" if (method == "steepest" or first) else method
+
+        # :170-176 -- try a conjugate step
+        bound, squareNorm, beta, failed = self._cg_trial(beta_mode, step_length, squareNorm_old)
+        if failed:
+            bound = bound_old - 1
+        evals = 1
+
+        # :182-193 -- revert to steepest (== VBEM) if the bound fell
+        if bound < bound_old:
+            bound, _, _, failed = self._cg_trial("steepest_retry", step_length, squareNorm_old)
+            if failed:
+                warnings.warn("Caught LinalgError in setting variational parameters, trying to continue with old parameter settings",
+                              LinAlgWarning)
+                bound = self._cg_restore()
+            evals = 2
+        self._cg_accept()
+        return bound, squareNorm, beta, evals
+
     def optimize(self, method="HS", maxiter=500, ftol=1e-6, gtol=1e-6, step_length=1.0, callback=None, verbose=True):
         """Conjugate natural-gradient ascent on the variational parameters; collapsed_vb.py:63-310."""
         assert method in ["FR", "PR", "HS", "steepest"], "invalid conjugate gradient method specified."
@@ -85,26 +108,8 @@ class CollapsedVB(object):
             if callback is not None:
                 callback()
 
-            # collapsed_vb.py:152-167 -- gradient at the accepted point, beta, search direction
-            first = not iteration
-            self._cg_gradient(with_old=not first)
-            beta_mode = "zero" if (method == "steepest" or first) else method
-
-            # collapsed_vb.py:170-176 -- try a conjugate step
-            bound, squareNorm, beta, failed = self._cg_trial(beta_mode, step_length, squareNorm_old)
-            if failed:
-                bound = bound_old - 1
-            iteration += 1
-
-            # collapsed_vb.py:182-193 -- revert to steepest (== VBEM) if the bound fell
-            if bound < bound_old:
-                bound, _, _, failed = self._cg_trial("steepest_retry", step_length, squareNorm_old)
-                if failed:
-                    warnings.warn("Caught LinalgError in setting variational parameters, trying to continue with old parameter settings",
-                                  LinAlgWarning)
-                    bound = self._cg_restore()
-                iteration += 1
-            self._cg_accept()
+            bound, squareNorm, beta, evals = self._cg_iteration(not iteration, method, step_length, bound_old, squareNorm_old)
+            iteration += evals
 
             self.optimize_trace.append((iteration, bound, squareNorm, beta))
             if say:
