@@ -31,8 +31,8 @@ PROTOTYPES = {
     "gpc_padded_rows": [_ll],
     "gpc_stats_len": [_i, _i],
     "gpc_default_grid": [_i],
-    "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
-    "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],

@@ -135,6 +135,7 @@ class CollapsedMixture(CollapsedVB):
         self._kbuf_K = K
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
         self._xbuf = [z(self._Npad, KP) for _ in range(3)]
+        self._lsebuf = [z(self._Npad) for _ in range(3)]  # row logsumexp of the matching logits buffer
         self._xi, self._xprev, self._xtrial = 0, None, 1
         self._ngbuf = [z(self._Npad, KP) for _ in range(2)]
         self._ngi = 0
@@ -279,14 +280,14 @@ class CollapsedMixture(CollapsedVB):
         """Context manager recording a CUDA-event pair around one launch on the current stream (bench only)."""
         return _EventPair(self, name)
 
-    def _s_pass(self, x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old):
+    def _s_pass(self, x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old):
         with self._timed("step_stats"):
-            self._launch_step_stats(x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old)
+            self._launch_step_stats(x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old)
         with self._timed("posterior"):
             self._launch_posterior()
 
-    def _launch_step_stats(self, x_base, ng, sd_old, sd_new, x_new, beta_mode, step, sq_old):
-        check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(self._ctrl[_C_SQ:]),
+    def _launch_step_stats(self, x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old):
+        check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(lse_new), ptr(self._ctrl[_C_SQ:]),
                                  float(sq_old), ptr(self._ctrl[_C_BETA:]), ptr(self._spart), float(step), _cabi.BETA[beta_mode], self.N,
                                  self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_step_stats")
         self.kernel_launches += 1
@@ -312,7 +313,7 @@ class CollapsedMixture(CollapsedVB):
     def do_computations(self):
         """Statistics, per-cluster posterior and bound at the current logits (MOHGP.py:70-90 / MOG.py:52-61).
         Raises numpy.linalg.LinAlgError when a per-cluster factorisation fails (GPy jitchol semantics)."""
-        self._s_pass(self._xbuf[self._xi], None, None, None, None, "zero", 0.0, 0.0)
+        self._s_pass(self._xbuf[self._xi], None, None, None, None, self._lsebuf[self._xi], "zero", 0.0, 0.0)
         bound, _, _, failed = self._readback()
         self._cache = {}
         if failed:
@@ -331,15 +332,17 @@ class CollapsedMixture(CollapsedVB):
             self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
 
     def _launch_natgrad(self, have_old):
-        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._Wt), ptr(self._bias),
-                              ptr(self._xbuf[self._xprev]) if have_old else None, ptr(self._ngbuf[1 - self._ngi]) if have_old else None,
+        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias),
+                              ptr(self._xbuf[self._xprev]) if have_old else None, ptr(self._lsebuf[self._xprev]) if have_old else None,
+                              ptr(self._ngbuf[1 - self._ngi]) if have_old else None,
                               ptr(self._ngbuf[self._ngi]), None, ptr(self._gpart), ptr(self._counter), ptr(self._ctrl[_C_SQ:]), self.N,
                               self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_natgrad")
         self.kernel_launches += 1
 
     def _cg_trial(self, beta_mode, step_length, sq_old):
         mode = "zero" if beta_mode == "steepest_retry" else beta_mode
-        self._s_pass(self._xbuf[self._xi], self._ngbuf[self._ngi], self._sd, self._sd, self._xbuf[self._xtrial], mode, step_length, sq_old)
+        self._s_pass(self._xbuf[self._xi], self._ngbuf[self._ngi], self._sd, self._sd, self._xbuf[self._xtrial], self._lsebuf[self._xtrial],
+                     mode, step_length, sq_old)
         bound, sq, beta, failed = self._readback()
         self._cache = {}
         self._trial_failed = failed
@@ -350,6 +353,7 @@ class CollapsedMixture(CollapsedVB):
         """collapsed_vb.py:189-190: set_vb_param(phi_old); bound = self.bound()."""
         self.do_computations()
         self._xbuf[self._xtrial].copy_(self._xbuf[self._xi])
+        self._lsebuf[self._xtrial].copy_(self._lsebuf[self._xi])
         self._trial_bound = self._bound_value
         self._trial_failed = False
         return self._bound_value
@@ -370,7 +374,8 @@ class CollapsedMixture(CollapsedVB):
         ng = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
         gr = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
         dots = torch.zeros(4, dtype=torch.float64, device=self.device)
-        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None, ptr(ng), ptr(gr),
+        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None,
+                              None, ptr(ng), ptr(gr),
                               ptr(self._gpart), ptr(self._counter), ptr(dots), self.N, self.K, self._KP, self._DP, self._grid,
                               self._stream()), "gpc_natgrad")
         self.kernel_launches += 1

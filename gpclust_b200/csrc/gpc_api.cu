@@ -25,7 +25,7 @@ size_t natgrad_smem(int KP, int DP) {
 }
 size_t step_stats_smem(int KP, int DP) {
   const VbSmemLayout L(DP);
-  return sizeof(double) * ((size_t)kStages * L.stage_doubles + 2 * (size_t)GPC_ROW_TILE * (KP + 4) + GPC_CONSUMER_WARPS * (KP + 1)) +
+  return sizeof(double) * ((size_t)kStages * L.stage_doubles + (size_t)GPC_ROW_TILE * (KP + 4) + GPC_CONSUMER_WARPS) +
          sizeof(uint64_t) * 2 * kStages;
 }
 
@@ -34,6 +34,8 @@ int launch_natgrad(const NatgradArgs &a, int grid, cudaStream_t st) {
   const size_t smem = natgrad_smem(KP, a.DP);
   cudaError_t e = cudaFuncSetAttribute(k_natgrad<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaFuncSetAttribute(k_natgrad<KP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return cuda_rc(e);
   k_natgrad<KP><<<grid, GPC_THREADS, smem, st>>>(a);
   return launch_rc();
 }
@@ -41,6 +43,8 @@ template <int KP>
 int launch_step_stats(const StepStatsArgs &a, int grid, cudaStream_t st) {
   const size_t smem = step_stats_smem(KP, a.DP);
   cudaError_t e = cudaFuncSetAttribute(k_step_stats<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaFuncSetAttribute(k_step_stats<KP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return cuda_rc(e);
   k_step_stats<KP><<<grid, GPC_THREADS, smem, st>>>(a);
   return launch_rc();
@@ -74,18 +78,20 @@ int gpc_default_grid(int device) {
   int sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) return cuda_rc(e);
-  return sms;
+  return sms * kCtasPerSm;
 }
 
-int gpc_natgrad(const double *F, const double *x, const double *Wt, const double *bias, const double *x_old, const double *ng_old,
-                double *ng_out, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
-                int DP, int grid, void *stream) {
-  if (!F || !x || !Wt || !bias || !ng_out || !partials || !counter || !dots) return GPC_EINVAL;
-  if ((x_old == nullptr) != (ng_old == nullptr)) return GPC_EINVAL;
+int gpc_natgrad(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, const double *x_old,
+                const double *lse_old, const double *ng_old, double *ng_out, double *grad_out, double *partials, unsigned int *counter,
+                double *dots, long long N, int K, int KP, int DP, int grid, void *stream) {
+  if (!F || !x || !lse || !Wt || !bias || !ng_out || !partials || !counter || !dots) return GPC_EINVAL;
+  if ((x_old == nullptr) != (ng_old == nullptr) || (x_old == nullptr) != (lse_old == nullptr)) return GPC_EINVAL;
   if (!geometry_ok(N, K, KP, DP, grid)) return GPC_EINVAL;
   NatgradArgs a;
   a.F = F;
   a.x = x;
+  a.lse = lse;
+  a.lse_old = lse_old;
   a.Wt = Wt;
   a.bias = bias;
   a.x_old = x_old;
@@ -112,7 +118,7 @@ int gpc_natgrad(const double *F, const double *x, const double *Wt, const double
 }
 
 int gpc_step_stats(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
-                   const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
+                   double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
                    int K, int KP, int DP, int grid, void *stream) {
   if (!F || !x_base || !partials) return GPC_EINVAL;
   if (ng && !x_new) return GPC_EINVAL;
@@ -126,6 +132,7 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
   a.sd_old = sd_old;
   a.sd_new = sd_new;
   a.x_new = x_new;
+  a.lse_new = lse_new;
   a.dots = dots;
   a.sq_old = sq_old;
   a.beta_out = beta_out;

@@ -12,7 +12,7 @@
                                          // allocated with roundup(N, GPC_ROW_TILE) rows, pad rows zero) and enums
 #define GPC_MAX_KP 64            // padded cluster count handled by the tensor kernels (8 n-tiles)
 #define GPC_MAX_DP 64            // padded feature count (time points / MOG features)
-#define GPC_THREADS 288          // 8 consumer warps + 1 producer warp
+#define GPC_THREADS 256          // 8 warps; warp 0 doubles as the F-tile producer
 #define GPC_CONSUMER_WARPS 8
 
 namespace gpc {

@@ -9,15 +9,23 @@
 //                  (collapsed_vb.py:167,172) fused with the softmax / entropy / phi_hat /
 //                  phi^T F sufficient statistics of collapsed_mixture.py:53-56, MOHGP.py:76, MOG.py:56-57.
 //
-// Layout: every N x K array is row-major with leading dimension KP (K padded to 16/32/64); the
+// Layout: every N x K array is row-major with leading dimension KP (K padded to 8/16/32/64); the
 // feature matrix F (= Y for MOHGP, [x_i x_j, x_i] for MOG) is row-major N x DP, DP = D padded to a
 // multiple of 8, pad columns zero.  All of them are allocated with roundup(N, 64) rows.
+//
+// Both kernels are persistent (grid = 2 x SM count, two CTAs resident per SM so that one CTA's
+// memory phase overlaps the other's FP64 phase) and 8 warps each own 8 rows of a 64-row tile; warp 0 also
+// streams the F row tile of the NEXT iteration into a 2-stage shared-memory ring with cp.async.bulk +
+// mbarrier (16 warps x 112 registers fill the four 16K-register files of an SM exactly).
+// The S pass leaves lse[n] = logsumexp_k x[n,:] behind, so the G pass gets phi = exp(x - lse) without
+// row reductions and can stream the "previous point" operands (x_old, ng_old) in small column chunks.
 #pragma once
 #include "gpc_common.cuh"
 
 namespace gpc {
 
-constexpr int kStages = 4;
+constexpr int kStages = 2;
+constexpr int kCtasPerSm = 2;
 
 struct VbSmemLayout {
   int f_stride;       // doubles per staged F row  (DP + 4)
@@ -25,75 +33,45 @@ struct VbSmemLayout {
   __host__ __device__ VbSmemLayout(int DP) : f_stride(DP + 4), stage_doubles(GPC_ROW_TILE * (DP + 4)) {}
 };
 
-// Producer warp: stream F row tiles [tile*64, tile*64+64) into the stage ring.
-__device__ __forceinline__ void produce_f_tiles(const double *__restrict__ F, int DP, int f_stride, double *stages, int stage_doubles,
-                                                uint64_t *full_bar, uint64_t *empty_bar, int first_tile, int tile_step, int num_tiles) {
+// Producer duty (done by consumer warp 0, one tile ahead of its use): stream F rows [tile*64, tile*64+64)
+// of this CTA's j-th tile into stage j % kStages.
+__device__ __forceinline__ void produce_f_tile(const double *__restrict__ F, int DP, int f_stride, double *stages, int stage_doubles,
+                                               uint64_t *full_bar, uint64_t *empty_bar, int j, int tile) {
   const int lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)DP * 8u;
-  int it = 0;
-  for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
-    const int s = it % kStages;
-    const uint32_t ph = (uint32_t)((it / kStages) & 1);
-    mbar_wait(&empty_bar[s], ph ^ 1u);
-    if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], row_bytes * GPC_ROW_TILE);
-    __syncwarp();
-    double *dst = stages + (size_t)s * stage_doubles;
-    const double *src = F + (size_t)tile * GPC_ROW_TILE * DP;
+  const int s = j % kStages;
+  const uint32_t ph = (uint32_t)((j / kStages) & 1);
+  mbar_wait(&empty_bar[s], ph ^ 1u);  // every consumer warp has finished the previous tile staged here
+  if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], row_bytes * GPC_ROW_TILE);
+  __syncwarp();
+  double *dst = stages + (size_t)s * stage_doubles;
+  const double *src = F + (size_t)tile * GPC_ROW_TILE * DP;
 #pragma unroll
-    for (int r = lane; r < GPC_ROW_TILE; r += 32) bulk_g2s(dst + r * f_stride, src + (size_t)r * DP, row_bytes, &full_bar[s]);
-  }
-}
-
-// exp(x - m) row softmax pieces for the C-fragment layout: each lane holds 2*NT entries of one row.
-template <int NT>
-__device__ __forceinline__ void row_softmax(const double (&x)[NT][2], int t, int K, double (&p)[NT][2], double &rowmax, double &rowsum) {
-  double m = -INFINITY;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int c = 8 * nt + 2 * t;
-    if (c < K) m = fmax(m, x[nt][0]);
-    if (c + 1 < K) m = fmax(m, x[nt][1]);
-  }
-  m = quad_max(m);
-  double s = 0.0;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int c = 8 * nt + 2 * t;
-    p[nt][0] = (c < K) ? exp(x[nt][0] - m) : 0.0;
-    p[nt][1] = (c + 1 < K) ? exp(x[nt][1] - m) : 0.0;
-    s += p[nt][0] + p[nt][1];
-  }
-  s = quad_sum(s);
-  const double inv = 1.0 / s;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    p[nt][0] *= inv;
-    p[nt][1] *= inv;
-  }
-  rowmax = m;
-  rowsum = s;
+  for (int r = lane; r < GPC_ROW_TILE; r += 32) bulk_g2s(dst + r * f_stride, src + (size_t)r * DP, row_bytes, &full_bar[s]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // G pass
 // ------------------------------------------------------------------------------------------------
 struct NatgradArgs {
-  const double *F;       // Npad x DP features
-  const double *x;       // Npad x KP logits at the current point
-  const double *Wt;      // KP x DP, Wt[k][d] = W[d][k]
-  const double *bias;    // KP
-  const double *x_old;   // logits at the previous accepted point (nullable -> no HS/PR dots)
-  const double *ng_old;  // natural gradient at the previous accepted point (nullable)
-  double *ng_out;        // Npad x KP natural gradient (ascent direction, un-negated)
-  double *grad_out;      // nullable: Npad x KP gradient = natgrad * phi
-  double *partials;      // gridDim.x * 4 doubles
-  unsigned int *counter; // zero on entry; reset to zero on exit
-  double *dots_out;      // [0]=natgrad.grad  [1]=(ng-ng_old).grad  [2]=(ng-ng_old).grad_old
+  const double *F;        // Npad x DP features
+  const double *x;        // Npad x KP logits at the current point
+  const double *lse;      // Npad : logsumexp of the rows of x (written by the S pass that produced x)
+  const double *Wt;       // KP x DP, Wt[k][d] = W[d][k]
+  const double *bias;     // KP
+  const double *x_old;    // logits at the previous accepted point (nullable -> no HS/PR dots)
+  const double *lse_old;  // Npad : logsumexp of the rows of x_old
+  const double *ng_old;   // natural gradient at the previous accepted point (nullable)
+  double *ng_out;         // Npad x KP natural gradient (ascent direction, un-negated)
+  double *grad_out;       // nullable: Npad x KP gradient = natgrad * phi
+  double *partials;       // gridDim.x * 4 doubles
+  unsigned int *counter;  // zero on entry; reset to zero on exit
+  double *dots_out;       // [0]=natgrad.grad  [1]=(ng-ng_old).grad  [2]=(ng-ng_old).grad_old
   int N, K, DP, num_tiles;
 };
 
 template <int KP>
-__global__ void __launch_bounds__(GPC_THREADS, 1) k_natgrad(const NatgradArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const VbSmemLayout L(a.DP);
@@ -122,39 +100,32 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_natgrad(const NatgradArgs a)
   for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = a.bias[i];
   __syncthreads();
 
-  if (warp == GPC_CONSUMER_WARPS) {
-    produce_f_tiles(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, blockIdx.x, gridDim.x, a.num_tiles);
-  } else {
+  {
     const bool has_old = (a.ng_old != nullptr);
     const int ksteps = a.DP / 4;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
     int it = 0;
+    if (warp == 0 && (int)blockIdx.x < a.num_tiles)
+      produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, 0, blockIdx.x);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles)
+        produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, it + 1, tile + gridDim.x);
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
       const int row = tile * GPC_ROW_TILE + warp * 8 + g;
       const bool row_ok = row < a.N;
       const size_t off = (size_t)row * KP + 2 * t;
 
-      // epilogue operands: issued before the DMMA loop so their HBM latency overlaps it
-      double x[NT][2], xo[NT][2], ngo[NT][2];
+      // current-point logits: issued before the DMMA loop so their HBM latency overlaps it
+      double x[NT][2];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const double2 v = ldg2_stream(a.x + off + 8 * nt);
         x[nt][0] = v.x;
         x[nt][1] = v.y;
       }
-      if (has_old) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const double2 v = ldg2_stream(a.x_old + off + 8 * nt);
-          xo[nt][0] = v.x;
-          xo[nt][1] = v.y;
-          const double2 u = ldg2_stream(a.ng_old + off + 8 * nt);
-          ngo[nt][0] = u.x;
-          ngo[nt][1] = u.y;
-        }
-      }
+      const double lse = a.lse[row];
+      const double lse_o = has_old ? a.lse_old[row] : 0.0;
 
       double acc[NT][2];
 #pragma unroll
@@ -163,7 +134,7 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_natgrad(const NatgradArgs a)
       mbar_wait(&full_bar[s], ph);
       const double *fa = stages + (size_t)s * L.stage_doubles + (warp * 8 + g) * L.f_stride + t;
       const double *wb = wt_s + g * L.f_stride + t;
-#pragma unroll 4
+#pragma unroll 2
       for (int ks = 0; ks < ksteps; ++ks) {
         const double af = fa[4 * ks];
 #pragma unroll
@@ -172,36 +143,54 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_natgrad(const NatgradArgs a)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
 
-      // ---- epilogue: softmax, natural gradient, dots
-      double p[NT][2], m, ssum;
-      row_softmax<NT>(x, t, a.K, p, m, ssum);
+      // previous-point operands are streamed in column chunks, PF chunks ahead of their use
+      constexpr int PF = (NT < 2) ? NT : 2;
+      double2 xo_q[PF], ngo_q[PF];
+      if (has_old) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          xo_q[q] = ldg2_stream(a.x_old + off + 8 * q);
+          ngo_q[q] = ldg2_stream(a.ng_old + off + 8 * q);
+        }
+      }
+
+      // ---- pass 1: phi = exp(x - lse) (in place of x), a = F.W + bias - x (in place of acc), sa = sum phi*a
       double sa = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        acc[nt][0] = (c < a.K) ? (acc[nt][0] + bias_s[c]) - x[nt][0] : 0.0;
-        acc[nt][1] = (c + 1 < a.K) ? (acc[nt][1] + bias_s[c + 1]) - x[nt][1] : 0.0;
-        sa += p[nt][0] * acc[nt][0] + p[nt][1] * acc[nt][1];
+        const double x0 = x[nt][0], x1 = x[nt][1];
+        acc[nt][0] = (c < a.K) ? (acc[nt][0] + bias_s[c]) - x0 : 0.0;
+        acc[nt][1] = (c + 1 < a.K) ? (acc[nt][1] + bias_s[c + 1]) - x1 : 0.0;
+        x[nt][0] = (c < a.K) ? exp(x0 - lse) : 0.0;
+        x[nt][1] = (c + 1 < a.K) ? exp(x1 - lse) : 0.0;
+        sa += x[nt][0] * acc[nt][0] + x[nt][1] * acc[nt][1];
       }
       sa = quad_sum(sa);
-      double po[NT][2];
-      if (has_old) {
-        double mo, so;
-        row_softmax<NT>(xo, t, a.K, po, mo, so);
-      }
+
+      // ---- pass 2: natural gradient, gradient, dots
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
         const double n0 = (c < a.K && row_ok) ? acc[nt][0] - sa : 0.0;
         const double n1 = (c + 1 < a.K && row_ok) ? acc[nt][1] - sa : 0.0;
-        const double g0 = n0 * p[nt][0], g1 = n1 * p[nt][1];
+        const double g0 = n0 * x[nt][0], g1 = n1 * x[nt][1];
         stg2(a.ng_out + off + 8 * nt, n0, n1);
         if (a.grad_out) stg2(a.grad_out + off + 8 * nt, g0, g1);
         d0 += n0 * g0 + n1 * g1;
-        if (has_old && row_ok) {
-          const double e0 = n0 - ngo[nt][0], e1 = n1 - ngo[nt][1];
-          d1 += e0 * g0 + e1 * g1;
-          d2 += e0 * (ngo[nt][0] * po[nt][0]) + e1 * (ngo[nt][1] * po[nt][1]);
+        if (has_old) {
+          const double2 xo = xo_q[nt % PF], ngo = ngo_q[nt % PF];
+          if (nt + PF < NT) {
+            xo_q[nt % PF] = ldg2_stream(a.x_old + off + 8 * (nt + PF));
+            ngo_q[nt % PF] = ldg2_stream(a.ng_old + off + 8 * (nt + PF));
+          }
+          if (row_ok) {
+            const double po0 = (c < a.K) ? exp(xo.x - lse_o) : 0.0;
+            const double po1 = (c + 1 < a.K) ? exp(xo.y - lse_o) : 0.0;
+            const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
+            d1 += e0 * g0 + e1 * g1;
+            d2 += e0 * (ngo.x * po0) + e1 * (ngo.y * po1);
+          }
         }
       }
     }
@@ -253,6 +242,7 @@ struct StepStatsArgs {
   const double *sd_old;  // previous search direction (nullable or ignored when beta == 0)
   double *sd_new;        // nullable
   double *x_new;         // trial logits (may be nullptr in "set" mode)
+  double *lse_new;       // Npad : logsumexp of the rows of x_new (of x_base in "set" mode); nullable
   const double *dots;    // [0]=sq [1]=num [2]=den of the G pass at x_base (device scalars, read when beta_mode != 0)
   double *beta_out;      // device scalar, written by CTA 0
   double *partials;      // gridDim.x * stat_len, stat_len = KP*DP + KP + 2  ([T KPxDP | phi_hat KP | H | pad]; even => 16-B aligned blocks)
@@ -263,7 +253,7 @@ struct StepStatsArgs {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsArgs a) {
+__global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const StepStatsArgs a) {
   constexpr int NT = KP / 8;
   constexpr int NGRP = GPC_CONSUMER_WARPS / NT;  // consumer warps sharing one 8-cluster m-tile in the stats GEMM
   constexpr int MAXDT = GPC_MAX_DP / 8;
@@ -272,9 +262,9 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const VbSmemLayout L(a.DP);
   double *stages = reinterpret_cast<double *>(smem_raw);
-  double *p_s = stages + (size_t)kStages * L.stage_doubles;  // 2 x GPC_ROW_TILE x P_STRIDE
-  double *red_s = p_s + 2 * GPC_ROW_TILE * P_STRIDE;         // GPC_CONSUMER_WARPS * (KP + 1)
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + GPC_CONSUMER_WARPS * (KP + 1));
+  double *p_s = stages + (size_t)kStages * L.stage_doubles;  // GPC_ROW_TILE x P_STRIDE (single buffer)
+  double *red_s = p_s + GPC_ROW_TILE * P_STRIDE;             // GPC_CONSUMER_WARPS
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + GPC_CONSUMER_WARPS);
   uint64_t *empty_bar = full_bar + kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -302,26 +292,25 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
   const bool use_old = (beta != 0.0) && (a.sd_old != nullptr);
 
   const int DT = a.DP / 8;
-  if (warp == GPC_CONSUMER_WARPS) {
-    produce_f_tiles(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, blockIdx.x, gridDim.x, a.num_tiles);
-  } else {
+  {
     const int mt = warp % NT, dgrp = warp / NT;
     double acc[DT_PER][2];
 #pragma unroll
     for (int i = 0; i < DT_PER; ++i) acc[i][0] = acc[i][1] = 0.0;
-    double colsum[NT][2];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) colsum[nt][0] = colsum[nt][1] = 0.0;
+    double colsum = 0.0;  // sum over rows == t (mod 4) of phi[row][8*mt + g]
     double Hpart = 0.0;
 
     int it = 0;
+    if (warp == 0 && (int)blockIdx.x < a.num_tiles)
+      produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, 0, blockIdx.x);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles)
+        produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, it + 1, tile + gridDim.x);
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
       const int row = tile * GPC_ROW_TILE + warp * 8 + g;
       const bool row_ok = row < a.N;
       const size_t off = (size_t)row * KP + 2 * t;
-      double *pt = p_s + (it & 1) * GPC_ROW_TILE * P_STRIDE;
 
       // ---- phase 1: CG step + softmax statistics for this warp's 8 rows
       double x[NT][2];
@@ -332,56 +321,78 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
         x[nt][1] = v.y;
       }
       if (a.ng != nullptr) {
-        double sd[NT][2];
+        // operands streamed in column chunks, PF chunks ahead of their use
+        constexpr int PF = (NT < 4) ? NT : 4;
+        double2 ng_q[PF], sd_q[PF];
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          ng_q[q] = ldg2_stream(a.ng + off + 8 * q);
+          if (use_old) sd_q[q] = ldg2_stream(a.sd_old + off + 8 * q);
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const double2 v = ldg2_stream(a.ng + off + 8 * nt);
-          sd[nt][0] = v.x;
-          sd[nt][1] = v.y;
-        }
-        if (use_old) {
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            const double2 v = ldg2_stream(a.sd_old + off + 8 * nt);
-            sd[nt][0] += beta * v.x;  // searchDir = natgrad + beta*searchDir_old  (collapsed_vb.py:167, ascent sign)
-            sd[nt][1] += beta * v.y;
+          double s0 = ng_q[nt % PF].x, s1 = ng_q[nt % PF].y;
+          if (use_old) {
+            s0 += beta * sd_q[nt % PF].x;  // searchDir = natgrad + beta*searchDir_old  (collapsed_vb.py:167, ascent sign)
+            s1 += beta * sd_q[nt % PF].y;
           }
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          x[nt][0] += a.step * sd[nt][0];  // collapsed_vb.py:172
-          x[nt][1] += a.step * sd[nt][1];
-          if (a.sd_new) stg2(a.sd_new + off + 8 * nt, sd[nt][0], sd[nt][1]);
+          if (nt + PF < NT) {
+            ng_q[nt % PF] = ldg2_stream(a.ng + off + 8 * (nt + PF));
+            if (use_old) sd_q[nt % PF] = ldg2_stream(a.sd_old + off + 8 * (nt + PF));
+          }
+          x[nt][0] += a.step * s0;  // collapsed_vb.py:172
+          x[nt][1] += a.step * s1;
+          if (a.sd_new) stg2(a.sd_new + off + 8 * nt, s0, s1);
           stg2(a.x_new + off + 8 * nt, x[nt][0], x[nt][1]);
         }
       }
-      double p[NT][2], m, ssum;
-      row_softmax<NT>(x, t, a.K, p, m, ssum);
-      const double lognorm = log(ssum);
-      double h = 0.0;
+      // row softmax: max, exp, sum   (np_utilities.py:25-40)
+      double m = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        if (!row_ok) p[nt][0] = p[nt][1] = 0.0;
-        // entropy term -phi*log(phi), log(phi) = (x - max) - log(sum)   (np_utilities.py:30-36)
-        if (c < a.K) h -= p[nt][0] * ((x[nt][0] - m) - lognorm);
-        if (c + 1 < a.K) h -= p[nt][1] * ((x[nt][1] - m) - lognorm);
-        colsum[nt][0] += p[nt][0];
-        colsum[nt][1] += p[nt][1];
-        *reinterpret_cast<double2 *>(pt + (warp * 8 + g) * P_STRIDE + c) = make_double2(p[nt][0], p[nt][1]);
+        if (c < a.K) m = fmax(m, x[nt][0]);
+        if (c + 1 < a.K) m = fmax(m, x[nt][1]);
       }
-      Hpart += h;  // h is zero for pad rows because p is zero there
+      m = quad_max(m);
+      double ssum = 0.0, px = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        const double e0 = (c < a.K) ? exp(x[nt][0] - m) : 0.0;
+        const double e1 = (c + 1 < a.K) ? exp(x[nt][1] - m) : 0.0;
+        ssum += e0 + e1;
+        if (c < a.K) px += e0 * (x[nt][0] - m);
+        if (c + 1 < a.K) px += e1 * (x[nt][1] - m);
+        x[nt][0] = e0;
+        x[nt][1] = e1;
+      }
+      ssum = quad_sum(ssum);
+      px = quad_sum(px);
+      const double inv = row_ok ? 1.0 / ssum : 0.0;
+      const double lognorm = log(ssum);
+      // row entropy -sum phi*log(phi) with log(phi) = (x - max) - log(sum)  ==  log(sum) - sum(e*(x - max))/sum
+      if (row_ok && t == 0) Hpart += lognorm - px * inv;
+      if (a.lse_new && t == 0) a.lse_new[row] = m + lognorm;
 
-      // all consumer warps have written their phi rows (and finished the GEMM of the previous tile)
+      // the previous tile's GEMM has finished reading p_s
       asm volatile("bar.sync 1, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        *reinterpret_cast<double2 *>(p_s + (warp * 8 + g) * P_STRIDE + c) = make_double2(x[nt][0] * inv, x[nt][1] * inv);
+      }
+      // all consumer warps have written their phi rows
+      asm volatile("bar.sync 2, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
 
-      // ---- phase 2: ybark[k][d] += sum_rows phi[row][k] * F[row][d]   (this warp: m-tile mt, d-tiles dgrp + i*NGRP)
+      // ---- phase 2: T[k][d] += sum_rows phi[row][k] * F[row][d]   (this warp: m-tile mt, d-tiles dgrp + i*NGRP)
       mbar_wait(&full_bar[s], ph);
       const double *fb = stages + (size_t)s * L.stage_doubles + t * L.f_stride + g;
-      const double *pa = pt + t * P_STRIDE + 8 * mt + g;
-#pragma unroll 4
+      const double *pa = p_s + t * P_STRIDE + 8 * mt + g;
+#pragma unroll 2
       for (int ks = 0; ks < GPC_ROW_TILE / 4; ++ks) {
         const double af = pa[4 * ks * P_STRIDE];
+        colsum += af;
 #pragma unroll
         for (int i = 0; i < DT_PER; ++i) {
           const int dt = dgrp + i * NGRP;
@@ -399,23 +410,17 @@ __global__ void __launch_bounds__(GPC_THREADS, 1) k_step_stats(const StepStatsAr
       const int dt = dgrp + i * NGRP;
       if (dt < DT) stg2(part + (size_t)(8 * mt + g) * a.DP + 8 * dt + 2 * t, acc[i][0], acc[i][1]);
     }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const double c0 = colgroup_sum(colsum[nt][0]), c1 = colgroup_sum(colsum[nt][1]);
-      if (g == 0) {
-        red_s[warp * (KP + 1) + 8 * nt + 2 * t] = c0;
-        red_s[warp * (KP + 1) + 8 * nt + 2 * t + 1] = c1;
-      }
-    }
+    colsum = quad_sum(colsum);
     Hpart = warp_sum(Hpart);
-    if (lane == 0) red_s[warp * (KP + 1) + KP] = Hpart;
+    if (dgrp == 0 && t == 0) part[(size_t)KP * a.DP + 8 * mt + g] = colsum;
+    if (lane == 0) red_s[warp] = Hpart;
     asm volatile("bar.sync 1, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
-    for (int j = threadIdx.x; j < KP + 1; j += GPC_CONSUMER_WARPS * 32) {
+    if (threadIdx.x == 0) {
       double v = 0.0;
-      for (int w = 0; w < GPC_CONSUMER_WARPS; ++w) v += red_s[w * (KP + 1) + j];
-      part[(size_t)KP * a.DP + j] = v;
+      for (int w = 0; w < GPC_CONSUMER_WARPS; ++w) v += red_s[w];
+      part[(size_t)KP * a.DP + KP] = v;
+      part[(size_t)KP * a.DP + KP + 1] = 0.0;
     }
-    if (threadIdx.x == 0) part[(size_t)KP * a.DP + KP + 1] = 0.0;
   }
 }
 

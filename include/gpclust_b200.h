@@ -54,7 +54,7 @@ int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 
 int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
 long long gpc_padded_rows(long long N);
 int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 2 (one pad double keeps blocks 16-B aligned)    */
-int gpc_default_grid(int device);  /* number of persistent CTAs (= SM count); <0 on CUDA error     */
+int gpc_default_grid(int device);  /* number of persistent CTAs (2 per SM); <0 on CUDA error          */
 
 /* ---- G pass: natural gradient + conjugate-gradient dot products ------------------------------
  * Replaces MOHGP.vb_grad_natgrad (MOHGP.py:137-153) / MOG.vb_grad_natgrad (MOG.py:72-84) including
@@ -62,11 +62,12 @@ int gpc_default_grid(int device);  /* number of persistent CTAs (= SM count); <0
  *   a[n,k]   = F[n,:] . Wt[k,:] + bias[k] - x[n,k]
  *   natgrad  = a - sum_k phi a ;  grad = natgrad * phi ;  phi = softmax_k(x)
  *   dots[0] = natgrad.grad  dots[1] = (natgrad - ng_old).grad  dots[2] = (natgrad - ng_old).grad_old
- * x_old / ng_old may both be NULL (first iteration): dots[1], dots[2] are then 0.
+ * lse / lse_old: Npad row-wise logsumexp of x / x_old, as left behind by gpc_step_stats (phi = exp(x - lse)).
+ * x_old / lse_old / ng_old may all be NULL (first iteration): dots[1], dots[2] are then 0.
  * grad_out may be NULL.  partials: grid*4 doubles.  counter: one zero-initialised unsigned int.     */
-int gpc_natgrad(const double *F, const double *x, const double *Wt, const double *bias, const double *x_old, const double *ng_old,
-                double *ng_out, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
-                int DP, int grid, void *stream);
+int gpc_natgrad(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, const double *x_old,
+                const double *lse_old, const double *ng_old, double *ng_out, double *grad_out, double *partials, unsigned int *counter,
+                double *dots, long long N, int K, int KP, int DP, int grid, void *stream);
 
 /* ---- S pass: conjugate step + softmax + sufficient statistics --------------------------------
  * Replaces collapsed_vb.py:167,172 (searchDir, phi_old + step*searchDir) fused with
@@ -74,10 +75,11 @@ int gpc_natgrad(const double *F, const double *x, const double *Wt, const double
  * of do_computations (MOHGP.py:76 ybark; MOG.py:56-57 Xsumk, Ck).
  *   beta from dots (device) according to beta_mode, nan / negative -> 0 (collapsed_vb.py:165-166)
  *   sd_new = ng + beta*sd_old ; x_new = x_base + step*sd_new ; stats of softmax(x_new)
- * ng == NULL: "set" mode -- statistics of x_base itself, nothing is written but the partials.
+ * lse_new (Npad, nullable) receives the row-wise logsumexp of x_new, the G pass needs it.
+ * ng == NULL: "set" mode -- statistics (and lse) of x_base itself, no N x K array is written.
  * sd_new may alias sd_old.  partials: grid * gpc_stats_len doubles -> reduce with gpc_reduce_partials. */
 int gpc_step_stats(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
-                   const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
+                   double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
                    int K, int KP, int DP, int grid, void *stream);
 
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
