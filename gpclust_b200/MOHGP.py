@@ -39,8 +39,9 @@ class MOHGP(CollapsedMixture):
         else:
             self._Y_host = _cabi.f64(Y)
             Yd = torch.from_numpy(self._Y_host).to(self.device)
-        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)
-        check(lib.gpc_pad_rows(ptr(Yd), N, self.D, DP, ptr(F), self._stream()), "gpc_pad_rows")
+        ldf = lib.gpc_feature_ld(DP)
+        F = torch.empty((self._Npad, ldf), dtype=torch.float64, device=self.device)
+        check(lib.gpc_pad_rows(ptr(Yd), N, self.D, ldf, ptr(F), self._stream()), "gpc_pad_rows")
         self.kernel_launches += 1
         del Yd
         self._X_dev = torch.from_numpy(self.X).to(self.device)
@@ -101,7 +102,7 @@ class MOHGP(CollapsedMixture):
         self.do_computations()
 
     def _launch_cluster(self):
-        check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),
+        check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),
                                     ptr(self._Wt), ptr(self._muk_t), ptr(self._per_k), ptr(self._Syi_ybark_t), ptr(self._Lambda_inv),
                                     ptr(self._C_chols_dev), self._info_ptr(), self.K, self.D, self._KP, self._DP, self._stream()),
               "gpc_mohgp_cluster")

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libgpclust_b200.so")
+LIB_PATH = os.environ.get("GPCLUST_B200_LIB") or os.path.join(_HERE, "_lib", "libgpclust_b200.so")  # env override: kernel-variant experiments
 
 GPC_ROW_TILE = 64
 GPC_EINVAL = 2
@@ -30,13 +30,14 @@ PROTOTYPES = {
     "gpc_padded_d": [_i],
     "gpc_padded_rows": [_ll],
     "gpc_stats_len": [_i, _i],
+    "gpc_feature_ld": [_i],
     "gpc_default_grid": [_i],
     "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
-    "gpc_mohgp_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "gpc_mohgp_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "gpc_mohgp_finalize": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p],
     "gpc_mog_features": [_p, _p, _ll, _i, _i, _p, _p],
     "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],

@@ -29,25 +29,24 @@ size_t step_stats_smem(int KP, int DP) {
          sizeof(uint64_t) * 2 * kStages;
 }
 
+template <typename Kern, typename Args>
+int launch_vb(Kern kern, const Args &a, size_t smem, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return cuda_rc(e);
+  kern<<<grid, GPC_THREADS, smem, st>>>(a);
+  return launch_rc();
+}
 template <int KP>
 int launch_natgrad(const NatgradArgs &a, int grid, cudaStream_t st) {
   const size_t smem = natgrad_smem(KP, a.DP);
-  cudaError_t e = cudaFuncSetAttribute(k_natgrad<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_rc(e);
-  e = cudaFuncSetAttribute(k_natgrad<KP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return cuda_rc(e);
-  k_natgrad<KP><<<grid, GPC_THREADS, smem, st>>>(a);
-  return launch_rc();
+  return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, st);
 }
 template <int KP>
 int launch_step_stats(const StepStatsArgs &a, int grid, cudaStream_t st) {
   const size_t smem = step_stats_smem(KP, a.DP);
-  cudaError_t e = cudaFuncSetAttribute(k_step_stats<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_rc(e);
-  e = cudaFuncSetAttribute(k_step_stats<KP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return cuda_rc(e);
-  k_step_stats<KP><<<grid, GPC_THREADS, smem, st>>>(a);
-  return launch_rc();
+  return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, st) : launch_vb(k_step_stats<KP, false>, a, smem, grid, st);
 }
 
 bool geometry_ok(long long N, int K, int KP, int DP, int grid) {
@@ -73,6 +72,7 @@ int gpc_padded_d(int D) {
 }
 long long gpc_padded_rows(long long N) { return (N + GPC_ROW_TILE - 1) / GPC_ROW_TILE * GPC_ROW_TILE; }
 int gpc_stats_len(int KP, int DP) { return KP * DP + KP + 2; }
+int gpc_feature_ld(int DP) { return DP + 4; }
 
 int gpc_default_grid(int device) {
   int sms = 0;
@@ -190,18 +190,18 @@ int gpc_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_lo
   return launch_rc();
 }
 
-int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Sy, const double *Sy_inv, const double *Sf,
-                      double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
+int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Ly_inv, const double *Sy,
+                      const double *Sy_inv, const double *Sf, double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
                       int K, int D, int KP, int DP, void *stream) {
-  if (!stats || !A || !Ly || !Sy || !Sy_inv || !Sf || !Wt || !muk_t || !per_k || !info) return GPC_EINVAL;
+  if (!stats || !A || !Ly || !Ly_inv || !Sy || !Sy_inv || !Sf || !Wt || !muk_t || !per_k || !info) return GPC_EINVAL;
   if (K < 1 || K > KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
-  const size_t smem = sizeof(double) * (3 * (size_t)D * (D + 1) + 2 * D + 32);
+  const size_t smem = sizeof(double) * (3 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + 3 * GPC_MAX_DP + 32);
   e = cudaFuncSetAttribute(k_mohgp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
-  MohgpClusterArgs a{stats, A, Ly, Sy, Sy_inv, Sf, Wt, muk_t, per_k, Syi_ybark_t, Lambda_inv, C_chols, info, K, D, KP, DP};
+  MohgpClusterArgs a{stats, A, Ly, Ly_inv, Sy, Sy_inv, Sf, Wt, muk_t, per_k, Syi_ybark_t, Lambda_inv, C_chols, info, K, D, KP, DP};
   k_mohgp_cluster<<<KP, kClusterThreads, smem, st>>>(a);
   return launch_rc();
 }
@@ -217,8 +217,9 @@ int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *c
 
 int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream) {
   if (!X || !centre || !F || N < 1 || D < 1 || D * (D + 1) / 2 + D > DP) return GPC_EINVAL;
-  const long long total = gpc_padded_rows(N) * DP;
-  k_mog_features<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, centre, (int)N, (int)gpc_padded_rows(N), D, DP, F);
+  const int ldf = gpc_feature_ld(DP);
+  const long long total = gpc_padded_rows(N) * ldf;
+  k_mog_features<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, centre, (int)N, (int)gpc_padded_rows(N), D, ldf, F);
   return launch_rc();
 }
 
@@ -293,7 +294,7 @@ int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, 
 
 int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream) {
   if (!F || !partials || Npad < kGramRows || (Npad % kGramRows) || DP < 8 || DP > GPC_MAX_DP || grid < 1) return GPC_EINVAL;
-  k_gram_partials<<<grid, 256, sizeof(double) * kGramRows * DP, as_stream(stream)>>>(F, (int)Npad, DP, partials);
+  k_gram_partials<<<grid, 256, sizeof(double) * kGramRows * DP, as_stream(stream)>>>(F, (int)Npad, DP, gpc_feature_ld(DP), partials);
   return launch_rc();
 }
 

@@ -81,6 +81,7 @@ struct MohgpClusterArgs {
   const double *stats;   // [ybark KP x DP | phi_hat KP | H], already summed over CTAs (and ranks)
   const double *A;       // D x D : Ly^-1 Sf Ly^-T             (MOHGP.py:79)
   const double *Ly;      // D x D : chol(Sy + 1e-6 I), lower   (MOHGP.py:49)
+  const double *Ly_inv;  // D x D : Ly^-1 (Sy_chol_inv of MOHGP.py:49) -- the dpotrs of MOHGP.py:88 as two triangular products
   const double *Sy;      // D x D : un-jittered                (MOHGP.py:85)
   const double *Sy_inv;  // D x D
   const double *Sf;      // D x D
@@ -94,15 +95,57 @@ struct MohgpClusterArgs {
   int K, D, KP, DP;
 };
 
+constexpr int kClMaxQ = GPC_MAX_DP / 4;  // register slots per thread: entries m = 4*mm + q of one row / column
+
+// Left-looking lower Cholesky of the D x D matrix in Cs (row stride ld), in place, by 4*D threads:
+// quad r = tid/4 owns row r; its factor entries L[r][4mm+q] stay in registers, the pivot row is read from
+// shared memory.  Two block barriers per column.  *flag_s must be 0 on entry (set on a bad pivot).
+__device__ __forceinline__ bool chol_lower_quadrows(double *Cs, int D, int ld, int *flag_s) {
+  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+  double Lr[kClMaxQ];
+#pragma unroll
+  for (int mm = 0; mm < kClMaxQ; ++mm) Lr[mm] = 0.0;
+  bool ok = true;
+  for (int j = 0; j < D && ok; ++j) {
+    double pp[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains: FP64 FMA latency, not throughput, bounds this loop
+#pragma unroll
+    for (int mm = 0; mm < kClMaxQ; ++mm) {
+      const int m = 4 * mm + q;
+      pp[mm & 3] += (m < j) ? Lr[mm] * Cs[j * ld + m] : 0.0;
+    }
+    const double part = quad_sum((pp[0] + pp[1]) + (pp[2] + pp[3]));
+    const double v = (r >= j && r < D) ? Cs[r * ld + j] - part : 0.0;
+    if (r == j && q == 0) {
+      if (!(v > 0.0) || isinf(v)) *flag_s = 1;
+      else Cs[j * ld + j] = sqrt(v);
+    }
+    __syncthreads();
+    ok = (*flag_s == 0);
+    const double dj = Cs[j * ld + j];
+    const double l = v / dj;
+    const bool mine = ok && r > j && r < D && q == (j & 3);
+    if (mine) Cs[r * ld + j] = l;
+#pragma unroll
+    for (int mm = 0; mm < kClMaxQ; ++mm) Lr[mm] = (mine && mm == (j >> 2)) ? l : Lr[mm];
+    __syncthreads();
+  }
+  return ok;
+}
+
+// One CTA (256 threads) per cluster.  Thread (r = tid/4, q = tid%4): the quad r owns row r of the
+// Cholesky factor and column r of the triangular solve, split over q by m = 4*mm + q and held in
+// registers, so the only block-wide synchronisation is two barriers per Cholesky column.
 __global__ void __launch_bounds__(kClusterThreads) k_mohgp_cluster(const MohgpClusterArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int D = a.D, ld = D + 1, k = blockIdx.x, tid = threadIdx.x;
-  double *C = sm;              // D x ld : C_k, then its Cholesky factor, then Lambda_inv
-  double *T = C + D * ld;      // D x ld : L_k^-1 Ly^T
-  double *Ls = T + D * ld;     // D x ld : Ly
-  double *vec_s = Ls + D * ld; // D      : s_k, then w_k
-  double *mu_s = vec_s + D;    // D
-  double *red_s = mu_s + D;    // 32
+  const int D = a.D, ld = GPC_MAX_DP + 1, k = blockIdx.x, tid = threadIdx.x;
+  const int r = tid >> 2, q = tid & 3;
+  double *Cs = sm;                  // D x ld : C_k -> its Cholesky factor -> Lambda_inv
+  double *Ts = Cs + GPC_MAX_DP * ld;  // D x ld : T = L_k^-1 Ly^T
+  double *Lis = Ts + GPC_MAX_DP * ld; // D x ld : Ly^-1
+  double *v_s = Lis + GPC_MAX_DP * ld;  // D : s_k
+  double *u_s = v_s + GPC_MAX_DP;       // D : scratch
+  double *mu_s = u_s + GPC_MAX_DP;      // D
+  double *red_s = mu_s + GPC_MAX_DP;    // 32
   __shared__ int flag_s;
 
   if (k >= a.K) {  // pad clusters: zero weights so that the G pass sees finite numbers
@@ -111,37 +154,37 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_cluster(const MohgpCl
     return;
   }
   const double phi_hat = a.stats[(size_t)a.KP * a.DP + k];
-  for (int e = tid; e < D * D; e += blockDim.x) {
-    const int i = e / D, j = e % D;
-    Ls[i * ld + j] = a.Ly[e];
-  }
+  for (int e = tid; e < D * D; e += blockDim.x) Lis[(e / D) * ld + (e % D)] = a.Ly_inv[e];
+  for (int d = tid; d < D; d += blockDim.x) v_s[d] = a.stats[(size_t)k * a.DP + d];
 
-  // jitchol semantics (GPy.util.linalg.jitchol): plain attempt, then mean(diag)*1e-6 * 10^i, i = 0..4
+  // ---- C_k = I + phi_hat*A and its Cholesky factor with GPy's jitchol retry
+  // (plain attempt, then jitter = mean(diag)*1e-6 * 10^i, i = 0..4)
   bool ok = false;
   double diag_mean = 0.0;
   for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
     double jitter = 0.0;
     if (attempt > 0) {
       jitter = diag_mean * 1e-6;
-      for (int q = 1; q < attempt; ++q) jitter *= 10.0;
+      for (int p = 1; p < attempt; ++p) jitter *= 10.0;
+      if (!isfinite(jitter)) break;
     }
     __syncthreads();
     for (int e = tid; e < D * D; e += blockDim.x) {
       const int i = e / D, j = e % D;
-      C[i * ld + j] = ((i == j) ? 1.0 + jitter : 0.0) + a.A[e] * phi_hat;  // MOHGP.py:80
+      Cs[i * ld + j] = ((i == j) ? 1.0 + jitter : 0.0) + a.A[e] * phi_hat;  // MOHGP.py:80
     }
+    if (tid == 0) flag_s = 0;
     __syncthreads();
     if (attempt == 0) {
       double dsum = 0.0, dmin = INFINITY;
       for (int i = 0; i < D; ++i) {  // every thread, same order: identical result everywhere
-        dsum += C[i * ld + i];
-        dmin = fmin(dmin, C[i * ld + i]);
+        dsum += Cs[i * ld + i];
+        dmin = fmin(dmin, Cs[i * ld + i]);
       }
       diag_mean = dsum / D;
       if (!(dmin > 0.0)) break;  // "not pd: non-positive diagonal elements"
     }
-    ok = chol_lower_smem(C, D, ld, &flag_s);
-    if (attempt > 0 && !isfinite(jitter)) break;
+    ok = chol_lower_quadrows(Cs, D, ld, &flag_s);
   }
   if (!ok) {
     if (tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
@@ -152,83 +195,152 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_cluster(const MohgpCl
   if (a.C_chols)
     for (int e = tid; e < D * D; e += blockDim.x) {
       const int i = e / D, j = e % D;
-      a.C_chols[(size_t)k * D * D + e] = (j <= i) ? C[i * ld + j] : 0.0;
+      a.C_chols[(size_t)k * D * D + e] = (j <= i) ? Cs[i * ld + j] : 0.0;
     }
   double ldd = 0.0;
   if (tid < 32) {
-    for (int i = tid; i < D; i += 32) ldd += log(C[i * ld + i]);
+    for (int i = tid; i < D; i += 32) ldd += log(Cs[i * ld + i]);
     ldd = 2.0 * warp_sum(ldd);  // MOHGP.py:83
   }
 
-  // T = L_k^-1 Ly^T  (MOHGP.py:84): 4 threads per right-hand-side column, split inner products
+  // ---- T = L_k^-1 Ly^T  (MOHGP.py:84): quad r solves right-hand-side column r, entries T[4mm+q][r] in registers
+  for (int e = tid; e < D * D; e += blockDim.x) {
+    const int i = e / D, j = e % D;
+    Ts[i * ld + j] = (j >= i) ? a.Ly[(size_t)j * D + i] : 0.0;  // Ly^T
+  }
+  for (int d = tid; d < D; d += blockDim.x) u_s[d] = 1.0 / Cs[d * ld + d];
+  __syncthreads();
   {
-    const int col = tid >> 2, q = tid & 3;
-    for (int cbase = 0; cbase < D; cbase += kClusterThreads / 4) {
-      const int j = cbase + col;
-      for (int i = 0; i < D; ++i) {
-        double acc = 0.0;
-        if (j < D)
-          for (int m = q; m < i; m += 4) acc += C[i * ld + m] * T[m * ld + j];
-        acc = quad_sum(acc);
-        if (j < D && q == 0) T[i * ld + j] = (((j >= i) ? Ls[j * ld + i] : 0.0) - acc) / C[i * ld + i];
-        __syncwarp();
+    double Tr[kClMaxQ];
+#pragma unroll
+    for (int mm = 0; mm < kClMaxQ; ++mm) Tr[mm] = 0.0;
+    for (int i = 0; i < D; ++i) {
+      double pp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) {
+        const int m = 4 * mm + q;
+        pp[mm & 3] += (m < i) ? Cs[i * ld + m] * Tr[mm] : 0.0;
+      }
+      const double part = quad_sum((pp[0] + pp[1]) + (pp[2] + pp[3]));
+      const double rhs = (r >= i && r < D) ? Ts[i * ld + r] : 0.0;  // (Ly^T)[i][r], staged below
+      const double val = (rhs - part) * u_s[i];                     // u_s[i] = 1 / L[i][i]
+      const bool mine = (q == (i & 3));
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) Tr[mm] = (mine && mm == (i >> 2)) ? val : Tr[mm];
+    }
+    __syncthreads();  // every quad has read its right-hand side out of Ts
+    if (r < D) {
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) {
+        const int m = 4 * mm + q;
+        if (m < D) Ts[m * ld + r] = Tr[mm];
       }
     }
   }
   __syncthreads();
 
-  // Lambda_inv = (Sy - T^T T) / phi_hat   or Sf when phi_hat <= 1e-6   (MOHGP.py:85)
+  // ---- Lambda_inv = (Sy - T^T T) / phi_hat   or Sf when phi_hat <= 1e-6   (MOHGP.py:85); 4 x 4 block per thread
   {
     const bool tiny = !(phi_hat > 1e-6);
-    for (int e = tid; e < D * D; e += blockDim.x) {
-      const int i = e / D, j = e % D;
-      double v;
-      if (tiny) v = a.Sf[e];
-      else {
-        double tt = 0.0;
-        for (int m = 0; m < D; ++m) tt += T[m * ld + i] * T[m * ld + j];
-        v = (a.Sy[e] - tt) / phi_hat;
+    const int a0 = 4 * (tid >> 4), b0 = 4 * (tid & 15);
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    if (!tiny && a0 < D && b0 < D) {
+      for (int m = 0; m < D; ++m) {
+        double ta[4], tb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ta[i] = Ts[m * ld + a0 + i];
+          tb[i] = Ts[m * ld + b0 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += ta[i] * tb[j];
       }
-      C[i * ld + j] = v;  // the Cholesky factor is no longer needed
+    }
+    // every thread has finished reading the factor (the solve above) -- Cs can take Lambda_inv
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ai = a0 + i, bj = b0 + j;
+        if (ai < D && bj < D) {
+          const double v = tiny ? a.Sf[ai * D + bj] : (a.Sy[ai * D + bj] - acc[i][j]) / phi_hat;
+          Cs[ai * ld + bj] = v;
+          if (a.Lambda_inv) a.Lambda_inv[(size_t)k * D * D + ai * D + bj] = v;
+        }
+      }
+  }
+  // ---- s_k = (Ly Ly^T)^-1 ybark_k = Ly^-T (Ly^-1 ybark_k)   (MOHGP.py:88)
+  auto solve_sy = [&](double *vec) {  // vec <- Sy_jittered^-1 vec, result also left in u_s? no: in vec
+    double part = 0.0;
+    if (r < D) {
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) {
+        const int m = 4 * mm + q;
+        if (m <= r) part += Lis[r * ld + m] * vec[m];
+      }
+    }
+    part = quad_sum(part);
+    __syncthreads();
+    if (r < D && q == 0) u_s[r] = part;
+    __syncthreads();
+    part = 0.0;
+    if (r < D) {
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) {
+        const int m = 4 * mm + q;
+        if (m >= r && m < D) part += Lis[m * ld + r] * u_s[m];
+      }
+    }
+    part = quad_sum(part);
+    __syncthreads();
+    if (r < D && q == 0) vec[r] = part;
+    __syncthreads();
+  };
+  __syncthreads();
+  solve_sy(v_s);
+  if (a.Syi_ybark_t)
+    for (int d = tid; d < D; d += blockDim.x) a.Syi_ybark_t[(size_t)k * D + d] = v_s[d];
+  // mu_k[j] = sum_i Lambda_inv[i][j] s[i]   (MOHGP.py:90)
+  {
+    double part = 0.0;
+    if (r < D) {
+#pragma unroll
+      for (int mm = 0; mm < kClMaxQ; ++mm) {
+        const int i = 4 * mm + q;
+        if (i < D) part += Cs[i * ld + r] * v_s[i];
+      }
+    }
+    part = quad_sum(part);
+    if (r < D && q == 0) {
+      mu_s[r] = part;
+      a.muk_t[(size_t)k * D + r] = part;
     }
   }
-  // s_k = (Ly Ly^T)^-1 ybark_k   (MOHGP.py:88)
-  for (int d = tid; d < D; d += blockDim.x) vec_s[d] = a.stats[(size_t)k * a.DP + d];
-  __syncthreads();
-  potrs_vec_warp0(Ls, D, ld, vec_s);
-  __syncthreads();
-  if (a.Lambda_inv)
-    for (int e = tid; e < D * D; e += blockDim.x) a.Lambda_inv[(size_t)k * D * D + e] = C[(e / D) * ld + (e % D)];
-  if (a.Syi_ybark_t)
-    for (int d = tid; d < D; d += blockDim.x) a.Syi_ybark_t[(size_t)k * D + d] = vec_s[d];
-  // mu_k[j] = sum_i Lambda_inv[i][j] s[i]   (MOHGP.py:90)
-  for (int j = tid; j < D; j += blockDim.x) {
-    double v = 0.0;
-    for (int i = 0; i < D; ++i) v += C[i * ld + j] * vec_s[i];
-    mu_s[j] = v;
-    a.muk_t[(size_t)k * D + j] = v;
-  }
-  __syncthreads();
   // quad = sum_ij s_i s_j Lambda_inv_ij (MOHGP.py:133) ; trace = sum_ij Lambda_inv_ij Sy_inv_ij (MOHGP.py:147)
   double quad = 0.0, tr = 0.0;
   for (int e = tid; e < D * D; e += blockDim.x) {
     const int i = e / D, j = e % D;
-    const double l = C[i * ld + j];
-    quad += vec_s[i] * vec_s[j] * l;
+    const double l = Cs[i * ld + j];
+    quad += v_s[i] * v_s[j] * l;
     tr += l * a.Sy_inv[e];
   }
   quad = block_sum(quad, red_s);
   tr = block_sum(tr, red_s);
   // w_k = (Ly Ly^T)^-1 mu_k : the GEMM form of multiple_mahalanobis(Y, muk.T, Sy_chol) (MOHGP.py:144)
   __syncthreads();
-  for (int d = tid; d < D; d += blockDim.x) vec_s[d] = mu_s[d];
+  for (int d = tid; d < D; d += blockDim.x) v_s[d] = mu_s[d];
   __syncthreads();
-  potrs_vec_warp0(Ls, D, ld, vec_s);
-  __syncthreads();
+  solve_sy(v_s);
   double m2 = 0.0;
-  for (int d = tid; d < D; d += blockDim.x) m2 += mu_s[d] * vec_s[d];
+  for (int d = tid; d < D; d += blockDim.x) m2 += mu_s[d] * v_s[d];
   m2 = block_sum(m2, red_s);
-  for (int d = tid; d < a.DP; d += blockDim.x) a.Wt[(size_t)k * a.DP + d] = (d < D) ? vec_s[d] : 0.0;
+  for (int d = tid; d < a.DP; d += blockDim.x) a.Wt[(size_t)k * a.DP + d] = (d < D) ? v_s[d] : 0.0;
   if (tid == 0) {
     a.per_k[k * 4 + 0] = ldd;
     a.per_k[k * 4 + 1] = quad;

@@ -41,16 +41,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots in a spin
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE;\n"
       "bra WAIT_LOOP;\n"
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 // global -> shared bulk copy (bytes multiple of 16, both addresses 16-B aligned), completion on mbarrier
@@ -58,6 +59,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 // ---------------------------------------------------------------- vector global access (16 B)
@@ -96,6 +102,54 @@ __device__ __forceinline__ double colgroup_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   return v;
+}
+
+// ---------------------------------------------------------------- exp for the softmax passes (FP64)
+// exp(x) for two arguments at once (x <= ~0 on this path: x - logsumexp or x - rowmax), ~1.5 ulp.
+// Cody-Waite reduction x = n ln2 + r with the 2^52 rounding trick, degree-11 near-minimax polynomial on
+// |r| <= ln2/2 (Chebyshev-node interpolant of exp, coefficients generated with mpmath at 60 digits),
+// scaling by 2^n through the exponent field.  Results below the normal range (n < -1021, i.e. x < -708)
+// are flushed to zero -- numpy would return denormals <= 2.2e-308 there -- and NaN maps to zero.  Both
+// evaluations share every constant, which halves the constant traffic of two libdevice exp() calls,
+// and there is no slow-path branch.
+// The constants live in constant memory so that DFMA takes them as c[bank][offset] operands instead of
+// UMOV-materialised immediates (two UMOVs per 64-bit literal per use otherwise).
+__constant__ double kExpC[17] = {
+    1.4426950408889634074,        // 0  log2(e)
+    6755399441055744.0,           // 1  1.5 * 2^52
+    -6.93147180369123816490e-01,  // 2  -ln2 hi
+    -1.90821492927058770002e-10,  // 3  -ln2 lo
+    -1100.0,                      // 4  clamp
+    0x1.af632e7d3bc8bp-26,        // 5  c11
+    0x1.28b413b5ef026p-22,        // 6  c10
+    0x1.71ddf56b28fcep-19,        // 7  c9
+    0x1.a019919d2943ep-16,        // 8  c8
+    0x1.a01a01b147016p-13,        // 9  c7
+    0x1.6c16c188019e5p-10,        // 10 c6
+    0x1.111111110f21cp-7,         // 11 c5
+    0x1.555555554f0b3p-5,         // 12 c4
+    0x1.555555555555ap-3,         // 13 c3
+    0x1.0000000000011p-1,         // 14 c2
+    1.0,                          // 15 c1
+    1.0};                         // 16 c0
+
+__device__ __forceinline__ void exp_pair(double x0, double x1, double &e0, double &e1) {
+  x0 = fmax(x0, kExpC[4]);
+  x1 = fmax(x1, kExpC[4]);
+  const double t0 = fma(x0, kExpC[0], kExpC[1]), t1 = fma(x1, kExpC[0], kExpC[1]);
+  const double n0 = t0 - kExpC[1], n1 = t1 - kExpC[1];
+  double r0 = fma(n0, kExpC[2], x0), r1 = fma(n1, kExpC[2], x1);
+  r0 = fma(n0, kExpC[3], r0);
+  r1 = fma(n1, kExpC[3], r1);
+  double p0 = kExpC[5], p1 = kExpC[5];
+#pragma unroll
+  for (int i = 6; i < 17; ++i) {
+    p0 = fma(p0, r0, kExpC[i]);
+    p1 = fma(p1, r1, kExpC[i]);
+  }
+  const int k0 = __double2loint(t0), k1 = __double2loint(t1);
+  e0 = (k0 < -1021) ? 0.0 : __hiloint2double(__double2hiint(p0) + (k0 << 20), __double2loint(p0));
+  e1 = (k1 < -1021) ? 0.0 : __hiloint2double(__double2hiint(p1) + (k1 << 20), __double2loint(p1));
 }
 
 // ---------------------------------------------------------------- special functions (FP64)

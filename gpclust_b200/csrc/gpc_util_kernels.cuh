@@ -71,7 +71,7 @@ __global__ void k_add_weighted_noise_diag(double *__restrict__ M, int n, const d
 // ------------------------------------------------------------------------------------------------
 // MOG features: row n -> [ xc_i*xc_j (i<=j, row-major upper) | xc_i | 0 pad ], xc = x - centre.
 __global__ void k_mog_features(const double *__restrict__ X, const double *__restrict__ centre, int N, int Npad, int D, int DP,
-                               double *__restrict__ F) {
+                               double *__restrict__ F) {  // DP here is the leading dimension of F (feature ld)
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)Npad * DP) return;
   const int n = (int)(e / DP), f = (int)(e % DP);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_mahalanobis_pairs(const double *__restr
 // ------------------------------------------------------------------------------------------------
 // Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP)
 constexpr int kGramRows = 32;
-__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, double *__restrict__ partials) {
+__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, int ldf, double *__restrict__ partials) {
   extern __shared__ __align__(16) double tile[];  // kGramRows x DP
   const int tid = threadIdx.x;
   const int nout = DP * DP;
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict_
   const int num_tiles = Npad / kGramRows;
   for (int tix = blockIdx.x; tix < num_tiles; tix += gridDim.x) {
     __syncthreads();
-    const double *src = F + (size_t)tix * kGramRows * DP;
-    for (int e = tid; e < kGramRows * DP; e += blockDim.x) tile[e] = src[e];
+    const double *src = F + (size_t)tix * kGramRows * ldf;
+    for (int e = tid; e < kGramRows * DP; e += blockDim.x) tile[e] = src[(e / DP) * ldf + (e % DP)];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 16; ++q) {

@@ -10,8 +10,10 @@
 //                  phi^T F sufficient statistics of collapsed_mixture.py:53-56, MOHGP.py:76, MOG.py:56-57.
 //
 // Layout: every N x K array is row-major with leading dimension KP (K padded to 8/16/32/64); the
-// feature matrix F (= Y for MOHGP, [x_i x_j, x_i] for MOG) is row-major N x DP, DP = D padded to a
-// multiple of 8, pad columns zero.  All of them are allocated with roundup(N, 64) rows.
+// feature matrix F (= Y for MOHGP, [x_i x_j, x_i] for MOG) is row-major with DP = D padded to a
+// multiple of 8 columns (pad zero) and leading dimension DP + 4: the 4 pad doubles per row make the
+// 64-bit DMMA fragment reads bank-conflict free once a 64-row tile has been copied VERBATIM into
+// shared memory by a single cp.async.bulk.  All N-sized arrays are allocated with roundup(N, 64) rows.
 //
 // Both kernels are persistent (grid = 2 x SM count, two CTAs resident per SM so that one CTA's
 // memory phase overlaps the other's FP64 phase) and 8 warps each own 8 rows of a 64-row tile; warp 0 also
@@ -26,6 +28,16 @@ namespace gpc {
 
 constexpr int kStages = 2;
 constexpr int kCtasPerSm = 2;
+#ifndef GPC_DMMA_UNROLL
+#define GPC_DMMA_UNROLL 2
+#endif
+#ifndef GPC_PF_G
+#define GPC_PF_G 2
+#endif
+#ifndef GPC_PF_S
+#define GPC_PF_S 4
+#endif
+constexpr int kDmmaUnroll = GPC_DMMA_UNROLL;
 
 struct VbSmemLayout {
   int f_stride;       // doubles per staged F row  (DP + 4)
@@ -33,28 +45,26 @@ struct VbSmemLayout {
   __host__ __device__ VbSmemLayout(int DP) : f_stride(DP + 4), stage_doubles(GPC_ROW_TILE * (DP + 4)) {}
 };
 
-// Producer duty (done by consumer warp 0, one tile ahead of its use): stream F rows [tile*64, tile*64+64)
-// of this CTA's j-th tile into stage j % kStages.
-__device__ __forceinline__ void produce_f_tile(const double *__restrict__ F, int DP, int f_stride, double *stages, int stage_doubles,
-                                               uint64_t *full_bar, uint64_t *empty_bar, int j, int tile) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t row_bytes = (uint32_t)DP * 8u;
+// Producer duty (done by warp 0, one tile ahead of its use): copy F rows [tile*64, tile*64+64) of this
+// CTA's j-th tile into stage j % kStages with one bulk copy (64 * (DP+4) * 8 bytes, contiguous in HBM).
+__device__ __forceinline__ void produce_f_tile(const double *__restrict__ F, int stage_doubles, double *stages, uint64_t *full_bar,
+                                               uint64_t *empty_bar, int j, int tile) {
   const int s = j % kStages;
   const uint32_t ph = (uint32_t)((j / kStages) & 1);
-  mbar_wait(&empty_bar[s], ph ^ 1u);  // every consumer warp has finished the previous tile staged here
-  if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], row_bytes * GPC_ROW_TILE);
+  mbar_wait(&empty_bar[s], ph ^ 1u);  // every warp has finished the previous tile staged here
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t bytes = (uint32_t)stage_doubles * 8u;
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_g2s(stages + (size_t)s * stage_doubles, F + (size_t)tile * stage_doubles, bytes, &full_bar[s]);
+  }
   __syncwarp();
-  double *dst = stages + (size_t)s * stage_doubles;
-  const double *src = F + (size_t)tile * GPC_ROW_TILE * DP;
-#pragma unroll
-  for (int r = lane; r < GPC_ROW_TILE; r += 32) bulk_g2s(dst + r * f_stride, src + (size_t)r * DP, row_bytes, &full_bar[s]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // G pass
 // ------------------------------------------------------------------------------------------------
 struct NatgradArgs {
-  const double *F;        // Npad x DP features
+  const double *F;        // Npad x (DP+4) features
   const double *x;        // Npad x KP logits at the current point
   const double *lse;      // Npad : logsumexp of the rows of x (written by the S pass that produced x)
   const double *Wt;       // KP x DP, Wt[k][d] = W[d][k]
@@ -70,7 +80,8 @@ struct NatgradArgs {
   int N, K, DP, num_tiles;
 };
 
-template <int KP>
+// FULLK: K == KP, no column masking
+template <int KP, bool FULLK>
 __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -106,10 +117,17 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
     int it = 0;
     if (warp == 0 && (int)blockIdx.x < a.num_tiles)
-      produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, 0, blockIdx.x);
+      produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, 0, blockIdx.x);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles)
-        produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, it + 1, tile + gridDim.x);
+      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles) {
+        produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, it + 1, tile + gridDim.x);
+        // pull the next tile's N x K operands into L2 so that the demand loads below are L2 hits
+        const size_t nxt = (size_t)(tile + gridDim.x) * GPC_ROW_TILE * KP;
+        const uint32_t bytes = GPC_ROW_TILE * KP * 8u;
+        if (lane == 0) bulk_prefetch_l2(a.x + nxt, bytes);
+        if (has_old && lane == 1) bulk_prefetch_l2(a.x_old + nxt, bytes);
+        if (has_old && lane == 2) bulk_prefetch_l2(a.ng_old + nxt, bytes);
+      }
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
       const int row = tile * GPC_ROW_TILE + warp * 8 + g;
@@ -134,7 +152,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
       mbar_wait(&full_bar[s], ph);
       const double *fa = stages + (size_t)s * L.stage_doubles + (warp * 8 + g) * L.f_stride + t;
       const double *wb = wt_s + g * L.f_stride + t;
-#pragma unroll 2
+#pragma unroll(kDmmaUnroll)
       for (int ks = 0; ks < ksteps; ++ks) {
         const double af = fa[4 * ks];
 #pragma unroll
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
       if (lane == 0) mbar_arrive(&empty_bar[s]);
 
       // previous-point operands are streamed in column chunks, PF chunks ahead of their use
-      constexpr int PF = (NT < 2) ? NT : 2;
+      constexpr int PF = (NT < GPC_PF_G) ? NT : GPC_PF_G;
       double2 xo_q[PF], ngo_q[PF];
       if (has_old) {
 #pragma unroll
@@ -159,11 +177,15 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
+        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
         const double x0 = x[nt][0], x1 = x[nt][1];
-        acc[nt][0] = (c < a.K) ? (acc[nt][0] + bias_s[c]) - x0 : 0.0;
-        acc[nt][1] = (c + 1 < a.K) ? (acc[nt][1] + bias_s[c + 1]) - x1 : 0.0;
-        x[nt][0] = (c < a.K) ? exp(x0 - lse) : 0.0;
-        x[nt][1] = (c + 1 < a.K) ? exp(x1 - lse) : 0.0;
+        const double2 bb = *reinterpret_cast<const double2 *>(bias_s + c);
+        acc[nt][0] = ok0 ? (acc[nt][0] + bb.x) - x0 : 0.0;
+        acc[nt][1] = ok1 ? (acc[nt][1] + bb.y) - x1 : 0.0;
+        double p0, p1;
+        exp_pair(x0 - lse, x1 - lse, p0, p1);
+        x[nt][0] = ok0 ? p0 : 0.0;
+        x[nt][1] = ok1 ? p1 : 0.0;
         sa += x[nt][0] * acc[nt][0] + x[nt][1] * acc[nt][1];
       }
       sa = quad_sum(sa);
@@ -172,8 +194,9 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        const double n0 = (c < a.K && row_ok) ? acc[nt][0] - sa : 0.0;
-        const double n1 = (c + 1 < a.K && row_ok) ? acc[nt][1] - sa : 0.0;
+        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const double n0 = (ok0 && row_ok) ? acc[nt][0] - sa : 0.0;
+        const double n1 = (ok1 && row_ok) ? acc[nt][1] - sa : 0.0;
         const double g0 = n0 * x[nt][0], g1 = n1 * x[nt][1];
         stg2(a.ng_out + off + 8 * nt, n0, n1);
         if (a.grad_out) stg2(a.grad_out + off + 8 * nt, g0, g1);
@@ -185,8 +208,10 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
             ngo_q[nt % PF] = ldg2_stream(a.ng_old + off + 8 * (nt + PF));
           }
           if (row_ok) {
-            const double po0 = (c < a.K) ? exp(xo.x - lse_o) : 0.0;
-            const double po1 = (c + 1 < a.K) ? exp(xo.y - lse_o) : 0.0;
+            double po0, po1;
+            exp_pair(xo.x - lse_o, xo.y - lse_o, po0, po1);
+            if (!ok0) po0 = 0.0;
+            if (!ok1) po1 = 0.0;
             const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
             d1 += e0 * g0 + e1 * g1;
             d2 += e0 * (ngo.x * po0) + e1 * (ngo.y * po1);
@@ -236,7 +261,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
 // beta modes: GPC_BETA_* of include/gpclust_b200.h
 
 struct StepStatsArgs {
-  const double *F;       // Npad x DP
+  const double *F;       // Npad x (DP+4)
   const double *x_base;  // Npad x KP logits at the accepted point
   const double *ng;      // natural gradient at x_base (nullable: "set" mode, x_new := x_base, nothing written)
   const double *sd_old;  // previous search direction (nullable or ignored when beta == 0)
@@ -252,7 +277,7 @@ struct StepStatsArgs {
   int N, K, DP, num_tiles;
 };
 
-template <int KP>
+template <int KP, bool FULLK>
 __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const StepStatsArgs a) {
   constexpr int NT = KP / 8;
   constexpr int NGRP = GPC_CONSUMER_WARPS / NT;  // consumer warps sharing one 8-cluster m-tile in the stats GEMM
@@ -302,10 +327,16 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
 
     int it = 0;
     if (warp == 0 && (int)blockIdx.x < a.num_tiles)
-      produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, 0, blockIdx.x);
+      produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, 0, blockIdx.x);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles)
-        produce_f_tile(a.F, a.DP, L.f_stride, stages, L.stage_doubles, full_bar, empty_bar, it + 1, tile + gridDim.x);
+      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles) {
+        produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, it + 1, tile + gridDim.x);
+        const size_t nxt = (size_t)(tile + gridDim.x) * GPC_ROW_TILE * KP;
+        const uint32_t bytes = GPC_ROW_TILE * KP * 8u;
+        if (lane == 0) bulk_prefetch_l2(a.x_base + nxt, bytes);
+        if (a.ng != nullptr && lane == 1) bulk_prefetch_l2(a.ng + nxt, bytes);
+        if (use_old && lane == 2) bulk_prefetch_l2(a.sd_old + nxt, bytes);
+      }
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
       const int row = tile * GPC_ROW_TILE + warp * 8 + g;
@@ -322,7 +353,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
       }
       if (a.ng != nullptr) {
         // operands streamed in column chunks, PF chunks ahead of their use
-        constexpr int PF = (NT < 4) ? NT : 4;
+        constexpr int PF = (NT < GPC_PF_S) ? NT : GPC_PF_S;
         double2 ng_q[PF], sd_q[PF];
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
@@ -351,19 +382,23 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        if (c < a.K) m = fmax(m, x[nt][0]);
-        if (c + 1 < a.K) m = fmax(m, x[nt][1]);
+        if (FULLK || c < a.K) m = fmax(m, x[nt][0]);
+        if (FULLK || c + 1 < a.K) m = fmax(m, x[nt][1]);
       }
       m = quad_max(m);
       double ssum = 0.0, px = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        const double e0 = (c < a.K) ? exp(x[nt][0] - m) : 0.0;
-        const double e1 = (c + 1 < a.K) ? exp(x[nt][1] - m) : 0.0;
+        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const double z0 = x[nt][0] - m, z1 = x[nt][1] - m;
+        double e0, e1;
+        exp_pair(z0, z1, e0, e1);
+        if (!ok0) e0 = 0.0;
+        if (!ok1) e1 = 0.0;
         ssum += e0 + e1;
-        if (c < a.K) px += e0 * (x[nt][0] - m);
-        if (c + 1 < a.K) px += e1 * (x[nt][1] - m);
+        if (ok0) px += e0 * z0;
+        if (ok1) px += e1 * z1;
         x[nt][0] = e0;
         x[nt][1] = e1;
       }
@@ -389,7 +424,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
       mbar_wait(&full_bar[s], ph);
       const double *fb = stages + (size_t)s * L.stage_doubles + t * L.f_stride + g;
       const double *pa = p_s + t * P_STRIDE + 8 * mt + g;
-#pragma unroll 2
+#pragma unroll(kDmmaUnroll)
       for (int ks = 0; ks < GPC_ROW_TILE / 4; ++ks) {
         const double af = pa[4 * ks * P_STRIDE];
         colsum += af;

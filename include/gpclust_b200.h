@@ -19,7 +19,8 @@
  * Layout of the N-sized arrays ("series" rows n, "cluster" columns k)
  *   - logits / natural gradient / search direction: Npad x KP, Npad = roundup(N, GPC_ROW_TILE),
  *     KP = gpc_padded_k(K) in {8,16,32,64}; pad rows and pad columns hold zeros;
- *   - features F: Npad x DP, DP = gpc_padded_d(D) (multiple of 8, <= 64), pad zero.
+ *   - features F: Npad rows of DP = gpc_padded_d(D) columns (multiple of 8, <= 64, pad zero) with leading
+ *     dimension gpc_feature_ld(DP) = DP + 4 (the row padding is the shared-memory bank skew).
  *     MOHGP: F = Y.  MOG: F = [x_i x_j (i<=j) | x_i] of the centred data (gpc_mog_features).
  *   - stats vector: [ T (KP x DP) | phi_hat (KP) | H (1) | pad (1) ],  T[k][f] = sum_n phi[n][k] F[n][f].
  */
@@ -53,6 +54,7 @@ int gpc_abi_version(void);
 int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
 int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
 long long gpc_padded_rows(long long N);
+int gpc_feature_ld(int DP);        /* DP + 4: leading dimension of the feature rows F                  */
 int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 2 (one pad double keeps blocks 16-B aligned)    */
 int gpc_default_grid(int device);  /* number of persistent CTAs (2 per SM); <0 on CUDA error          */
 
@@ -97,8 +99,8 @@ int gpc_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_lo
  * and the G-pass weights Wt[k,:] = Sy^-1 mu_k.  per_k: KP x 4 = [log_det_diff, s^T Lambda_inv s,
  * tr(Lambda_inv Sy_inv), mu^T Sy^-1 mu].  Syi_ybark_t, Lambda_inv, C_chols may be NULL.  *info is
  * cleared first.                                                                                     */
-int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Sy, const double *Sy_inv, const double *Sf,
-                      double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
+int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Ly_inv, const double *Sy,
+                      const double *Sy_inv, const double *Sf, double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
                       int K, int D, int KP, int DP, void *stream);
 /* mixing-proportion bound and gradient (collapsed_mixture.py:66-94), bound assembly, G-pass bias.
  * scalars: [0] bound, [1] mixing_prop_bound, [2] H.  mixgrad_out (K doubles) may be NULL.             */
@@ -106,6 +108,7 @@ int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *c
                        double *mixgrad_out, double alpha, int prior, int K, int KP, int DP, void *stream);
 
 /* ---- MOG (MOG.py:34-84) ------------------------------------------------------------------------ */
+/* F (Npad x gpc_feature_ld(DP)) <- [xc_i xc_j (i<=j) | xc_i | 0], xc = x - centre                       */
 int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream);
 /* per_k: KP x 4 = [kN, vN, Sns_halflogdet, grad const].  mun_c: K x D (centred), Sns / Sns_inv: K x D x D.
  * D <= 10.  *info is cleared first.                                                                   */
@@ -131,7 +134,8 @@ int gpc_multiple_mahalanobis(const double *X1, const double *X2, const double *L
                              void *stream);
 /* multiple_pdinv (np_utilities.py:6-22): A, inv are D x D x K (K last); hld K doubles.  D <= 64.     */
 int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, int *info, void *stream);
-/* Y^T Y (MOHGP.py:53): partials grid x DP x DP, then gpc_reduce_partials(len = DP*DP).               */
+/* Y^T Y (MOHGP.py:53) of the feature rows F (ld = gpc_feature_ld(DP)): partials grid x DP x DP, then
+ * gpc_reduce_partials(len = DP*DP).                                                                    */
 int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream);
 /* layout helpers: contiguous N x D  <->  padded Npad x ld                                             */
 int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, void *stream);
