@@ -23,6 +23,7 @@ from numpy.linalg import LinAlgError
 from . import _cabi
 from ._cabi import lib, check, ptr
 from .collapsed_vb import CollapsedVB
+from .sharding import RowShards
 
 # control block layout (doubles)
 _C_BOUND, _C_MIX, _C_H, _C_SQ, _C_NUM, _C_DEN, _C_BETA, _C_INFO = 0, 1, 2, 3, 4, 5, 6, 8
@@ -65,18 +66,9 @@ class CollapsedMixture(CollapsedVB):
             check(self._grid or -1, "gpc_default_grid")
 
         # row sharding (one process per GPU); a single process is world 1
-        self._dist = None
-        self._group = group
-        self._world, self._rank = 1, 0
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                self._dist = dist
-                self._world = dist.get_world_size(group)
-                self._rank = dist.get_rank(group)
-        except ImportError:
-            pass
-        self._row_start, self.N_total = self._row_partition(self.N)
+        self._shards = RowShards(group)
+        self._world, self._rank = self._shards.world, self._shards.rank
+        self._row_start, self.N_total = self._shards.partition(self.N, self.device)
 
         self._Npad = _cabi.padded_rows(self.N)
         self._F = None          # Npad x DP features, set by the subclass
@@ -102,24 +94,11 @@ class CollapsedMixture(CollapsedVB):
     def _is_root(self):
         return self._rank == 0
 
-    def _row_partition(self, n_local):
-        if self._world == 1:
-            return 0, int(n_local)
-        t = self.torch.zeros(self._world, dtype=self.torch.int64, device=self.device)
-        t[self._rank] = n_local
-        self._dist.all_reduce(t, group=self._group)
-        counts = t.cpu().numpy()
-        return int(counts[:self._rank].sum()), int(counts.sum())
-
     def _draw_rows(self, K):
-        if self._world == 1:
-            return np.random.randn(self.N, K)
-        full = np.random.randn(self.N_total, K)  # same stream on every rank
-        return full[self._row_start:self._row_start + self.N].copy()
+        return self._shards.draw_rows(self.N, self._row_start, self.N_total, K)
 
     def _allreduce(self, t):
-        if self._world > 1:
-            self._dist.all_reduce(t, group=self._group)
+        self._shards.allreduce(t)
 
     # ------------------------------------------------------------------ device buffers
     def _stream(self):

@@ -1,0 +1,66 @@
+"""torchrun --nproc-per-node G tools/check_multi_gpu.py : the row-sharded G-rank run must reproduce the
+single-rank run (same trace, bound to 1e-12 relative, identical assignments).  Every rank builds (a) its
+shard of the model on the default NCCL group and (b) the full model on a solo group, then compares."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from helpers import mohgp_problem, product_kernels
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+solo = [dist.new_group([r]) for r in range(world)][rank]
+from gpclust_b200 import MOHGP, MOG
+from gpclust_b200.sharding import RowShards
+
+ok = True
+for (N, D, K, prior) in [(5000, 64, 64, "symmetric"), (3001, 24, 7, "DP")]:
+    X, Y, _ = mohgp_problem(N, D, K, seed=1)
+    np.random.seed(4)
+    phi0 = np.random.randn(N, K)
+    lo, hi = RowShards.even_split(N, world, rank)
+    kF, kY = product_kernels()
+    ms = MOHGP(X, kF, kY, Y[lo:hi], K=K, prior_Z=prior, phi_init=phi0[lo:hi])
+    kF, kY = product_kernels()
+    m1 = MOHGP(X, kF, kY, Y, K=K, prior_Z=prior, phi_init=phi0, group=solo)
+    assert ms.N_total == N and m1.N_total == N
+    b_s, b_1 = ms.bound(), m1.bound()
+    ms.optimize(maxiter=25, verbose=False)
+    m1.optimize(maxiter=25, verbose=False)
+    ts, t1 = ms.optimize_trace, m1.optimize_trace
+    same_iters = [r[0] for r in ts] == [r[0] for r in t1]
+    rel = max(abs(a[1] - b[1]) / abs(b[1]) for a, b in zip(ts, t1))
+    assign = np.array_equal(ms.phi.argmax(1), m1.phi.argmax(1)[lo:hi])
+    good = same_iters and rel < 1e-10 and abs(b_s - b_1) < 1e-12 * abs(b_1) and assign
+    ok = ok and good
+    if rank == 0:
+        print("MOHGP N=%d D=%d K=%d %s: init bound rel diff %.2e, trace rel diff %.2e, iters equal %s, assignments equal %s -> %s"
+              % (N, D, K, prior, abs(b_s - b_1) / abs(b_1), rel, same_iters, assign, "OK" if good else "FAIL"))
+
+# MOG shard check
+rng = np.random.RandomState(0)
+Xm = rng.randn(4000, 2) * 0.3 + rng.randint(0, 3, (4000, 1)) * 2.0
+np.random.seed(5)
+phi0 = np.random.randn(4000, 6)
+lo, hi = RowShards.even_split(4000, world, rank)
+ms = MOG(Xm[lo:hi], K=6, phi_init=phi0[lo:hi])
+m1 = MOG(Xm, K=6, phi_init=phi0, group=solo)
+ms.optimize(maxiter=20, verbose=False)
+m1.optimize(maxiter=20, verbose=False)
+rel = max(abs(a[1] - b[1]) / abs(b[1]) for a, b in zip(ms.optimize_trace, m1.optimize_trace))
+good = rel < 1e-10 and [r[0] for r in ms.optimize_trace] == [r[0] for r in m1.optimize_trace]
+ok = ok and good
+if rank == 0:
+    print("MOG N=4000 D=2 K=6: trace rel diff %.2e -> %s" % (rel, "OK" if good else "FAIL"))
+flag = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(flag)
+dist.destroy_process_group()
+sys.exit(int(flag.item() != 0))
