@@ -14,9 +14,12 @@ Parity pins:
     iteration numbering over 61 + 52 + 55 printed lines, bounds to 4e-12 relative (the notebook prints 12
     significant digits), K = 4 -> 5 -> 11 through the splits, posterior mean/covariance and predictive
     densities to the printed digits.
-  * MOHGP and OMGP: "parity unpinned" -- the reference ships no seeded output for them and the
-    drosophila data file is missing; they are checked by oracle-independent identities only
-    (finite-difference gradient, Woodbury identity, pairwise-vs-GEMM Mahalanobis).
+  * MOHGP, OMGP (and MOG again): PINNED against outputs of the reference's own modules -- /root/reference/GPclust
+    imported unmodified in the build container with a stub `GPy` (tests/golden/make_reference_goldens.py) --
+    stored in tests/golden/reference_*.npz and checked by tests/test_reference_goldens.py: start bound, gradient,
+    natural gradient, posterior means, full optimisation trace (iteration numbering, bounds, betas), final phi.
+    What remains the shim's (not the reference's) is the GPy layer itself (thin LAPACK wrappers, closed-form
+    covariances): GPy is a third-party dependency absent from /root/reference (`GPy>=0.6`, setup.py:14).
 """
 import sys
 

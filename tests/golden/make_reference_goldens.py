@@ -1,0 +1,193 @@
+"""Generate golden vectors by running the REFERENCE'S OWN Python modules (unmodified, imported from
+/root/reference) on small seeded inputs.  Run in the build container only; the fixtures it writes
+(tests/golden/reference_*.npz) are committed and are what travels to the GPU box.
+
+The reference imports GPy at module level (not installable here).  Only thin pieces of GPy are touched on
+the hot path, so a stub `GPy` package is placed in sys.modules before the import:
+
+    GPy.core.Model                        plain base class: link_parameter(s) / unlink_parameter set / drop
+                                          attributes, optimizer_array is empty (kernel hyper-parameters fixed,
+                                          so optimize_parameters() returns 0. exactly as collapsed_vb.py:322-323)
+    GPy.core.parameterization.param.Param, ...transformations.Logexp
+                                          a (1,) float array with a name -- what GPy's scalar Param is
+    GPy.util.linalg.*, GPy.util.diag.subtract, GPy.kern.*
+                                          oracle/gpy_shim.py (thin LAPACK wrappers / closed-form covariances)
+
+Everything else that executes -- CollapsedVB.optimize, CollapsedMixture, MOHGP, MOG, OMGP, np_utilities (the
+Python-3 fallbacks, since `scipy.weave` does not exist) -- is the reference's code.
+"""
+import contextlib
+import io
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("GPCLUST_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from oracle import gpy_shim as G  # noqa: E402
+
+
+def install_gpy_stub():
+    class Model(object):
+        def __init__(self, name):
+            self.name = name
+            self._linked = []
+
+        def link_parameter(self, p):
+            self._linked.append(p)
+            if isinstance(p, Param):
+                setattr(self, p.name, p)
+
+        def link_parameters(self, *ps):
+            for p in ps:
+                self.link_parameter(p)
+
+        def unlink_parameter(self, p):
+            self._linked = [q for q in self._linked if q is not p]
+
+        @property
+        def optimizer_array(self):
+            return np.zeros(0)
+
+        def randomize(self):
+            pass
+
+    class Param(np.ndarray):
+        def __new__(cls, name, value, *transforms):
+            obj = np.atleast_1d(np.asarray(value, dtype=np.float64)).view(cls)
+            obj.name = name
+            return obj
+
+        def __array_finalize__(self, obj):
+            self.name = getattr(obj, "name", None)
+
+    class Logexp(object):
+        pass
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def subtract(A, b):  # GPy.util.diag.subtract: in-place on the diagonal
+        A[np.diag_indices(A.shape[0])] -= b
+        return A
+
+    linalg = mod("GPy.util.linalg", mdot=G.mdot, pdinv=G.pdinv, backsub_both_sides=G.backsub_both_sides, dpotrs=G.dpotrs,
+                 jitchol=G.jitchol, dtrtrs=G.dtrtrs, dpotri=G.dpotri, tdot_numpy=G.tdot, tdot=G.tdot)
+    diag = mod("GPy.util.diag", subtract=subtract)
+    util = mod("GPy.util", linalg=linalg, diag=diag)
+    param = mod("GPy.core.parameterization.param", Param=Param)
+    transformations = mod("GPy.core.parameterization.transformations", Logexp=Logexp)
+    parameterization = mod("GPy.core.parameterization", param=param, transformations=transformations)
+    model = mod("GPy.core.model", Model=Model)
+    core = mod("GPy.core", Model=Model, model=model, parameterization=parameterization)
+    kern = mod("GPy.kern", RBF=G.RBF, Matern32=G.Matern32, Matern52=G.Matern52, Bias=G.Bias, White=G.White)
+    mod("GPy", core=core, util=util, kern=kern)
+
+
+LINE = re.compile(r"iteration (\d+) bound=(\S+) grad=(\S+), beta=(\S+)")
+
+
+def run_optimize(m, **kw):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        m.optimize(verbose=True, **kw)
+    rows = [(int(a), float(b), float(c), float(d)) for a, b, c, d in LINE.findall(buf.getvalue().replace("\r", "\n"))]
+    return np.array(rows, dtype=np.float64).reshape(-1, 4)
+
+
+def mohgp_case(GPclust, name, N, D, K, prior_Z, alpha, seed, kernF, kernY, X=None, method="HS", maxiter=25):
+    rng = np.random.RandomState(seed)
+    X = np.linspace(0, 10, D)[:, None] if X is None else X
+    Sf, Sy = kernF.K(X), kernY.K(X)
+    z = rng.randint(0, K, N)
+    means = (np.linalg.cholesky(Sf + 1e-8 * np.eye(D)).dot(rng.randn(D, K))).T
+    Y = means[z] + (np.linalg.cholesky(Sy + 1e-8 * np.eye(D)).dot(rng.randn(D, N))).T
+    np.random.seed(seed + 1)
+    m = GPclust.MOHGP(X, kernF, kernY, Y, K=K, alpha=alpha, prior_Z=prior_Z)
+    out = {"X": X, "Y": Y, "phi0": m.phi_.copy(), "K": K, "alpha": alpha, "prior_Z": prior_Z, "method": method,
+           "kernF": json.dumps(kernF.spec()), "kernY": json.dumps(kernY.spec())}
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound0=m.bound(), grad0=g, natgrad0=ng, phi_init=m.phi.copy(), phi_hat0=m.phi_hat.copy(), H0=m.H, muk0=m.muk.copy(),
+               Lambda_inv0=m.Lambda_inv.copy(), log_det_diff0=m.log_det_diff.copy(), ybark0=m.ybark.copy(),
+               Sy_chol=m.Sy_chol.copy(), Sy_logdet=m.Sy_logdet, mix0=m.mixing_prop_bound(), mixgrad0=m.mixing_prop_bound_grad().copy())
+    out["trace"] = run_optimize(m, method=method, maxiter=maxiter)
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy(), muk1=m.muk.copy())
+    np.savez_compressed(os.path.join(HERE, "reference_mohgp_%s.npz" % name), **out)
+    print("mohgp", name, "bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
+
+
+def omgp_case(GPclust, name, N, Dy, K, prior_Z, alpha, seed, variance, kernels, maxiter=12):
+    rng = np.random.RandomState(seed)
+    X = np.sort(rng.uniform(0, 10, N))[:, None]
+    comp = rng.randint(0, K, N)
+    Y = np.zeros((N, Dy))
+    for d in range(Dy):
+        for i in range(K):
+            sel = comp == i
+            Y[sel, d] = np.sin(X[sel, 0] * (0.6 + 0.5 * i) + d + i) * (1.0 + 0.3 * i) + 0.1 * rng.randn(sel.sum())
+    np.random.seed(seed + 1)
+    m = GPclust.OMGP(X, Y, K=K, kernels=kernels, variance=variance, alpha=alpha, prior_Z=prior_Z)
+    out = {"X": X, "Y": Y, "phi0": m.phi_.copy(), "K": K, "alpha": alpha, "prior_Z": prior_Z, "variance": variance,
+           "kernels": json.dumps([k.spec() for k in m.kern])}
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound0=m.bound(), grad0=g, natgrad0=ng, phi_init=m.phi.copy())
+    out["trace"] = run_optimize(m, method="HS", maxiter=maxiter)
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy())
+    Xnew = np.linspace(0, 10, 7)[:, None]
+    mu, va = m.predict(Xnew, 0)
+    out.update(Xnew=Xnew, pred_mu0=mu, pred_va0=va)
+    np.savez_compressed(os.path.join(HERE, "reference_omgp_%s.npz" % name), **out)
+    print("omgp", name, "bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
+
+
+def mog_case(GPclust, name, N, D, K, prior_Z, alpha, seed, maxiter=30):
+    rng = np.random.RandomState(seed)
+    centres = rng.randn(K, D) * 4.0
+    X = centres[rng.randint(0, K, N)] + rng.randn(N, D)
+    np.random.seed(seed + 1)
+    m = GPclust.MOG(X, K=K, prior_Z=prior_Z, alpha=alpha)
+    out = {"X": X, "phi0": m.phi_.copy(), "K": K, "alpha": alpha, "prior_Z": prior_Z}
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound0=m.bound(), grad0=g, natgrad0=ng, mun0=m.mun.copy(), Sns0=m.Sns.copy())
+    out["trace"] = run_optimize(m, method="HS", maxiter=maxiter)
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy())
+    np.savez_compressed(os.path.join(HERE, "reference_mog_%s.npz" % name), **out)
+    print("mog", name, "bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
+
+
+def main():
+    install_gpy_stub()
+    sys.path.insert(0, REF)
+    import GPclust
+    assert os.path.realpath(GPclust.__file__).startswith(os.path.realpath(REF)), GPclust.__file__
+
+    mohgp_case(GPclust, "sym", N=60, D=12, K=4, prior_Z="symmetric", alpha=1.0, seed=0,
+               kernF=G.RBF(1, 1.0, 2.0), kernY=G.RBF(1, 0.1, 1.0) + G.White(1, 0.05))
+    mohgp_case(GPclust, "dp", N=45, D=9, K=5, prior_Z="DP", alpha=3.0, seed=1,
+               kernF=G.Matern52(1, 1.0, 3.0), kernY=G.Matern32(1, 0.2, 1.5) + G.White(1, 0.05) + G.Bias(1, 0.1), method="PR")
+    # replicated time points (drosophila design: 8 replicates per hour, rows of data/kalinka09_pdata.csv) -> singular Sf
+    hours = np.repeat(np.arange(2.0, 9.0), 2)[:, None]
+    mohgp_case(GPclust, "replicates", N=40, D=14, K=3, prior_Z="DP", alpha=1.0, seed=2,
+               kernF=G.Matern52(1, 1.0, 12.0), kernY=G.Matern52(1, 0.1, 12.0) + G.White(1, 0.05), X=hours, method="FR", maxiter=15)
+    omgp_case(GPclust, "k2", N=36, Dy=1, K=2, prior_Z="symmetric", alpha=1.0, seed=3, variance=0.01,
+              kernels=[G.RBF(1, 1.0, 1.0), G.RBF(1, 1.0, 2.0)])
+    omgp_case(GPclust, "k3", N=30, Dy=2, K=3, prior_Z="DP", alpha=2.0, seed=4, variance=0.05, kernels=None)
+    mog_case(GPclust, "d3", N=80, D=3, K=4, prior_Z="symmetric", alpha=1.0, seed=5)
+    mog_case(GPclust, "dp", N=70, D=2, K=5, prior_Z="DP", alpha=4.0, seed=6)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+"""Pins against outputs of the REFERENCE'S OWN modules (tests/golden/reference_*.npz, produced by
+tests/golden/make_reference_goldens.py, which imports /root/reference/GPclust unmodified with a stub GPy).
+
+  * CPU (`-m "not gpu"`): the oracle restatement reproduces the reference's bound, gradients, responsibilities and
+    optimisation trace on the same inputs.
+  * GPU (`-m gpu`): the product path (Python mirror -> C-ABI -> sm_100a kernels) does, within 1e-9 relative
+    (north_star), max-norm-relative for arrays.
+"""
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, relerr
+from oracle import gpy_shim as G
+from oracle.vb_oracle import MOGOracle, MOHGPOracle, OMGPOracle, mahalanobis_pairs_solve
+
+TOL = 1e-9
+
+
+def _load(path):
+    d = np.load(path)
+    return {k: d[k] for k in d.files}
+
+
+def _cases(prefix):
+    return sorted(glob.glob(os.path.join(GOLDEN, "reference_%s_*.npz" % prefix)))
+
+
+def _kern(spec, mod):
+    """spec: [(kind, variance, lengthscale), ...] -> a kernel of `mod` (oracle.gpy_shim or gpclust_b200.kern)."""
+    ctor = {"rbf": mod.RBF, "matern32": mod.Matern32, "matern52": mod.Matern52}
+    parts = []
+    for kind, var, ls in spec:
+        if kind in ctor:
+            parts.append(ctor[kind](1, var, ls))
+        elif kind == "bias":
+            parts.append(mod.Bias(1, var))
+        else:
+            parts.append(mod.White(1, var))
+    out = parts[0]
+    for p in parts[1:]:
+        out = out + p
+    return out
+
+
+def _scalar(v):
+    return v.item() if hasattr(v, "item") else v
+
+
+def _check_trace(trace, ref):
+    trace = np.asarray(trace, dtype=np.float64).reshape(-1, 4)
+    assert trace.shape == ref.shape, (trace.shape, ref.shape)
+    assert np.array_equal(trace[:, 0], ref[:, 0])  # identical iteration numbering (accept / reject decisions)
+    # the reference prints str(float) -> full precision; bounds to 1e-9 relative
+    assert np.max(np.abs(trace[:, 1] - ref[:, 1]) / np.abs(ref[:, 1])) < TOL
+    assert relerr(trace[:, 2], ref[:, 2]) < 1e-7  # squared gradient norms
+    assert np.allclose(trace[:, 3], ref[:, 3], rtol=1e-6, atol=1e-9)  # beta: ratio of small differences
+
+
+def _check_model(m, d, trace, after=True):
+    if after:
+        assert abs(m.bound() - _scalar(d["bound1"])) < TOL * abs(_scalar(d["bound1"]))
+        assert relerr(m.phi, d["phi1"]) < 1e-8
+        assert np.array_equal(np.argmax(m.phi, 1), np.argmax(d["phi1"], 1))
+        g, ng = m.vb_grad_natgrad()
+        assert relerr(ng, d["natgrad1"]) < 1e-7 and relerr(g, d["grad1"]) < 1e-7
+    _check_trace(trace, d["trace"])
+
+
+def _check_start(m, d):
+    assert np.array_equal(m.phi_, d["phi0"])
+    assert abs(m.bound() - _scalar(d["bound0"])) < TOL * abs(_scalar(d["bound0"]))
+    g, ng = m.vb_grad_natgrad()
+    assert relerr(ng, d["natgrad0"]) < TOL and relerr(g, d["grad0"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ oracle (CPU)
+@pytest.mark.parametrize("path", _cases("mohgp"))
+def test_oracle_mohgp_matches_reference(path):
+    d = _load(path)
+    seed_state = np.random.get_state()
+    m = MOHGPOracle(d["X"], _kern(json.loads(str(d["kernF"])), G), _kern(json.loads(str(d["kernY"])), G), d["Y"], K=int(d["K"]),
+                    alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]), mahalanobis=mahalanobis_pairs_solve)
+    np.random.set_state(seed_state)
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    assert relerr(m.muk, d["muk0"]) < TOL and relerr(m.log_det_diff, d["log_det_diff0"]) < TOL
+    assert relerr(m.Lambda_inv, d["Lambda_inv0"]) < 1e-9 and relerr(m.ybark, d["ybark0"]) < 1e-13
+    assert relerr(m.phi, d["phi_init"]) < 1e-14 and abs(m.H - _scalar(d["H0"])) < 1e-12 * abs(_scalar(d["H0"]))
+    assert abs(m.mixing_prop_bound() - _scalar(d["mix0"])) < 1e-12 * max(1.0, abs(_scalar(d["mix0"])))
+    assert relerr(m.mixing_prop_bound_grad(), d["mixgrad0"]) < 1e-14
+    m.out = io.StringIO()
+    m.optimize(method=str(d["method"]), maxiter=int(d["trace"][-1, 0]) if len(d["trace"]) else 25, verbose=False)
+    _check_model(m, d, m.trace)
+
+
+@pytest.mark.parametrize("path", _cases("omgp"))
+def test_oracle_omgp_matches_reference(path):
+    d = _load(path)
+    kernels = [_kern(s, G) for s in json.loads(str(d["kernels"]))]
+    m = OMGPOracle(d["X"], d["Y"], K=int(d["K"]), kernels=kernels, variance=float(d["variance"]), alpha=float(d["alpha"]),
+                   prior_Z=str(d["prior_Z"]))
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    m.out = io.StringIO()
+    m.optimize(method="HS", maxiter=12, verbose=False)
+    _check_model(m, d, m.trace)
+
+
+@pytest.mark.parametrize("path", _cases("mog"))
+def test_oracle_mog_matches_reference(path):
+    d = _load(path)
+    m = MOGOracle(d["X"], K=int(d["K"]), prior_Z=str(d["prior_Z"]), alpha=float(d["alpha"]))
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    assert relerr(m.mun, d["mun0"]) < 1e-12 and relerr(m.Sns, d["Sns0"]) < 1e-12
+    m.out = io.StringIO()
+    m.optimize(method="HS", maxiter=30, verbose=False)
+    _check_model(m, d, m.trace)
+
+
+# ------------------------------------------------------------------------------------------------ product (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _cases("mohgp"))
+def test_gpu_mohgp_matches_reference(path):
+    from gpclust_b200 import MOHGP, kern
+    d = _load(path)
+    m = MOHGP(d["X"], _kern(json.loads(str(d["kernF"])), kern), _kern(json.loads(str(d["kernY"])), kern), d["Y"], K=int(d["K"]),
+              alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]), phi_init=d["phi0"])
+    _check_start(m, d)
+    assert relerr(m.muk, d["muk0"]) < TOL and relerr(m.log_det_diff, d["log_det_diff0"]) < TOL
+    assert relerr(m.Lambda_inv, d["Lambda_inv0"]) < 1e-7 and relerr(m.ybark, d["ybark0"]) < 1e-12
+    assert relerr(m.phi, d["phi_init"]) < 1e-13
+    assert relerr(m.mixing_prop_bound_grad(), d["mixgrad0"]) < 1e-13
+    m.optimize(method=str(d["method"]), maxiter=int(d["trace"][-1, 0]), verbose=False)
+    _check_model(m, d, m.optimize_trace)
+    assert relerr(m.muk, d["muk1"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _cases("mog"))
+def test_gpu_mog_matches_reference(path):
+    from gpclust_b200 import MOG
+    d = _load(path)
+    np.random.seed(0)
+    m = MOG(d["X"], K=int(d["K"]), prior_Z=str(d["prior_Z"]), alpha=float(d["alpha"]))
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    assert relerr(m.mun, d["mun0"]) < 1e-10 and relerr(m.Sns, d["Sns0"]) < 1e-10
+    m.optimize(method="HS", maxiter=30, verbose=False)
+    _check_model(m, d, m.optimize_trace)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _cases("omgp"))
+def test_gpu_omgp_matches_reference(path):
+    from gpclust_b200 import OMGP, kern
+    d = _load(path)
+    spec = json.loads(str(d["kernels"]))
+    default = all(s == [["rbf", 1.0, 1.0]] for s in spec)
+    np.random.seed(0)
+    m = OMGP(d["X"], d["Y"], K=int(d["K"]), kernels=None if default else [_kern(s, kern) for s in spec], variance=float(d["variance"]),
+             alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]))
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    m.optimize(method="HS", maxiter=12, verbose=False)
+    _check_model(m, d, m.optimize_trace)
+    mu, va = m.predict(d["Xnew"], 0)
+    assert relerr(mu, d["pred_mu0"]) < 1e-7 and relerr(va, d["pred_va0"]) < 1e-7
