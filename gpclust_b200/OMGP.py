@@ -1,10 +1,294 @@
 """Host mirror of GPclust/OMGP.py (class OMGP): overlapping mixtures of Gaussian processes.
 
-Placeholder until the dense per-component path lands.
+Same constructor, attributes and methods as the reference (OMGP.py:14-193, plotting excluded).  For every
+component i the reference factorises the dense N x N matrix  B = K_i(X) + diag(variance / (phi_i + 1e-6))
+three times per iteration (bound, gradient, kernel gradients: OMGP.py:104-108, :132-136, :62-71).  Here it is
+built, factorised (blocked Cholesky on the FP64 tensor pipe) and inverted-triangular ONCE per
+set_vb_param; bound() and vb_grad_natgrad() read the cached per-component results:
+
+    gpc_softmax_rows                phi, log phi, H                                collapsed_mixture.py:53-56
+    gpc_omgp_build                  B (N x N, HBM)                                 OMGP.py:104-105
+    gpc_chol_blocked                L = jitchol(B), logdet                         OMGP.py:108 (pdinv)
+    gpc_tri_inverse_blocked         W = L^-1
+    gpc_omgp_component              tr(B^-1 Y Y^T), alpha = B^-1 Y, diag(B^-1), grad_Lm column   OMGP.py:113-121,136-140
+    gpc_omgp_finalize               bound + mixing-proportion terms                OMGP.py:123
+    gpc_dense_natgrad, gpc_cg_axpy  natural gradient, CG dots, search direction    OMGP.py:142-147, collapsed_vb.py:152-172
+
+N does not shard (dense coupling between all points of a component); components are independent.
+`update_kern_grads` (OMGP.py:55-94, kernel hyper-parameter gradients) is a "next" row.
 """
+import ctypes
+
+import numpy as np
+from numpy.linalg import LinAlgError
+
+from . import _cabi
+from . import kern as _kern
+from ._cabi import lib, check, ptr
 from .collapsed_mixture import CollapsedMixture
+from .collapsed_vb import CollapsedVB
+
+
+class _Point(object):
+    """Everything computed at one setting of the variational parameters."""
+    __slots__ = ("x", "phi", "logphi", "hpart", "grad_Lm", "comp", "scalars", "phi_hat", "mixgrad", "bound")
 
 
 class OMGP(CollapsedMixture):
     def __init__(self, X, Y, K=2, kernels=None, variance=1.0, alpha=1.0, prior_Z="symmetric", name="OMGP"):
-        raise NotImplementedError("OMGP: the dense per-component device path is not built yet")
+        torch = _cabi.require_cuda()
+        self.torch = torch
+        CollapsedVB.__init__(self, name)
+        Y = _cabi.f64(Y)
+        N, self.D = Y.shape
+        if self.D > 8:
+            raise ValueError("OMGP: at most 8 output dimensions are supported by the device path (got %d)" % self.D)
+        self.Y = Y
+        self.X = _cabi.f64(np.asarray(X).reshape(N, -1))
+        if kernels is None:  # OMGP.py:22-25
+            self.kern = [_kern.RBF(input_dim=1) for _ in range(K)]
+        else:
+            self.kern = list(kernels)
+        self.variance = float(np.asarray(variance).reshape(-1)[0])
+
+        # CollapsedMixture.__init__ (collapsed_mixture.py:24-47) without the feature-row machinery of MOHGP / MOG
+        self.N, self.K = int(N), int(K)
+        assert prior_Z in ["symmetric", "DP"]
+        self.prior_Z, self.alpha = prior_Z, alpha
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._world, self._rank, self.N_total = 1, 0, self.N
+        self.kernel_launches = 0
+        self._kernel_events = None
+
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        self._Npad = int(lib.gpc_omgp_padded_n(self.N))
+        Np = self._Npad
+        self._Xd = torch.from_numpy(self.X).to(self.device)
+        Yd = torch.from_numpy(Y).to(self.device)
+        self._Yd = z(Np, self.D)
+        check(lib.gpc_pad_rows(ptr(Yd), self.N, self.D, self.D, ptr(self._Yd), self._stream()), "gpc_pad_rows")
+        self._B, self._W = z(Np, Np), z(Np, Np)
+        self._dinv, self._ldsum = z(Np, 64), z(Np // 64)
+        self._tbuf = z(Np, self.D)
+        self._part = z(int(lib.gpc_omgp_slabs(Np)) * Np * int(lib.gpc_omgp_part_stride()))
+        self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._dots = z(4)
+        self._cur = None
+        self._trial = None
+        self._ng = self._grad = self._ng_old = self._grad_old = self._sd = self._sd_trial = None
+
+        self.phi_ = np.random.randn(self.N, self.K)  # collapsed_mixture.py:41 (setter recomputes)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _kern_arrays(self, k):
+        spec = k.parts_spec()
+        return (len(spec), _cabi.as_c_array([_cabi.KERN[s[0]] for s in spec], ctypes.c_int),
+                _cabi.as_c_array([float(s[1]) for s in spec], ctypes.c_double), _cabi.as_c_array([float(s[2]) for s in spec], ctypes.c_double),
+                sum(float(s[1]) for s in spec))  # k(x, x) of a sum of stationary / bias / white parts
+
+    def _factor_component(self, phi, i, eps):
+        """B_i -> L (in self._B), W = L^-1 (self._W), with GPy's jitchol retry (jitter = mean(diag)*1e-6*10^t)."""
+        torch = self.torch
+        nparts, kinds, var, ls, kdiag = self._kern_arrays(self.kern[i])
+        jitter = 0.0
+        for attempt in range(6):
+            if attempt == 1:
+                diag_mean = float((kdiag + 1.0 / ((phi[:, i] + eps) / self.variance)).mean())
+                jitter = diag_mean * 1e-6
+            elif attempt > 1:
+                jitter *= 10.0
+            if not np.isfinite(jitter):
+                break
+            check(lib.gpc_omgp_build(ptr(self._Xd), self.N, self._Xd.shape[1], nparts, kinds, var, ls, ptr(phi[:, i]), phi.shape[1],
+                                     float(self.variance), float(eps), float(jitter), ptr(self._B), self._stream()), "gpc_omgp_build")
+            check(lib.gpc_chol_blocked(ptr(self._B), self._Npad, ptr(self._dinv), ptr(self._ldsum), ptr(self._info), self._stream()),
+                  "gpc_chol_blocked")
+            self.kernel_launches += 1 + 3 * (self._Npad // 64)
+            if int(self._info.item()) == 0:
+                check(lib.gpc_tri_inverse_blocked(ptr(self._B), self._Npad, ptr(self._dinv), ptr(self._W), self._stream()),
+                      "gpc_tri_inverse_blocked")
+                self.kernel_launches += 1 + 2 * (self._Npad // 64)
+                return
+        raise LinAlgError("not positive definite, even with jitter.")
+
+    def _evaluate(self, x):
+        """All per-point quantities at logits x (N x K CUDA tensor)."""
+        torch = self.torch
+        N, K = self.N, self.K
+        p = _Point()
+        p.x = x
+        p.phi = torch.empty((N, K), dtype=torch.float64, device=self.device)
+        p.logphi = torch.empty_like(p.phi)
+        grid = max(1, min(1024, (N + 7) // 8))
+        p.hpart = torch.zeros(grid, dtype=torch.float64, device=self.device)
+        check(lib.gpc_softmax_rows(ptr(x), N, K, K, ptr(p.phi), ptr(p.logphi), K, ptr(p.hpart), grid, self._stream()), "gpc_softmax_rows")
+        p.grad_Lm = torch.empty_like(p.phi)
+        p.comp = torch.zeros((K, 4), dtype=torch.float64, device=self.device)
+        for i in range(K):
+            self._factor_component(p.phi, i, 1e-6)
+            check(lib.gpc_omgp_component(ptr(self._W), ptr(self._Yd), ptr(self._ldsum), ptr(p.phi[:, i]), K, N, self.D, float(self.variance),
+                                         ptr(self._tbuf), ptr(self._part), ptr(p.grad_Lm[:, i]), K, ptr(p.comp[i]), self._stream()),
+                  "gpc_omgp_component")
+            self.kernel_launches += 3
+        p.scalars = torch.zeros(4, dtype=torch.float64, device=self.device)
+        p.phi_hat = torch.zeros(K, dtype=torch.float64, device=self.device)
+        p.mixgrad = torch.zeros(K, dtype=torch.float64, device=self.device)
+        check(lib.gpc_omgp_finalize(ptr(p.comp), ptr(p.hpart), grid, ptr(p.scalars), ptr(p.phi_hat), ptr(p.mixgrad), float(self.variance),
+                                    float(self.alpha), _cabi.PRIOR[self.prior_Z], K, self.D, self._stream()), "gpc_omgp_finalize")
+        self.kernel_launches += 2
+        p.bound = float(p.scalars[0].item())
+        return p
+
+    # ------------------------------------------------------------------ reference API
+    def do_computations(self):
+        """OMGP.py:40-53 (kernel list follows K, growing by ONE per call) + the cached per-component work."""
+        if len(self.kern) < self.K:
+            self.kern.append(self.kern[-1].copy())
+        if len(self.kern) > self.K:
+            self.kern = self.kern[:self.K]
+        self._cur = self._evaluate(self._x)
+
+    def parameters_changed(self):
+        self.do_computations()
+
+    def set_vb_param(self, phi_):
+        torch = self.torch
+        if isinstance(phi_, torch.Tensor):
+            x = phi_.to(device=self.device, dtype=torch.float64).reshape(self.N, self.K).contiguous().clone()
+        else:
+            x = torch.from_numpy(_cabi.f64(np.asarray(phi_).reshape(self.N, self.K))).to(self.device)
+        self._x = x
+        self._ng_old = self._grad_old = self._sd = None  # CG history refers to the old point
+        self.do_computations()
+
+    def get_vb_param(self):
+        return self.phi_.flatten()
+
+    @property
+    def phi_(self):
+        return self._x.cpu().numpy()
+
+    @phi_.setter
+    def phi_(self, value):
+        value = np.asarray(value)
+        if value.ndim == 2:
+            self.K = value.shape[1]
+        self.set_vb_param(value)
+
+    phi = property(lambda self: self._cur.phi.cpu().numpy())
+    Hgrad = property(lambda self: (-self._cur.logphi).cpu().numpy())
+    phi_hat = property(lambda self: self._cur.phi_hat.cpu().numpy())
+    H = property(lambda self: float(self._cur.scalars[2].item()))
+
+    def phi_device(self):
+        return self._cur.phi
+
+    def mixing_prop_bound(self):
+        return float(self._cur.scalars[1].item())
+
+    def mixing_prop_bound_grad(self):
+        return self._cur.mixgrad.cpu().numpy()
+
+    def bound(self):
+        """OMGP.py:96-123."""
+        return self._cur.bound
+
+    def _natgrad(self, p, ng_old, grad_old):
+        torch = self.torch
+        ng, gr = torch.empty_like(p.phi), torch.empty_like(p.phi)
+        nblk = (self.N + 127) // 128
+        part = torch.empty(nblk * 4, dtype=torch.float64, device=self.device)
+        check(lib.gpc_dense_natgrad(ptr(p.grad_Lm), ptr(p.mixgrad), ptr(p.phi), ptr(p.logphi), ptr(ng_old), ptr(grad_old), self.N, self.K,
+                                    ptr(ng), ptr(gr), ptr(part), self._stream()), "gpc_dense_natgrad")
+        check(lib.gpc_reduce_partials(ptr(part), nblk, 4, ptr(self._dots), self._stream()), "gpc_reduce_partials")
+        self.kernel_launches += 2
+        return ng, gr
+
+    def vb_grad_natgrad(self):
+        """OMGP.py:125-147 -> flattened (grad, natgrad)."""
+        ng, gr = self._natgrad(self._cur, None, None)
+        return gr.cpu().numpy().flatten(), ng.cpu().numpy().flatten()
+
+    # ------------------------------------------------------------------ CG hooks (collapsed_vb.py:152-193)
+    def _cg_gradient(self, with_old):
+        have_old = with_old and self._ng_old is not None
+        self._ng, self._grad = self._natgrad(self._cur, self._ng_old if have_old else None, self._grad_old if have_old else None)
+        self._dots_host = self._dots.cpu().numpy().copy()
+
+    def _cg_trial(self, beta_mode, step_length, sq_old):
+        torch = self.torch
+        sq, num, den = [float(v) for v in self._dots_host[:3]]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if beta_mode in ("zero", "steepest_retry") or self._sd is None:
+                beta = 0.0
+            elif beta_mode == "HS":
+                beta = float(np.float64(num) / np.float64(den))
+            elif beta_mode == "PR":
+                beta = float(np.float64(num) / np.float64(sq_old))
+            else:
+                beta = float(np.float64(sq) / np.float64(sq_old))
+        if np.isnan(beta) or beta < 0.0:
+            beta = 0.0
+        sd_new, x_new = torch.empty_like(self._x), torch.empty_like(self._x)
+        check(lib.gpc_cg_axpy(ptr(self._x), ptr(self._ng), ptr(self._sd) if beta != 0.0 else None, beta, float(step_length), self._x.numel(),
+                              ptr(sd_new), ptr(x_new), self._stream()), "gpc_cg_axpy")
+        self.kernel_launches += 1
+        self._sd_trial = sd_new
+        try:
+            self._trial = self._evaluate(x_new)
+            return self._trial.bound, sq, beta, False
+        except LinAlgError:
+            self._trial = None
+            return 0.0, sq, beta, True
+
+    def _cg_restore(self):
+        self._trial = self._evaluate(self._x.clone())
+        return self._trial.bound
+
+    def _cg_accept(self):
+        self._cur = self._trial
+        self._x = self._trial.x
+        self._trial = None
+        self._ng_old, self._grad_old, self._sd = self._ng, self._grad, self._sd_trial
+
+    # ------------------------------------------------------------------ prediction (OMGP.py:149-193): read-out algebra
+    def predict(self, Xnew, i):
+        """Predictive mean and covariance for component i (OMGP.py:149-166; note: no 1e-6 in the noise here)."""
+        torch = self.torch
+        Xnew = _cabi.f64(np.asarray(Xnew).reshape(-1, self.X.shape[1]))
+        k = self.kern[i]
+        self._factor_component(self._cur.phi, i, 0.0)
+        N = self.N
+        Wn = self._W[:N, :N]
+        Xn = torch.from_numpy(Xnew).to(self.device)
+        kx = k.K_device(self._Xd, Xn)
+        kxx = k.K_device(Xn, Xn)
+        A = Wn @ kx
+        mu = A.T @ (Wn @ self._Yd[:N])
+        va = self.variance + kxx - A.T @ A
+        return mu.cpu().numpy(), va.cpu().numpy()
+
+    def predict_components(self, Xnew):
+        """The predictive density under each component (OMGP.py:168-177)."""
+        mus, vas = [], []
+        for i in range(len(self.kern)):
+            mu, va = self.predict(Xnew, i)
+            mus.append(mu)
+            vas.append(va)
+        return np.array(mus)[:, :, 0].T, np.array(vas)[:, :, 0].T
+
+    def sample(self, Xnew, gp=0, size=10, full_cov=True):
+        """Sample the posterior of a component (OMGP.py:179-193)."""
+        mu, va = self.predict(Xnew, gp)
+        samples = []
+        for i in range(mu.shape[1]):
+            cov = va if full_cov else np.diag(np.diag(va))
+            samples.append(np.random.multivariate_normal(mean=mu[:, i], cov=cov, size=size))
+        return np.stack(samples, -1)
+
+    # merge/split over sharded rows is meaningless here (single process)
+    def _is_root(self):
+        return True

@@ -43,6 +43,16 @@ PROTOTYPES = {
     "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],
     "gpc_mog_finalize": [_p, _p, _p, _p, _p, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i, _p],
     "gpc_kern_fill": [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _d, _p, _p],
+    "gpc_omgp_padded_n": [_ll],
+    "gpc_omgp_slabs": [_ll],
+    "gpc_omgp_part_stride": [],
+    "gpc_omgp_build": [_p, _ll, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _p, _i, _d, _d, _d, _p, _p],
+    "gpc_chol_blocked": [_p, _ll, _p, _p, _p, _p],
+    "gpc_tri_inverse_blocked": [_p, _ll, _p, _p, _p],
+    "gpc_omgp_component": [_p, _p, _p, _p, _i, _ll, _i, _d, _p, _p, _p, _i, _p, _p],
+    "gpc_omgp_finalize": [_p, _p, _i, _p, _p, _p, _d, _d, _i, _i, _i, _p],
+    "gpc_dense_natgrad": [_p, _p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p],
+    "gpc_cg_axpy": [_p, _p, _p, _d, _d, _ll, _p, _p, _p],
     "gpc_softmax_rows": [_p, _ll, _i, _i, _p, _p, _i, _p, _i, _p],
     "gpc_multiple_mahalanobis": [_p, _p, _p, _ll, _i, _i, _p, _p],
     "gpc_multiple_pdinv": [_p, _i, _i, _p, _p, _p, _p],
@@ -50,7 +60,7 @@ PROTOTYPES = {
     "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],
     "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
 }
-_RESTYPE = {"gpc_padded_rows": _ll}
+_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll}
 
 
 class GpclustLibraryError(RuntimeError):

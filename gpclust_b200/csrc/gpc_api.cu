@@ -7,6 +7,7 @@
 
 #include "gpc_cluster_kernels.cuh"
 #include "gpc_common.cuh"
+#include "gpc_omgp_kernels.cuh"
 #include "gpc_util_kernels.cuh"
 #include "gpc_vb_kernels.cuh"
 
@@ -47,6 +48,23 @@ template <int KP>
 int launch_step_stats(const StepStatsArgs &a, int grid, cudaStream_t st) {
   const size_t smem = step_stats_smem(KP, a.DP);
   return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, st) : launch_vb(k_step_stats<KP, false>, a, smem, grid, st);
+}
+
+constexpr size_t kTileSmem = sizeof(double) * (size_t)kOB * (kOStrideT + kOStrideN);
+template <typename Kern>
+int tile_attr(Kern kern) {
+  return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+}
+bool make_kern_spec(int nparts, const int *kinds, const double *variances, const double *lengthscales, KernSpec &spec) {
+  if (nparts < 1 || nparts > kMaxKernParts || !kinds || !variances || !lengthscales) return false;
+  spec.nparts = nparts;
+  for (int p = 0; p < kMaxKernParts; ++p) {
+    spec.kind[p] = p < nparts ? kinds[p] : 0;
+    spec.variance[p] = p < nparts ? variances[p] : 0.0;
+    spec.lengthscale[p] = p < nparts ? lengthscales[p] : 1.0;
+    if (p < nparts && (kinds[p] < GPC_KERN_RBF || kinds[p] > GPC_KERN_WHITE)) return false;
+  }
+  return true;
 }
 
 bool geometry_ok(long long N, int K, int KP, int DP, int grid) {
@@ -250,13 +268,7 @@ int gpc_kern_fill(const double *X, const double *X2, int n, int m, int q, int np
     return GPC_EINVAL;
   if (!X2 && m != n) return GPC_EINVAL;
   KernSpec spec;
-  spec.nparts = nparts;
-  for (int p = 0; p < kMaxKernParts; ++p) {
-    spec.kind[p] = p < nparts ? kinds[p] : 0;
-    spec.variance[p] = p < nparts ? variances[p] : 0.0;
-    spec.lengthscale[p] = p < nparts ? lengthscales[p] : 1.0;
-    if (p < nparts && (kinds[p] < GPC_KERN_RBF || kinds[p] > GPC_KERN_WHITE)) return GPC_EINVAL;
-  }
+  if (!make_kern_spec(nparts, kinds, variances, lengthscales, spec)) return GPC_EINVAL;
   const long long total = (long long)n * m;
   k_kern_fill<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, X2, n, m, q, spec, diag_add, out);
   return launch_rc();
@@ -309,6 +321,95 @@ int gpc_unpad_rows(const double *src, long long N, int K, int ld, double *dst, v
   if (!src || !dst || N < 1 || K < 1 || ld < K) return GPC_EINVAL;
   const long long total = N * K;
   k_unpad_rows<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, (int)N, K, ld, dst);
+  return launch_rc();
+}
+
+// ------------------------------------------------------------------------------------------------ OMGP
+long long gpc_omgp_padded_n(long long N) { return (N + kOB - 1) / kOB * kOB; }
+int gpc_omgp_slabs(long long Npad) { return (int)((Npad + kOmgpSlabRows - 1) / kOmgpSlabRows); }
+int gpc_omgp_part_stride(void) { return kOmgpMaxDy + 1; }
+
+int gpc_omgp_build(const double *X, long long N, int q, int nparts, const int *kinds, const double *variances, const double *lengthscales,
+                   const double *w, int w_stride, double variance, double eps, double jitter, double *B, void *stream) {
+  if (!X || !w || !B || N < 1 || N > 0x3fffffffLL || q < 1 || w_stride < 1) return GPC_EINVAL;
+  KernSpec spec;
+  if (!make_kern_spec(nparts, kinds, variances, lengthscales, spec)) return GPC_EINVAL;
+  const long long Npad = gpc_omgp_padded_n(N), total = Npad * Npad;
+  k_omgp_build<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, (int)N, (int)Npad, q, spec, w, w_stride, variance, eps, jitter, B);
+  return launch_rc();
+}
+
+int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int *info, void *stream) {
+  if (!A || !dinv || !ldsum || !info || Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (rc) return rc;
+  constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
+  if ((rc = cuda_rc(cudaFuncSetAttribute(k_omgp_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem)))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
+  const int nb = (int)(Npad / kOB), ld = (int)Npad;
+  for (int jb = 0; jb < nb; ++jb) {
+    k_omgp_chol_diag<<<1, kClusterThreads, diag_smem, st>>>(A, ld, jb, dinv, ldsum, info);
+    const int m = nb - jb - 1;
+    if (m > 0) {
+      k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
+      k_omgp_chol_trail<<<m * (m + 1) / 2, 256, kTileSmem, st>>>(A, ld, jb);
+    }
+  }
+  return launch_rc();
+}
+
+int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv, double *W, void *stream) {
+  if (!L || !dinv || !W || Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = tile_attr(k_omgp_inv_row))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_trail))) return rc;
+  const int nb = (int)(Npad / kOB), ld = (int)Npad;
+  const long long total = Npad * Npad;
+  k_omgp_inv_init<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ld, dinv);
+  for (int ib = 0; ib < nb; ++ib) {
+    if (ib > 0) k_omgp_inv_row<<<ib, 256, kTileSmem, st>>>(W, ld, ib, dinv);
+    if (ib + 1 < nb) k_omgp_inv_trail<<<dim3(ib + 1, nb - ib - 1), 256, kTileSmem, st>>>(W, ld, L, ld, ib);
+  }
+  return launch_rc();
+}
+
+int gpc_omgp_component(const double *W, const double *Y, const double *ldsum, const double *phi_col, int phi_stride, long long N, int Dy,
+                       double variance, double *tbuf, double *part, double *grad_col, int grad_stride, double *comp, void *stream) {
+  if (!W || !Y || !ldsum || !phi_col || !tbuf || !part || !grad_col || !comp || N < 1 || Dy < 1 || Dy > kOmgpMaxDy) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  const int Npad = (int)gpc_omgp_padded_n(N), nslab = gpc_omgp_slabs(Npad);
+  k_omgp_wy<<<(Npad + 7) / 8, 256, 0, st>>>(W, Npad, Y, Dy, tbuf);
+  k_omgp_colstats<<<dim3(Npad / 64, nslab), 256, 0, st>>>(W, Npad, tbuf, Dy, kOmgpSlabRows, part);
+  OmgpCompArgs a{part, Y, phi_col, ldsum, grad_col, comp, variance, (int)N, Npad, Dy, nslab, phi_stride, grad_stride};
+  k_omgp_component<<<1, 1024, 0, st>>>(a);
+  return launch_rc();
+}
+
+int gpc_omgp_finalize(const double *comp, const double *Hpart, int n_hpart, double *scalars, double *phi_hat, double *mixgrad, double variance,
+                      double alpha, int prior, int K, int Dy, void *stream) {
+  if (!comp || !Hpart || !scalars || !phi_hat || !mixgrad || K < 1 || K > kMaxMixK || n_hpart < 1) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  OmgpFinalizeArgs a{comp, Hpart, n_hpart, scalars, phi_hat, mixgrad, variance, alpha, prior, K, Dy};
+  k_omgp_finalize<<<1, kClusterThreads, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_dense_natgrad(const double *grad_Lm, const double *mixgrad, const double *phi, const double *logphi, const double *ng_old,
+                      const double *grad_old, long long N, int K, double *ng_out, double *grad_out, double *partials, void *stream) {
+  if (!grad_Lm || !mixgrad || !phi || !logphi || !ng_out || !grad_out || !partials || N < 1 || K < 1 || N > 0x7fffffffLL) return GPC_EINVAL;
+  if ((ng_old == nullptr) != (grad_old == nullptr)) return GPC_EINVAL;
+  k_dense_natgrad<<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(grad_Lm, mixgrad, phi, logphi, ng_old, grad_old, (int)N, K, ng_out,
+                                                                             grad_out, partials);
+  return launch_rc();
+}
+
+int gpc_cg_axpy(const double *x, const double *ng, const double *sd_old, double beta, double step, long long len, double *sd_new, double *x_new,
+                void *stream) {
+  if (!x || !ng || !sd_new || !x_new || len < 1) return GPC_EINVAL;
+  k_cg_axpy<<<(unsigned)((len + 255) / 256), 256, 0, as_stream(stream)>>>(x, ng, sd_old, beta, step, len, sd_new, x_new);
   return launch_rc();
 }
 

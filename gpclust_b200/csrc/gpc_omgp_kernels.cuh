@@ -1,0 +1,385 @@
+// gpclust_b200 -- OMGP (overlapping mixtures of GPs) device path: dense N x N work per component.
+//
+// OMGP.py:96-147 needs, for every component i,
+//     B = K_i(X) + diag(variance / (phi_i + 1e-6)),  L = jitchol(B),  logdet B,  alpha = B^-1 Y,
+//     tr(B^-1 Y Y^T) = sum(Y o alpha),  diag(B^-1)
+// The matrix lives in HBM padded to a multiple of 64 rows/columns (pad = identity, which leaves every
+// quantity above unchanged).  Factorisation and triangular inverse are right-looking blocked algorithms
+// with 64 x 64 tiles: the diagonal tile is handled by one CTA in shared memory, every other tile update is a
+// 64 x 64 x 64 FP64 DMMA product (mma.sync.m8n8k4.f64).  diag(B^-1) are the squared column norms of
+// W = L^-1 and alpha = W^T (W Y), so nothing is ever solved against an N x N right-hand side
+// (the reference's dpotrs(LB, YYT), OMGP.py:113, is an N^3 solve whose trace is all that is used).
+#pragma once
+#include "gpc_cluster_kernels.cuh"
+#include "gpc_common.cuh"
+#include "gpc_util_kernels.cuh"
+
+namespace gpc {
+
+constexpr int kOB = 64;        // tile edge
+constexpr int kOStrideT = 68;  // shared-memory row stride of row-major fragments read along k (bank skew 4)
+constexpr int kOStrideN = 72;  // shared-memory row stride of the non-transposed B operand (bank skew 8)
+constexpr int kOmgpMaxDy = 8;
+constexpr int kOmgpSlabRows = 512;  // rows per partial-sum slab of the column statistics
+
+// ------------------------------------------------------------------------------------------------
+// B (Npad x Npad) = K(X, X) + diag(1 / ((w + eps) / variance) + jitter); pad rows/columns = identity.
+// OMGP.py:104-105 (bound), :132-135 (gradient).  w has stride w_stride (a column of the N x K phi).
+__global__ void k_omgp_build(const double *__restrict__ X, int N, int Npad, int q, const KernSpec spec, const double *__restrict__ w,
+                             int w_stride, double variance, double eps, double jitter, double *__restrict__ B) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)Npad * Npad) return;
+  const int i = (int)(e / Npad), j = (int)(e % Npad);
+  double v;
+  if (i < N && j < N) {
+    v = kern_value(spec, X + (size_t)i * q, X + (size_t)j * q, q, true, i == j);
+    if (i == j) v += 1.0 / ((w[(size_t)i * w_stride] + eps) / variance) + jitter;
+  } else {
+    v = (i == j) ? 1.0 : 0.0;
+  }
+  B[e] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64 x 64 x 64 tile product on the FP64 tensor pipe.  256 threads; warp w owns rows 8w..8w+7.
+//   C = (SUB ? C - P*op(Q) : P*op(Q)),  op(Q) = Q^T when QT (Q given as n x k rows), Q otherwise (k x n rows)
+// P may alias C (it is staged in shared memory before anything is written).
+template <bool QT, bool SUB>
+__device__ __forceinline__ void tile_product_64(const double *__restrict__ P, int ldp, const double *__restrict__ Q, int ldq, double *C, int ldc,
+                                                double *Ps, double *Qs) {
+  constexpr int QS = QT ? kOStrideT : kOStrideN;
+  const int tid = threadIdx.x;
+  __syncthreads();  // previous user of the staging buffers is done
+  for (int e = tid; e < kOB * kOB / 2; e += blockDim.x) {
+    const int r = e >> 5, c2 = (e & 31) * 2;
+    *reinterpret_cast<double2 *>(Ps + r * kOStrideT + c2) = ldg2(P + (size_t)r * ldp + c2);
+    *reinterpret_cast<double2 *>(Qs + r * QS + c2) = ldg2(Q + (size_t)r * ldq + c2);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  double acc[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  const double *pa = Ps + (warp * 8 + g) * kOStrideT + t;
+#pragma unroll 4
+  for (int ks = 0; ks < kOB / 4; ++ks) {
+    const double af = pa[4 * ks];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double bf = QT ? Qs[(8 * nt + g) * QS + 4 * ks + t] : Qs[(4 * ks + t) * QS + 8 * nt + g];
+      dmma884(acc[nt][0], acc[nt][1], af, bf);
+    }
+  }
+  double *crow = C + (size_t)(warp * 8 + g) * ldc + 2 * t;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (SUB) {
+      const double2 c = *reinterpret_cast<const double2 *>(crow + 8 * nt);
+      stg2(crow + 8 * nt, c.x - acc[nt][0], c.y - acc[nt][1]);
+    } else {
+      stg2(crow + 8 * nt, acc[nt][0], acc[nt][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile jb: in-place lower Cholesky (strict upper of the tile zeroed), inverse of the factor to
+// dinv[jb] (64 x 64 row-major), sum of log diag to ldsum[jb].  One CTA of 256 threads.
+__global__ void __launch_bounds__(kClusterThreads) k_omgp_chol_diag(double *A, int ld, int jb, double *__restrict__ dinv, double *__restrict__ ldsum,
+                                                                    int *info) {
+  extern __shared__ __align__(16) double sm[];
+  double *Ls = sm, *Li = sm + kOB * (kOB + 1);
+  __shared__ int flag_s;
+  const int tid = threadIdx.x, lds = kOB + 1;
+  double *T = A + (size_t)jb * kOB * ld + (size_t)jb * kOB;
+  for (int e = tid; e < kOB * kOB; e += blockDim.x) Ls[(e >> 6) * lds + (e & 63)] = T[(size_t)(e >> 6) * ld + (e & 63)];
+  if (tid == 0) flag_s = 0;
+  __syncthreads();
+  const bool ok = chol_lower_quadrows(Ls, kOB, lds, &flag_s);
+  if (!ok) {
+    if (tid == 0) atomicOr(info, GPC_INFO_NOT_PD);
+    // leave an identity behind so that the remaining steps stay finite; the host re-runs with jitter
+    for (int e = tid; e < kOB * kOB; e += blockDim.x) {
+      const int i = e >> 6, j = e & 63;
+      T[(size_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+      dinv[(size_t)jb * kOB * kOB + e] = (i == j) ? 1.0 : 0.0;
+    }
+    if (tid == 0) ldsum[jb] = 0.0;
+    return;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double s = 0.0;
+    for (int i = tid; i < kOB; i += 32) s += log(Ls[i * lds + i]);
+    s = warp_sum(s);
+    if (tid == 0) ldsum[jb] = s;
+  }
+  // inverse of the factor: quad r = tid/4 solves column r of L X = I by forward substitution, the column held
+  // in registers split over q = tid%4 (same scheme as the triangular solve of k_mohgp_cluster)
+  {
+    const int r = tid >> 2, q = tid & 3;
+    double Xr[kOB / 4];
+#pragma unroll
+    for (int mm = 0; mm < kOB / 4; ++mm) Xr[mm] = 0.0;
+    for (int i = 0; i < kOB; ++i) {
+      double pp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int mm = 0; mm < kOB / 4; ++mm) {
+        const int m = 4 * mm + q;
+        pp[mm & 3] += (m < i) ? Ls[i * lds + m] * Xr[mm] : 0.0;
+      }
+      const double part = quad_sum((pp[0] + pp[1]) + (pp[2] + pp[3]));
+      const double rhs = (i == r) ? 1.0 : 0.0;
+      const double val = (i >= r) ? (rhs - part) / Ls[i * lds + i] : 0.0;
+      const bool mine = (q == (i & 3));
+#pragma unroll
+      for (int mm = 0; mm < kOB / 4; ++mm) Xr[mm] = (mine && mm == (i >> 2)) ? val : Xr[mm];
+    }
+#pragma unroll
+    for (int mm = 0; mm < kOB / 4; ++mm) Li[(4 * mm + q) * lds + r] = Xr[mm];
+  }
+  __syncthreads();
+  for (int e = tid; e < kOB * kOB; e += blockDim.x) {
+    const int i = e >> 6, j = e & 63;
+    T[(size_t)i * ld + j] = (j <= i) ? Ls[i * lds + j] : 0.0;
+    dinv[(size_t)jb * kOB * kOB + e] = (j <= i) ? Li[i * lds + j] : 0.0;
+  }
+}
+
+// Panel below diagonal tile jb: A[i][jb] <- A[i][jb] * Linv_jb^T   (i = jb+1+blockIdx.x)
+__global__ void __launch_bounds__(256) k_omgp_chol_panel(double *A, int ld, int jb, const double *__restrict__ dinv) {
+  extern __shared__ __align__(16) double sm[];
+  const int ib = jb + 1 + blockIdx.x;
+  double *T = A + (size_t)ib * kOB * ld + (size_t)jb * kOB;
+  tile_product_64<true, false>(T, ld, dinv + (size_t)jb * kOB * kOB, kOB, T, ld, sm, sm + kOB * kOStrideT);
+}
+
+// Trailing update after panel jb: A[i][k] -= A[i][jb] A[k][jb]^T for jb < k <= i (lower tiles only).
+__global__ void __launch_bounds__(256) k_omgp_chol_trail(double *A, int ld, int jb) {
+  extern __shared__ __align__(16) double sm[];
+  // decode the triangular tile index: blockIdx.x = a(a+1)/2 + b, 0 <= b <= a
+  int a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
+  while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
+  const int b = blockIdx.x - a * (a + 1) / 2;
+  const int ib = jb + 1 + a, kb = jb + 1 + b;
+  tile_product_64<true, true>(A + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld, A + (size_t)kb * kOB * ld + (size_t)jb * kOB, ld,
+                              A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// W = L^-1 by right-looking blocked forward substitution on the identity.
+// init: W = 0, diagonal tiles W[i][i] = Linv_i.
+__global__ void k_omgp_inv_init(double *__restrict__ W, int Npad, const double *__restrict__ dinv) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)Npad * Npad) return;
+  const int i = (int)(e / Npad), j = (int)(e % Npad);
+  W[e] = ((i >> 6) == (j >> 6)) ? dinv[(size_t)(i >> 6) * kOB * kOB + (i & 63) * kOB + (j & 63)] : 0.0;
+}
+// step ib, part (a): W[ib][j] <- Linv_ib * W[ib][j]  for j < ib   (blockIdx.x = j)
+__global__ void __launch_bounds__(256) k_omgp_inv_row(double *W, int ld, int ib, const double *__restrict__ dinv) {
+  extern __shared__ __align__(16) double sm[];
+  double *T = W + (size_t)ib * kOB * ld + (size_t)blockIdx.x * kOB;
+  tile_product_64<false, false>(dinv + (size_t)ib * kOB * kOB, kOB, T, ld, T, ld, sm, sm + kOB * kOStrideT);
+}
+// step ib, part (b): W[m][j] -= L[m][ib] * W[ib][j]  for m > ib, j <= ib   (grid: x = j, y = m - ib - 1)
+__global__ void __launch_bounds__(256) k_omgp_inv_trail(double *W, int ld, const double *__restrict__ L, int ldl, int ib) {
+  extern __shared__ __align__(16) double sm[];
+  const int jb = blockIdx.x, mb = ib + 1 + blockIdx.y;
+  tile_product_64<false, true>(L + (size_t)mb * kOB * ldl + (size_t)ib * kOB, ldl, W + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld,
+                               W + (size_t)mb * kOB * ld + (size_t)jb * kOB, ld, sm, sm + kOB * kOStrideT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// t = W Y  (W lower triangular Npad x Npad, Y Npad x Dy with zero pad rows): one warp per row.
+__global__ void __launch_bounds__(256) k_omgp_wy(const double *__restrict__ W, int Npad, const double *__restrict__ Y, int Dy, double *__restrict__ t) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= Npad) return;
+  double acc[kOmgpMaxDy];
+#pragma unroll
+  for (int d = 0; d < kOmgpMaxDy; ++d) acc[d] = 0.0;
+  const double *wr = W + (size_t)m * Npad;
+  for (int j = lane; j <= m; j += 32) {
+    const double w = wr[j];
+#pragma unroll
+    for (int d = 0; d < kOmgpMaxDy; ++d)
+      if (d < Dy) acc[d] += w * Y[(size_t)j * Dy + d];
+  }
+#pragma unroll
+  for (int d = 0; d < kOmgpMaxDy; ++d)
+    if (d < Dy) {
+      const double v = warp_sum(acc[d]);
+      if (lane == 0) t[(size_t)m * Dy + d] = v;
+    }
+}
+
+// Column statistics of W over a slab of rows: part[s][j][0] = sum_m W[m][j]^2, part[s][j][1+d] = sum_m W[m][j] t[m][d]
+// grid: x = column block of 64, y = slab; block 256 = 64 columns x 4 row lanes.
+__global__ void __launch_bounds__(256) k_omgp_colstats(const double *__restrict__ W, int Npad, const double *__restrict__ t, int Dy, int slab_rows,
+                                                       double *__restrict__ part) {
+  __shared__ double red[4][64][kOmgpMaxDy + 1];
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + c;
+  const int r0 = blockIdx.y * slab_rows, r1 = min(Npad, r0 + slab_rows);
+  double acc[kOmgpMaxDy + 1];
+#pragma unroll
+  for (int d = 0; d <= kOmgpMaxDy; ++d) acc[d] = 0.0;
+  const int start = max(r0, blockIdx.x * 64);  // rows above the column block hold zeros (W is lower triangular)
+  for (int m = start + rl; m < r1; m += 4) {
+    const double w = W[(size_t)m * Npad + j];
+    acc[0] += w * w;
+#pragma unroll
+    for (int d = 0; d < kOmgpMaxDy; ++d)
+      if (d < Dy) acc[1 + d] += w * t[(size_t)m * Dy + d];
+  }
+#pragma unroll
+  for (int d = 0; d <= kOmgpMaxDy; ++d) red[rl][c][d] = acc[d];
+  __syncthreads();
+  if (rl == 0) {
+    double *o = part + ((size_t)blockIdx.y * Npad + j) * (kOmgpMaxDy + 1);
+#pragma unroll
+    for (int d = 0; d <= kOmgpMaxDy; ++d) o[d] = (red[0][c][d] + red[1][c][d]) + (red[2][c][d] + red[3][c][d]);
+  }
+}
+
+// Per-component wrap-up (one CTA): diag(B^-1), alpha, grad_Lm column, and the scalars
+//   comp[0] = tr(B^-1 Y Y^T) = sum(Y o alpha)   comp[1] = logdet B   comp[2] = sum_j phi_ji   (OMGP.py:113,117,121)
+//   grad_Lm[j] = -0.5 variance (sum_d alpha_jd^2 - diag(B^-1)_j) / (phi_ji^2 + 1e-6)             (OMGP.py:138-140)
+struct OmgpCompArgs {
+  const double *part;   // nslab x Npad x (kOmgpMaxDy+1)
+  const double *Y;      // Npad x Dy
+  const double *phi;    // column i of the N x K responsibilities (stride phi_stride)
+  const double *ldsum;  // Npad/64
+  double *grad_col;     // column i of grad_Lm (stride grad_stride)
+  double *comp;         // 4 doubles
+  double variance;
+  int N, Npad, Dy, nslab, phi_stride, grad_stride;
+};
+__global__ void __launch_bounds__(1024) k_omgp_component(const OmgpCompArgs a) {
+  __shared__ double red_s[32];
+  double tr = 0.0, ps = 0.0;
+  for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+    double v[kOmgpMaxDy + 1];
+#pragma unroll
+    for (int d = 0; d <= kOmgpMaxDy; ++d) v[d] = 0.0;
+    for (int s = 0; s < a.nslab; ++s) {
+      const double *p = a.part + ((size_t)s * a.Npad + j) * (kOmgpMaxDy + 1);
+#pragma unroll
+      for (int d = 0; d <= kOmgpMaxDy; ++d) v[d] += p[d];
+    }
+    double a2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < kOmgpMaxDy; ++d)
+      if (d < a.Dy) {
+        a2 += v[1 + d] * v[1 + d];
+        tr += a.Y[(size_t)j * a.Dy + d] * v[1 + d];
+      }
+    const double ph = a.phi[(size_t)j * a.phi_stride];
+    ps += ph;
+    a.grad_col[(size_t)j * a.grad_stride] = -0.5 * a.variance * (a2 - v[0]) / (ph * ph + 1e-6);
+  }
+  tr = block_sum(tr, red_s);
+  ps = block_sum(ps, red_s);
+  double ld = 0.0;
+  for (int b = threadIdx.x; b < a.Npad / kOB; b += blockDim.x) ld += a.ldsum[b];
+  ld = block_sum(ld, red_s);
+  if (threadIdx.x == 0) {
+    a.comp[0] = tr;
+    a.comp[1] = 2.0 * ld;
+    a.comp[2] = ps;
+    a.comp[3] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bound assembly (OMGP.py:96-123) + mixing-proportion gradient.  comp: K x 4 from k_omgp_component.
+struct OmgpFinalizeArgs {
+  const double *comp;
+  const double *Hpart;  // softmax entropy partials
+  int n_hpart;
+  double *scalars;      // [0]=bound [1]=mix [2]=H
+  double *phi_hat;      // out K
+  double *mixgrad;      // out K
+  double variance, alpha;
+  int prior, K, Dy;
+};
+__global__ void __launch_bounds__(kClusterThreads) k_omgp_finalize(const OmgpFinalizeArgs a) {
+  __shared__ double mixgrad[kMaxMixK];
+  __shared__ double phi_hat[kMaxMixK];
+  __shared__ MixScratch scratch;
+  __shared__ double mix_s;
+  for (int k = threadIdx.x; k < a.K; k += blockDim.x) phi_hat[k] = a.comp[k * 4 + 2];
+  __syncthreads();
+  mixing_terms(phi_hat, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
+  if (threadIdx.x == 0) {
+    double H = 0.0;
+    for (int c = 0; c < a.n_hpart; ++c) H += a.Hpart[c];
+    double gp = 0.0;
+    for (int k = 0; k < a.K; ++k) {
+      gp -= 0.5 * a.comp[k * 4 + 0];
+      gp -= 0.5 * a.comp[k * 4 + 1];
+      gp -= 0.5 * a.Dy * (a.comp[k * 4 + 2] * log(2.0 * M_PI * a.variance));
+    }
+    a.scalars[0] = gp + mix_s + H;
+    a.scalars[1] = mix_s;
+    a.scalars[2] = H;
+  }
+  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+    a.phi_hat[k] = phi_hat[k];
+    a.mixgrad[k] = mixgrad[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Natural gradient for models whose per-point likelihood gradient is materialised (OMGP.py:142-147):
+//   grad_phi = grad_Lm + mixgrad + Hgrad ; natgrad = grad_phi - sum_k phi grad_phi ; grad = natgrad * phi
+// plus the CG dots of collapsed_vb.py:154,160-164 against the previous (ng_old, grad_old), nullable.
+// One thread per row; per-CTA partial dots in partials[blockIdx.x*4 + {0,1,2}].
+__global__ void __launch_bounds__(128) k_dense_natgrad(const double *__restrict__ grad_Lm, const double *__restrict__ mixgrad, const double *__restrict__ phi,
+                                                       const double *__restrict__ logphi, const double *__restrict__ ng_old,
+                                                       const double *__restrict__ grad_old, int N, int K, double *__restrict__ ng_out,
+                                                       double *__restrict__ grad_out, double *__restrict__ partials) {
+  __shared__ double red_s[32];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  if (n < N) {
+    const size_t o = (size_t)n * K;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += phi[o + k] * ((grad_Lm[o + k] + mixgrad[k]) - logphi[o + k]);
+    for (int k = 0; k < K; ++k) {
+      const double gp = (grad_Lm[o + k] + mixgrad[k]) - logphi[o + k];
+      const double ng = gp - s, gr = ng * phi[o + k];
+      ng_out[o + k] = ng;
+      grad_out[o + k] = gr;
+      d0 += ng * gr;
+      if (ng_old) {
+        const double e = ng - ng_old[o + k];
+        d1 += e * gr;
+        d2 += e * grad_old[o + k];
+      }
+    }
+  }
+  d0 = block_sum(d0, red_s);
+  d1 = block_sum(d1, red_s);
+  d2 = block_sum(d2, red_s);
+  if (threadIdx.x == 0) {
+    partials[(size_t)blockIdx.x * 4 + 0] = d0;
+    partials[(size_t)blockIdx.x * 4 + 1] = d1;
+    partials[(size_t)blockIdx.x * 4 + 2] = d2;
+    partials[(size_t)blockIdx.x * 4 + 3] = 0.0;
+  }
+}
+
+// sd_new = ng + beta*sd_old (sd_old nullable / beta == 0) ; x_new = x + step*sd_new    (collapsed_vb.py:167,172)
+__global__ void k_cg_axpy(const double *__restrict__ x, const double *__restrict__ ng, const double *sd_old, double beta, double step,
+                          long long len, double *sd_new, double *__restrict__ x_new) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  double s = ng[e];
+  if (sd_old != nullptr && beta != 0.0) s += beta * sd_old[e];
+  sd_new[e] = s;
+  x_new[e] = x[e] + step * s;
+}
+
+}  // namespace gpc

@@ -24,16 +24,10 @@ struct KernSpec {
   double lengthscale[kMaxKernParts];
 };
 
-// out[i][j] = sum_parts k_p(x_i, x2_j).  r^2 is formed the way GPy's Stationary._unscaled_dist does:
-// -2 x.x2 + |x|^2 + |x2|^2, diagonal forced to zero when X2 is absent, clipped at zero.
-__global__ void k_kern_fill(const double *__restrict__ X, const double *__restrict__ X2, int n, int m, int q, const KernSpec spec,
-                            double diag_add, double *__restrict__ out) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)n * m) return;
-  const int i = (int)(e / m), j = (int)(e % m);
-  const bool self = (X2 == nullptr);
-  const double *xi = X + (size_t)i * q;
-  const double *xj = (self ? X : X2) + (size_t)j * q;
+// sum_parts k_p(x_i, x_j).  r^2 is formed the way GPy's Stationary._unscaled_dist does:
+// -2 x.x2 + |x|^2 + |x2|^2, diagonal forced to zero when X2 is absent (`self`), clipped at zero.
+// `same` = (self && i == j): White contributes only there.
+__device__ __forceinline__ double kern_value(const KernSpec &spec, const double *xi, const double *xj, int q, bool self, bool same) {
   double dot = 0.0, si = 0.0, sj = 0.0;
   for (int c = 0; c < q; ++c) {
     dot += xi[c] * xj[c];
@@ -41,7 +35,7 @@ __global__ void k_kern_fill(const double *__restrict__ X, const double *__restri
     sj += xj[c] * xj[c];
   }
   double r2 = -2.0 * dot + (si + sj);
-  if (self && i == j) r2 = 0.0;
+  if (same) r2 = 0.0;
   r2 = fmax(r2, 0.0);
   const double r_un = sqrt(r2);
   double v = 0.0;
@@ -54,18 +48,23 @@ __global__ void k_kern_fill(const double *__restrict__ X, const double *__restri
       case GPC_KERN_MATERN32: kp = var * (1.0 + sqrt(3.0) * r) * exp(-sqrt(3.0) * r); break;
       case GPC_KERN_MATERN52: kp = var * (1.0 + sqrt(5.0) * r + 5.0 / 3.0 * (r * r)) * exp(-sqrt(5.0) * r); break;
       case GPC_KERN_BIAS: kp = var; break;
-      default: kp = (self && i == j) ? var : 0.0; break;  // white
+      default: kp = same ? var : 0.0; break;  // white
     }
     v = (p == 0) ? kp : v + kp;
   }
-  if (self && i == j) v += diag_add;
-  out[e] = v;
+  return v;
 }
 
-// out[i] += var / (w[i] + eps)  on the diagonal of an n x n matrix (OMGP.py:105,135: diag(variance/(phi_i+1e-6)))
-__global__ void k_add_weighted_noise_diag(double *__restrict__ M, int n, const double *__restrict__ w, int w_stride, double variance, double eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) M[(size_t)i * n + i] += 1.0 / ((w[(size_t)i * w_stride] + eps) / variance);
+// out[i][j] = sum_parts k_p(x_i, x2_j)  (+ diag_add on the diagonal when X2 is absent)
+__global__ void k_kern_fill(const double *__restrict__ X, const double *__restrict__ X2, int n, int m, int q, const KernSpec spec,
+                            double diag_add, double *__restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n * m) return;
+  const int i = (int)(e / m), j = (int)(e % m);
+  const bool self = (X2 == nullptr);
+  double v = kern_value(spec, X + (size_t)i * q, (self ? X : X2) + (size_t)j * q, q, self, self && i == j);
+  if (self && i == j) v += diag_add;
+  out[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------------

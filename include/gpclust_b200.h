@@ -124,6 +124,38 @@ int gpc_mog_finalize(const double *stats, const double *per_k, double *bias, dou
 int gpc_kern_fill(const double *X, const double *X2, int n, int m, int q, int nparts, const int *kinds, const double *variances,
                   const double *lengthscales, double diag_add, double *out, void *stream);
 
+/* ---- OMGP (OMGP.py:96-147): dense N x N work per component ------------------------------------
+ * Matrices are Npad x Npad row-major, Npad = gpc_omgp_padded_n(N) (multiple of 64; pad = identity).
+ * Per component i the host mirror calls build -> chol -> tri_inverse -> component; then once finalize.   */
+long long gpc_omgp_padded_n(long long N);
+int gpc_omgp_slabs(long long Npad);  /* row slabs of the column statistics: part holds slabs*Npad*gpc_omgp_part_stride() doubles */
+int gpc_omgp_part_stride(void);
+/* B = K(X,X) + diag(1/((w + eps)/variance) + jitter)  (OMGP.py:104-105,132-135; eps = 0 for :158).  X: N x q,
+ * w: phi column with stride w_stride.  kinds/variances/lengthscales: HOST arrays as in gpc_kern_fill.      */
+int gpc_omgp_build(const double *X, long long N, int q, int nparts, const int *kinds, const double *variances, const double *lengthscales,
+                   const double *w, int w_stride, double variance, double eps, double jitter, double *B, void *stream);
+/* in-place blocked lower Cholesky (the dpotrf inside GPy pdinv/jitchol): diagonal-tile inverses to dinv
+ * (Npad x 64), per-tile sum(log diag) to ldsum (Npad/64).  *info is cleared first; GPC_INFO_NOT_PD on a bad
+ * pivot (the host retries with jitter = mean(diag)*1e-6*10^i, GPy jitchol).                               */
+int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int *info, void *stream);
+/* W = L^-1 (lower triangular, strict upper zero) -- the dtrtri of GPy pdinv                                */
+int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv, double *W, void *stream);
+/* comp[0] = tr(B^-1 Y Y^T), comp[1] = logdet B, comp[2] = sum_n phi_ni; grad_col (stride grad_stride) =
+ * -0.5 variance (sum_d alpha^2 - diag(B^-1)) / (phi^2 + 1e-6)  (OMGP.py:113,117,121,138-140).
+ * Y: Npad x Dy (pad rows zero), Dy <= 8.  tbuf: Npad x Dy.  part: see gpc_omgp_slabs.                       */
+int gpc_omgp_component(const double *W, const double *Y, const double *ldsum, const double *phi_col, int phi_stride, long long N, int Dy,
+                       double variance, double *tbuf, double *part, double *grad_col, int grad_stride, double *comp, void *stream);
+/* bound (OMGP.py:96-123) from comp (K x 4) + entropy partials; phi_hat, mixing-proportion gradient (K each) */
+int gpc_omgp_finalize(const double *comp, const double *Hpart, int n_hpart, double *scalars, double *phi_hat, double *mixgrad, double variance,
+                      double alpha, int prior, int K, int Dy, void *stream);
+/* OMGP.py:142-147 + the CG dots of collapsed_vb.py:154,160-164 on contiguous N x K arrays; ng_old / grad_old
+ * nullable together.  partials: ceil(N/128) x 4 -> gpc_reduce_partials(len = 4).                              */
+int gpc_dense_natgrad(const double *grad_Lm, const double *mixgrad, const double *phi, const double *logphi, const double *ng_old,
+                      const double *grad_old, long long N, int K, double *ng_out, double *grad_out, double *partials, void *stream);
+/* sd_new = ng + beta*sd_old ; x_new = x + step*sd_new  (collapsed_vb.py:167,172); sd_old nullable         */
+int gpc_cg_axpy(const double *x, const double *ng, const double *sd_old, double beta, double step, long long len, double *sd_new, double *x_new,
+                void *stream);
+
 /* ---- the reference's L1 utilities, same meaning as np_utilities.py ---------------------------- */
 /* softmax (np_utilities.py:25-40): x is N x K with leading dimension ldx; phi / logphi (either may be
  * NULL) get leading dimension ldo; Hpart must hold `grid` doubles, H = sum(Hpart) (gpc_reduce_partials). */

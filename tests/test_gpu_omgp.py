@@ -1,0 +1,121 @@
+"""GPU parity of the OMGP path (blocked Cholesky / triangular inverse on the FP64 tensor pipe, per-component
+bound and gradient terms, dense natural gradient) against the CPU oracle (OMGP.py:96-147) on seeded inputs.
+Tolerance: 1e-9 relative (north_star) for bound / gradients in max-norm-relative terms."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+from helpers import relerr
+from oracle import gpy_shim as G
+from oracle.vb_oracle import OMGPOracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _data(N, Dy, K, seed):
+    rng = np.random.RandomState(seed)
+    X = np.sort(rng.uniform(0, 10, N))[:, None]
+    comp = rng.randint(0, K, N)
+    Y = np.zeros((N, Dy))
+    for d in range(Dy):
+        for i in range(K):
+            sel = comp == i
+            Y[sel, d] = np.sin(X[sel, 0] * (0.5 + 0.4 * i) + d + i) * (1.0 + 0.3 * i) + 0.1 * rng.randn(sel.sum())
+    return X, Y
+
+
+def _pair(N, Dy, K, prior_Z="symmetric", alpha=1.0, variance=0.01, seed=0, lengthscales=None):
+    from gpclust_b200 import OMGP, kern
+    X, Y = _data(N, Dy, K, seed)
+    ls = lengthscales or [1.0 + 0.5 * i for i in range(K)]
+    np.random.seed(seed + 1)
+    mo = OMGPOracle(X, Y, K=K, kernels=[G.RBF(1, 1.0, l) for l in ls], variance=variance, alpha=alpha, prior_Z=prior_Z)
+    np.random.seed(seed + 1)
+    mp = OMGP(X, Y, K=K, kernels=[kern.RBF(1, 1.0, l) for l in ls], variance=variance, alpha=alpha, prior_Z=prior_Z)
+    assert np.array_equal(mp.phi_, mo.phi_)
+    return mo, mp
+
+
+@pytest.mark.parametrize("N,Dy,K", [(50, 1, 2), (64, 2, 2), (130, 1, 3), (200, 2, 2), (333, 1, 4), (700, 1, 2)])
+@pytest.mark.parametrize("prior_Z", ["symmetric", "DP"])
+def test_bound_and_gradient(N, Dy, K, prior_Z):
+    mo, mp = _pair(N, Dy, K, prior_Z, alpha=1.0 if prior_Z == "symmetric" else 2.5)
+    assert relerr(mp.phi, mo.phi) < 1e-13
+    assert relerr(mp.phi_hat, mo.phi_hat) < 1e-12
+    assert abs(mp.H - mo.H) < 1e-11 * abs(mo.H)
+    assert abs(mp.mixing_prop_bound() - mo.mixing_prop_bound()) < 1e-11 * max(1.0, abs(mo.mixing_prop_bound()))
+    assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
+    g_p, ng_p = mp.vb_grad_natgrad()
+    g_o, ng_o = mo.vb_grad_natgrad()
+    assert relerr(ng_p, ng_o) < TOL and relerr(g_p, g_o) < TOL
+
+
+@pytest.mark.parametrize("method", ["HS", "PR", "FR", "steepest"])
+def test_optimize_trace(method):
+    mo, mp = _pair(90, 1, 2, seed=2)
+    mo.out = io.StringIO()
+    mo.optimize(method=method, maxiter=14, verbose=False)
+    mp.optimize(method=method, maxiter=14, verbose=False)
+    to, tp = np.array(mo.trace), np.array(mp.optimize_trace)
+    assert to.shape == tp.shape and np.array_equal(to[:, 0], tp[:, 0])
+    assert np.max(np.abs(to[:, 1] - tp[:, 1]) / np.abs(to[:, 1])) < 1e-8
+    assert relerr(mp.phi, mo.phi) < 1e-6
+    assert np.array_equal(np.argmax(mp.phi, 1), np.argmax(mo.phi, 1))
+
+
+def test_blocked_cholesky_and_inverse_against_lapack():
+    import torch
+    from gpclust_b200._cabi import lib, check, ptr
+    rng = np.random.RandomState(0)
+    n = 320
+    M = rng.randn(n, n)
+    A = M.dot(M.T) / n + np.eye(n) * 0.5
+    Ad = torch.from_numpy(A.copy()).cuda()
+    dinv = torch.zeros((n, 64), dtype=torch.float64, device="cuda")
+    ldsum = torch.zeros(n // 64, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    W = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.gpc_chol_blocked(ptr(Ad), n, ptr(dinv), ptr(ldsum), ptr(info), st), "chol")
+    check(lib.gpc_tri_inverse_blocked(ptr(Ad), n, ptr(dinv), ptr(W), st), "inv")
+    assert int(info.item()) == 0
+    L = np.linalg.cholesky(A)
+    assert relerr(np.tril(Ad.cpu().numpy()), L) < 1e-12
+    assert abs(2 * float(ldsum.sum().item()) - np.linalg.slogdet(A)[1]) < 1e-10 * abs(np.linalg.slogdet(A)[1])
+    Wh = W.cpu().numpy()
+    assert np.allclose(np.triu(Wh, 1), 0.0)
+    assert relerr(Wh, np.linalg.inv(L)) < 1e-11
+    # not positive definite -> flag
+    Bd = torch.from_numpy(A - 2.0 * np.eye(n)).cuda()
+    check(lib.gpc_chol_blocked(ptr(Bd), n, ptr(dinv), ptr(ldsum), ptr(info), st), "chol")
+    assert int(info.item()) != 0
+
+
+def test_split_and_predict():
+    """try_split (collapsed_mixture.py:112-189) and predict (OMGP.py:149-177) run on the device-computed state and
+    follow the oracle."""
+    mo, mp = _pair(80, 1, 2, seed=5, variance=0.02)
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=10, verbose=False)
+    mp.optimize(maxiter=10, verbose=False)
+    np.random.seed(7)
+    ro = mo.try_split(0, verbose=False, maxiter=6, optimize_params={"maxiter": 6, "verbose": False})
+    np.random.seed(7)
+    rp = mp.try_split(0, verbose=False, maxiter=6, optimize_params={"maxiter": 6, "verbose": False})
+    assert ro == rp and mo.K == mp.K and len(mp.kern) == mp.K
+    assert abs(mp.bound() - mo.bound()) < 1e-7 * abs(mo.bound())
+    Xnew = np.linspace(0, 10, 9)[:, None]
+    mu, va = mp.predict_components(Xnew)
+    assert mu.shape == (9, mp.K) and va.shape[0] == 9
+    # oracle-side formula of OMGP.py:149-166 for component 0
+    k = mo.kern[0]
+    Binv = np.diag(1.0 / (mo.phi[:, 0] / mo.variance))
+    KBi = np.linalg.inv(k.K(mo.X) + Binv)
+    kx = k.K(mo.X, Xnew)
+    mu0 = kx.T.dot(KBi.dot(mo.Y))
+    va0 = mo.variance + k.K(Xnew, Xnew) - kx.T.dot(KBi.dot(kx))
+    m0, v0 = mp.predict(Xnew, 0)
+    assert relerr(m0, mu0) < 1e-6 and relerr(v0, va0) < 1e-6

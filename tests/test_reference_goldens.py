@@ -66,8 +66,11 @@ def _check_model(m, d, trace, after=True):
         assert abs(m.bound() - _scalar(d["bound1"])) < TOL * abs(_scalar(d["bound1"]))
         assert relerr(m.phi, d["phi1"]) < 1e-8
         assert np.array_equal(np.argmax(m.phi, 1), np.argmax(d["phi1"], 1))
+        # at convergence the gradient is rounding noise (1e-14): measure the error against the scale of the start gradient
         g, ng = m.vb_grad_natgrad()
-        assert relerr(ng, d["natgrad1"]) < 1e-7 and relerr(g, d["grad1"]) < 1e-7
+        for got, ref, start in ((ng, d["natgrad1"], d["natgrad0"]), (g, d["grad1"], d["grad0"])):
+            scale = max(np.max(np.abs(ref)), 1e-4 * np.max(np.abs(start)))
+            assert np.max(np.abs(got - ref)) < 1e-7 * scale
     _check_trace(trace, d["trace"])
 
 
