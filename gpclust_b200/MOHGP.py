@@ -4,9 +4,11 @@ Same constructor, attributes and methods as the reference; the arithmetic of do_
 bound / vb_grad_natgrad (MOHGP.py:70-90, :124-135, :137-153) runs in the sm_100a kernels:
 
     S pass (gpc_step_stats)      softmax, phi_hat, H, ybark = phi^T Y                MOHGP.py:76
-    gpc_mohgp_cluster            C_k = I + phi_hat_k A, jitchol, Lambda_inv, muk     MOHGP.py:79-90
-    gpc_mohgp_finalize           bound                                                MOHGP.py:124-135
+    gpc_mohgp_post               per-cluster posterior in the eigenbasis of A = Ly^-1 Sf Ly^-T (no per-cluster
+                                 factorisation), bound, G-pass weights                MOHGP.py:79-90, :124-135
     G pass (gpc_natgrad)         Mahalanobis terms as one GEMM, natural gradient      MOHGP.py:137-153
+    gpc_mohgp_cluster            the reference's literal Cholesky / TRSM / SYRK per cluster -- only when the
+                                 K x D x D attributes (Lambda_inv, _C_chols) are read MOHGP.py:79-85
 
 Y may be a numpy array or a CUDA tensor (N x D; N = the rows this rank holds).  The dead N x D x D
 `YYT` of MOHGP.py:52 is not materialised.
@@ -51,6 +53,7 @@ class MOHGP(CollapsedMixture):
         self._Ly, self._Ly_inv, self._Sy_inv, self._A = z(D, D), z(D, D), z(D, D), z(D, D)
         self._Sy_logdet, self._const = z(1), z(1)
         self._YTY = z(D, D)
+        self._eig_ws = z(int(lib.gpc_mohgp_eig_ws_len(D)))
         self._set_features(F, DP)
 
         # Computations that can be done outside the optimisation loop (MOHGP.py:52-53)
@@ -70,8 +73,8 @@ class MOHGP(CollapsedMixture):
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
         self._muk_t = z(K, D)
         self._Syi_ybark_t = z(K, D)
-        self._Lambda_inv = z(K, D, D)
-        self._C_chols_dev = z(K, D, D)
+        self._Lambda_inv = None  # K x D x D attributes: allocated and filled on first read (_dense_posterior)
+        self._C_chols_dev = None
 
     def _compute_YTY(self):
         torch = self.torch
@@ -95,24 +98,48 @@ class MOHGP(CollapsedMixture):
                                   ptr(self._Sy_logdet), self._info_ptr(), D, self._stream()), "gpc_mohgp_setup")
         check(lib.gpc_mohgp_const(ptr(self._YTY), ptr(self._Sy_inv), ptr(self._Sy_logdet), float(self.N_total), D, ptr(self._const),
                                   self._stream()), "gpc_mohgp_const")
-        self.kernel_launches += 4
+        check(lib.gpc_mohgp_eig(ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._Sf), D, ptr(self._eig_ws),
+                                self._stream()), "gpc_mohgp_eig")
+        self.kernel_launches += 5
         _, _, _, failed = self._readback()
         if failed:
             raise np.linalg.LinAlgError("not positive definite, even with jitter.")
         self.do_computations()
 
-    def _launch_cluster(self):
-        check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),
-                                    ptr(self._Wt), ptr(self._muk_t), ptr(self._per_k), ptr(self._Syi_ybark_t), ptr(self._Lambda_inv),
-                                    ptr(self._C_chols_dev), self._info_ptr(), self.K, self.D, self._KP, self._DP, self._stream()),
-              "gpc_mohgp_cluster")
+    def _launch_posterior(self):
+        """Statistics -> posterior -> bound in one launch (two + an all-reduce when rows are sharded)."""
+        if self._world > 1:
+            check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+            self.kernel_launches += 1
+            self._allreduce(self._stats)
+            parts, nparts = self._stats, 1
+        else:
+            parts, nparts = self._spart, self._grid
+        check(lib.gpc_mohgp_post(ptr(parts), nparts, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
+                                 ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias), ptr(self._ctrl),
+                                 ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z],
+                                 self.K, self.D, self._KP, self._DP, self._stream()), "gpc_mohgp_post")
         self.kernel_launches += 1
 
-    def _launch_finalize(self):
-        check(lib.gpc_mohgp_finalize(ptr(self._stats), ptr(self._per_k), ptr(self._const), ptr(self._bias), ptr(self._ctrl),
-                                     ptr(self._mixgrad), float(self.alpha), _cabi.PRIOR[self.prior_Z], self.K, self._KP, self._DP,
-                                     self._stream()), "gpc_mohgp_finalize")
-        self.kernel_launches += 1
+    def _dense_posterior(self):
+        """The reference's literal per-cluster route (MOHGP.py:79-85) for the K x D x D attributes; results of the
+        hot-loop route (Wt, muk, per-cluster scalars) are left untouched."""
+        self._ensure_state()
+        if "dense" not in self._cache:
+            torch = self.torch
+            D, KP = self.D, self._KP
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+            self._Lambda_inv, self._C_chols_dev = z(KP, D, D), z(KP, D, D)
+            scratch = {"Wt": z(KP, self._DP), "muk_t": z(KP, D), "per_k": z(KP, 4), "s": z(KP, D), "info": torch.zeros(1, dtype=torch.int32, device=self.device)}
+            check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),
+                                        ptr(scratch["Wt"]), ptr(scratch["muk_t"]), ptr(scratch["per_k"]), ptr(scratch["s"]), ptr(self._Lambda_inv),
+                                        ptr(self._C_chols_dev), ptr(scratch["info"]), self.K, self.D, self._KP, self._DP, self._stream()),
+                  "gpc_mohgp_cluster")
+            self.kernel_launches += 1
+            if int(scratch["info"].item()):
+                raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+            self._cache["dense"] = scratch
+        return self._cache["dense"]
 
     # ---- reference attributes (copied from the device on access)
     def _np(self, t):
@@ -144,12 +171,12 @@ class MOHGP(CollapsedMixture):
 
     @property
     def Lambda_inv(self):  # K x D x D (MOHGP.py:85)
-        self._ensure_state()
+        self._dense_posterior()
         return self._np(self._Lambda_inv[:self.K])
 
     @property
     def _C_chols(self):  # list of K lower factors (MOHGP.py:82)
-        self._ensure_state()
+        self._dense_posterior()
         return list(self._np(self._C_chols_dev[:self.K]))
 
     @property

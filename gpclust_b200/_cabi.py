@@ -38,6 +38,9 @@ PROTOTYPES = {
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
     "gpc_mohgp_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "gpc_mohgp_eig_ws_len": [_i],
+    "gpc_mohgp_eig": [_p, _p, _p, _p, _p, _i, _p, _p],
+    "gpc_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p],
     "gpc_mohgp_finalize": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p],
     "gpc_mog_features": [_p, _p, _ll, _i, _i, _p, _p],
     "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],

@@ -175,7 +175,7 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
 
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
   if (!partials || !out || num_parts < 1 || len < 1) return GPC_EINVAL;
-  k_reduce_partials<<<(len + 127) / 128, 128, 0, as_stream(stream)>>>(partials, num_parts, len, out);
+  k_reduce_partials<<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, num_parts, len, out);
   return launch_rc();
 }
 
@@ -221,6 +221,36 @@ int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, co
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpClusterArgs a{stats, A, Ly, Ly_inv, Sy, Sy_inv, Sf, Wt, muk_t, per_k, Syi_ybark_t, Lambda_inv, C_chols, info, K, D, KP, DP};
   k_mohgp_cluster<<<KP, kClusterThreads, smem, st>>>(a);
+  return launch_rc();
+}
+
+int gpc_mohgp_eig_ws_len(int D) { return (D < 1 || D > GPC_MAX_DP) ? -1 : eig_ws_len(D); }
+
+int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const double *Sy_inv, const double *Sf, int D, double *ws,
+                  void *stream) {
+  if (!A || !Ly || !Ly_inv || !Sy_inv || !Sf || !ws || D < 1 || D > GPC_MAX_DP) return GPC_EINVAL;
+  const size_t smem = sizeof(double) * (2 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + GPC_MAX_DP + 32);
+  cudaError_t e = cudaFuncSetAttribute(k_mohgp_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MohgpEigArgs a{A, Ly, Ly_inv, Sy_inv, Sf, ws, D};
+  k_mohgp_eig<<<1, kClusterThreads, smem, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                   const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
+                   double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream) {
+  if (!partials || num_parts < 1 || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !Wt || !muk_t || !per_k || !bias || !scalars ||
+      !counter || !info)
+    return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > GPC_MAX_KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MohgpPostArgs a{partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
+                  counter, info, alpha, prior, K, D, KP, DP};
+  k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
   return launch_rc();
 }
 

@@ -452,6 +452,375 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_finalize(const MohgpF
 }
 
 // ------------------------------------------------------------------------------------------------
+// MOHGP posterior in the eigenbasis of A = Ly^-1 Sf Ly^-T  (DESIGN.md section 5).
+//
+// C_k = I + phi_hat_k A has the same eigenvectors for every cluster and every iteration, so with
+// A = Q diag(lam) Q^T (k_mohgp_eig, once per kernel-parameter change), V = Ly Q, U = Ly^-T Q,
+// den_i = 1 + phi_hat_k lam_i, c_i = lam_i / den_i and z = U^T ybark_k:
+//     log_det_diff_k          = sum_i log(den_i)                                   MOHGP.py:83
+//     s_k = Sy^-1 ybark_k     = U z                                                MOHGP.py:88
+//     Lambda_inv_k            = V diag(c) V^T - (1e-6/phi_hat_k) I                 MOHGP.py:85 (Sy vs Sy + 1e-6 I)
+//     mu_k = Lambda_inv_k s_k = V (c o z) - (1e-6/phi_hat_k) s_k                   MOHGP.py:90
+//     s^T Lambda_inv s        = sum c z^2 - (1e-6/phi_hat_k) |s|^2                 MOHGP.py:133
+//     tr(Lambda_inv Sy_inv)   = sum c - (1e-6/phi_hat_k) tr(Sy_inv)                MOHGP.py:147
+//     w_k = Sy^-1 mu_k        = U (c o z) - (1e-6/phi_hat_k) Sy_inv s_k            (GEMM form of MOHGP.py:144)
+// i.e. five D x D matrix-vector products per cluster instead of a Cholesky, a D x D triangular solve and a SYRK.
+// phi_hat_k <= 1e-6 takes the reference's Lambda_inv := Sf branch.
+
+// workspace layout (doubles): [lam 64 | U D*D | Ut D*D | Vt D*D | tr(Sy_inv), sum(Sf o Sy_inv), sweeps, off-norm, 4 spare]
+__host__ __device__ inline int eig_ws_len(int D) { return GPC_MAX_DP + 3 * D * D + 8; }
+
+struct MohgpEigArgs {
+  const double *A, *Ly, *Ly_inv, *Sy_inv, *Sf;
+  double *ws;
+  int D;
+};
+
+// One CTA.  Two-sided cyclic Jacobi with the round-robin parallel ordering: n/2 disjoint rotations per round.
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_eig(const MohgpEigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, n = (D + 1) & ~1, ld = GPC_MAX_DP + 1, tid = threadIdx.x, nth = blockDim.x;
+  double *As = sm;                    // n x ld
+  double *Qs = As + GPC_MAX_DP * ld;  // n x ld
+  double *cs = Qs + GPC_MAX_DP * ld;  // n/2 cosines
+  double *sn = cs + GPC_MAX_DP / 2;   // n/2 sines
+  double *red_s = sn + GPC_MAX_DP / 2;  // 32
+  __shared__ int pp[GPC_MAX_DP / 2], qq[GPC_MAX_DP / 2];
+  for (int e = tid; e < n * n; e += nth) {
+    const int i = e / n, j = e % n;
+    // symmetrise: A is symmetric up to rounding, Jacobi wants it exactly so
+    As[i * ld + j] = (i < D && j < D) ? 0.5 * (a.A[i * D + j] + a.A[j * D + i]) : 0.0;
+    Qs[i * ld + j] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  double fro = 0.0;
+  for (int e = tid; e < n * n; e += nth) fro += As[(e / n) * ld + (e % n)] * As[(e / n) * ld + (e % n)];
+  fro = block_sum(fro, red_s);
+  int sweeps = 0;
+  double off = 0.0;
+  for (; sweeps < 30; ++sweeps) {
+    off = 0.0;
+    for (int e = tid; e < n * n; e += nth) {
+      const int i = e / n, j = e % n;
+      if (i != j) off += As[i * ld + j] * As[i * ld + j];
+    }
+    off = block_sum(off, red_s);
+    if (!(off > 1e-34 * fro)) break;
+    for (int round = 0; round < n - 1; ++round) {
+      if (tid < n / 2) {
+        int p, q;
+        if (tid == 0) {
+          p = n - 1;
+          q = round;
+        } else {
+          p = (round + tid) % (n - 1);
+          q = (round - tid + (n - 1)) % (n - 1);
+        }
+        if (p > q) {
+          const int t = p;
+          p = q;
+          q = t;
+        }
+        const double apq = As[p * ld + q], app = As[p * ld + p], aqq = As[q * ld + q];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1e-300) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+        }
+        pp[tid] = p;
+        qq[tid] = q;
+        cs[tid] = c;
+        sn[tid] = s;
+      }
+      __syncthreads();
+      // columns: [A_ip, A_iq] <- [c A_ip - s A_iq, s A_ip + c A_iq]; same for the eigenvector accumulator
+      for (int e = tid; e < (n / 2) * n; e += nth) {
+        const int r = e / n, i = e % n;
+        const int p = pp[r], q = qq[r];
+        const double c = cs[r], s = sn[r];
+        const double x = As[i * ld + p], y = As[i * ld + q];
+        As[i * ld + p] = c * x - s * y;
+        As[i * ld + q] = s * x + c * y;
+        const double u = Qs[i * ld + p], v = Qs[i * ld + q];
+        Qs[i * ld + p] = c * u - s * v;
+        Qs[i * ld + q] = s * u + c * v;
+      }
+      __syncthreads();
+      // rows
+      for (int e = tid; e < (n / 2) * n; e += nth) {
+        const int r = e / n, j = e % n;
+        const int p = pp[r], q = qq[r];
+        const double c = cs[r], s = sn[r];
+        const double x = As[p * ld + j], y = As[q * ld + j];
+        As[p * ld + j] = c * x - s * y;
+        As[q * ld + j] = s * x + c * y;
+      }
+      __syncthreads();
+    }
+  }
+  double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
+  for (int i = tid; i < GPC_MAX_DP; i += nth) lam[i] = (i < D) ? As[i * ld + i] : 0.0;
+  // U = Ly^-T Q ; V = Ly Q   (Ly, Ly_inv lower triangular with zero strict upper)
+  for (int e = tid; e < D * D; e += nth) {
+    const int i = e / D, j = e % D;
+    double u = 0.0, v = 0.0;
+    for (int m = i; m < D; ++m) u += a.Ly_inv[m * D + i] * Qs[m * ld + j];
+    for (int m = 0; m <= i; ++m) v += a.Ly[i * D + m] * Qs[m * ld + j];
+    U[i * D + j] = u;
+    Ut[j * D + i] = u;
+    Vt[j * D + i] = v;
+  }
+  double t1 = 0.0, t2 = 0.0;
+  for (int e = tid; e < D * D; e += nth) {
+    if (e / D == e % D) t1 += a.Sy_inv[e];
+    t2 += a.Sf[e] * a.Sy_inv[e];
+  }
+  t1 = block_sum(t1, red_s);
+  t2 = block_sum(t2, red_s);
+  if (tid == 0) {
+    scal[0] = t1;
+    scal[1] = t2;
+    scal[2] = (double)sweeps;
+    scal[3] = sqrt(off / (fro > 0.0 ? fro : 1.0));
+  }
+}
+
+struct MohgpPostArgs {
+  const double *partials;  // num_parts x stats_len per-CTA statistics of the S pass (or the all-reduced vector, num_parts = 1)
+  int num_parts;
+  double *stats;           // out: [ybark KP x DP | phi_hat KP | H | pad]  (may alias partials when num_parts == 1)
+  const double *ws;        // k_mohgp_eig workspace
+  const double *Sy_inv;    // D x D
+  const double *Sf;        // D x D
+  const double *const_term;
+  double *Wt;              // out KP x DP
+  double *muk_t;           // out K x D
+  double *Syi_ybark_t;     // out K x D
+  double *per_k;           // out KP x 4 : log_det_diff, s^T Lambda_inv s, tr(Lambda_inv Sy_inv), mu^T Sy^-1 mu
+  double *bias;            // out KP
+  double *scalars;         // out [0]=bound [1]=mix [2]=H
+  double *mixgrad_out;     // out K (nullable)
+  unsigned int *counter;   // zero on entry, reset on exit
+  int *info;               // NOT cleared here: the caller's flag word (cleared by the launcher)
+  double alpha;
+  int prior, K, D, KP, DP;
+};
+
+// y[r] = sum_j Mt[j*D + r] x[j]  for r < D, all 256 threads (4 j-groups), result in out_s[r]; x in shared memory.
+__device__ __forceinline__ double matvec_t_part(const double *__restrict__ Mt, const double *x_s, int D, int r, int pg) {
+  double v0 = 0.0, v1 = 0.0;
+  if (r < D) {
+    int j = pg;
+    for (; j + 4 < D; j += 8) {
+      v0 += Mt[j * D + r] * x_s[j];
+      v1 += Mt[(j + 4) * D + r] * x_s[j + 4];
+    }
+    if (j < D) v0 += Mt[j * D + r] * x_s[j];
+  }
+  return v0 + v1;
+}
+
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostArgs a) {
+  __shared__ double red[4][GPC_MAX_DP];
+  __shared__ double yb_s[GPC_MAX_DP], z_s[GPC_MAX_DP], cz_s[GPC_MAX_DP], s_s[GPC_MAX_DP], mu_s[GPC_MAX_DP], w_s[GPC_MAX_DP], c_s[GPC_MAX_DP];
+  __shared__ double red_s[32];
+  __shared__ double mixgrad[kMaxMixK];
+  __shared__ MixScratch scratch;
+  __shared__ double mix_s;
+  __shared__ bool is_last;
+  const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
+  const int r = tid & 63, pg = tid >> 6;
+  const int len = KP * DP + KP + 2;
+  const double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
+
+  // ---- this cluster's statistics: fixed-order sum over the per-CTA partials
+  {
+    double v0 = 0.0, v1 = 0.0;
+    if (r < DP) {
+      int p = pg;
+      const double *src = a.partials + (size_t)k * DP + r;
+      for (; p + 4 < a.num_parts; p += 8) {
+        v0 += src[(size_t)p * len];
+        v1 += src[(size_t)(p + 4) * len];
+      }
+      if (p < a.num_parts) v0 += src[(size_t)p * len];
+    }
+    red[pg][r] = v0 + v1;
+  }
+  double phi_hat = 0.0;
+  if (tid < 32) {
+    for (int p = tid; p < a.num_parts; p += 32) phi_hat += a.partials[(size_t)p * len + (size_t)KP * DP + k];
+    phi_hat = warp_sum(phi_hat);
+    if (tid == 0) red_s[0] = phi_hat;
+  }
+  __syncthreads();
+  phi_hat = red_s[0];
+  if (tid < DP) {
+    const double v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    yb_s[tid] = v;
+    a.stats[(size_t)k * DP + tid] = v;
+  }
+  if (tid == 0) a.stats[(size_t)KP * DP + k] = phi_hat;
+  __syncthreads();
+
+  if (k < a.K) {
+    // ---- den_i = 1 + jitter + phi_hat lam_i with GPy's jitchol retry: a failed factorisation <=> some den_i <= 0
+    double jitter = 0.0;
+    bool ok = false;
+    {
+      double lmin = INFINITY, lsum = 0.0;
+      for (int i = 0; i < D; ++i) {  // every thread, same order
+        lmin = fmin(lmin, lam[i]);
+        lsum += lam[i];
+      }
+      const double diag_mean = 1.0 + phi_hat * lsum / D;
+      for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
+        if (attempt == 1) jitter = diag_mean * 1e-6;
+        else if (attempt > 1) jitter *= 10.0;
+        if (!isfinite(jitter)) break;
+        ok = (1.0 + jitter + phi_hat * lmin > 0.0) && isfinite(phi_hat);
+      }
+    }
+    if (!ok) {
+      if (tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
+      for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = 0.0;
+      if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
+    } else {
+      const bool tiny = !(phi_hat > 1e-6);
+      const double shift = tiny ? 0.0 : 1e-6 / phi_hat;
+      // z = U^T ybark
+      red[pg][r] = matvec_t_part(U, yb_s, D, r, pg);
+      __syncthreads();
+      double ldd = 0.0;
+      if (tid < D) {
+        const double z = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        const double pl = phi_hat * lam[tid];
+        const double den = (1.0 + jitter) + pl;
+        const double c = (jitter == 0.0) ? lam[tid] / den : (jitter + pl) / (den * phi_hat);
+        z_s[tid] = z;
+        c_s[tid] = c;
+        cz_s[tid] = c * z;
+        ldd = (jitter == 0.0) ? log1p(pl) : log(den);
+      }
+      __syncthreads();
+      // s = U z ; V (c o z) ; U (c o z)
+      const double ps = matvec_t_part(Ut, z_s, D, r, pg);
+      const double pv = tiny ? 0.0 : matvec_t_part(Vt, cz_s, D, r, pg);
+      const double pu = tiny ? 0.0 : matvec_t_part(Ut, cz_s, D, r, pg);
+      __syncthreads();
+      red[pg][r] = ps;
+      __syncthreads();
+      if (tid < D) s_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      __syncthreads();
+      red[pg][r] = pv;
+      __syncthreads();
+      if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      __syncthreads();
+      red[pg][r] = pu;
+      __syncthreads();
+      if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+      __syncthreads();
+      if (tiny) {
+        // Lambda_inv := Sf (MOHGP.py:85): mu = Sf^T s
+        red[pg][r] = matvec_t_part(a.Sf, s_s, D, r, pg);
+        __syncthreads();
+        if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        __syncthreads();
+        red[pg][r] = matvec_t_part(a.Sy_inv, mu_s, D, r, pg);  // w = Sy_inv mu (Sy_inv symmetric)
+        __syncthreads();
+        if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        __syncthreads();
+      } else {
+        red[pg][r] = matvec_t_part(a.Sy_inv, s_s, D, r, pg);  // h = Sy_inv s
+        __syncthreads();
+        if (tid < D) {
+          const double h = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+          mu_s[tid] -= shift * s_s[tid];
+          w_s[tid] -= shift * h;
+        }
+        __syncthreads();
+      }
+      double quad = 0.0, tr = 0.0, m2 = 0.0, ss = 0.0;
+      if (tid < D) {
+        if (tiny) quad = s_s[tid] * mu_s[tid];
+        else {
+          quad = c_s[tid] * z_s[tid] * z_s[tid];
+          ss = s_s[tid] * s_s[tid];
+          tr = c_s[tid];
+        }
+        m2 = mu_s[tid] * w_s[tid];
+      }
+      ldd = block_sum(ldd, red_s);
+      quad = block_sum(quad, red_s);
+      ss = block_sum(ss, red_s);
+      tr = block_sum(tr, red_s);
+      m2 = block_sum(m2, red_s);
+      if (tid < D) {
+        a.muk_t[(size_t)k * D + tid] = mu_s[tid];
+        if (a.Syi_ybark_t) a.Syi_ybark_t[(size_t)k * D + tid] = s_s[tid];
+      }
+      for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = (d < D) ? w_s[d] : 0.0;
+      if (tid == 0) {
+        a.per_k[k * 4 + 0] = ldd;
+        a.per_k[k * 4 + 1] = tiny ? quad : quad - shift * ss;
+        a.per_k[k * 4 + 2] = tiny ? scal[1] : tr - shift * scal[0];
+        a.per_k[k * 4 + 3] = m2;
+      }
+    }
+  } else {  // pad clusters: zero weights so that the G pass sees finite numbers
+    for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = 0.0;
+    if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
+  }
+
+  // ---- the last CTA to finish assembles the bound and the G-pass bias (MOHGP.py:124-135, :146-148)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    double H = 0.0;
+    if (tid < 32) {
+      for (int p = tid; p < a.num_parts; p += 32) H += a.partials[(size_t)p * len + (size_t)KP * DP + KP];
+      H = warp_sum(H);
+      if (tid == 0) {
+        red_s[0] = H;
+        a.stats[(size_t)KP * DP + KP] = H;
+      }
+    }
+    __syncthreads();
+    H = red_s[0];
+    __syncthreads();
+    // other CTAs' results: read through L2 (ld.global.cg), this SM's L1 never held these lines coherently
+    __shared__ double phi_hat_sh[kMaxMixK];
+    for (int kk = tid; kk < a.K; kk += blockDim.x) phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
+    __syncthreads();
+    mixing_terms(phi_hat_sh, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
+    if (tid == 0) {
+      double ldd = 0.0, quad = 0.0;
+      for (int kk = 0; kk < a.K; ++kk) {
+        ldd += __ldcg(a.per_k + kk * 4 + 0);
+        quad += __ldcg(a.per_k + kk * 4 + 1);
+      }
+      a.scalars[0] = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
+      a.scalars[1] = mix_s;
+      a.scalars[2] = H;
+      *a.counter = 0u;
+    }
+    for (int kk = tid; kk < KP; kk += blockDim.x)
+      a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
+    if (a.mixgrad_out)
+      for (int kk = tid; kk < a.K; kk += blockDim.x) a.mixgrad_out[kk] = mixgrad[kk];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MOG: features f = [x_i x_j (i <= j, row-major upper) | x_i], NF = D(D+1)/2 + D, computed from data
 // centred at `centre` (the posterior is translation invariant; centring limits cancellation).
 struct MogClusterArgs {

@@ -459,20 +459,25 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
   }
 }
 
-// out[j] = sum over CTAs of partials[c][j], fixed order (deterministic)
-__global__ void k_reduce_partials(const double *__restrict__ partials, int num_parts, int len, double *__restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= len) return;
-  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-  int c = 0;
-  for (; c + 3 < num_parts; c += 4) {
-    v0 += partials[(size_t)c * len + j];
-    v1 += partials[(size_t)(c + 1) * len + j];
-    v2 += partials[(size_t)(c + 2) * len + j];
-    v3 += partials[(size_t)(c + 3) * len + j];
+// out[j] = sum over CTAs of partials[c][j], fixed order (deterministic).  Block = 32 columns x 8 part-groups:
+// group q sums parts q, q+8, ... (two independent chains), the 8 group sums are combined in a fixed tree.
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int num_parts, int len, double *__restrict__ out) {
+  __shared__ double red[8][33];
+  const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
+  double v0 = 0.0, v1 = 0.0;
+  if (j < len) {
+    int p = q;
+    for (; p + 8 < num_parts; p += 16) {
+      v0 += partials[(size_t)p * len + j];
+      v1 += partials[(size_t)(p + 8) * len + j];
+    }
+    if (p < num_parts) v0 += partials[(size_t)p * len + j];
   }
-  for (; c < num_parts; ++c) v0 += partials[(size_t)c * len + j];
-  out[j] = (v0 + v1) + (v2 + v3);
+  red[q][c] = v0 + v1;
+  __syncthreads();
+  if (q == 0 && j < len)
+    out[j] = ((red[0][c] + red[1][c]) + (red[2][c] + red[3][c])) + ((red[4][c] + red[5][c]) + (red[6][c] + red[7][c]));
 }
 
 }  // namespace gpc

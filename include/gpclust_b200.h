@@ -102,6 +102,20 @@ int gpc_mohgp_const(const double *YTY, const double *Sy_inv, const double *Sy_lo
 int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, const double *Ly_inv, const double *Sy,
                       const double *Sy_inv, const double *Sf, double *Wt, double *muk_t, double *per_k, double *Syi_ybark_t, double *Lambda_inv, double *C_chols, int *info,
                       int K, int D, int KP, int DP, void *stream);
+/* ---- the same posterior WITHOUT per-cluster factorisations (the hot-loop form) ----
+ * once per kernel-parameter change: A = Q diag(lam) Q^T by one-CTA cyclic Jacobi; ws (gpc_mohgp_eig_ws_len(D)
+ * doubles) receives lam, U = Ly^-T Q, U^T, (Ly Q)^T, tr(Sy_inv), sum(Sf o Sy_inv).                             */
+int gpc_mohgp_eig_ws_len(int D);
+int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const double *Sy_inv, const double *Sf, int D, double *ws,
+                  void *stream);
+/* per bound evaluation, ONE launch (KP CTAs): fixed-order reduction of this cluster's statistics over `num_parts`
+ * per-CTA partial vectors of gpc_step_stats (num_parts = 1 and partials == stats after an all-reduce), posterior
+ * mean / G-pass weights / per-cluster scalars in the eigenbasis (MOHGP.py:79-90), and -- in the last CTA to
+ * finish -- the mixing-proportion terms, the bound (MOHGP.py:124-135) and the G-pass bias.  Outputs as
+ * gpc_mohgp_cluster + gpc_mohgp_finalize.  counter: one zero-initialised unsigned int.  *info is cleared first. */
+int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                   const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
+                   double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream);
 /* mixing-proportion bound and gradient (collapsed_mixture.py:66-94), bound assembly, G-pass bias.
  * scalars: [0] bound, [1] mixing_prop_bound, [2] H.  mixgrad_out (K doubles) may be NULL.             */
 int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
