@@ -55,7 +55,7 @@ class MOG(CollapsedMixture):
         self._S0_dev = torch.from_numpy(_cabi.f64(self.S0)).to(self.device)
 
         DP = _cabi.padded_d(D * (D + 1) // 2 + D)
-        F = torch.empty((self._Npad, lib.gpc_feature_ld(DP)), dtype=torch.float64, device=self.device)
+        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major
         check(lib.gpc_mog_features(ptr(Xd), ptr(self._centre_dev), self.N, D, DP, ptr(F), self._stream()), "gpc_mog_features")
         self.kernel_launches += 1
         self._Xd = Xd

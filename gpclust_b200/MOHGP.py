@@ -33,7 +33,7 @@ class MOHGP(CollapsedMixture):
         self.kernF = kernF
         self.kernY = kernY
 
-        # features: F = Y, padded to Npad x DP
+        # features: F = Y, fragment-major, Npad x DP
         DP = _cabi.padded_d(self.D)
         if isinstance(Y, torch.Tensor):
             Yd = Y.to(device=self.device, dtype=torch.float64).contiguous()
@@ -41,9 +41,8 @@ class MOHGP(CollapsedMixture):
         else:
             self._Y_host = _cabi.f64(Y)
             Yd = torch.from_numpy(self._Y_host).to(self.device)
-        ldf = lib.gpc_feature_ld(DP)
-        F = torch.empty((self._Npad, ldf), dtype=torch.float64, device=self.device)
-        check(lib.gpc_pad_rows(ptr(Yd), N, self.D, ldf, ptr(F), self._stream()), "gpc_pad_rows")
+        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major (include/gpclust_b200.h "Layout")
+        check(lib.gpc_pack_rows(ptr(Yd), N, self.D, DP, _cabi.LAYOUT["features"], ptr(F), self._stream()), "gpc_pack_rows")
         self.kernel_launches += 1
         del Yd
         self._X_dev = torch.from_numpy(self.X).to(self.device)
@@ -64,7 +63,9 @@ class MOHGP(CollapsedMixture):
     @property
     def Y(self):
         if self._Y_host is None:
-            self._Y_host = self._F[:self.N, :self.D].cpu().numpy()
+            out = self.torch.empty((self.N, self.D), dtype=self.torch.float64, device=self.device)
+            check(lib.gpc_unpack_rows(ptr(self._F), self.N, self.D, self._DP, _cabi.LAYOUT["features"], ptr(out), self._stream()), "gpc_unpack_rows")
+            self._Y_host = out.cpu().numpy()
         return self._Y_host
 
     def _alloc_model(self):

@@ -16,6 +16,7 @@ GPC_EINVAL = 2
 GPC_INFO_NOT_PD = 1
 PRIOR = {"symmetric": 0, "DP": 1}
 BETA = {"zero": 0, "HS": 1, "PR": 2, "FR": 3}
+LAYOUT = {"features": 0, "logits": 1}
 KERN = {"rbf": 0, "matern32": 1, "matern52": 2, "bias": 3, "white": 4}
 
 _p = ctypes.c_void_p
@@ -30,7 +31,6 @@ PROTOTYPES = {
     "gpc_padded_d": [_i],
     "gpc_padded_rows": [_ll],
     "gpc_stats_len": [_i, _i],
-    "gpc_feature_ld": [_i],
     "gpc_default_grid": [_i],
     "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
@@ -60,6 +60,8 @@ PROTOTYPES = {
     "gpc_multiple_mahalanobis": [_p, _p, _p, _ll, _i, _i, _p, _p],
     "gpc_multiple_pdinv": [_p, _i, _i, _p, _p, _p, _p],
     "gpc_gram_partials": [_p, _ll, _i, _p, _i, _p],
+    "gpc_pack_rows": [_p, _ll, _i, _i, _i, _p, _p],
+    "gpc_unpack_rows": [_p, _ll, _i, _i, _i, _p, _p],
     "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],
     "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
 }

@@ -2,7 +2,7 @@
 resident in HBM.
 
 What lives where
-  device (torch CUDA float64 tensors, row-major, padded -- include/gpclust_b200.h "Layout"):
+  device (torch CUDA float64 tensors, fragment-major, padded -- include/gpclust_b200.h "Layout"):
       logits phi_ (three rotating buffers: accepted / previous accepted / trial), natural gradient
       (current / previous), search direction, the feature rows F, per-CTA partials, the reduced
       statistics [T | phi_hat | H], per-cluster posterior outputs, the control block that is read
@@ -154,7 +154,7 @@ class CollapsedMixture(CollapsedVB):
         else:
             src = torch.from_numpy(_cabi.f64(np.asarray(x).reshape(self.N, K))).to(self.device)
         cur = self._xbuf[self._xi]
-        check(lib.gpc_pad_rows(ptr(src), self.N, K, self._KP, ptr(cur), self._stream()), "gpc_pad_rows")
+        check(lib.gpc_pack_rows(ptr(src), self.N, K, self._KP, _cabi.LAYOUT["logits"], ptr(cur), self._stream()), "gpc_pack_rows")
         self.kernel_launches += 1
         self._xprev = None
         self._xtrial = (self._xi + 1) % 3
@@ -172,7 +172,7 @@ class CollapsedMixture(CollapsedVB):
 
     def _unpad(self, buf):
         out = self.torch.empty((self.N, self.K), dtype=self.torch.float64, device=self.device)
-        check(lib.gpc_unpad_rows(ptr(buf), self.N, self.K, self._KP, ptr(out), self._stream()), "gpc_unpad_rows")
+        check(lib.gpc_unpack_rows(ptr(buf), self.N, self.K, self._KP, _cabi.LAYOUT["logits"], ptr(out), self._stream()), "gpc_unpack_rows")
         self.kernel_launches += 1
         return out
 
@@ -197,7 +197,8 @@ class CollapsedMixture(CollapsedVB):
             logphi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
             grid = min(self._grid * 4, (self.N + 7) // 8)
             hpart = torch.zeros(grid, dtype=torch.float64, device=self.device)
-            check(lib.gpc_softmax_rows(ptr(self._xbuf[self._xi]), self.N, self.K, self._KP, ptr(phi), ptr(logphi), self.K, ptr(hpart), grid,
+            x = self._unpad(self._xbuf[self._xi])
+            check(lib.gpc_softmax_rows(ptr(x), self.N, self.K, self.K, ptr(phi), ptr(logphi), self.K, ptr(hpart), grid,
                                        self._stream()), "gpc_softmax_rows")
             self.kernel_launches += 1
             self._cache["softmax"] = (phi, logphi, hpart)

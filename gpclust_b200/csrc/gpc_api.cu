@@ -19,35 +19,46 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 inline int launch_rc() { return cuda_rc(cudaGetLastError()); }
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-size_t natgrad_smem(int KP, int DP) {
-  const VbSmemLayout L(DP);
-  return sizeof(double) * ((size_t)kStages * L.stage_doubles + (size_t)KP * L.f_stride + KP + GPC_CONSUMER_WARPS * 4) +
-         sizeof(uint64_t) * 2 * kStages;
+// ring depth: as many group stages as fit next to the fixed part in the 227 KB of one SM (capped)
+constexpr int kMaxStages = 24;
+int natgrad_stages(int KP, int DP) {
+  const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;
+  const size_t per = sizeof(double) * (size_t)g_stage_doubles(KP, DP) + 2 * sizeof(uint64_t);
+  const int s = (int)((kSmemBudget - fixed) / per);
+  return s > kMaxStages ? kMaxStages : s;
 }
-size_t step_stats_smem(int KP, int DP) {
-  const VbSmemLayout L(DP);
-  return sizeof(double) * ((size_t)kStages * L.stage_doubles + (size_t)GPC_ROW_TILE * (KP + 4) + GPC_CONSUMER_WARPS) +
-         sizeof(uint64_t) * 2 * kStages;
+size_t natgrad_smem(int KP, int DP, int S) {
+  return sizeof(double) * ((size_t)S * g_stage_doubles(KP, DP) + g_fixed_doubles(KP, DP)) + sizeof(uint64_t) * 2 * S;
+}
+int step_stats_stages(int KP, int DP) {
+  const size_t fixed = sizeof(double) * kSSoftmaxWarps + 64;
+  const size_t per = sizeof(double) * (size_t)s_stage_doubles(KP, DP) + 3 * sizeof(uint64_t);
+  const int s = (int)((kSmemBudget - fixed) / per);
+  return s > kMaxStages ? kMaxStages : s;
+}
+size_t step_stats_smem(int KP, int DP, int S) {
+  return sizeof(double) * ((size_t)S * s_stage_doubles(KP, DP) + kSSoftmaxWarps) + sizeof(uint64_t) * 3 * S;
 }
 
 template <typename Kern, typename Args>
-int launch_vb(Kern kern, const Args &a, size_t smem, int grid, cudaStream_t st) {
+int launch_vb(Kern kern, const Args &a, size_t smem, int grid, int threads, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return cuda_rc(e);
-  kern<<<grid, GPC_THREADS, smem, st>>>(a);
+  kern<<<grid, threads, smem, st>>>(a);
   return launch_rc();
 }
 template <int KP>
-int launch_natgrad(const NatgradArgs &a, int grid, cudaStream_t st) {
-  const size_t smem = natgrad_smem(KP, a.DP);
-  return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, st);
+int launch_natgrad(NatgradArgs &a, int grid, cudaStream_t st) {
+  a.stages = natgrad_stages(KP, a.DP);
+  const size_t smem = natgrad_smem(KP, a.DP, a.stages);
+  return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, kGThreads, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, kGThreads, st);
 }
 template <int KP>
-int launch_step_stats(const StepStatsArgs &a, int grid, cudaStream_t st) {
-  const size_t smem = step_stats_smem(KP, a.DP);
-  return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, st) : launch_vb(k_step_stats<KP, false>, a, smem, grid, st);
+int launch_step_stats(StepStatsArgs &a, int grid, cudaStream_t st) {
+  a.stages = step_stats_stages(KP, a.DP);
+  const size_t smem = step_stats_smem(KP, a.DP, a.stages);
+  return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, kSThreads, st)
+                   : launch_vb(k_step_stats<KP, false>, a, smem, grid, kSThreads, st);
 }
 
 constexpr size_t kTileSmem = sizeof(double) * (size_t)kOB * (kOStrideT + kOStrideN);
@@ -90,7 +101,6 @@ int gpc_padded_d(int D) {
 }
 long long gpc_padded_rows(long long N) { return (N + GPC_ROW_TILE - 1) / GPC_ROW_TILE * GPC_ROW_TILE; }
 int gpc_stats_len(int KP, int DP) { return KP * DP + KP + 2; }
-int gpc_feature_ld(int DP) { return DP + 4; }
 
 int gpc_default_grid(int device) {
   int sms = 0;
@@ -122,9 +132,9 @@ int gpc_natgrad(const double *F, const double *x, const double *lse, const doubl
   a.N = (int)N;
   a.K = K;
   a.DP = DP;
-  a.num_tiles = (int)(gpc_padded_rows(N) / GPC_ROW_TILE);
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
   if (N > 0x7fffffffLL) return GPC_EINVAL;
-  if (grid > a.num_tiles) grid = a.num_tiles;
+  if (grid > a.num_groups) grid = a.num_groups;
   cudaStream_t st = as_stream(stream);
   switch (KP) {
     case 8: return launch_natgrad<8>(a, grid, st);
@@ -160,7 +170,7 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
   a.N = (int)N;
   a.K = K;
   a.DP = DP;
-  a.num_tiles = (int)(gpc_padded_rows(N) / GPC_ROW_TILE);
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
   // NOTE: every CTA of the launch grid writes one partial block, so the grid is NOT clamped here:
   // CTAs without a tile write zeros.
   cudaStream_t st = as_stream(stream);
@@ -265,9 +275,9 @@ int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *c
 
 int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream) {
   if (!X || !centre || !F || N < 1 || D < 1 || D * (D + 1) / 2 + D > DP) return GPC_EINVAL;
-  const int ldf = gpc_feature_ld(DP);
-  const long long total = gpc_padded_rows(N) * ldf;
-  k_mog_features<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, centre, (int)N, (int)gpc_padded_rows(N), D, ldf, F);
+  if (DP < 8 || DP > GPC_MAX_DP || (DP % 8)) return GPC_EINVAL;
+  const long long total = gpc_padded_rows(N) * DP;
+  k_mog_features<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(X, centre, (int)N, (int)gpc_padded_rows(N), D, DP, F);
   return launch_rc();
 }
 
@@ -336,7 +346,7 @@ int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, 
 
 int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream) {
   if (!F || !partials || Npad < kGramRows || (Npad % kGramRows) || DP < 8 || DP > GPC_MAX_DP || grid < 1) return GPC_EINVAL;
-  k_gram_partials<<<grid, 256, sizeof(double) * kGramRows * DP, as_stream(stream)>>>(F, (int)Npad, DP, gpc_feature_ld(DP), partials);
+  k_gram_partials<<<grid, 256, sizeof(double) * kGramRows * DP, as_stream(stream)>>>(F, (int)Npad, DP, partials);
   return launch_rc();
 }
 
@@ -344,6 +354,32 @@ int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, voi
   if (!src || !dst || N < 1 || D < 1 || DP < D) return GPC_EINVAL;
   const long long total = gpc_padded_rows(N) * DP;
   k_pad_rows<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, (int)N, D, (int)gpc_padded_rows(N), DP, dst);
+  return launch_rc();
+}
+
+int gpc_pack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream) {
+  if (!src || !dst || N < 1 || C < 1 || CP < C || (CP % 8) || N > 0x7fffffffLL) return GPC_EINVAL;
+  const long long total = gpc_padded_rows(N) * CP;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (layout == GPC_LAYOUT_LOGITS)
+    k_pack_rows<true><<<blocks, 256, 0, as_stream(stream)>>>(src, (int)N, C, (int)gpc_padded_rows(N), CP, dst);
+  else if (layout == GPC_LAYOUT_FEATURES)
+    k_pack_rows<false><<<blocks, 256, 0, as_stream(stream)>>>(src, (int)N, C, (int)gpc_padded_rows(N), CP, dst);
+  else
+    return GPC_EINVAL;
+  return launch_rc();
+}
+
+int gpc_unpack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream) {
+  if (!src || !dst || N < 1 || C < 1 || CP < C || (CP % 8) || N > 0x7fffffffLL) return GPC_EINVAL;
+  const long long total = N * C;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (layout == GPC_LAYOUT_LOGITS)
+    k_unpack_rows<true><<<blocks, 256, 0, as_stream(stream)>>>(src, (int)N, C, CP, dst);
+  else if (layout == GPC_LAYOUT_FEATURES)
+    k_unpack_rows<false><<<blocks, 256, 0, as_stream(stream)>>>(src, (int)N, C, CP, dst);
+  else
+    return GPC_EINVAL;
   return launch_rc();
 }
 

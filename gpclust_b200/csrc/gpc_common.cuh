@@ -1,9 +1,9 @@
 // gpclust_b200 -- shared device helpers for the sm_100a kernels (FP64 throughout).
 //
 // FP64 tensor work on sm_100a is warp-level `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4); tcgen05 has no
-// f64 kind, so there is no TMEM path for this data type.  Operand tiles are staged in shared memory
-// by 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP) into a row-padded
-// layout that makes the 64-bit fragment reads bank-conflict free.
+// f64 kind, so there is no TMEM path for this data type.  Operands are staged in shared memory by 1-D bulk
+// async copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP); the HBM layout itself is fragment-major
+// (gpc_vb_kernels.cuh) so that the copied bytes are already in the order the lanes read them.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,8 +12,6 @@
                                          // allocated with roundup(N, GPC_ROW_TILE) rows, pad rows zero) and enums
 #define GPC_MAX_KP 64            // padded cluster count handled by the tensor kernels (8 n-tiles)
 #define GPC_MAX_DP 64            // padded feature count (time points / MOG features)
-#define GPC_THREADS 256          // 8 warps; warp 0 doubles as the F-tile producer
-#define GPC_CONSUMER_WARPS 8
 
 namespace gpc {
 

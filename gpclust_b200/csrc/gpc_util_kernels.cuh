@@ -68,9 +68,14 @@ __global__ void k_kern_fill(const double *__restrict__ X, const double *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// MOG features: row n -> [ xc_i*xc_j (i<=j, row-major upper) | xc_i | 0 pad ], xc = x - centre.
+// Offsets inside one 8-row group of the fragment-major HBM layouts (gpc_vb_kernels.cuh header)
+__host__ __device__ __forceinline__ int frag_off_features(int r, int d) { return (d >> 2) * 32 + r * 4 + (d & 3); }
+__host__ __device__ __forceinline__ int frag_off_logits(int r, int c) { return (((c >> 3) * 32 + r * 4 + ((c & 7) >> 1)) << 1) + (c & 1); }
+
+// MOG features: row n -> [ xc_i*xc_j (i<=j, row-major upper) | xc_i | 0 pad ], xc = x - centre; written in the
+// fragment-major feature layout (DP columns per row).
 __global__ void k_mog_features(const double *__restrict__ X, const double *__restrict__ centre, int N, int Npad, int D, int DP,
-                               double *__restrict__ F) {  // DP here is the leading dimension of F (feature ld)
+                               double *__restrict__ F) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)Npad * DP) return;
   const int n = (int)(e / DP), f = (int)(e % DP);
@@ -90,7 +95,35 @@ __global__ void k_mog_features(const double *__restrict__ X, const double *__res
       v = X[(size_t)n * D + i] - centre[i];
     }
   }
-  F[e] = v;
+  F[(size_t)(n >> 3) * 8 * DP + frag_off_features(n & 7, f)] = v;
+}
+
+// contiguous N x C row-major  ->  fragment-major (Npad rows, CP columns, pad = 0); LOGITS selects the C-fragment order
+template <bool LOGITS>
+__global__ void k_pack_rows(const double *__restrict__ src, int N, int C, int Npad, int CP, double *__restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index into dst
+  if (e >= (long long)Npad * CP) return;
+  const int grp = (int)(e / (8 * CP)), o = (int)(e % (8 * CP));
+  int r, c;
+  if (LOGITS) {  // o = ((c/8)*32 + r*4 + (c%8)/2)*2 + c%2
+    const int h = o >> 1;
+    c = ((h >> 5) << 3) + ((h & 3) << 1) + (o & 1);
+    r = (h >> 2) & 7;
+  } else {  // o = (d/4)*32 + r*4 + d%4
+    c = ((o >> 5) << 2) + (o & 3);
+    r = (o >> 2) & 7;
+  }
+  const int n = grp * 8 + r;
+  dst[e] = (n < N && c < C) ? src[(size_t)n * C + c] : 0.0;
+}
+// and back: fragment-major -> contiguous N x C
+template <bool LOGITS>
+__global__ void k_unpack_rows(const double *__restrict__ src, int N, int C, int CP, double *__restrict__ dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * C) return;
+  const int n = (int)(e / C), c = (int)(e % C);
+  const int o = LOGITS ? frag_off_logits(n & 7, c) : frag_off_features(n & 7, c);
+  dst[e] = src[(size_t)(n >> 3) * 8 * CP + o];
 }
 
 // Copy an N x D matrix into the padded Npad x DP feature layout (pad = 0).
@@ -171,10 +204,10 @@ __global__ void __launch_bounds__(128) k_mahalanobis_pairs(const double *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP)
+// Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP); F fragment-major
 constexpr int kGramRows = 32;
-__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, int ldf, double *__restrict__ partials) {
-  extern __shared__ __align__(16) double tile[];  // kGramRows x DP
+__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, double *__restrict__ partials) {
+  extern __shared__ __align__(16) double tile[];  // kGramRows x DP, row-major
   const int tid = threadIdx.x;
   const int nout = DP * DP;
   // each thread owns outputs tid, tid+256, ... (at most 16 for DP = 64)
@@ -184,8 +217,12 @@ __global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict_
   const int num_tiles = Npad / kGramRows;
   for (int tix = blockIdx.x; tix < num_tiles; tix += gridDim.x) {
     __syncthreads();
-    const double *src = F + (size_t)tix * kGramRows * ldf;
-    for (int e = tid; e < kGramRows * DP; e += blockDim.x) tile[e] = src[(e / DP) * ldf + (e % DP)];
+    const double *src = F + (size_t)tix * kGramRows * DP;  // 4 consecutive groups
+    for (int e = tid; e < kGramRows * DP; e += blockDim.x) {
+      const int grp = e / (8 * DP), o = e % (8 * DP);
+      const int d = ((o >> 5) << 2) + (o & 3), r = (o >> 2) & 7;
+      tile[(grp * 8 + r) * DP + d] = src[e];
+    }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 16; ++q) {

@@ -1,6 +1,6 @@
 // gpclust_b200 -- the two N-sized passes of one collapsed-VB iteration (FP64, sm_100a).
 //
-//   k_natgrad    : G pass.  a[n,k] = F[n,:] . W[:,k] + bias[k] - x[n,k]   (DMMA, F tile staged by bulk copy)
+//   k_natgrad    : G pass.  a[n,k] = F[n,:] . W[:,k] + bias[k] - x[n,k]   (DMMA)
 //                  natgrad = a - sum_k phi*a ; grad = natgrad*phi ; the three CG dot products.
 //                  Restates MOHGP.py:137-153 (multiple_mahalanobis utilities.py:108-172 in GEMM form,
 //                  row-constant terms dropped because the row-centering at MOHGP.py:150 removes them),
@@ -9,215 +9,189 @@
 //                  (collapsed_vb.py:167,172) fused with the softmax / entropy / phi_hat /
 //                  phi^T F sufficient statistics of collapsed_mixture.py:53-56, MOHGP.py:76, MOG.py:56-57.
 //
-// Layout: every N x K array is row-major with leading dimension KP (K padded to 8/16/32/64); the
-// feature matrix F (= Y for MOHGP, [x_i x_j, x_i] for MOG) is row-major with DP = D padded to a
-// multiple of 8 columns (pad zero) and leading dimension DP + 4: the 4 pad doubles per row make the
-// 64-bit DMMA fragment reads bank-conflict free once a 64-row tile has been copied VERBATIM into
-// shared memory by a single cp.async.bulk.  All N-sized arrays are allocated with roundup(N, 64) rows.
+// HBM layout ("fragment-major", private to this library -- gpc_pack_rows / gpc_unpack_rows translate):
+// rows are handled in GROUPS of 8 (the M of mma.m8n8k4).  Within a group
+//   N x K arrays (logits, natural gradient, search direction):  element (r, c) of the group sits at
+//       ((c/8)*32 + r*4 + (c%8)/2)*2 + c%2          -- the DMMA C-fragment order: lane (g=r, t) owns columns 8nt+2t, +1
+//   features F:                                                  element (r, d) sits at (d/4)*32 + r*4 + d%4
+//                                                                -- the DMMA A-fragment order: lane (g=r, t) owns column 4ks+t
+// so one group of every operand is ONE contiguous 16-B-aligned block (4 KB at K = D = 64) that a single
+// cp.async.bulk lands in shared memory exactly in the order the lanes read it: conflict-free LDS, no padding
+// bytes in HBM, and the global stores of a warp are 512 contiguous bytes.
 //
-// Both kernels are persistent (grid = 2 x SM count, two CTAs resident per SM so that one CTA's
-// memory phase overlaps the other's FP64 phase) and 8 warps each own 8 rows of a 64-row tile; warp 0 also
-// streams the F row tile of the NEXT iteration into a 2-stage shared-memory ring with cp.async.bulk +
-// mbarrier (16 warps x 112 registers fill the four 16K-register files of an SM exactly).
-// The S pass leaves lse[n] = logsumexp_k x[n,:] behind, so the G pass gets phi = exp(x - lse) without
-// row reductions and can stream the "previous point" operands (x_old, ng_old) in small column chunks.
+// Both kernels are persistent, one CTA per SM, warp-specialised around a ring of group-sized shared-memory
+// stages fed by a producer warp with cp.async.bulk + mbarrier (complete_tx):
+//   G pass: 1 producer warp + 8 consumer warps (one group each, round-robin), W resident in shared memory.
+//   S pass: 1 producer warp + 8 softmax warps (CG step, softmax, entropy; leave phi in the stage in A-fragment
+//           order) + 4 statistics warps (every group: T += phi^T F on the tensor pipe, 16 of the 64 8x8 tiles each).
+// Consumers never wait on HBM, only on the ring; the ring depth (11 / 13 stages of ~16 KB) is what hides the
+// HBM latency.  The S pass leaves lse[n] = logsumexp_k x[n,:] behind so that the G pass gets phi = exp(x - lse)
+// without row reductions.
 #pragma once
 #include "gpc_common.cuh"
 
 namespace gpc {
 
-constexpr int kStages = 2;
-constexpr int kCtasPerSm = 2;
-#ifndef GPC_DMMA_UNROLL
-#define GPC_DMMA_UNROLL 2
-#endif
-#ifndef GPC_PF_G
-#define GPC_PF_G 2
-#endif
-#ifndef GPC_PF_S
-#define GPC_PF_S 4
-#endif
-constexpr int kDmmaUnroll = GPC_DMMA_UNROLL;
-
-struct VbSmemLayout {
-  int f_stride;       // doubles per staged F row  (DP + 4)
-  int stage_doubles;  // GPC_ROW_TILE * f_stride
-  __host__ __device__ VbSmemLayout(int DP) : f_stride(DP + 4), stage_doubles(GPC_ROW_TILE * (DP + 4)) {}
-};
-
-// Producer duty (done by warp 0, one tile ahead of its use): copy F rows [tile*64, tile*64+64) of this
-// CTA's j-th tile into stage j % kStages with one bulk copy (64 * (DP+4) * 8 bytes, contiguous in HBM).
-__device__ __forceinline__ void produce_f_tile(const double *__restrict__ F, int stage_doubles, double *stages, uint64_t *full_bar,
-                                               uint64_t *empty_bar, int j, int tile) {
-  const int s = j % kStages;
-  const uint32_t ph = (uint32_t)((j / kStages) & 1);
-  mbar_wait(&empty_bar[s], ph ^ 1u);  // every warp has finished the previous tile staged here
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t bytes = (uint32_t)stage_doubles * 8u;
-    mbar_arrive_expect_tx(&full_bar[s], bytes);
-    bulk_g2s(stages + (size_t)s * stage_doubles, F + (size_t)tile * stage_doubles, bytes, &full_bar[s]);
-  }
-  __syncwarp();
-}
+constexpr int kGroupRows = 8;
+constexpr int kCtasPerSm = 1;
+constexpr int kGConsumers = 8;                     // G pass consumer warps
+constexpr int kGThreads = (kGConsumers + 1) * 32;  // + producer warp
+constexpr int kSSoftmaxWarps = 8;                  // S pass
+constexpr int kSStatWarps = 4;
+constexpr int kSThreads = (kSSoftmaxWarps + kSStatWarps + 1) * 32;
+constexpr int kSmemBudget = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------
 // G pass
 // ------------------------------------------------------------------------------------------------
 struct NatgradArgs {
-  const double *F;        // Npad x (DP+4) features
-  const double *x;        // Npad x KP logits at the current point
+  const double *F;        // groups x (8*DP) features, A-fragment order
+  const double *x;        // groups x (8*KP) logits at the current point, C-fragment order
   const double *lse;      // Npad : logsumexp of the rows of x (written by the S pass that produced x)
-  const double *Wt;       // KP x DP, Wt[k][d] = W[d][k]
+  const double *Wt;       // KP x DP row-major, Wt[k][d] = W[d][k]
   const double *bias;     // KP
   const double *x_old;    // logits at the previous accepted point (nullable -> no HS/PR dots)
   const double *lse_old;  // Npad : logsumexp of the rows of x_old
   const double *ng_old;   // natural gradient at the previous accepted point (nullable)
-  double *ng_out;         // Npad x KP natural gradient (ascent direction, un-negated)
-  double *grad_out;       // nullable: Npad x KP gradient = natgrad * phi
+  double *ng_out;         // natural gradient (ascent direction, un-negated), C-fragment order
+  double *grad_out;       // nullable: gradient = natgrad * phi
   double *partials;       // gridDim.x * 4 doubles
   unsigned int *counter;  // zero on entry; reset to zero on exit
   double *dots_out;       // [0]=natgrad.grad  [1]=(ng-ng_old).grad  [2]=(ng-ng_old).grad_old
-  int N, K, DP, num_tiles;
+  int N, K, DP, num_groups, stages;
 };
+
+__host__ __device__ inline int g_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP + 2 * kGroupRows; }
+__host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP + KP + kGConsumers * 4; }
 
 // FULLK: K == KP, no column masking
 template <int KP, bool FULLK>
-__global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const NatgradArgs a) {
+__global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
+  constexpr int XG = kGroupRows * KP;  // doubles of one N x K operand per group
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const VbSmemLayout L(a.DP);
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages;
+  const int stage_doubles = g_stage_doubles(KP, DP);
   double *stages = reinterpret_cast<double *>(smem_raw);
-  double *wt_s = stages + (size_t)kStages * L.stage_doubles;  // KP x f_stride
-  double *bias_s = wt_s + KP * L.f_stride;                    // KP
-  double *red_s = bias_s + KP;                                // GPC_CONSUMER_WARPS * 4
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + GPC_CONSUMER_WARPS * 4);
-  uint64_t *empty_bar = full_bar + kStages;
+  double *w_s = stages + (size_t)S * stage_doubles;  // B fragments: ((ks*NT + nt)*32 + lane)
+  double *bias_s = w_s + KP * DP;                     // KP
+  double *red_s = bias_s + KP;                        // kGConsumers * 4
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + kGConsumers * 4);
+  uint64_t *empty_bar = full_bar + S;
   __shared__ bool is_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const bool has_old = (a.ng_old != nullptr);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GPC_CONSUMER_WARPS);
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < KP * a.DP; i += blockDim.x) {
-    const int k = i / a.DP, d = i - k * a.DP;
-    wt_s[k * L.f_stride + d] = a.Wt[i];
+  for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
+    const int ln = i & 31, f = i >> 5;  // f = ks*NT + nt
+    const int nt = f % NT, ks = f / NT;
+    w_s[i] = a.Wt[(size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3)];
   }
   for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = a.bias[i];
   __syncthreads();
 
-  {
-    const bool has_old = (a.ng_old != nullptr);
-    const int ksteps = a.DP / 4;
+  if (warp == kGConsumers) {
+    // ---------------- producer: one elected lane streams groups into the ring
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? 2 * XG + kGroupRows : 0)) * 8u;
+      int j = 0;
+      for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
+        const int s = j % S;
+        if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
+        double *st = stages + (size_t)s * stage_doubles;
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
+        bulk_g2s(st + FG, a.x + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        bulk_g2s(st + FG + 3 * XG, a.lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
+        if (has_old) {
+          bulk_g2s(st + FG + XG, a.x_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+          bulk_g2s(st + FG + 2 * XG, a.ng_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+          bulk_g2s(st + FG + 3 * XG + kGroupRows, a.lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers: warp w owns this CTA's groups j = w, w + 8, ...
+    const int ksteps = DP / 4;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-    int it = 0;
-    if (warp == 0 && (int)blockIdx.x < a.num_tiles)
-      produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, 0, blockIdx.x);
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles) {
-        produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, it + 1, tile + gridDim.x);
-        // pull the next tile's N x K operands into L2 so that the demand loads below are L2 hits
-        const size_t nxt = (size_t)(tile + gridDim.x) * GPC_ROW_TILE * KP;
-        const uint32_t bytes = GPC_ROW_TILE * KP * 8u;
-        if (lane == 0) bulk_prefetch_l2(a.x + nxt, bytes);
-        if (has_old && lane == 1) bulk_prefetch_l2(a.x_old + nxt, bytes);
-        if (has_old && lane == 2) bulk_prefetch_l2(a.ng_old + nxt, bytes);
-      }
-      const int s = it % kStages;
-      const uint32_t ph = (uint32_t)((it / kStages) & 1);
-      const int row = tile * GPC_ROW_TILE + warp * 8 + g;
+    int j = warp;
+    for (int grp = blockIdx.x + warp * gridDim.x; grp < a.num_groups; grp += kGConsumers * gridDim.x, j += kGConsumers) {
+      const int s = j % S;
+      const double *st = stages + (size_t)s * stage_doubles;
+      const int row = grp * kGroupRows + g;
       const bool row_ok = row < a.N;
-      const size_t off = (size_t)row * KP + 2 * t;
-
-      // current-point logits: issued before the DMMA loop so their HBM latency overlaps it
-      double x[NT][2];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const double2 v = ldg2_stream(a.x + off + 8 * nt);
-        x[nt][0] = v.x;
-        x[nt][1] = v.y;
-      }
-      const double lse = a.lse[row];
-      const double lse_o = has_old ? a.lse_old[row] : 0.0;
+      mbar_wait(&full_bar[s], (uint32_t)((j / S) & 1));
 
       double acc[NT][2];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-
-      mbar_wait(&full_bar[s], ph);
-      const double *fa = stages + (size_t)s * L.stage_doubles + (warp * 8 + g) * L.f_stride + t;
-      const double *wb = wt_s + g * L.f_stride + t;
-#pragma unroll(kDmmaUnroll)
+      const double *fa = st + lane;
+      const double *wb = w_s + lane;
+#pragma unroll 2
       for (int ks = 0; ks < ksteps; ++ks) {
-        const double af = fa[4 * ks];
+        const double af = fa[ks * 32];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], af, wb[nt * 8 * L.f_stride + 4 * ks]);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], af, wb[(ks * NT + nt) * 32]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      const double *xs = st + FG + 2 * lane;
+      const double lse = st[FG + 3 * XG + g];
+      const double lse_o = has_old ? st[FG + 3 * XG + kGroupRows + g] : 0.0;
 
-      // previous-point operands are streamed in column chunks, PF chunks ahead of their use
-      constexpr int PF = (NT < GPC_PF_G) ? NT : GPC_PF_G;
-      double2 xo_q[PF], ngo_q[PF];
-      if (has_old) {
-#pragma unroll
-        for (int q = 0; q < PF; ++q) {
-          xo_q[q] = ldg2_stream(a.x_old + off + 8 * q);
-          ngo_q[q] = ldg2_stream(a.ng_old + off + 8 * q);
-        }
-      }
-
-      // ---- pass 1: phi = exp(x - lse) (in place of x), a = F.W + bias - x (in place of acc), sa = sum phi*a
+      // ---- pass 1: phi = exp(x - lse), a = F.W + bias - x (in place of acc), sa = sum phi*a
+      double phi[NT][2];
       double sa = 0.0;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double x0 = x[nt][0], x1 = x[nt][1];
+        const double2 xv = *reinterpret_cast<const double2 *>(xs + nt * 64);
         const double2 bb = *reinterpret_cast<const double2 *>(bias_s + c);
-        acc[nt][0] = ok0 ? (acc[nt][0] + bb.x) - x0 : 0.0;
-        acc[nt][1] = ok1 ? (acc[nt][1] + bb.y) - x1 : 0.0;
+        acc[nt][0] = ok0 ? (acc[nt][0] + bb.x) - xv.x : 0.0;
+        acc[nt][1] = ok1 ? (acc[nt][1] + bb.y) - xv.y : 0.0;
         double p0, p1;
-        exp_pair(x0 - lse, x1 - lse, p0, p1);
-        x[nt][0] = ok0 ? p0 : 0.0;
-        x[nt][1] = ok1 ? p1 : 0.0;
-        sa += x[nt][0] * acc[nt][0] + x[nt][1] * acc[nt][1];
+        exp_pair(xv.x - lse, xv.y - lse, p0, p1);
+        phi[nt][0] = ok0 ? p0 : 0.0;
+        phi[nt][1] = ok1 ? p1 : 0.0;
+        sa += phi[nt][0] * acc[nt][0] + phi[nt][1] * acc[nt][1];
       }
       sa = quad_sum(sa);
 
       // ---- pass 2: natural gradient, gradient, dots
+      double *ngo_g = a.ng_out + (size_t)grp * XG + 2 * lane;
+      double *gro_g = a.grad_out ? a.grad_out + (size_t)grp * XG + 2 * lane : nullptr;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
         const double n0 = (ok0 && row_ok) ? acc[nt][0] - sa : 0.0;
         const double n1 = (ok1 && row_ok) ? acc[nt][1] - sa : 0.0;
-        const double g0 = n0 * x[nt][0], g1 = n1 * x[nt][1];
-        stg2(a.ng_out + off + 8 * nt, n0, n1);
-        if (a.grad_out) stg2(a.grad_out + off + 8 * nt, g0, g1);
+        const double g0 = n0 * phi[nt][0], g1 = n1 * phi[nt][1];
+        stg2(ngo_g + nt * 64, n0, n1);
+        if (gro_g) stg2(gro_g + nt * 64, g0, g1);
         d0 += n0 * g0 + n1 * g1;
         if (has_old) {
-          const double2 xo = xo_q[nt % PF], ngo = ngo_q[nt % PF];
-          if (nt + PF < NT) {
-            xo_q[nt % PF] = ldg2_stream(a.x_old + off + 8 * (nt + PF));
-            ngo_q[nt % PF] = ldg2_stream(a.ng_old + off + 8 * (nt + PF));
-          }
-          if (row_ok) {
-            double po0, po1;
-            exp_pair(xo.x - lse_o, xo.y - lse_o, po0, po1);
-            if (!ok0) po0 = 0.0;
-            if (!ok1) po1 = 0.0;
-            const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
-            d1 += e0 * g0 + e1 * g1;
-            d2 += e0 * (ngo.x * po0) + e1 * (ngo.y * po1);
-          }
+          const double2 xo = *reinterpret_cast<const double2 *>(xs + XG + nt * 64);
+          const double2 ngo = *reinterpret_cast<const double2 *>(xs + 2 * XG + nt * 64);
+          double po0, po1;
+          exp_pair(xo.x - lse_o, xo.y - lse_o, po0, po1);
+          if (!ok0 || !row_ok) po0 = 0.0;
+          if (!ok1 || !row_ok) po1 = 0.0;
+          const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
+          d1 += e0 * g0 + e1 * g1;
+          d2 += e0 * (ngo.x * po0) + e1 * (ngo.y * po1);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
     d0 = warp_sum(d0);
     d1 = warp_sum(d1);
@@ -232,7 +206,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
   // deterministic two-level reduction: per-CTA partial, last CTA sums all partials in index order
   if (threadIdx.x < 3) {
     double v = 0.0;
-    for (int w = 0; w < GPC_CONSUMER_WARPS; ++w) v += red_s[w * 4 + threadIdx.x];
+    for (int w = 0; w < kGConsumers; ++w) v += red_s[w * 4 + threadIdx.x];
     a.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
   }
   __threadfence();
@@ -246,7 +220,7 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
     __threadfence();
     if (warp < 3) {
       double v = 0.0;
-      for (int c = lane; c < (int)gridDim.x; c += 32) v += a.partials[(size_t)c * 4 + warp];
+      for (int c = lane; c < (int)gridDim.x; c += 32) v += __ldcg(a.partials + (size_t)c * 4 + warp);
       // fixed lane->CTA assignment and fixed shuffle tree => run-to-run deterministic
       v = warp_sum(v);
       if (lane == 0) a.dots_out[warp] = v;
@@ -261,8 +235,8 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_natgrad(const Natgr
 // beta modes: GPC_BETA_* of include/gpclust_b200.h
 
 struct StepStatsArgs {
-  const double *F;       // Npad x (DP+4)
-  const double *x_base;  // Npad x KP logits at the accepted point
+  const double *F;       // groups x (8*DP), A-fragment order
+  const double *x_base;  // logits at the accepted point, C-fragment order
   const double *ng;      // natural gradient at x_base (nullable: "set" mode, x_new := x_base, nothing written)
   const double *sd_old;  // previous search direction (nullable or ignored when beta == 0)
   double *sd_new;        // nullable
@@ -270,35 +244,37 @@ struct StepStatsArgs {
   double *lse_new;       // Npad : logsumexp of the rows of x_new (of x_base in "set" mode); nullable
   const double *dots;    // [0]=sq [1]=num [2]=den of the G pass at x_base (device scalars, read when beta_mode != 0)
   double *beta_out;      // device scalar, written by CTA 0
-  double *partials;      // gridDim.x * stat_len, stat_len = KP*DP + KP + 2  ([T KPxDP | phi_hat KP | H | pad]; even => 16-B aligned blocks)
+  double *partials;      // gridDim.x * stat_len, stat_len = KP*DP + KP + 2  ([T KPxDP | phi_hat KP | H | pad])
   double step;
   double sq_old;         // natgrad.grad of the previous iteration (PR / FR only; the host read it back already)
   int beta_mode;
-  int N, K, DP, num_tiles;
+  int N, K, DP, num_groups, stages;
 };
 
+__host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
+
 template <int KP, bool FULLK>
-__global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const StepStatsArgs a) {
+__global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs a) {
   constexpr int NT = KP / 8;
-  constexpr int NGRP = GPC_CONSUMER_WARPS / NT;  // consumer warps sharing one 8-cluster m-tile in the stats GEMM
-  constexpr int MAXDT = GPC_MAX_DP / 8;
-  constexpr int DT_PER = (MAXDT + NGRP - 1) / NGRP;
-  constexpr int P_STRIDE = KP + 4;
+  constexpr int XG = kGroupRows * KP;
+  constexpr int TPW = NT * 8 / kSStatWarps;  // 8x8 tiles of T per statistics warp q: tile i -> (mt = i/2, dt = 4*(i%2) + q)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const VbSmemLayout L(a.DP);
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages, DT = DP / 8;
+  const int stage_doubles = s_stage_doubles(KP, DP);
   double *stages = reinterpret_cast<double *>(smem_raw);
-  double *p_s = stages + (size_t)kStages * L.stage_doubles;  // GPC_ROW_TILE x P_STRIDE (single buffer)
-  double *red_s = p_s + GPC_ROW_TILE * P_STRIDE;             // GPC_CONSUMER_WARPS
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + GPC_CONSUMER_WARPS);
-  uint64_t *empty_bar = full_bar + kStages;
+  double *red_s = stages + (size_t)S * stage_doubles;  // kSSoftmaxWarps
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + kSSoftmaxWarps);
+  uint64_t *phi_bar = full_bar + S;
+  uint64_t *empty_bar = phi_bar + S;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GPC_CONSUMER_WARPS);
+      mbar_init(&phi_bar[s], 1);
+      mbar_init(&empty_bar[s], kSStatWarps);
     }
     mbar_fence_init();
   }
@@ -314,67 +290,60 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
     if (isnan(beta) || beta < 0.0) beta = 0.0;  // collapsed_vb.py:165-166
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
-  const bool use_old = (beta != 0.0) && (a.sd_old != nullptr);
+  const bool has_ng = (a.ng != nullptr);
+  const bool use_old = has_ng && (beta != 0.0) && (a.sd_old != nullptr);
+  double *part = a.partials + (size_t)blockIdx.x * (KP * DP + KP + 2);
 
-  const int DT = a.DP / 8;
-  {
-    const int mt = warp % NT, dgrp = warp / NT;
-    double acc[DT_PER][2];
-#pragma unroll
-    for (int i = 0; i < DT_PER; ++i) acc[i][0] = acc[i][1] = 0.0;
-    double colsum = 0.0;  // sum over rows == t (mod 4) of phi[row][8*mt + g]
-    double Hpart = 0.0;
-
-    int it = 0;
-    if (warp == 0 && (int)blockIdx.x < a.num_tiles)
-      produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, 0, blockIdx.x);
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-      if (warp == 0 && tile + (int)gridDim.x < a.num_tiles) {
-        produce_f_tile(a.F, L.stage_doubles, stages, full_bar, empty_bar, it + 1, tile + gridDim.x);
-        const size_t nxt = (size_t)(tile + gridDim.x) * GPC_ROW_TILE * KP;
-        const uint32_t bytes = GPC_ROW_TILE * KP * 8u;
-        if (lane == 0) bulk_prefetch_l2(a.x_base + nxt, bytes);
-        if (a.ng != nullptr && lane == 1) bulk_prefetch_l2(a.ng + nxt, bytes);
-        if (use_old && lane == 2) bulk_prefetch_l2(a.sd_old + nxt, bytes);
+  if (warp == kSSoftmaxWarps + kSStatWarps) {
+    // ---------------- producer
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (use_old ? XG : 0)) * 8u;
+      int j = 0;
+      for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
+        const int s = j % S;
+        if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
+        double *st = stages + (size_t)s * stage_doubles;
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
+        bulk_g2s(st + FG, a.x_base + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        if (has_ng) bulk_g2s(st + FG + XG, a.ng + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        if (use_old) bulk_g2s(st + FG + 2 * XG, a.sd_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
       }
-      const int s = it % kStages;
-      const uint32_t ph = (uint32_t)((it / kStages) & 1);
-      const int row = tile * GPC_ROW_TILE + warp * 8 + g;
+    }
+  } else if (warp < kSSoftmaxWarps) {
+    // ---------------- softmax warps: CG step + softmax statistics of one group each
+    double Hpart = 0.0;
+    int j = warp;
+    for (int grp = blockIdx.x + warp * gridDim.x; grp < a.num_groups; grp += kSSoftmaxWarps * gridDim.x, j += kSSoftmaxWarps) {
+      const int s = j % S;
+      double *st = stages + (size_t)s * stage_doubles;
+      const int row = grp * kGroupRows + g;
       const bool row_ok = row < a.N;
-      const size_t off = (size_t)row * KP + 2 * t;
-
-      // ---- phase 1: CG step + softmax statistics for this warp's 8 rows
+      mbar_wait(&full_bar[s], (uint32_t)((j / S) & 1));
+      double *xs = st + FG + 2 * lane;
       double x[NT][2];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const double2 v = ldg2_stream(a.x_base + off + 8 * nt);
+        const double2 v = *reinterpret_cast<const double2 *>(xs + nt * 64);
         x[nt][0] = v.x;
         x[nt][1] = v.y;
       }
-      if (a.ng != nullptr) {
-        // operands streamed in column chunks, PF chunks ahead of their use
-        constexpr int PF = (NT < GPC_PF_S) ? NT : GPC_PF_S;
-        double2 ng_q[PF], sd_q[PF];
-#pragma unroll
-        for (int q = 0; q < PF; ++q) {
-          ng_q[q] = ldg2_stream(a.ng + off + 8 * q);
-          if (use_old) sd_q[q] = ldg2_stream(a.sd_old + off + 8 * q);
-        }
+      if (has_ng) {
+        double *sdo_g = a.sd_new ? a.sd_new + (size_t)grp * XG + 2 * lane : nullptr;
+        double *xn_g = a.x_new + (size_t)grp * XG + 2 * lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          double s0 = ng_q[nt % PF].x, s1 = ng_q[nt % PF].y;
+          const double2 ngv = *reinterpret_cast<const double2 *>(xs + XG + nt * 64);
+          double s0 = ngv.x, s1 = ngv.y;
           if (use_old) {
-            s0 += beta * sd_q[nt % PF].x;  // searchDir = natgrad + beta*searchDir_old  (collapsed_vb.py:167, ascent sign)
-            s1 += beta * sd_q[nt % PF].y;
-          }
-          if (nt + PF < NT) {
-            ng_q[nt % PF] = ldg2_stream(a.ng + off + 8 * (nt + PF));
-            if (use_old) sd_q[nt % PF] = ldg2_stream(a.sd_old + off + 8 * (nt + PF));
+            const double2 sdv = *reinterpret_cast<const double2 *>(xs + 2 * XG + nt * 64);
+            s0 += beta * sdv.x;  // searchDir = natgrad + beta*searchDir_old  (collapsed_vb.py:167, ascent sign)
+            s1 += beta * sdv.y;
           }
           x[nt][0] += a.step * s0;  // collapsed_vb.py:172
           x[nt][1] += a.step * s1;
-          if (a.sd_new) stg2(a.sd_new + off + 8 * nt, s0, s1);
-          stg2(a.x_new + off + 8 * nt, x[nt][0], x[nt][1]);
+          if (sdo_g) stg2(sdo_g + nt * 64, s0, s1);
+          stg2(xn_g + nt * 64, x[nt][0], x[nt][1]);
         }
       }
       // row softmax: max, exp, sum   (np_utilities.py:25-40)
@@ -410,52 +379,74 @@ __global__ void __launch_bounds__(GPC_THREADS, kCtasPerSm) k_step_stats(const St
       if (row_ok && t == 0) Hpart += lognorm - px * inv;
       if (a.lse_new && t == 0) a.lse_new[row] = m + lognorm;
 
-      // the previous tile's GEMM has finished reading p_s
-      asm volatile("bar.sync 1, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
+      // phi -> the stage's x region, in the A-fragment order of phi^T: element (row r, cluster k) at
+      // ((k/8)*2 + r/4)*32 + (k%8)*4 + r%4.  Every lane has read its x values above.
+      __syncwarp();
+      double *ps = st + FG + (g >> 2) * 32 + (g & 3);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const int c = 8 * nt + 2 * t;
-        *reinterpret_cast<double2 *>(p_s + (warp * 8 + g) * P_STRIDE + c) = make_double2(x[nt][0] * inv, x[nt][1] * inv);
+        ps[nt * 64 + (2 * t) * 4] = x[nt][0] * inv;
+        ps[nt * 64 + (2 * t + 1) * 4] = x[nt][1] * inv;
       }
-      // all consumer warps have written their phi rows
-      asm volatile("bar.sync 2, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
-
-      // ---- phase 2: T[k][d] += sum_rows phi[row][k] * F[row][d]   (this warp: m-tile mt, d-tiles dgrp + i*NGRP)
-      mbar_wait(&full_bar[s], ph);
-      const double *fb = stages + (size_t)s * L.stage_doubles + t * L.f_stride + g;
-      const double *pa = p_s + t * P_STRIDE + 8 * mt + g;
-#pragma unroll(kDmmaUnroll)
-      for (int ks = 0; ks < GPC_ROW_TILE / 4; ++ks) {
-        const double af = pa[4 * ks * P_STRIDE];
-        colsum += af;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&phi_bar[s]);
+    }
+    Hpart = warp_sum(Hpart);
+    if (lane == 0) red_s[warp] = Hpart;
+  } else {
+    // ---------------- statistics warps: T[k][d] += sum_rows phi[row][k] F[row][d] for every group of this CTA
+    const int q = warp - kSSoftmaxWarps;
+    double acc[TPW][2];
 #pragma unroll
-        for (int i = 0; i < DT_PER; ++i) {
-          const int dt = dgrp + i * NGRP;
-          if (dt < DT) dmma884(acc[i][0], acc[i][1], af, fb[4 * ks * L.f_stride + 8 * dt]);
+    for (int i = 0; i < TPW; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double colsum[NT];  // sum over rows == t (mod 4) of phi[row][8*mt + g]
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) colsum[mt] = 0.0;
+    int j = 0;
+    for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
+      const int s = j % S;
+      const double *st = stages + (size_t)s * stage_doubles;
+      mbar_wait(&phi_bar[s], (uint32_t)((j / S) & 1));
+      const double *pa = st + FG + lane;
+      // B fragment of F for (ks', dt): lane (g, t) reads F[row 4ks'+t][8dt+g] = st[(2dt + g/4)*32 + (4ks'+t)*4 + g%4]
+      const double *fb = st + (g >> 2) * 32 + t * 4 + (g & 3);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        double af[NT];
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) {
+          af[mt] = pa[(mt * 2 + ks) * 32];
+          colsum[mt] += af[mt];
+        }
+#pragma unroll
+        for (int i = 0; i < TPW; ++i) {
+          const int mt = i >> 1, dt = ((i & 1) << 2) + q;  // tile ti = 4*i + q
+          if (dt < DT) dmma884(acc[i][0], acc[i][1], af[mt], fb[dt * 64 + ks * 16]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
-
     // ---- per-CTA partial statistics
-    double *part = a.partials + (size_t)blockIdx.x * (KP * a.DP + KP + 2);
 #pragma unroll
-    for (int i = 0; i < DT_PER; ++i) {
-      const int dt = dgrp + i * NGRP;
-      if (dt < DT) stg2(part + (size_t)(8 * mt + g) * a.DP + 8 * dt + 2 * t, acc[i][0], acc[i][1]);
+    for (int i = 0; i < TPW; ++i) {
+      const int mt = i >> 1, dt = ((i & 1) << 2) + q;
+      if (dt < DT) stg2(part + (size_t)(8 * mt + g) * DP + 8 * dt + 2 * t, acc[i][0], acc[i][1]);
     }
-    colsum = quad_sum(colsum);
-    Hpart = warp_sum(Hpart);
-    if (dgrp == 0 && t == 0) part[(size_t)KP * a.DP + 8 * mt + g] = colsum;
-    if (lane == 0) red_s[warp] = Hpart;
-    asm volatile("bar.sync 1, %0;\n" ::"n"(GPC_CONSUMER_WARPS * 32) : "memory");
-    if (threadIdx.x == 0) {
-      double v = 0.0;
-      for (int w = 0; w < GPC_CONSUMER_WARPS; ++w) v += red_s[w];
-      part[(size_t)KP * a.DP + KP] = v;
-      part[(size_t)KP * a.DP + KP + 1] = 0.0;
+    if (q == 0) {
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) {
+        const double cs = quad_sum(colsum[mt]);
+        if (t == 0) part[(size_t)KP * DP + 8 * mt + g] = cs;
+      }
     }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < kSSoftmaxWarps; ++w) v += red_s[w];
+    part[(size_t)KP * DP + KP] = v;
+    part[(size_t)KP * DP + KP + 1] = 0.0;
   }
 }
 

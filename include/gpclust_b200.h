@@ -16,12 +16,15 @@
  *     (bit GPC_INFO_NOT_PD), which the host mirror turns into numpy.linalg.LinAlgError so that
  *     collapsed_vb.py:174,187 keep their meaning.
  *
- * Layout of the N-sized arrays ("series" rows n, "cluster" columns k)
- *   - logits / natural gradient / search direction: Npad x KP, Npad = roundup(N, GPC_ROW_TILE),
- *     KP = gpc_padded_k(K) in {8,16,32,64}; pad rows and pad columns hold zeros;
- *   - features F: Npad rows of DP = gpc_padded_d(D) columns (multiple of 8, <= 64, pad zero) with leading
- *     dimension gpc_feature_ld(DP) = DP + 4 (the row padding is the shared-memory bank skew).
- *     MOHGP: F = Y.  MOG: F = [x_i x_j (i<=j) | x_i] of the centred data (gpc_mog_features).
+ * Layout of the N-sized arrays ("series" rows n, "cluster" columns k): FRAGMENT-MAJOR, private to the library.
+ *   Rows are padded to Npad = roundup(N, GPC_ROW_TILE) and handled in groups of 8; within a group
+ *   - logits / natural gradient / search direction (KP = gpc_padded_k(K) in {8,16,32,64} columns): element
+ *     (r, c) at ((c/8)*32 + r*4 + (c%8)/2)*2 + c%2 -- the mma.m8n8k4 C-fragment order; group = 8*KP doubles;
+ *   - features F (DP = gpc_padded_d(D) columns, multiple of 8, <= 64): element (r, d) at (d/4)*32 + r*4 + d%4
+ *     -- the A-fragment order; group = 8*DP doubles.  MOHGP: F = Y.  MOG: F = [x_i x_j (i<=j) | x_i] of the
+ *     centred data (gpc_mog_features).
+ *   One group of any operand is one contiguous block that cp.async.bulk lands in shared memory in lane order.
+ *   gpc_pack_rows / gpc_unpack_rows convert from / to contiguous row-major; pad rows and columns hold zeros.
  *   - stats vector: [ T (KP x DP) | phi_hat (KP) | H (1) | pad (1) ],  T[k][f] = sum_n phi[n][k] F[n][f].
  */
 #ifndef GPCLUST_B200_H
@@ -43,6 +46,9 @@ extern "C" {
 #define GPC_BETA_PR 2   /* collapsed_vb.py:159-160 */
 #define GPC_BETA_FR 3   /* collapsed_vb.py:161-162 */
 
+#define GPC_LAYOUT_FEATURES 0 /* fragment-major feature rows F (DMMA A-fragment order)      */
+#define GPC_LAYOUT_LOGITS 1   /* fragment-major N x K arrays (DMMA C-fragment order)          */
+
 #define GPC_KERN_RBF 0
 #define GPC_KERN_MATERN32 1
 #define GPC_KERN_MATERN52 2
@@ -54,9 +60,8 @@ int gpc_abi_version(void);
 int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
 int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
 long long gpc_padded_rows(long long N);
-int gpc_feature_ld(int DP);        /* DP + 4: leading dimension of the feature rows F                  */
 int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 2 (one pad double keeps blocks 16-B aligned)    */
-int gpc_default_grid(int device);  /* number of persistent CTAs (2 per SM); <0 on CUDA error          */
+int gpc_default_grid(int device);  /* number of persistent CTAs (1 per SM); <0 on CUDA error          */
 
 /* ---- G pass: natural gradient + conjugate-gradient dot products ------------------------------
  * Replaces MOHGP.vb_grad_natgrad (MOHGP.py:137-153) / MOG.vb_grad_natgrad (MOG.py:72-84) including
@@ -122,7 +127,7 @@ int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *c
                        double *mixgrad_out, double alpha, int prior, int K, int KP, int DP, void *stream);
 
 /* ---- MOG (MOG.py:34-84) ------------------------------------------------------------------------ */
-/* F (Npad x gpc_feature_ld(DP)) <- [xc_i xc_j (i<=j) | xc_i | 0], xc = x - centre                       */
+/* F (fragment-major, Npad x DP) <- [xc_i xc_j (i<=j) | xc_i | 0], xc = x - centre                        */
 int gpc_mog_features(const double *X, const double *centre, long long N, int D, int DP, double *F, void *stream);
 /* per_k: KP x 4 = [kN, vN, Sns_halflogdet, grad const].  mun_c: K x D (centred), Sns / Sns_inv: K x D x D.
  * D <= 10.  *info is cleared first.                                                                   */
@@ -180,10 +185,13 @@ int gpc_multiple_mahalanobis(const double *X1, const double *X2, const double *L
                              void *stream);
 /* multiple_pdinv (np_utilities.py:6-22): A, inv are D x D x K (K last); hld K doubles.  D <= 64.     */
 int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, int *info, void *stream);
-/* Y^T Y (MOHGP.py:53) of the feature rows F (ld = gpc_feature_ld(DP)): partials grid x DP x DP, then
+/* Y^T Y (MOHGP.py:53) of the feature rows F (fragment-major): partials grid x DP x DP, then
  * gpc_reduce_partials(len = DP*DP).                                                                    */
 int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream);
-/* layout helpers: contiguous N x D  <->  padded Npad x ld                                             */
+/* contiguous N x C row-major  <->  the fragment-major device layout (Npad rows, CP columns, pad = 0)   */
+int gpc_pack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream);
+int gpc_unpack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream);
+/* layout helpers: contiguous N x D  <->  row-major padded Npad x ld                                  */
 int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, void *stream);
 int gpc_unpad_rows(const double *src, long long N, int K, int ld, double *dst, void *stream);
 
