@@ -103,21 +103,19 @@ __device__ __forceinline__ double colgroup_sum(double v) {
 }
 
 // ---------------------------------------------------------------- exp for the softmax passes (FP64)
-// exp(x) for two arguments at once (x <= ~0 on this path: x - logsumexp or x - rowmax), ~1.5 ulp.
+// exp(x) for a BATCH of arguments (x <= ~0 on this path: x - logsumexp or x - rowmax), ~1.5 ulp.
 // Cody-Waite reduction x = n ln2 + r with the 2^52 rounding trick, degree-11 near-minimax polynomial on
 // |r| <= ln2/2 (Chebyshev-node interpolant of exp, coefficients generated with mpmath at 60 digits),
-// scaling by 2^n through the exponent field.  Results below the normal range (n < -1021, i.e. x < -708)
-// are flushed to zero -- numpy would return denormals <= 2.2e-308 there -- and NaN maps to zero.  Both
-// evaluations share every constant, which halves the constant traffic of two libdevice exp() calls,
-// and there is no slow-path branch.
-// The constants live in constant memory so that DFMA takes them as c[bank][offset] operands instead of
-// UMOV-materialised immediates (two UMOVs per 64-bit literal per use otherwise).
+// scaling by 2^n through the exponent field.  Arguments are clamped at -708 (exp = 3.3e-308, the smallest
+// normal range) instead of being flushed to zero / denormals: no branch, no special cases, and every
+// Horner step is issued for all N chains back to back -- FP64 FMA latency, not throughput, is what a
+// one-at-a-time evaluation pays for.  NaN maps to exp(-708).
 __constant__ double kExpC[17] = {
     1.4426950408889634074,        // 0  log2(e)
     6755399441055744.0,           // 1  1.5 * 2^52
     -6.93147180369123816490e-01,  // 2  -ln2 hi
     -1.90821492927058770002e-10,  // 3  -ln2 lo
-    -1100.0,                      // 4  clamp
+    -708.0,                       // 4  clamp
     0x1.af632e7d3bc8bp-26,        // 5  c11
     0x1.28b413b5ef026p-22,        // 6  c10
     0x1.71ddf56b28fcep-19,        // 7  c9
@@ -131,23 +129,39 @@ __constant__ double kExpC[17] = {
     1.0,                          // 15 c1
     1.0};                         // 16 c0
 
-__device__ __forceinline__ void exp_pair(double x0, double x1, double &e0, double &e1) {
-  x0 = fmax(x0, kExpC[4]);
-  x1 = fmax(x1, kExpC[4]);
-  const double t0 = fma(x0, kExpC[0], kExpC[1]), t1 = fma(x1, kExpC[0], kExpC[1]);
-  const double n0 = t0 - kExpC[1], n1 = t1 - kExpC[1];
-  double r0 = fma(n0, kExpC[2], x0), r1 = fma(n1, kExpC[2], x1);
-  r0 = fma(n0, kExpC[3], r0);
-  r1 = fma(n1, kExpC[3], r1);
-  double p0 = kExpC[5], p1 = kExpC[5];
+template <int N>
+__device__ __forceinline__ void exp_batch(double (&x)[N]) {  // in place: x[i] <- exp(x[i])
+  int k[N];
+  const double l2e = kExpC[0], shift = kExpC[1], ln2hi = kExpC[2], ln2lo = kExpC[3], lo = kExpC[4];
 #pragma unroll
-  for (int i = 6; i < 17; ++i) {
-    p0 = fma(p0, r0, kExpC[i]);
-    p1 = fma(p1, r1, kExpC[i]);
+  for (int i = 0; i < N; ++i) {
+    const double xi = (x[i] > lo) ? x[i] : lo;
+    const double t = fma(xi, l2e, shift);
+    const double n = t - shift;
+    k[i] = __double2loint(t);
+    x[i] = fma(n, ln2lo, fma(n, ln2hi, xi));  // r
   }
-  const int k0 = __double2loint(t0), k1 = __double2loint(t1);
-  e0 = (k0 < -1021) ? 0.0 : __hiloint2double(__double2hiint(p0) + (k0 << 20), __double2loint(p0));
-  e1 = (k1 < -1021) ? 0.0 : __hiloint2double(__double2hiint(p1) + (k1 << 20), __double2loint(p1));
+  double p[N];
+  {
+    const double c11 = kExpC[5], c10 = kExpC[6];
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(c11, x[i], c10);
+  }
+#pragma unroll
+  for (int c = 7; c < 17; ++c) {
+    const double cc = kExpC[c];
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], x[i], cc);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = __hiloint2double(__double2hiint(p[i]) + (k[i] << 20), __double2loint(p[i]));
+}
+
+__device__ __forceinline__ void exp_pair(double x0, double x1, double &e0, double &e1) {
+  double v[2] = {x0, x1};
+  exp_batch<2>(v);
+  e0 = v[0];
+  e1 = v[1];
 }
 
 // ---------------------------------------------------------------- special functions (FP64)

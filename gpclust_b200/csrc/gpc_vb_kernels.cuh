@@ -34,12 +34,16 @@ namespace gpc {
 
 constexpr int kGroupRows = 8;
 constexpr int kCtasPerSm = 1;
-constexpr int kGConsumers = 8;                     // G pass consumer warps
-constexpr int kGThreads = (kGConsumers + 1) * 32;  // + producer warp
-constexpr int kSSoftmaxWarps = 8;                  // S pass
+constexpr int kGConsumers = 10;                    // G pass consumer warps (5 units of 2; 12 warps -> 168 registers each)
+constexpr int kGThreads = (kGConsumers + 2) * 32;  // + producer warp + one idle warp (register allocation is per 4 warps)
+constexpr int kSSoftmaxWarps = 7;                  // S pass (7 + 4 + 1 = 12 warps -> 168 registers each)
 constexpr int kSStatWarps = 4;
 constexpr int kSThreads = (kSSoftmaxWarps + kSStatWarps + 1) * 32;
 constexpr int kSmemBudget = 227 * 1024;
+#ifndef GPC_L2_AHEAD
+#define GPC_L2_AHEAD 16
+#endif
+constexpr int kL2Ahead = GPC_L2_AHEAD;  // groups (per CTA) pulled into L2 ahead of the shared-memory ring: HBM latency is paid there
 
 // ------------------------------------------------------------------------------------------------
 // G pass
@@ -61,14 +65,22 @@ struct NatgradArgs {
   int N, K, DP, num_groups, stages;
 };
 
-__host__ __device__ inline int g_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP + 2 * kGroupRows; }
-__host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP + KP + kGConsumers * 4; }
+// ring stage: [F group | x group | lse (8) | lse_old (8)]; the previous-point operands x_old / ng_old go straight
+// from HBM to registers (the fragment-major layout makes those loads 512 contiguous bytes per warp instruction)
+__host__ __device__ inline int g_stage_doubles(int KP, int DP) { return kGroupRows * DP + kGroupRows * KP + 2 * kGroupRows; }
+__host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP + KP + kGConsumers * 4 + 2 * kGConsumers * kGroupRows; }
 
-// FULLK: K == KP, no column masking
+// FULLK: K == KP, no column masking.
+// Consumer warps work in units of NSPLIT warps that share one group: warp h of a unit owns the n-tiles
+// [h*NTW, (h+1)*NTW) (clusters), so the unit's row reduction sum_k phi*a is exchanged through shared memory once per
+// group.  Twice the warps per group in flight halves the time a ring stage is held.
 template <int KP, bool FULLK>
 __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
-  constexpr int XG = kGroupRows * KP;  // doubles of one N x K operand per group
+  constexpr int NSPLIT = (NT >= 2) ? 2 : 1;
+  constexpr int NTW = NT / NSPLIT;           // n-tiles per warp
+  constexpr int UNITS = kGConsumers / NSPLIT;
+  constexpr int XG = kGroupRows * KP;        // doubles of one N x K operand per group
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int DP = a.DP, FG = kGroupRows * DP, S = a.stages;
   const int stage_doubles = g_stage_doubles(KP, DP);
@@ -76,7 +88,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   double *w_s = stages + (size_t)S * stage_doubles;  // B fragments: ((ks*NT + nt)*32 + lane)
   double *bias_s = w_s + KP * DP;                     // KP
   double *red_s = bias_s + KP;                        // kGConsumers * 4
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + kGConsumers * 4);
+  double *sax_s = red_s + kGConsumers * 4;            // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sax_s + 2 * kGConsumers * kGroupRows);
   uint64_t *empty_bar = full_bar + S;
   __shared__ bool is_last;
 
@@ -87,7 +100,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], NSPLIT);
     }
     mbar_fence_init();
   }
@@ -97,12 +110,13 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
     w_s[i] = a.Wt[(size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3)];
   }
   for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = a.bias[i];
+  for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) red_s[i] = 0.0;
   __syncthreads();
 
   if (warp == kGConsumers) {
     // ---------------- producer: one elected lane streams groups into the ring
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? 2 * XG + kGroupRows : 0)) * 8u;
+      const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? kGroupRows : 0)) * 8u;
       int j = 0;
       for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
         const int s = j % S;
@@ -111,87 +125,111 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
         bulk_g2s(st + FG, a.x + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        bulk_g2s(st + FG + 3 * XG, a.lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
-        if (has_old) {
-          bulk_g2s(st + FG + XG, a.x_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-          bulk_g2s(st + FG + 2 * XG, a.ng_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-          bulk_g2s(st + FG + 3 * XG + kGroupRows, a.lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
-        }
+        bulk_g2s(st + FG + XG, a.lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
+        if (has_old) bulk_g2s(st + FG + XG + kGroupRows, a.lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
       }
     }
-  } else {
-    // ---------------- consumers: warp w owns this CTA's groups j = w, w + 8, ...
+  } else if (warp < kGConsumers) {
+    // ---------------- consumers: unit u owns this CTA's groups j = u, u + UNITS, ...
+    const int unit = warp / NSPLIT, h = warp % NSPLIT, nt0 = h * NTW;
     const int ksteps = DP / 4;
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-    int j = warp;
-    for (int grp = blockIdx.x + warp * gridDim.x; grp < a.num_groups; grp += kGConsumers * gridDim.x, j += kGConsumers) {
+    int j = unit;
+    for (int grp = blockIdx.x + unit * gridDim.x; grp < a.num_groups; grp += UNITS * gridDim.x, j += UNITS) {
       const int s = j % S;
       const double *st = stages + (size_t)s * stage_doubles;
       const int row = grp * kGroupRows + g;
       const bool row_ok = row < a.N;
+      const size_t goff = (size_t)grp * XG + (size_t)nt0 * 64 + 2 * lane;
+
+      // previous-point operands: HBM -> registers, in flight behind the DMMA loop and pass 1
+      double2 xo[NTW], ngo[NTW];
+      if (has_old) {
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) {
+          xo[i] = ldg2_stream(a.x_old + goff + i * 64);
+          ngo[i] = ldg2_stream(a.ng_old + goff + i * 64);
+        }
+      }
       mbar_wait(&full_bar[s], (uint32_t)((j / S) & 1));
 
-      double acc[NT][2];
+      double acc[NTW][2];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+      for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = 0.0;
       const double *fa = st + lane;
-      const double *wb = w_s + lane;
-#pragma unroll 2
+      const double *wb = w_s + nt0 * 32 + lane;
+#pragma unroll 4
       for (int ks = 0; ks < ksteps; ++ks) {
         const double af = fa[ks * 32];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], af, wb[(ks * NT + nt) * 32]);
+        for (int i = 0; i < NTW; ++i) dmma884(acc[i][0], acc[i][1], af, wb[(ks * NT + i) * 32]);
       }
-      const double *xs = st + FG + 2 * lane;
-      const double lse = st[FG + 3 * XG + g];
-      const double lse_o = has_old ? st[FG + 3 * XG + kGroupRows + g] : 0.0;
+      const double *xs = st + FG + nt0 * 64 + 2 * lane;
+      const double lse = st[FG + XG + g];
+      const double lse_o = has_old ? st[FG + XG + kGroupRows + g] : 0.0;
 
-      // ---- pass 1: phi = exp(x - lse), a = F.W + bias - x (in place of acc), sa = sum phi*a
-      double phi[NT][2];
-      double sa = 0.0;
+      // ---- pass 1: phi = exp(x - lse), a = F.W + bias - x (in place of acc), partial sa = sum phi*a
+      double phi[2 * NTW];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int c = 8 * nt + 2 * t;
+      for (int i = 0; i < NTW; ++i) {
+        const int c = 8 * (nt0 + i) + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double2 xv = *reinterpret_cast<const double2 *>(xs + nt * 64);
+        const double2 xv = *reinterpret_cast<const double2 *>(xs + i * 64);
         const double2 bb = *reinterpret_cast<const double2 *>(bias_s + c);
-        acc[nt][0] = ok0 ? (acc[nt][0] + bb.x) - xv.x : 0.0;
-        acc[nt][1] = ok1 ? (acc[nt][1] + bb.y) - xv.y : 0.0;
-        double p0, p1;
-        exp_pair(xv.x - lse, xv.y - lse, p0, p1);
-        phi[nt][0] = ok0 ? p0 : 0.0;
-        phi[nt][1] = ok1 ? p1 : 0.0;
-        sa += phi[nt][0] * acc[nt][0] + phi[nt][1] * acc[nt][1];
-      }
-      sa = quad_sum(sa);
-
-      // ---- pass 2: natural gradient, gradient, dots
-      double *ngo_g = a.ng_out + (size_t)grp * XG + 2 * lane;
-      double *gro_g = a.grad_out ? a.grad_out + (size_t)grp * XG + 2 * lane : nullptr;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int c = 8 * nt + 2 * t;
-        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double n0 = (ok0 && row_ok) ? acc[nt][0] - sa : 0.0;
-        const double n1 = (ok1 && row_ok) ? acc[nt][1] - sa : 0.0;
-        const double g0 = n0 * phi[nt][0], g1 = n1 * phi[nt][1];
-        stg2(ngo_g + nt * 64, n0, n1);
-        if (gro_g) stg2(gro_g + nt * 64, g0, g1);
-        d0 += n0 * g0 + n1 * g1;
-        if (has_old) {
-          const double2 xo = *reinterpret_cast<const double2 *>(xs + XG + nt * 64);
-          const double2 ngo = *reinterpret_cast<const double2 *>(xs + 2 * XG + nt * 64);
-          double po0, po1;
-          exp_pair(xo.x - lse_o, xo.y - lse_o, po0, po1);
-          if (!ok0 || !row_ok) po0 = 0.0;
-          if (!ok1 || !row_ok) po1 = 0.0;
-          const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
-          d1 += e0 * g0 + e1 * g1;
-          d2 += e0 * (ngo.x * po0) + e1 * (ngo.y * po1);
-        }
+        acc[i][0] = ok0 ? (acc[i][0] + bb.x) - xv.x : 0.0;
+        acc[i][1] = ok1 ? (acc[i][1] + bb.y) - xv.y : 0.0;
+        phi[2 * i] = xv.x - lse;
+        phi[2 * i + 1] = xv.y - lse;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (lane == 0) mbar_arrive(&empty_bar[s]);  // last read of the stage is done
+      exp_batch<2 * NTW>(phi);
+      double sa = 0.0;
+#pragma unroll
+      for (int i = 0; i < NTW; ++i) {
+        const int c = 8 * (nt0 + i) + 2 * t;
+        if (!(FULLK || c < a.K)) phi[2 * i] = 0.0;
+        if (!(FULLK || c + 1 < a.K)) phi[2 * i + 1] = 0.0;
+        sa += phi[2 * i] * acc[i][0] + phi[2 * i + 1] * acc[i][1];
+      }
+      sa = quad_sum(sa);
+      if (NSPLIT > 1) {
+        // the unit's other warp holds the rest of the row: exchange through shared memory (fixed summation order)
+        double *sx = sax_s + (((j / UNITS) & 1) * UNITS + unit) * (NSPLIT * kGroupRows);
+        if (t == 0) sx[h * kGroupRows + g] = sa;
+        asm volatile("bar.sync %0, %1;\n" ::"r"(1 + unit), "n"(NSPLIT * 32) : "memory");
+        sa = sx[g] + sx[kGroupRows + g];
+      }
+
+      // ---- pass 2: natural gradient, gradient, dots
+      double po[2 * NTW];
+      if (has_old) {
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) {
+          po[2 * i] = xo[i].x - lse_o;
+          po[2 * i + 1] = xo[i].y - lse_o;
+        }
+        exp_batch<2 * NTW>(po);
+      }
+      double *ngo_g = a.ng_out + goff;
+      double *gro_g = a.grad_out ? a.grad_out + goff : nullptr;
+#pragma unroll
+      for (int i = 0; i < NTW; ++i) {
+        const int c = 8 * (nt0 + i) + 2 * t;
+        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const double n0 = (ok0 && row_ok) ? acc[i][0] - sa : 0.0;
+        const double n1 = (ok1 && row_ok) ? acc[i][1] - sa : 0.0;
+        const double g0 = n0 * phi[2 * i], g1 = n1 * phi[2 * i + 1];
+        stg2(ngo_g + i * 64, n0, n1);
+        if (gro_g) stg2(gro_g + i * 64, g0, g1);
+        d0 += n0 * g0 + n1 * g1;
+        if (has_old) {
+          const double po0 = (ok0 && row_ok) ? po[2 * i] : 0.0, po1 = (ok1 && row_ok) ? po[2 * i + 1] : 0.0;
+          const double e0 = n0 - ngo[i].x, e1 = n1 - ngo[i].y;
+          d1 += e0 * g0 + e1 * g1;
+          d2 += e0 * (ngo[i].x * po0) + e1 * (ngo[i].y * po1);
+        }
+      }
     }
     d0 = warp_sum(d0);
     d1 = warp_sum(d1);
@@ -301,6 +339,15 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       int j = 0;
       for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
         const int s = j % S;
+        if (kL2Ahead > 0) {
+          const long long pg = (long long)grp + (long long)kL2Ahead * gridDim.x;
+          if (pg < a.num_groups) {
+            bulk_prefetch_l2(a.F + (size_t)pg * FG, FG * 8u);
+            bulk_prefetch_l2(a.x_base + (size_t)pg * XG, XG * 8u);
+            if (has_ng) bulk_prefetch_l2(a.ng + (size_t)pg * XG, XG * 8u);
+            if (use_old) bulk_prefetch_l2(a.sd_old + (size_t)pg * XG, XG * 8u);
+          }
+        }
         if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
         double *st = stages + (size_t)s * stage_doubles;
         mbar_arrive_expect_tx(&full_bar[s], bytes);
@@ -356,18 +403,23 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       }
       m = quad_max(m);
       double ssum = 0.0, px = 0.0;
+      double ex[2 * NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        x[nt][0] -= m;
+        x[nt][1] -= m;
+        ex[2 * nt] = x[nt][0];
+        ex[2 * nt + 1] = x[nt][1];
+      }
+      exp_batch<2 * NT>(ex);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double z0 = x[nt][0] - m, z1 = x[nt][1] - m;
-        double e0, e1;
-        exp_pair(z0, z1, e0, e1);
-        if (!ok0) e0 = 0.0;
-        if (!ok1) e1 = 0.0;
+        const double e0 = ok0 ? ex[2 * nt] : 0.0, e1 = ok1 ? ex[2 * nt + 1] : 0.0;
         ssum += e0 + e1;
-        if (ok0) px += e0 * z0;
-        if (ok1) px += e1 * z1;
+        if (ok0) px += e0 * x[nt][0];
+        if (ok1) px += e1 * x[nt][1];
         x[nt][0] = e0;
         x[nt][1] = e1;
       }
@@ -410,22 +462,27 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       const double *pa = st + FG + lane;
       // B fragment of F for (ks', dt): lane (g, t) reads F[row 4ks'+t][8dt+g] = st[(2dt + g/4)*32 + (4ks'+t)*4 + g%4]
       const double *fb = st + (g >> 2) * 32 + t * 4 + (g & 3);
+      // all fragments of the group first (one shared-memory round trip per group), then the 2*TPW DMMAs back to back
+      double af[2][NT], bf[2][2];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        double af[NT];
 #pragma unroll
-        for (int mt = 0; mt < NT; ++mt) {
-          af[mt] = pa[(mt * 2 + ks) * 32];
-          colsum[mt] += af[mt];
-        }
+        for (int mt = 0; mt < NT; ++mt) af[ks][mt] = pa[(mt * 2 + ks) * 32];
 #pragma unroll
-        for (int i = 0; i < TPW; ++i) {
-          const int mt = i >> 1, dt = ((i & 1) << 2) + q;  // tile ti = 4*i + q
-          if (dt < DT) dmma884(acc[i][0], acc[i][1], af[mt], fb[dt * 64 + ks * 16]);
+        for (int e = 0; e < 2; ++e) {
+          const int dt = (e << 2) + q;
+          bf[ks][e] = (dt < DT) ? fb[dt * 64 + ks * 16] : 0.0;
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (lane == 0) mbar_arrive(&empty_bar[s]);  // the stage is in registers now
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) colsum[mt] += af[ks][mt];
+#pragma unroll
+        for (int i = 0; i < TPW; ++i) dmma884(acc[i][0], acc[i][1], af[ks][i >> 1], bf[ks][i & 1]);  // tile (mt = i/2, dt = 4*(i%2) + q)
+      }
     }
     // ---- per-CTA partial statistics
 #pragma unroll
