@@ -88,6 +88,16 @@ class MOG(CollapsedMixture):
                                    _cabi.PRIOR[self.prior_Z], self.K, self._KP, self._DP, self.D, self._stream()), "gpc_mog_finalize")
         self.kernel_launches += 1
 
+    def _loop_posterior(self, phase):
+        check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+        self._allreduce(self._stats)
+        check(lib.gpc_loop_mog_post(ptr(self._stats), ptr(self._m0c_dev), ptr(self._S0_dev), ptr(self._Wt), ptr(self._per_k), ptr(self._mun_c),
+                                    ptr(self._Sns), ptr(self._Sns_inv), self._info_ptr(), float(self.k0), float(self.v0), ptr(self._bias),
+                                    ptr(self._ctrl), ptr(self._mixgrad), float(self.N_total), float(self.S0_halflogdet), float(self.alpha),
+                                    _cabi.PRIOR[self.prior_Z], self.K, self.D, self._KP, self._DP, ptr(self._ctrl[3:]), ptr(self._ctrl[6:]),
+                                    ptr(self._loop_dev), phase, self._stream()), "gpc_loop_mog_post")
+        self.kernel_launches += 3
+
     # ---- reference attributes (MOG.py:54-61), K LAST as in the reference
     @property
     def kNs(self):

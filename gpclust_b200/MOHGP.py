@@ -65,7 +65,7 @@ class MOHGP(CollapsedMixture):
         if self._Y_host is None:
             out = self.torch.empty((self.N, self.D), dtype=self.torch.float64, device=self.device)
             check(lib.gpc_unpack_rows(ptr(self._F), self.N, self.D, self._DP, _cabi.LAYOUT["features"], ptr(out), self._stream()), "gpc_unpack_rows")
-            self._Y_host = out.cpu().numpy()
+            self._Y_host = _cabi.to_host(out)
         return self._Y_host
 
     def _alloc_model(self):
@@ -120,6 +120,21 @@ class MOHGP(CollapsedMixture):
                                  ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias), ptr(self._ctrl),
                                  ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z],
                                  self.K, self.D, self._KP, self._DP, self._stream()), "gpc_mohgp_post")
+        self.kernel_launches += 1
+
+    def _loop_posterior(self, phase):
+        if self._world > 1:
+            check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+            self.kernel_launches += 1
+            self._allreduce(self._stats)
+            parts, nparts = self._stats, 1
+        else:
+            parts, nparts = self._spart, self._grid
+        check(lib.gpc_loop_mohgp_post(ptr(parts), nparts, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
+                                      ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias), ptr(self._ctrl),
+                                      ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z],
+                                      self.K, self.D, self._KP, self._DP, ptr(self._ctrl[3:]), ptr(self._ctrl[6:]), ptr(self._loop_dev), phase,
+                                      self._stream()), "gpc_loop_mohgp_post")
         self.kernel_launches += 1
 
     def _dense_posterior(self):

@@ -289,6 +289,9 @@ class OMGP(CollapsedMixture):
             samples.append(np.random.multivariate_normal(mean=mu[:, i], cov=cov, size=size))
         return np.stack(samples, -1)
 
+    def _device_loop_ok(self):
+        return False  # every bound evaluation needs the host (jitchol retry per component): host-driven loop
+
     # merge/split over sharded rows is meaningless here (single process)
     def _is_root(self):
         return True

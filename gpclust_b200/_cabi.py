@@ -34,6 +34,8 @@ PROTOTYPES = {
     "gpc_default_grid": [_i],
     "gpc_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_step_stats": [_p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
@@ -41,10 +43,12 @@ PROTOTYPES = {
     "gpc_mohgp_eig_ws_len": [_i],
     "gpc_mohgp_eig": [_p, _p, _p, _p, _p, _i, _p, _p],
     "gpc_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p],
+    "gpc_loop_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "gpc_mohgp_finalize": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p],
     "gpc_mog_features": [_p, _p, _ll, _i, _i, _p, _p],
     "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],
     "gpc_mog_finalize": [_p, _p, _p, _p, _p, _d, _d, _d, _d, _d, _i, _i, _i, _i, _i, _p],
+    "gpc_loop_mog_post": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _d, _d, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "gpc_kern_fill": [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _d, _p, _p],
     "gpc_omgp_padded_n": [_ll],
     "gpc_omgp_slabs": [_ll],
@@ -66,6 +70,21 @@ PROTOTYPES = {
     "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
 }
 _RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll}
+
+
+class GpcBufs(ctypes.Structure):
+    """gpc_bufs_t of include/gpclust_b200.h"""
+    _fields_ = [("x", _p * 3), ("lse", _p * 3), ("ng", _p * 2), ("sd", _p)]
+
+
+class GpcLoop(ctypes.Structure):
+    """gpc_loop_t of include/gpclust_b200.h (the trace rows follow it in device memory)"""
+    _fields_ = [("bound_old", _d), ("sq_old", _d), ("ftol", _d), ("gtol", _d), ("maxiter", _d), ("step", _d),
+                ("iteration", _i), ("method", _i), ("first", _i), ("xi", _i), ("xprev", _i), ("xtrial", _i), ("ngi", _i),
+                ("need_retry", _i), ("done", _i), ("n_trace", _i), ("trace_cap", _i), ("pad", _i)]
+
+
+DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT = 1, 2, 4, 8
 
 
 class GpclustLibraryError(RuntimeError):
@@ -137,3 +156,15 @@ def require_cuda():
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def to_host(t):
+    """Device tensor -> numpy array through PINNED host memory (torch's caching host allocator keeps the staging
+    blocks, so repeated read-outs of N x K arrays run at PCIe speed instead of the pageable-copy rate)."""
+    import torch
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()

@@ -80,6 +80,8 @@ class CollapsedMixture(CollapsedVB):
         self._gpart = torch.zeros(self._grid * 4, dtype=torch.float64, device=self.device)
         self._state_valid = False
         self._bound_value = None
+        self._loop_dev = None   # gpc_loop_t + trace rows (device-resident loop state), allocated on first optimize()
+        self._loop_host = None
         self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
         self._kernel_events = None  # bench.py: {"natgrad": [(start, end), ...], "step_stats": [...]} CUDA events
 
@@ -159,6 +161,7 @@ class CollapsedMixture(CollapsedVB):
         self._xprev = None
         self._xtrial = (self._xi + 1) % 3
         self._state_valid = False
+        self._pass_state = None
         self._cache = {}
 
     # ------------------------------------------------------------------ reference API: parameters
@@ -178,7 +181,7 @@ class CollapsedMixture(CollapsedVB):
 
     @property
     def phi_(self):
-        return self._unpad(self._xbuf[self._xi]).cpu().numpy()
+        return _cabi.to_host(self._unpad(self._xbuf[self._xi]))
 
     @phi_.setter
     def phi_(self, value):
@@ -206,11 +209,11 @@ class CollapsedMixture(CollapsedVB):
 
     @property
     def phi(self):
-        return self._softmax_readout()[0].cpu().numpy()
+        return _cabi.to_host(self._softmax_readout()[0])
 
     @property
     def Hgrad(self):
-        return (-self._softmax_readout()[1]).cpu().numpy()  # collapsed_mixture.py:56
+        return _cabi.to_host(-self._softmax_readout()[1])  # collapsed_mixture.py:56
 
     def _ensure_state(self):
         if not self._state_valid:
@@ -346,6 +349,124 @@ class CollapsedMixture(CollapsedVB):
         self._state_valid = not self._trial_failed
         self._cache = {}
 
+    # ------------------------------------------------------------------ device-resident loop (collapsed_vb.py:143-303)
+    _TRACE_CAP = 64   # trace rows kept on the device between two read-backs
+    _BATCH = 16       # loop-body passes enqueued per read-back
+
+    def _device_loop_ok(self):
+        return True
+
+    def _bufs(self):
+        b = _cabi.GpcBufs()
+        for i in range(3):
+            b.x[i] = self._xbuf[i].data_ptr()
+            b.lse[i] = self._lsebuf[i].data_ptr()
+        for i in range(2):
+            b.ng[i] = self._ngbuf[i].data_ptr()
+        b.sd = self._sd.data_ptr()
+        return b
+
+    def _loop_upload(self, L):
+        torch = self.torch
+        nbytes = ctypes.sizeof(_cabi.GpcLoop) + self._TRACE_CAP * 32
+        if self._loop_dev is None:
+            self._loop_dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._loop_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        ctypes.memmove(self._loop_host.data_ptr(), ctypes.addressof(L), ctypes.sizeof(_cabi.GpcLoop))
+        self._loop_dev[:ctypes.sizeof(_cabi.GpcLoop)].copy_(self._loop_host[:ctypes.sizeof(_cabi.GpcLoop)], non_blocking=True)
+
+    def _loop_download(self):
+        """-> (gpc_loop_t snapshot, trace rows [(iteration, bound, squareNorm, beta), ...]); one D2H copy + sync."""
+        self._loop_host.copy_(self._loop_dev, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        raw = ctypes.string_at(self._loop_host.data_ptr(), self._loop_host.numel())
+        L = _cabi.GpcLoop.from_buffer_copy(raw[:ctypes.sizeof(_cabi.GpcLoop)])
+        rows = np.frombuffer(raw[ctypes.sizeof(_cabi.GpcLoop):], dtype=np.float64).reshape(-1, 4)[:L.n_trace]
+        return L, [(int(r[0]), float(r[1]), float(r[2]), float(r[3])) for r in rows]
+
+    def _loop_posterior(self, phase):
+        """Subclass hook: statistics -> posterior -> bound -> device-side accept / reject for `phase`."""
+        raise NotImplementedError
+
+    def _enqueue_pass(self, bufs):
+        """One pass of the loop body collapsed_vb.py:152-193 as a fixed launch sequence; nothing is read back."""
+        lp, st = ptr(self._loop_dev), self._stream()
+        dots, beta = ptr(self._ctrl[_C_SQ:]), ptr(self._ctrl[_C_BETA:])
+        with self._timed("natgrad"):
+            check(lib.gpc_loop_natgrad(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._counter), dots, lp,
+                                       self.N, self.K, self._KP, self._DP, self._grid, st), "gpc_loop_natgrad")
+        if self._world > 1:
+            self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
+        for phase in (0, 1):  # GPC_PHASE_CONJ, GPC_PHASE_RETRY (the latter returns at once unless the bound fell)
+            with self._timed("step_stats" if phase == 0 else "step_stats_retry"):
+                check(lib.gpc_loop_step_stats(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, phase, self.N, self.K, self._KP,
+                                              self._DP, self._grid, st), "gpc_loop_step_stats")
+            with self._timed("posterior" if phase == 0 else "posterior_retry"):
+                self._loop_posterior(phase)
+        self.kernel_launches += 3
+
+    def _loop_sync_host(self, L):
+        """Adopt the device loop state on the host side (buffer selectors, bound, control block)."""
+        self._xi, self._xprev, self._xtrial, self._ngi = L.xi, (None if L.xprev < 0 else L.xprev), L.xtrial, L.ngi
+        self._readback()
+        self._bound_value = L.bound_old
+        self._state_valid = True
+        self._cache = {}
+
+    def _run_on_device(self, method, maxiter, ftol, gtol, step_length, iteration, bound_old, sq_old, first, say=False, max_passes=None):
+        """Drive the loop from the device-resident state until it terminates (or `max_passes` passes were enqueued).
+        -> (iteration, bound_old, sq_old, first, done bits, trace rows)"""
+        self._ensure_state()
+        L = _cabi.GpcLoop()
+        L.bound_old, L.sq_old, L.ftol, L.gtol, L.maxiter, L.step = bound_old, sq_old, ftol, gtol, float(maxiter), step_length
+        L.iteration, L.method, L.first = iteration, _cabi.BETA["zero" if method == "steepest" else method], int(first)
+        L.xi, L.xprev, L.xtrial, L.ngi = self._xi, (-1 if self._xprev is None else self._xprev), self._xtrial, self._ngi
+        L.need_retry = L.done = L.n_trace = 0
+        L.trace_cap = self._TRACE_CAP
+        self._loop_upload(L)
+        bufs = self._bufs()
+        rows_all, passes = [], 0
+        while True:
+            remaining = max(1, int(np.ceil(float(maxiter) - L.iteration))) if np.isfinite(maxiter) else self._BATCH
+            n = min(self._BATCH, remaining)
+            if max_passes is not None:
+                n = min(n, max_passes - passes)
+            for _ in range(n):
+                self._enqueue_pass(bufs)
+            passes += n
+            L, rows = self._loop_download()
+            rows_all.extend(rows)
+            if say:
+                for it, b, sq, beta in rows:
+                    sys.stdout.write("\riteration " + str(it) + " bound=" + str(b) + " grad=" + str(sq) + ", beta=" + str(beta) + "\n")
+                sys.stdout.flush()
+            if L.done or (max_passes is not None and passes >= max_passes):
+                break
+            # rewind the trace cursor for the next batch (a 4-byte field; everything else stays device-owned)
+            off = _cabi.GpcLoop.n_trace.offset
+            self._loop_dev[off:off + 4].zero_()
+        self._loop_sync_host(L)
+        return L.iteration, L.bound_old, L.sq_old, bool(L.first), L.done, rows_all
+
+    def run_passes(self, n, method="HS", step_length=1.0):
+        """Exactly n passes of the loop body with the termination tests disabled (bench / profiling): one enqueue,
+        one read-back.  -> trace rows."""
+        self._ensure_state()
+        st = getattr(self, "_pass_state", None)
+        if st is None or st["xi"] != self._xi:
+            st = {"iteration": 0, "bound_old": self.bound(), "sq_old": 0.0, "first": True}
+        cap, self._TRACE_CAP = self._TRACE_CAP, max(self._TRACE_CAP, n)
+        if self._loop_dev is not None and self._loop_dev.numel() < ctypes.sizeof(_cabi.GpcLoop) + self._TRACE_CAP * 32:
+            self._loop_dev = None
+        batch, self._BATCH = self._BATCH, n
+        try:
+            it, b, sq, first, done, rows = self._run_on_device(method, np.inf, -1.0, -1.0, step_length, st["iteration"], st["bound_old"], st["sq_old"],
+                                                               st["first"], max_passes=n)
+        finally:
+            self._BATCH = batch
+        self._pass_state = {"iteration": it, "bound_old": b, "sq_old": sq, "first": first, "xi": self._xi}
+        return rows
+
     def vb_grad_natgrad(self):
         """Flattened (grad, natgrad) as numpy arrays -- the reference's return convention
         (MOHGP.py:137-153, MOG.py:72-84).  Does not disturb the optimiser's device state."""
@@ -359,7 +480,7 @@ class CollapsedMixture(CollapsedVB):
                               ptr(self._gpart), ptr(self._counter), ptr(dots), self.N, self.K, self._KP, self._DP, self._grid,
                               self._stream()), "gpc_natgrad")
         self.kernel_launches += 1
-        return self._unpad(gr).cpu().numpy().flatten(), self._unpad(ng).cpu().numpy().flatten()
+        return _cabi.to_host(self._unpad(gr)).reshape(-1), _cabi.to_host(self._unpad(ng)).reshape(-1)
 
     # ------------------------------------------------------------------ merge / split search (host control)
     def reorder(self):

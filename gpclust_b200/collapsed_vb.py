@@ -73,6 +73,12 @@ class CollapsedVB(object):
     def _is_root(self):
         return True
 
+    def _device_loop_ok(self):
+        return False
+
+    def _run_on_device(self, *args, **kwargs):
+        raise NotImplementedError
+
     def _cg_iteration(self, first, method, step_length, bound_old, squareNorm_old):
         """One pass of the loop body collapsed_vb.py:152-193 -> (bound, squareNorm, beta, bound evaluations)."""
         # :152-167 -- gradient at the accepted point, beta, search direction (HS / PR need the previous point)
@@ -103,12 +109,24 @@ class CollapsedVB(object):
         iteration = 0
         bound_old = self.bound()
         squareNorm_old = 0.0
+        first = True
         self.optimize_trace = []
+        if callback is None and self.optimizer_array.size == 0 and self._device_loop_ok():
+            # no per-iteration host work is required: accept / reject and the termination tests run on the device,
+            # the host enqueues batches of passes and reads the trace back once per batch
+            iteration, bound_old, squareNorm_old, first, done, rows = self._run_on_device(method, maxiter, ftol, gtol, step_length, iteration,
+                                                                                       bound_old, squareNorm_old, first, say=say)
+            self.optimize_trace.extend(rows)
+            if not (done & 8):  # GPC_DONE_FAULT: a factorisation failed twice -> continue below on the host path
+                if say:  # the reference tests ftol, gtol, maxiter in this order and breaks at the first hit (collapsed_vb.py:229-291)
+                    print("vb converged (ftol)" if done & 1 else ("vb converged (gtol)" if done & 2 else "maxiter exceeded"))
+                return iteration
         while True:
             if callback is not None:
                 callback()
 
-            bound, squareNorm, beta, evals = self._cg_iteration(not iteration, method, step_length, bound_old, squareNorm_old)
+            bound, squareNorm, beta, evals = self._cg_iteration(first, method, step_length, bound_old, squareNorm_old)
+            first = False
             iteration += evals
 
             self.optimize_trace.append((iteration, bound, squareNorm, beta))

@@ -21,14 +21,18 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 // ring depth: as many group stages as fit next to the fixed part in the 227 KB of one SM (capped)
 constexpr int kMaxStages = 24;
+constexpr int kMaxUnitSlots = 4;
 int natgrad_stages(int KP, int DP) {
+  // every unit of consumer warps owns the same number of ring slots (at most kMaxUnitSlots)
+  const int units = kGConsumers / ((KP / 8 >= 2) ? 2 : 1);
   const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;
-  const size_t per = sizeof(double) * (size_t)g_stage_doubles(KP, DP) + 2 * sizeof(uint64_t);
-  const int s = (int)((kSmemBudget - fixed) / per);
-  return s > kMaxStages ? kMaxStages : s;
+  const size_t per = sizeof(double) * (size_t)g_stage_doubles(KP, DP) + sizeof(uint64_t);
+  int r = (int)((kSmemBudget - fixed) / per) / units;
+  if (r > kMaxUnitSlots) r = kMaxUnitSlots;
+  return r * units;
 }
 size_t natgrad_smem(int KP, int DP, int S) {
-  return sizeof(double) * ((size_t)S * g_stage_doubles(KP, DP) + g_fixed_doubles(KP, DP)) + sizeof(uint64_t) * 2 * S;
+  return sizeof(double) * ((size_t)S * g_stage_doubles(KP, DP) + g_fixed_doubles(KP, DP)) + sizeof(uint64_t) * S;
 }
 int step_stats_stages(int KP, int DP) {
   const size_t fixed = sizeof(double) * kSSoftmaxWarps + 64;
@@ -109,13 +113,43 @@ int gpc_default_grid(int device) {
   return sms * kCtasPerSm;
 }
 
+namespace {
+int dispatch_natgrad(NatgradArgs &a, int KP, int grid, cudaStream_t st) {
+  if (grid > a.num_groups) grid = a.num_groups;
+  switch (KP) {
+    case 8: return launch_natgrad<8>(a, grid, st);
+    case 16: return launch_natgrad<16>(a, grid, st);
+    case 32: return launch_natgrad<32>(a, grid, st);
+    case 64: return launch_natgrad<64>(a, grid, st);
+  }
+  return GPC_EINVAL;
+}
+int dispatch_step_stats(StepStatsArgs &a, int KP, int grid, cudaStream_t st) {
+  // NOTE: every CTA of the launch grid writes one partial block, so the grid is NOT clamped here:
+  // CTAs without a group write zeros.
+  switch (KP) {
+    case 8: return launch_step_stats<8>(a, grid, st);
+    case 16: return launch_step_stats<16>(a, grid, st);
+    case 32: return launch_step_stats<32>(a, grid, st);
+    case 64: return launch_step_stats<64>(a, grid, st);
+  }
+  return GPC_EINVAL;
+}
+bool bufs_ok(const gpc_bufs_t *b) {
+  if (!b || !b->sd) return false;
+  for (int i = 0; i < 3; ++i)
+    if (!b->x[i] || !b->lse[i]) return false;
+  return b->ng[0] && b->ng[1];
+}
+}  // namespace
+
 int gpc_natgrad(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, const double *x_old,
                 const double *lse_old, const double *ng_old, double *ng_out, double *grad_out, double *partials, unsigned int *counter,
                 double *dots, long long N, int K, int KP, int DP, int grid, void *stream) {
   if (!F || !x || !lse || !Wt || !bias || !ng_out || !partials || !counter || !dots) return GPC_EINVAL;
   if ((x_old == nullptr) != (ng_old == nullptr) || (x_old == nullptr) != (lse_old == nullptr)) return GPC_EINVAL;
-  if (!geometry_ok(N, K, KP, DP, grid)) return GPC_EINVAL;
-  NatgradArgs a;
+  if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
+  NatgradArgs a{};
   a.F = F;
   a.x = x;
   a.lse = lse;
@@ -133,16 +167,28 @@ int gpc_natgrad(const double *F, const double *x, const double *lse, const doubl
   a.K = K;
   a.DP = DP;
   a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
-  if (N > 0x7fffffffLL) return GPC_EINVAL;
-  if (grid > a.num_groups) grid = a.num_groups;
-  cudaStream_t st = as_stream(stream);
-  switch (KP) {
-    case 8: return launch_natgrad<8>(a, grid, st);
-    case 16: return launch_natgrad<16>(a, grid, st);
-    case 32: return launch_natgrad<32>(a, grid, st);
-    case 64: return launch_natgrad<64>(a, grid, st);
-  }
-  return GPC_EINVAL;
+  a.loop = nullptr;
+  return dispatch_natgrad(a, KP, grid, as_stream(stream));
+}
+
+int gpc_loop_natgrad(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                     double *dots, const gpc_loop_t *loop, long long N, int K, int KP, int DP, int grid, void *stream) {
+  if (!F || !bufs_ok(bufs) || !Wt || !bias || !partials || !counter || !dots || !loop) return GPC_EINVAL;
+  if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
+  NatgradArgs a{};
+  a.F = F;
+  a.Wt = Wt;
+  a.bias = bias;
+  a.partials = partials;
+  a.counter = counter;
+  a.dots_out = dots;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.loop = loop;
+  a.bufs = *bufs;
+  return dispatch_natgrad(a, KP, grid, as_stream(stream));
 }
 
 int gpc_step_stats(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
@@ -153,7 +199,7 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
   if (beta_mode != GPC_BETA_ZERO && (!dots || !ng)) return GPC_EINVAL;
   if (beta_mode < GPC_BETA_ZERO || beta_mode > GPC_BETA_FR) return GPC_EINVAL;
   if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
-  StepStatsArgs a;
+  StepStatsArgs a{};
   a.F = F;
   a.x_base = x_base;
   a.ng = ng;
@@ -171,16 +217,29 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
   a.K = K;
   a.DP = DP;
   a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
-  // NOTE: every CTA of the launch grid writes one partial block, so the grid is NOT clamped here:
-  // CTAs without a tile write zeros.
-  cudaStream_t st = as_stream(stream);
-  switch (KP) {
-    case 8: return launch_step_stats<8>(a, grid, st);
-    case 16: return launch_step_stats<16>(a, grid, st);
-    case 32: return launch_step_stats<32>(a, grid, st);
-    case 64: return launch_step_stats<64>(a, grid, st);
-  }
-  return GPC_EINVAL;
+  a.loop = nullptr;
+  a.phase = GPC_PHASE_CONJ;
+  return dispatch_step_stats(a, KP, grid, as_stream(stream));
+}
+
+int gpc_loop_step_stats(const double *F, const gpc_bufs_t *bufs, const double *dots, double *beta_out, double *partials,
+                        const gpc_loop_t *loop, int phase, long long N, int K, int KP, int DP, int grid, void *stream) {
+  if (!F || !bufs_ok(bufs) || !dots || !beta_out || !partials || !loop) return GPC_EINVAL;
+  if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
+  if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
+  StepStatsArgs a{};
+  a.F = F;
+  a.dots = dots;
+  a.beta_out = beta_out;
+  a.partials = partials;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.loop = loop;
+  a.bufs = *bufs;
+  a.phase = phase;
+  return dispatch_step_stats(a, KP, grid, as_stream(stream));
 }
 
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
@@ -247,21 +306,31 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
   return launch_rc();
 }
 
-int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
-                   const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
-                   double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream) {
+int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                        const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
+                        double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP,
+                        const double *dots, const double *beta, gpc_loop_t *loop, int phase, void *stream) {
   if (!partials || num_parts < 1 || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !Wt || !muk_t || !per_k || !bias || !scalars ||
       !counter || !info)
     return GPC_EINVAL;
   if (K < 1 || K > KP || KP > GPC_MAX_KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  if (loop && (!dots || !beta || (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY))) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
+  // the flag word is cleared by a tiny kernel-ordered memset; in loop mode a skipped evaluation leaves it cleared too
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpPostArgs a{partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
-                  counter, info, alpha, prior, K, D, KP, DP};
+                  counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase};
   k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
   return launch_rc();
+}
+
+int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                   const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
+                   double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream) {
+  return gpc_loop_mohgp_post(partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
+                             counter, info, alpha, prior, K, D, KP, DP, nullptr, nullptr, nullptr, GPC_PHASE_CONJ, stream);
 }
 
 int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
@@ -288,7 +357,7 @@ int gpc_mog_cluster(const double *stats, const double *m0c, const double *S0, do
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
-  MogClusterArgs a{stats, m0c, S0, Wt, per_k, mun_c, Sns, Sns_inv, info, k0, v0, K, D, KP, DP};
+  MogClusterArgs a{stats, m0c, S0, Wt, per_k, mun_c, Sns, Sns_inv, info, k0, v0, K, D, KP, DP, nullptr, GPC_PHASE_CONJ};
   k_mog_cluster<<<(KP + 31) / 32, 32, 0, st>>>(a);
   return launch_rc();
 }
@@ -297,8 +366,26 @@ int gpc_mog_finalize(const double *stats, const double *per_k, double *bias, dou
                      double k0, double v0, double S0_halflogdet, double alpha, int prior, int K, int KP, int DP, int D, void *stream) {
   if (!stats || !per_k || !bias || !scalars || K < 1 || K > KP || KP > kMaxMixK) return GPC_EINVAL;
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
-  MogFinalizeArgs a{stats, per_k, bias, scalars, mixgrad_out, n_total, k0, v0, S0_halflogdet, alpha, prior, K, KP, DP, D};
+  MogFinalizeArgs a{stats, per_k, bias, scalars, mixgrad_out, n_total, k0, v0, S0_halflogdet, alpha, prior, K, KP, DP, D, nullptr, nullptr, nullptr, nullptr, GPC_PHASE_CONJ};
   k_mog_finalize<<<1, kClusterThreads, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_loop_mog_post(const double *stats, const double *m0c, const double *S0, double *Wt, double *per_k, double *mun_c, double *Sns,
+                      double *Sns_inv, int *info, double k0, double v0, double *bias, double *scalars, double *mixgrad_out, double n_total,
+                      double S0_halflogdet, double alpha, int prior, int K, int D, int KP, int DP, const double *dots, const double *beta,
+                      gpc_loop_t *loop, int phase, void *stream) {
+  if (!stats || !m0c || !S0 || !Wt || !per_k || !mun_c || !Sns || !Sns_inv || !info || !bias || !scalars || !dots || !beta || !loop) return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > kMaxMixK || D < 1 || D > kMogMaxD || D * (D + 1) / 2 + D > DP) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MogClusterArgs c{stats, m0c, S0, Wt, per_k, mun_c, Sns, Sns_inv, info, k0, v0, K, D, KP, DP, loop, phase};
+  k_mog_cluster<<<(KP + 31) / 32, 32, 0, st>>>(c);
+  MogFinalizeArgs f{stats, per_k, bias, scalars, mixgrad_out, n_total, k0, v0, S0_halflogdet, alpha, prior, K, KP, DP, D, dots, beta, info, loop, phase};
+  k_mog_finalize<<<1, kClusterThreads, 0, st>>>(f);
   return launch_rc();
 }
 

@@ -414,6 +414,55 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-side tail of one bound evaluation inside the conjugate natural-gradient loop (one thread):
+// accept / reject (collapsed_vb.py:170-193), buffer rotation, iteration count, trace row, termination tests
+// (collapsed_vb.py:229-291 with optimize_parameters() == 0, i.e. no free kernel parameters), carry-over (:294-303).
+__device__ inline void cg_decide(gpc_loop_t *L, int phase, double bound_trial, bool failed, double sq, double beta) {
+  const double bound_old = L->bound_old;
+  int evals = 1;
+  if (phase == GPC_PHASE_CONJ) {
+    const double bound = failed ? bound_old - 1.0 : bound_trial;  // collapsed_vb.py:174-176
+    if (bound < bound_old) {                                       // :182 -- fall back to the steepest step
+      L->need_retry = 1;
+      return;
+    }
+    bound_trial = bound;
+  } else {
+    L->need_retry = 0;
+    if (failed) {  // :187-190 -- the host restores the accepted point and carries on from there
+      L->done |= GPC_DONE_FAULT;
+      return;
+    }
+    evals = 2;
+  }
+  // the trial point becomes the accepted point: rotate the logits buffers, swap the natural-gradient buffers
+  const int xi = L->xi, xp = L->xprev, xt = L->xtrial;
+  const int free_buf = (xp >= 0) ? xp : 3 - xi - xt;
+  L->xprev = xi;
+  L->xi = xt;
+  L->xtrial = free_buf;
+  L->ngi = 1 - L->ngi;
+  L->first = 0;
+  const int iteration = L->iteration + evals;
+  L->iteration = iteration;
+  if (L->n_trace < L->trace_cap) {
+    double *row = reinterpret_cast<double *>(L + 1) + 4 * L->n_trace;
+    row[0] = (double)iteration;
+    row[1] = bound_trial;
+    row[2] = sq;
+    row[3] = beta;
+    L->n_trace += 1;
+  }
+  int done = 0;
+  if (fabs(bound_trial - bound_old) <= L->ftol) done |= GPC_DONE_FTOL;
+  if (sq <= L->gtol) done |= GPC_DONE_GTOL;
+  if ((double)iteration >= L->maxiter) done |= GPC_DONE_MAXITER;
+  L->done = done;
+  L->sq_old = sq;
+  L->bound_old = bound_trial;
+}
+
 struct MohgpFinalizeArgs {
   const double *stats;  // [ybark | phi_hat | H]
   const double *per_k;  // KP x 4
@@ -606,6 +655,10 @@ struct MohgpPostArgs {
   int *info;               // NOT cleared here: the caller's flag word (cleared by the launcher)
   double alpha;
   int prior, K, D, KP, DP;
+  const double *dots;  // loop mode: [0] = natgrad.grad of the G pass
+  const double *beta;  // loop mode: beta of the conjugate S pass
+  gpc_loop_t *loop;    // nullable
+  int phase;
 };
 
 // y[r] = sum_j Mt[j*D + r] x[j]  for r < D, all 256 threads (4 j-groups), result in out_s[r]; x in shared memory.
@@ -630,6 +683,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   __shared__ MixScratch scratch;
   __shared__ double mix_s;
   __shared__ bool is_last;
+  if (loop_skip(a.loop, a.phase)) return;
   const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
   const int r = tid & 63, pg = tid >> 6;
   const int len = KP * DP + KP + 2;
@@ -808,10 +862,12 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
         ldd += __ldcg(a.per_k + kk * 4 + 0);
         quad += __ldcg(a.per_k + kk * 4 + 1);
       }
-      a.scalars[0] = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
+      const double bound = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
+      a.scalars[0] = bound;
       a.scalars[1] = mix_s;
       a.scalars[2] = H;
       *a.counter = 0u;
+      if (a.loop) cg_decide(a.loop, a.phase, bound, atomicOr(a.info, 0) != 0, a.dots[0], a.beta[0]);
     }
     for (int kk = tid; kk < KP; kk += blockDim.x)
       a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
@@ -835,11 +891,14 @@ struct MogClusterArgs {
   int *info;
   double k0, v0;
   int K, D, KP, DP;
+  const gpc_loop_t *loop;  // nullable
+  int phase;
 };
 
 constexpr int kMogMaxD = 10;
 
 __global__ void k_mog_cluster(const MogClusterArgs a) {
+  if (loop_skip(a.loop, a.phase)) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.KP) return;
   const int D = a.D;
@@ -958,6 +1017,11 @@ struct MogFinalizeArgs {
   double *mixgrad_out;  // nullable
   double n_total, k0, v0, S0_halflogdet, alpha;
   int prior, K, KP, DP, D;
+  const double *dots;  // loop mode
+  const double *beta;
+  const int *info;
+  gpc_loop_t *loop;    // nullable
+  int phase;
 };
 
 __device__ inline double lngammad_dev(double v, int D) {  // np_utilities.py:62-64
@@ -967,6 +1031,7 @@ __device__ inline double lngammad_dev(double v, int D) {  // np_utilities.py:62-
 }
 
 __global__ void __launch_bounds__(kClusterThreads) k_mog_finalize(const MogFinalizeArgs a) {
+  if (loop_skip(a.loop, a.phase)) return;
   __shared__ double mixgrad[kMaxMixK];
   __shared__ MixScratch scratch;
   __shared__ double mix_s;
@@ -983,11 +1048,14 @@ __global__ void __launch_bounds__(kClusterThreads) k_mog_finalize(const MogFinal
       t3 += lngammad_dev(vN, a.D);
     }
     // MOG.py:63-70
-    a.scalars[0] = -0.5 * a.D * t1 + a.K * a.v0 * a.S0_halflogdet - t2 + t3 - a.K * lngammad_dev(a.v0, a.D) + mix + H -
-                   0.5 * a.n_total * a.D * log(M_PI);
+    const double bound = -0.5 * a.D * t1 + a.K * a.v0 * a.S0_halflogdet - t2 + t3 - a.K * lngammad_dev(a.v0, a.D) + mix + H -
+                         0.5 * a.n_total * a.D * log(M_PI);
+    a.scalars[0] = bound;
     a.scalars[1] = mix;
     a.scalars[2] = H;
   }
+  __syncthreads();  // bias / mixgrad below are written before the loop state may flip (same thread order is not needed: next kernel)
+  if (threadIdx.x == 0 && a.loop) cg_decide(a.loop, a.phase, a.scalars[0], *a.info != 0, a.dots[0], a.beta[0]);
   __syncthreads();
   for (int k = threadIdx.x; k < a.KP; k += blockDim.x) a.bias[k] = (k < a.K) ? a.per_k[k * 4 + 3] + mixgrad[k] : 0.0;
   if (a.mixgrad_out)

@@ -64,6 +64,17 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
+// ---------------------------------------------------------------- device-resident loop state (gpc_loop_t)
+// true when this kernel of the enqueued sequence has nothing to do: the loop has terminated, or it is a RETRY-phase
+// kernel and the conjugate step was accepted.  Uniform over the grid (the state was written by an earlier kernel).
+__device__ __forceinline__ bool loop_skip(const gpc_loop_t *loop, int phase) {
+  if (loop == nullptr) return false;
+  if (loop->done != 0) return true;
+  return phase == GPC_PHASE_RETRY && loop->need_retry == 0;
+}
+template <typename T>
+__device__ __forceinline__ T sel3(T p0, T p1, T p2, int i) { return i == 0 ? p0 : (i == 1 ? p1 : p2); }
+
 // ---------------------------------------------------------------- vector global access (16 B)
 __device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ double2 ldg2_stream(const double *p) {

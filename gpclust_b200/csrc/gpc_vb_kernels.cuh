@@ -34,16 +34,12 @@ namespace gpc {
 
 constexpr int kGroupRows = 8;
 constexpr int kCtasPerSm = 1;
-constexpr int kGConsumers = 10;                    // G pass consumer warps (5 units of 2; 12 warps -> 168 registers each)
-constexpr int kGThreads = (kGConsumers + 2) * 32;  // + producer warp + one idle warp (register allocation is per 4 warps)
+constexpr int kGConsumers = 12;                    // G pass: every warp computes (6 units of 2; 12 warps -> 168 registers each)
+constexpr int kGThreads = kGConsumers * 32;
 constexpr int kSSoftmaxWarps = 7;                  // S pass (7 + 4 + 1 = 12 warps -> 168 registers each)
 constexpr int kSStatWarps = 4;
 constexpr int kSThreads = (kSSoftmaxWarps + kSStatWarps + 1) * 32;
 constexpr int kSmemBudget = 227 * 1024;
-#ifndef GPC_L2_AHEAD
-#define GPC_L2_AHEAD 16
-#endif
-constexpr int kL2Ahead = GPC_L2_AHEAD;  // groups (per CTA) pulled into L2 ahead of the shared-memory ring: HBM latency is paid there
 
 // ------------------------------------------------------------------------------------------------
 // G pass
@@ -63,6 +59,8 @@ struct NatgradArgs {
   unsigned int *counter;  // zero on entry; reset to zero on exit
   double *dots_out;       // [0]=natgrad.grad  [1]=(ng-ng_old).grad  [2]=(ng-ng_old).grad_old
   int N, K, DP, num_groups, stages;
+  const gpc_loop_t *loop;  // nullable: device-resident loop state; the N x K operands then come from `bufs`
+  gpc_bufs_t bufs;
 };
 
 // ring stage: [F group | x group | lse (8) | lse_old (8)]; the previous-point operands x_old / ng_old go straight
@@ -71,9 +69,12 @@ __host__ __device__ inline int g_stage_doubles(int KP, int DP) { return kGroupRo
 __host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP + KP + kGConsumers * 4 + 2 * kGConsumers * kGroupRows; }
 
 // FULLK: K == KP, no column masking.
-// Consumer warps work in units of NSPLIT warps that share one group: warp h of a unit owns the n-tiles
+// All 12 warps compute.  They work in units of NSPLIT warps that share one group: warp h of a unit owns the n-tiles
 // [h*NTW, (h+1)*NTW) (clusters), so the unit's row reduction sum_k phi*a is exchanged through shared memory once per
-// group.  Twice the warps per group in flight halves the time a ring stage is held.
+// group.  Every unit feeds ITSELF: it owns R = stages / UNITS ring slots, and lane 0 of its first warp re-arms the
+// slot it has just finished with the unit's group R visits ahead (cp.async.bulk + mbarrier complete_tx) -- no
+// producer warp, no empty barriers (the unit's own exchange barrier orders "both warps are done reading" before
+// the refill), and the four schedulers carry three compute warps each.
 template <int KP, bool FULLK>
 __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
@@ -82,26 +83,37 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   constexpr int UNITS = kGConsumers / NSPLIT;
   constexpr int XG = kGroupRows * KP;        // doubles of one N x K operand per group
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages;
+  const int DP = a.DP, FG = kGroupRows * DP;
+  const int R = a.stages / UNITS;            // ring slots per unit
   const int stage_doubles = g_stage_doubles(KP, DP);
   double *stages = reinterpret_cast<double *>(smem_raw);
-  double *w_s = stages + (size_t)S * stage_doubles;  // B fragments: ((ks*NT + nt)*32 + lane)
-  double *bias_s = w_s + KP * DP;                     // KP
-  double *red_s = bias_s + KP;                        // kGConsumers * 4
-  double *sax_s = red_s + kGConsumers * 4;            // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
+  double *w_s = stages + (size_t)a.stages * stage_doubles;  // B fragments: ((ks*NT + nt)*32 + lane)
+  double *bias_s = w_s + KP * DP;                            // KP
+  double *red_s = bias_s + KP;                               // kGConsumers * 4
+  double *sax_s = red_s + kGConsumers * 4;                   // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sax_s + 2 * kGConsumers * kGroupRows);
-  uint64_t *empty_bar = full_bar + S;
   __shared__ bool is_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const bool has_old = (a.ng_old != nullptr);
+  const double *p_x = a.x, *p_lse = a.lse, *p_x_old = a.x_old, *p_lse_old = a.lse_old, *p_ng_old = a.ng_old;
+  double *p_ng_out = a.ng_out;
+  if (a.loop != nullptr) {
+    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
+    const int xi = a.loop->xi, xp = a.loop->xprev, ngi = a.loop->ngi, method = a.loop->method;
+    p_x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi);
+    p_lse = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xi);
+    p_ng_out = ngi ? a.bufs.ng[1] : a.bufs.ng[0];
+    // HS / PR need the previous accepted point (collapsed_vb.py:159-164); none on the first pass
+    const bool ho = (a.loop->first == 0) && xp >= 0 && (method == GPC_BETA_HS || method == GPC_BETA_PR);
+    p_x_old = ho ? sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xp) : nullptr;
+    p_lse_old = ho ? sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xp) : nullptr;
+    p_ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) : nullptr;
+  }
+  const bool has_old = (p_ng_old != nullptr);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NSPLIT);
-    }
+    for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
@@ -113,31 +125,33 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) red_s[i] = 0.0;
   __syncthreads();
 
-  if (warp == kGConsumers) {
-    // ---------------- producer: one elected lane streams groups into the ring
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? kGroupRows : 0)) * 8u;
-      int j = 0;
-      for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
-        const int s = j % S;
-        if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
-        double *st = stages + (size_t)s * stage_doubles;
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
-        bulk_g2s(st + FG, a.x + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        bulk_g2s(st + FG + XG, a.lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
-        if (has_old) bulk_g2s(st + FG + XG + kGroupRows, a.lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &full_bar[s]);
-      }
-    }
-  } else if (warp < kGConsumers) {
-    // ---------------- consumers: unit u owns this CTA's groups j = u, u + UNITS, ...
+  {
     const int unit = warp / NSPLIT, h = warp % NSPLIT, nt0 = h * NTW;
     const int ksteps = DP / 4;
+    const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? kGroupRows : 0)) * 8u;
+    double *ustages = stages + (size_t)unit * R * stage_doubles;
+    uint64_t *ubar = full_bar + unit * R;
+    const int gstride = UNITS * gridDim.x;
+    const int grp0 = blockIdx.x + unit * gridDim.x;
+    // arm ring slot `slot` with group `grp` (one elected lane of the unit)
+    auto feed = [&](int slot, int grp) {
+      double *st = ustages + (size_t)slot * stage_doubles;
+      mbar_arrive_expect_tx(&ubar[slot], bytes);
+      bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &ubar[slot]);
+      bulk_g2s(st + FG, p_x + (size_t)grp * XG, XG * 8u, &ubar[slot]);
+      bulk_g2s(st + FG + XG, p_lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
+      if (has_old) bulk_g2s(st + FG + XG + kGroupRows, p_lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
+    };
+    if (h == 0 && lane == 0)
+      for (int i = 0; i < R; ++i) {
+        const long long grp = (long long)grp0 + (long long)i * gstride;
+        if (grp < a.num_groups) feed(i, (int)grp);
+      }
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-    int j = unit;
-    for (int grp = blockIdx.x + unit * gridDim.x; grp < a.num_groups; grp += UNITS * gridDim.x, j += UNITS) {
-      const int s = j % S;
-      const double *st = stages + (size_t)s * stage_doubles;
+    int i = 0;
+    for (int grp = grp0; grp < a.num_groups; grp += gstride, ++i) {
+      const int slot = i % R;
+      const double *st = ustages + (size_t)slot * stage_doubles;
       const int row = grp * kGroupRows + g;
       const bool row_ok = row < a.N;
       const size_t goff = (size_t)grp * XG + (size_t)nt0 * 64 + 2 * lane;
@@ -146,23 +160,23 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       double2 xo[NTW], ngo[NTW];
       if (has_old) {
 #pragma unroll
-        for (int i = 0; i < NTW; ++i) {
-          xo[i] = ldg2_stream(a.x_old + goff + i * 64);
-          ngo[i] = ldg2_stream(a.ng_old + goff + i * 64);
+        for (int q = 0; q < NTW; ++q) {
+          xo[q] = ldg2_stream(p_x_old + goff + q * 64);
+          ngo[q] = ldg2_stream(p_ng_old + goff + q * 64);
         }
       }
-      mbar_wait(&full_bar[s], (uint32_t)((j / S) & 1));
+      mbar_wait(&ubar[slot], (uint32_t)((i / R) & 1));
 
       double acc[NTW][2];
 #pragma unroll
-      for (int i = 0; i < NTW; ++i) acc[i][0] = acc[i][1] = 0.0;
+      for (int q = 0; q < NTW; ++q) acc[q][0] = acc[q][1] = 0.0;
       const double *fa = st + lane;
       const double *wb = w_s + nt0 * 32 + lane;
 #pragma unroll 4
       for (int ks = 0; ks < ksteps; ++ks) {
         const double af = fa[ks * 32];
 #pragma unroll
-        for (int i = 0; i < NTW; ++i) dmma884(acc[i][0], acc[i][1], af, wb[(ks * NT + i) * 32]);
+        for (int q = 0; q < NTW; ++q) dmma884(acc[q][0], acc[q][1], af, wb[(ks * NT + q) * 32]);
       }
       const double *xs = st + FG + nt0 * 64 + 2 * lane;
       const double lse = st[FG + XG + g];
@@ -171,63 +185,68 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       // ---- pass 1: phi = exp(x - lse), a = F.W + bias - x (in place of acc), partial sa = sum phi*a
       double phi[2 * NTW];
 #pragma unroll
-      for (int i = 0; i < NTW; ++i) {
-        const int c = 8 * (nt0 + i) + 2 * t;
+      for (int q = 0; q < NTW; ++q) {
+        const int c = 8 * (nt0 + q) + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double2 xv = *reinterpret_cast<const double2 *>(xs + i * 64);
+        const double2 xv = *reinterpret_cast<const double2 *>(xs + q * 64);
         const double2 bb = *reinterpret_cast<const double2 *>(bias_s + c);
-        acc[i][0] = ok0 ? (acc[i][0] + bb.x) - xv.x : 0.0;
-        acc[i][1] = ok1 ? (acc[i][1] + bb.y) - xv.y : 0.0;
-        phi[2 * i] = xv.x - lse;
-        phi[2 * i + 1] = xv.y - lse;
+        acc[q][0] = ok0 ? (acc[q][0] + bb.x) - xv.x : 0.0;
+        acc[q][1] = ok1 ? (acc[q][1] + bb.y) - xv.y : 0.0;
+        phi[2 * q] = xv.x - lse;
+        phi[2 * q + 1] = xv.y - lse;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);  // last read of the stage is done
       exp_batch<2 * NTW>(phi);
       double sa = 0.0;
 #pragma unroll
-      for (int i = 0; i < NTW; ++i) {
-        const int c = 8 * (nt0 + i) + 2 * t;
-        if (!(FULLK || c < a.K)) phi[2 * i] = 0.0;
-        if (!(FULLK || c + 1 < a.K)) phi[2 * i + 1] = 0.0;
-        sa += phi[2 * i] * acc[i][0] + phi[2 * i + 1] * acc[i][1];
+      for (int q = 0; q < NTW; ++q) {
+        const int c = 8 * (nt0 + q) + 2 * t;
+        if (!(FULLK || c < a.K)) phi[2 * q] = 0.0;
+        if (!(FULLK || c + 1 < a.K)) phi[2 * q + 1] = 0.0;
+        sa += phi[2 * q] * acc[q][0] + phi[2 * q + 1] * acc[q][1];
       }
       sa = quad_sum(sa);
       if (NSPLIT > 1) {
         // the unit's other warp holds the rest of the row: exchange through shared memory (fixed summation order)
-        double *sx = sax_s + (((j / UNITS) & 1) * UNITS + unit) * (NSPLIT * kGroupRows);
+        double *sx = sax_s + ((i & 1) * UNITS + unit) * (NSPLIT * kGroupRows);
         if (t == 0) sx[h * kGroupRows + g] = sa;
         asm volatile("bar.sync %0, %1;\n" ::"r"(1 + unit), "n"(NSPLIT * 32) : "memory");
         sa = sx[g] + sx[kGroupRows + g];
+      } else {
+        __syncwarp();
+      }
+      // every warp of the unit has finished reading the slot: re-arm it with the group R visits ahead
+      if (h == 0 && lane == 0) {
+        const long long nxt = (long long)grp + (long long)R * gstride;
+        if (nxt < a.num_groups) feed(slot, (int)nxt);
       }
 
       // ---- pass 2: natural gradient, gradient, dots
       double po[2 * NTW];
       if (has_old) {
 #pragma unroll
-        for (int i = 0; i < NTW; ++i) {
-          po[2 * i] = xo[i].x - lse_o;
-          po[2 * i + 1] = xo[i].y - lse_o;
+        for (int q = 0; q < NTW; ++q) {
+          po[2 * q] = xo[q].x - lse_o;
+          po[2 * q + 1] = xo[q].y - lse_o;
         }
         exp_batch<2 * NTW>(po);
       }
-      double *ngo_g = a.ng_out + goff;
+      double *ngo_g = p_ng_out + goff;
       double *gro_g = a.grad_out ? a.grad_out + goff : nullptr;
 #pragma unroll
-      for (int i = 0; i < NTW; ++i) {
-        const int c = 8 * (nt0 + i) + 2 * t;
+      for (int q = 0; q < NTW; ++q) {
+        const int c = 8 * (nt0 + q) + 2 * t;
         const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
-        const double n0 = (ok0 && row_ok) ? acc[i][0] - sa : 0.0;
-        const double n1 = (ok1 && row_ok) ? acc[i][1] - sa : 0.0;
-        const double g0 = n0 * phi[2 * i], g1 = n1 * phi[2 * i + 1];
-        stg2(ngo_g + i * 64, n0, n1);
-        if (gro_g) stg2(gro_g + i * 64, g0, g1);
+        const double n0 = (ok0 && row_ok) ? acc[q][0] - sa : 0.0;
+        const double n1 = (ok1 && row_ok) ? acc[q][1] - sa : 0.0;
+        const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
+        stg2(ngo_g + q * 64, n0, n1);
+        if (gro_g) stg2(gro_g + q * 64, g0, g1);
         d0 += n0 * g0 + n1 * g1;
         if (has_old) {
-          const double po0 = (ok0 && row_ok) ? po[2 * i] : 0.0, po1 = (ok1 && row_ok) ? po[2 * i + 1] : 0.0;
-          const double e0 = n0 - ngo[i].x, e1 = n1 - ngo[i].y;
+          const double po0 = (ok0 && row_ok) ? po[2 * q] : 0.0, po1 = (ok1 && row_ok) ? po[2 * q + 1] : 0.0;
+          const double e0 = n0 - ngo[q].x, e1 = n1 - ngo[q].y;
           d1 += e0 * g0 + e1 * g1;
-          d2 += e0 * (ngo[i].x * po0) + e1 * (ngo[i].y * po1);
+          d2 += e0 * (ngo[q].x * po0) + e1 * (ngo[q].y * po1);
         }
       }
     }
@@ -287,6 +306,9 @@ struct StepStatsArgs {
   double sq_old;         // natgrad.grad of the previous iteration (PR / FR only; the host read it back already)
   int beta_mode;
   int N, K, DP, num_groups, stages;
+  const gpc_loop_t *loop;  // nullable: device-resident loop state (operands from `bufs`, beta mode / step / sq_old from it)
+  gpc_bufs_t bufs;
+  int phase;               // GPC_PHASE_CONJ / GPC_PHASE_RETRY
 };
 
 __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
@@ -318,18 +340,35 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   }
   __syncthreads();
 
+  const double *p_x_base = a.x_base, *p_ng = a.ng, *p_sd_old = a.sd_old;
+  double *p_sd_new = a.sd_new, *p_x_new = a.x_new, *p_lse_new = a.lse_new, *p_beta_out = a.beta_out;
+  int beta_mode = a.beta_mode;
+  double sq_old = a.sq_old, step = a.step;
+  if (a.loop != nullptr) {
+    if (loop_skip(a.loop, a.phase)) return;
+    const int xi = a.loop->xi, xt = a.loop->xtrial, ngi = a.loop->ngi;
+    p_x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi);
+    p_x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt);
+    p_lse_new = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xt);
+    p_ng = ngi ? a.bufs.ng[1] : a.bufs.ng[0];
+    p_sd_old = p_sd_new = a.bufs.sd;
+    // collapsed_vb.py:157-158 (first pass / steepest) and :182-184 (retry with searchDir = -natgrad)
+    beta_mode = (a.phase == GPC_PHASE_RETRY || a.loop->first != 0) ? GPC_BETA_ZERO : a.loop->method;
+    if (a.phase == GPC_PHASE_RETRY) p_beta_out = nullptr;  // the trace reports the conjugate beta
+    sq_old = a.loop->sq_old;
+    step = a.loop->step;
+  }
   double beta = 0.0;
-  if (a.beta_mode != GPC_BETA_ZERO) {
+  if (beta_mode != GPC_BETA_ZERO) {
     const double sq = a.dots[0], num = a.dots[1], den = a.dots[2];
-    const double sq_old = a.sq_old;
-    if (a.beta_mode == GPC_BETA_HS) beta = num / den;
-    else if (a.beta_mode == GPC_BETA_PR) beta = num / sq_old;
+    if (beta_mode == GPC_BETA_HS) beta = num / den;
+    else if (beta_mode == GPC_BETA_PR) beta = num / sq_old;
     else beta = sq / sq_old;
     if (isnan(beta) || beta < 0.0) beta = 0.0;  // collapsed_vb.py:165-166
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
-  const bool has_ng = (a.ng != nullptr);
-  const bool use_old = has_ng && (beta != 0.0) && (a.sd_old != nullptr);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p_beta_out) *p_beta_out = beta;
+  const bool has_ng = (p_ng != nullptr);
+  const bool use_old = has_ng && (beta != 0.0) && (p_sd_old != nullptr);
   double *part = a.partials + (size_t)blockIdx.x * (KP * DP + KP + 2);
 
   if (warp == kSSoftmaxWarps + kSStatWarps) {
@@ -339,22 +378,13 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       int j = 0;
       for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
         const int s = j % S;
-        if (kL2Ahead > 0) {
-          const long long pg = (long long)grp + (long long)kL2Ahead * gridDim.x;
-          if (pg < a.num_groups) {
-            bulk_prefetch_l2(a.F + (size_t)pg * FG, FG * 8u);
-            bulk_prefetch_l2(a.x_base + (size_t)pg * XG, XG * 8u);
-            if (has_ng) bulk_prefetch_l2(a.ng + (size_t)pg * XG, XG * 8u);
-            if (use_old) bulk_prefetch_l2(a.sd_old + (size_t)pg * XG, XG * 8u);
-          }
-        }
         if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
         double *st = stages + (size_t)s * stage_doubles;
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
-        bulk_g2s(st + FG, a.x_base + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        if (has_ng) bulk_g2s(st + FG + XG, a.ng + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        if (use_old) bulk_g2s(st + FG + 2 * XG, a.sd_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        bulk_g2s(st + FG, p_x_base + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        if (has_ng) bulk_g2s(st + FG + XG, p_ng + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        if (use_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
       }
     }
   } else if (warp < kSSoftmaxWarps) {
@@ -376,8 +406,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         x[nt][1] = v.y;
       }
       if (has_ng) {
-        double *sdo_g = a.sd_new ? a.sd_new + (size_t)grp * XG + 2 * lane : nullptr;
-        double *xn_g = a.x_new + (size_t)grp * XG + 2 * lane;
+        double *sdo_g = p_sd_new ? p_sd_new + (size_t)grp * XG + 2 * lane : nullptr;
+        double *xn_g = p_x_new + (size_t)grp * XG + 2 * lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const double2 ngv = *reinterpret_cast<const double2 *>(xs + XG + nt * 64);
@@ -387,8 +417,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
             s0 += beta * sdv.x;  // searchDir = natgrad + beta*searchDir_old  (collapsed_vb.py:167, ascent sign)
             s1 += beta * sdv.y;
           }
-          x[nt][0] += a.step * s0;  // collapsed_vb.py:172
-          x[nt][1] += a.step * s1;
+          x[nt][0] += step * s0;  // collapsed_vb.py:172
+          x[nt][1] += step * s1;
           if (sdo_g) stg2(sdo_g + nt * 64, s0, s1);
           stg2(xn_g + nt * 64, x[nt][0], x[nt][1]);
         }
@@ -429,7 +459,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       const double lognorm = log(ssum);
       // row entropy -sum phi*log(phi) with log(phi) = (x - max) - log(sum)  ==  log(sum) - sum(e*(x - max))/sum
       if (row_ok && t == 0) Hpart += lognorm - px * inv;
-      if (a.lse_new && t == 0) a.lse_new[row] = m + lognorm;
+      if (p_lse_new && t == 0) p_lse_new[row] = m + lognorm;
 
       // phi -> the stage's x region, in the A-fragment order of phi^T: element (row r, cluster k) at
       // ((k/8)*2 + r/4)*32 + (k%8)*4 + r%4.  Every lane has read its x values above.

@@ -55,6 +55,41 @@ extern "C" {
 #define GPC_KERN_BIAS 3
 #define GPC_KERN_WHITE 4
 
+/* ---- device-resident loop state of the conjugate natural-gradient ascent (collapsed_vb.py:143-303) ----
+ * With a gpc_loop_t in device memory the accept / reject decision (collapsed_vb.py:182-193), the buffer rotation,
+ * the iteration count and the termination tests (collapsed_vb.py:229-291) are taken ON THE DEVICE by the kernel
+ * that finishes a bound evaluation, and every kernel of the sequence
+ *     gpc_loop_natgrad -> gpc_loop_step_stats(CONJ) -> [reduce, all-reduce] -> gpc_loop_*_post(CONJ)
+ *                      -> gpc_loop_step_stats(RETRY) -> [reduce, all-reduce] -> gpc_loop_*_post(RETRY)
+ * reads it to pick its buffers or to return at once (`done`, or RETRY without `need_retry`).  The host enqueues a
+ * batch of such sequences without synchronising and reads the trace back once per batch.                    */
+#define GPC_PHASE_CONJ 0
+#define GPC_PHASE_RETRY 1
+#define GPC_DONE_FTOL 1
+#define GPC_DONE_GTOL 2
+#define GPC_DONE_MAXITER 4
+#define GPC_DONE_FAULT 8
+typedef struct {
+  double bound_old; /* bound at the accepted point                                   */
+  double sq_old;    /* natgrad.grad of the previous iteration (PR / FR)              */
+  double ftol, gtol, maxiter, step;
+  int iteration;    /* bound evaluations so far (collapsed_vb.py:177,191)            */
+  int method;       /* GPC_BETA_*                                                    */
+  int first;        /* 1 until the first step has been taken (beta = 0, no history)  */
+  int xi, xprev, xtrial, ngi; /* buffer selectors; xprev = -1: no previous point     */
+  int need_retry;   /* the conjugate step lowered the bound: the RETRY kernels run   */
+  int done;         /* GPC_DONE_* bits; once set every later kernel returns at once  */
+  int n_trace, trace_cap;
+  int pad;
+  /* followed by trace_cap rows [iteration, bound, squareNorm, beta] of doubles      */
+} gpc_loop_t;
+typedef struct {
+  double *x[3];   /* logits: accepted / previous accepted / trial, rotating            */
+  double *lse[3]; /* row logsumexp of the matching logits buffer                        */
+  double *ng[2];  /* natural gradient: current / previous                               */
+  double *sd;     /* search direction (updated in place)                                */
+} gpc_bufs_t;
+
 /* ---- library / geometry queries (host only, no GPU needed) ---------------------------------- */
 int gpc_abi_version(void);
 int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
@@ -89,6 +124,12 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
                    double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode, long long N,
                    int K, int KP, int DP, int grid, void *stream);
 
+/* the same two passes driven by a device-resident gpc_loop_t (see above); `bufs` is read on the host.        */
+int gpc_loop_natgrad(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                     double *dots, const gpc_loop_t *loop, long long N, int K, int KP, int DP, int grid, void *stream);
+int gpc_loop_step_stats(const double *F, const gpc_bufs_t *bufs, const double *dots, double *beta_out, double *partials,
+                        const gpc_loop_t *loop, int phase, long long N, int K, int KP, int DP, int grid, void *stream);
+
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);
 
@@ -121,6 +162,11 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
 int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
                    const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
                    double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream);
+/* gpc_mohgp_post + the device-side accept / reject / termination step (dots, beta: as written by the two passes) */
+int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                        const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
+                        double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP,
+                        const double *dots, const double *beta, gpc_loop_t *loop, int phase, void *stream);
 /* mixing-proportion bound and gradient (collapsed_mixture.py:66-94), bound assembly, G-pass bias.
  * scalars: [0] bound, [1] mixing_prop_bound, [2] H.  mixgrad_out (K doubles) may be NULL.             */
 int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
@@ -135,6 +181,12 @@ int gpc_mog_cluster(const double *stats, const double *m0c, const double *S0, do
                     double *Sns_inv, int *info, double k0, double v0, int K, int D, int KP, int DP, void *stream);
 int gpc_mog_finalize(const double *stats, const double *per_k, double *bias, double *scalars, double *mixgrad_out, double n_total,
                      double k0, double v0, double S0_halflogdet, double alpha, int prior, int K, int KP, int DP, int D, void *stream);
+
+/* gpc_mog_cluster + gpc_mog_finalize driven by a gpc_loop_t (skip logic + device-side decision)            */
+int gpc_loop_mog_post(const double *stats, const double *m0c, const double *S0, double *Wt, double *per_k, double *mun_c, double *Sns,
+                      double *Sns_inv, int *info, double k0, double v0, double *bias, double *scalars, double *mixgrad_out, double n_total,
+                      double S0_halflogdet, double alpha, int prior, int K, int D, int KP, int DP, const double *dots, const double *beta,
+                      gpc_loop_t *loop, int phase, void *stream);
 
 /* ---- covariance fills (GPy kern.K(X, X2); call sites MOHGP.py:47-48,61-62, OMGP.py:104,132) ---- */
 /* out (n x m) = sum_p k_p(X_i, X2_j) ; X2 == NULL -> X2 = X, m = n (White contributes, diagonal r = 0).

@@ -1,0 +1,37 @@
+"""Wall-clock breakdown of the end-to-end call sequence of bench.py (construct from pinned host arrays, optimize, read back)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import bench
+from gpclust_b200 import MOHGP, kern
+
+X, Y, phi0 = bench.synth(1000000, bench.D, bench.K)
+pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+Y, phi0 = pin(Y), pin(phi0)
+
+
+def T(label, t0):
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print("  %-28s %8.1f ms" % (label, (t1 - t0) * 1e3))
+    return t1
+
+
+for rep in range(2):
+    print("rep", rep)
+    t = time.perf_counter()
+    m = MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05), Y, K=bench.K, phi_init=phi0)
+    t = T("construct", t)
+    m.optimize(method="HS", maxiter=30, ftol=-1.0, gtol=-1.0, verbose=False)
+    t = T("optimize(30)", t)
+    phi = m.phi
+    t = T("m.phi", t)
+    b = m.bound()
+    t = T("m.bound()", t)
+    del m
