@@ -661,18 +661,26 @@ struct MohgpPostArgs {
   int phase;
 };
 
-// y[r] = sum_j Mt[j*D + r] x[j]  for r < D, all 256 threads (4 j-groups), result in out_s[r]; x in shared memory.
+// partial of y[r] = sum_j Mt[j*D + r] x[j] over j == pg (mod 4), for r < D; x in shared memory.  Sixteen independent
+// loads are in flight per thread: these matrices live in L2 and the kernel is latency-, not bandwidth-bound.
 __device__ __forceinline__ double matvec_t_part(const double *__restrict__ Mt, const double *x_s, int D, int r, int pg) {
-  double v0 = 0.0, v1 = 0.0;
-  if (r < D) {
-    int j = pg;
-    for (; j + 4 < D; j += 8) {
-      v0 += Mt[j * D + r] * x_s[j];
-      v1 += Mt[(j + 4) * D + r] * x_s[j + 4];
+  // unconditional loads from clamped addresses (a predicated load is not hoisted above its use by the compiler)
+  const int rc = r < D ? r : D - 1;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j = pg; j < D; j += 64) {
+    double m[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int jj = j + 4 * u;
+      m[u] = __ldg(Mt + (jj < D ? jj : D - 1) * D + rc);
     }
-    if (j < D) v0 += Mt[j * D + r] * x_s[j];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int jj = j + 4 * u;
+      v[u & 3] += m[u] * (jj < D ? x_s[jj] : 0.0);
+    }
   }
-  return v0 + v1;
+  return r < D ? (v[0] + v[1]) + (v[2] + v[3]) : 0.0;
 }
 
 __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostArgs a) {
@@ -688,25 +696,42 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   const int r = tid & 63, pg = tid >> 6;
   const int len = KP * DP + KP + 2;
   const double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
+  // the two N-sized passes have swept the L2 since the last evaluation: pull the replicated D x D operands back in
+  // while the statistics are being reduced (fire-and-forget bulk prefetches, 16-B granular)
+  if (tid == 0) {
+    bulk_prefetch_l2(a.ws, (uint32_t)((eig_ws_len(D) * 8) & ~15));
+    bulk_prefetch_l2(a.Sy_inv, (uint32_t)((D * D * 8) & ~15));
+  }
 
-  // ---- this cluster's statistics: fixed-order sum over the per-CTA partials
+  // ---- this cluster's statistics: fixed-order sum over the per-CTA partials (8 independent loads in flight)
   {
-    double v0 = 0.0, v1 = 0.0;
-    if (r < DP) {
-      int p = pg;
-      const double *src = a.partials + (size_t)k * DP + r;
-      for (; p + 4 < a.num_parts; p += 8) {
-        v0 += src[(size_t)p * len];
-        v1 += src[(size_t)(p + 4) * len];
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    {
+      const double *src = a.partials + (size_t)k * DP + (r < DP ? r : DP - 1);
+      const int last = a.num_parts - 1;
+      // up to 160 partial vectors (one per SM and then some): all 40 loads of this thread are issued before the first
+      // use -- clamped, unconditional addresses, because a predicated load is not hoisted above its use
+      for (int p0 = pg; p0 < a.num_parts; p0 += 160) {
+        double w[40];
+#pragma unroll
+        for (int u = 0; u < 40; ++u) {
+          const int pp = p0 + 4 * u;
+          w[u] = __ldcg(src + (size_t)(pp < last ? pp : last) * len);
+        }
+#pragma unroll
+        for (int u = 0; u < 40; ++u) v[u & 7] += (p0 + 4 * u <= last) ? w[u] : 0.0;
       }
-      if (p < a.num_parts) v0 += src[(size_t)p * len];
     }
-    red[pg][r] = v0 + v1;
+    red[pg][r] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
   }
   double phi_hat = 0.0;
   if (tid < 32) {
-    for (int p = tid; p < a.num_parts; p += 32) phi_hat += a.partials[(size_t)p * len + (size_t)KP * DP + k];
-    phi_hat = warp_sum(phi_hat);
+    double q0 = 0.0, q1 = 0.0;
+    for (int p = tid; p < a.num_parts; p += 64) {
+      q0 += __ldcg(a.partials + (size_t)p * len + (size_t)KP * DP + k);
+      if (p + 32 < a.num_parts) q1 += __ldcg(a.partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
+    }
+    phi_hat = warp_sum(q0 + q1);
     if (tid == 0) red_s[0] = phi_hat;
   }
   __syncthreads();
@@ -724,11 +749,14 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
     double jitter = 0.0;
     bool ok = false;
     {
-      double lmin = INFINITY, lsum = 0.0;
-      for (int i = 0; i < D; ++i) {  // every thread, same order
-        lmin = fmin(lmin, lam[i]);
-        lsum += lam[i];
-      }
+      double lmin = (tid < D) ? lam[tid] : INFINITY, lsum = (tid < D) ? lam[tid] : 0.0;
+      lsum = block_sum(lsum, red_s);
+      lmin = warp_max(-lmin);
+      __syncthreads();
+      if ((tid & 31) == 0) red_s[tid >> 5] = lmin;
+      __syncthreads();
+      lmin = -fmax(fmax(red_s[0], red_s[1]), fmax(fmax(red_s[2], red_s[3]), fmax(fmax(red_s[4], red_s[5]), fmax(red_s[6], red_s[7]))));
+      __syncthreads();
       const double diag_mean = 1.0 + phi_hat * lsum / D;
       for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
         if (attempt == 1) jitter = diag_mean * 1e-6;
@@ -839,29 +867,23 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   if (!is_last) return;
   __threadfence();
   {
+    // every load of this serial tail is issued by a different thread (one L2 round trip, not num_parts of them)
     double H = 0.0;
-    if (tid < 32) {
-      for (int p = tid; p < a.num_parts; p += 32) H += a.partials[(size_t)p * len + (size_t)KP * DP + KP];
-      H = warp_sum(H);
-      if (tid == 0) {
-        red_s[0] = H;
-        a.stats[(size_t)KP * DP + KP] = H;
-      }
-    }
-    __syncthreads();
-    H = red_s[0];
-    __syncthreads();
-    // other CTAs' results: read through L2 (ld.global.cg), this SM's L1 never held these lines coherently
+    for (int p = tid; p < a.num_parts; p += blockDim.x) H += __ldcg(a.partials + (size_t)p * len + (size_t)KP * DP + KP);
+    H = block_sum(H, red_s);
+    if (tid == 0) a.stats[(size_t)KP * DP + KP] = H;
     __shared__ double phi_hat_sh[kMaxMixK];
-    for (int kk = tid; kk < a.K; kk += blockDim.x) phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
+    double ldd = 0.0, quad = 0.0;
+    for (int kk = tid; kk < a.K; kk += blockDim.x) {
+      phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
+      ldd += __ldcg(a.per_k + kk * 4 + 0);
+      quad += __ldcg(a.per_k + kk * 4 + 1);
+    }
+    ldd = block_sum(ldd, red_s);
+    quad = block_sum(quad, red_s);
     __syncthreads();
     mixing_terms(phi_hat_sh, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
     if (tid == 0) {
-      double ldd = 0.0, quad = 0.0;
-      for (int kk = 0; kk < a.K; ++kk) {
-        ldd += __ldcg(a.per_k + kk * 4 + 0);
-        quad += __ldcg(a.per_k + kk * 4 + 1);
-      }
       const double bound = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
       a.scalars[0] = bound;
       a.scalars[1] = mix_s;
