@@ -36,6 +36,9 @@ N_TOTAL, D, K = 1000000, 64, 64
 METRIC = "MOHGP VB iterations/sec (N=1M,D=64,K=64)"
 UNIT = "iterations/s"
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 1M rows, HS, from the ncu --set full capture summarised in
+# profiles/ncu_r01_v3_summary.csv (scaled linearly to the rows this rank holds)
+NCU_DRAM_BYTES_PER_LAUNCH_1M = {"natgrad": 2.064148e9 + 0.480519e9, "step_stats": 2.048132e9 + 1.000140e9}
 
 
 def synth(n_total, d, k, seed=0):
@@ -335,7 +338,10 @@ def run_gpu(args):
                 "bound": b_e2e},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_kind": peak_kind, "traffic": None, "alg_bytes_per_launch": alg[dom], "ms_per_launch": kernel_ms[dom],
+                     "peak_kind": peak_kind,
+                     "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_1M[dom] * n_loc / 1e6) if method == "HS" else None,
+                     "traffic_source": "profiles/ncu_r01_v3_summary.csv (ncu --set full, 1M rows, scaled by rows per GPU)",
+                     "alg_bytes_per_launch": alg[dom], "ms_per_launch": kernel_ms[dom],
                      "iteration_hbm_frac": iter_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         "kernels_ms": kernel_ms,
         "fp64_tensor": {"achieved": tensor_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tensor_tf / FP64_DMMA_PEAK_TFLOPS,
