@@ -122,7 +122,23 @@ class MOHGP(CollapsedMixture):
                                  self.K, self.D, self._KP, self._DP, self._stream()), "gpc_mohgp_post")
         self.kernel_launches += 1
 
+    def _use_peer_exchange(self):
+        return True
+
     def _loop_posterior(self, phase):
+        if self._peers is not None:
+            # rows sharded over the GPUs of one box: the reduced statistics go straight into every peer's inbox over
+            # NVLink (no NCCL call, no host involvement); the posterior kernel sums the W inbox vectors in rank order
+            px = ptr(self._peers["desc"])
+            check(lib.gpc_reduce_push(ptr(self._spart), self._grid, self._stats_len, px, ptr(self._counter[2:]), ptr(self._loop_dev), phase,
+                                      self._stream()), "gpc_reduce_push")
+            check(lib.gpc_loop_mohgp_post_px(px, self._world, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
+                                             ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias),
+                                             ptr(self._ctrl), ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha),
+                                             _cabi.PRIOR[self.prior_Z], self.K, self.D, self._KP, self._DP, ptr(self._ctrl[3:]), ptr(self._ctrl[6:]),
+                                             ptr(self._loop_dev), phase, self._stream()), "gpc_loop_mohgp_post_px")
+            self.kernel_launches += 2
+            return
         if self._world > 1:
             check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
             self.kernel_launches += 1

@@ -36,6 +36,10 @@ PROTOTYPES = {
     "gpc_step_stats": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_loop_natgrad": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "gpc_loop_step_stats": [_p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_natgrad_px": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_step_stats_px": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_reduce_push": [_p, _i, _i, _p, _p, _p, _i, _p],
+    "gpc_xchg_doubles": [_i, _i],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
@@ -44,6 +48,7 @@ PROTOTYPES = {
     "gpc_mohgp_eig": [_p, _p, _p, _p, _p, _i, _p, _p],
     "gpc_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p],
     "gpc_loop_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
+    "gpc_loop_mohgp_post_px": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "gpc_mohgp_finalize": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p],
     "gpc_mog_features": [_p, _p, _ll, _i, _i, _p, _p],
     "gpc_mog_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _i, _i, _p],
@@ -69,7 +74,7 @@ PROTOTYPES = {
     "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],
     "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
 }
-_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll}
+_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_xchg_doubles": _ll}
 
 
 class GpcBufs(ctypes.Structure):
@@ -82,6 +87,11 @@ class GpcLoop(ctypes.Structure):
     _fields_ = [("bound_old", _d), ("sq_old", _d), ("ftol", _d), ("gtol", _d), ("maxiter", _d), ("step", _d),
                 ("iteration", _i), ("method", _i), ("first", _i), ("xi", _i), ("xprev", _i), ("xtrial", _i), ("ngi", _i),
                 ("need_retry", _i), ("done", _i), ("n_trace", _i), ("trace_cap", _i), ("pad", _i)]
+
+
+class GpcPeers(ctypes.Structure):
+    """gpc_peers_t of include/gpclust_b200.h"""
+    _fields_ = [("world", _i), ("rank", _i), ("stats_len", _i), ("pad", _i), ("inbox", _p * 8), ("epochs", _p)]
 
 
 DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT = 1, 2, 4, 8

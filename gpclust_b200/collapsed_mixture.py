@@ -80,6 +80,7 @@ class CollapsedMixture(CollapsedVB):
         self._gpart = torch.zeros(self._grid * 4, dtype=torch.float64, device=self.device)
         self._state_valid = False
         self._bound_value = None
+        self._peers = None      # peer-memory exchange descriptor (rows sharded over the GPUs of one box), see sharding.py
         self._loop_dev = None   # gpc_loop_t + trace rows (device-resident loop state), allocated on first optimize()
         self._loop_host = None
         self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
@@ -136,10 +137,15 @@ class CollapsedMixture(CollapsedVB):
         self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
         self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
         self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
+        self._peers = self._shards.setup_peers(self._stats_len, self.device) if self._use_peer_exchange() else None
         self._alloc_model()
 
     def _alloc_model(self):
         """Subclass hook: per-cluster output buffers (K x D x D ...)."""
+
+    def _use_peer_exchange(self):
+        """Subclass switch: True when the model's posterior kernel can consume the peer inbox directly."""
+        return False
 
     def _set_features(self, F, DP):
         self._F, self._DP = F, DP
@@ -392,15 +398,16 @@ class CollapsedMixture(CollapsedVB):
         """One pass of the loop body collapsed_vb.py:152-193 as a fixed launch sequence; nothing is read back."""
         lp, st = ptr(self._loop_dev), self._stream()
         dots, beta = ptr(self._ctrl[_C_SQ:]), ptr(self._ctrl[_C_BETA:])
+        px = ptr(self._peers["desc"]) if self._peers is not None else None
         with self._timed("natgrad"):
-            check(lib.gpc_loop_natgrad(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._counter), dots, lp,
-                                       self.N, self.K, self._KP, self._DP, self._grid, st), "gpc_loop_natgrad")
-        if self._world > 1:
+            check(lib.gpc_loop_natgrad_px(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._counter), dots,
+                                          lp, px, self.N, self.K, self._KP, self._DP, self._grid, st), "gpc_loop_natgrad")
+        if self._world > 1 and px is None:
             self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
         for phase in (0, 1):  # GPC_PHASE_CONJ, GPC_PHASE_RETRY (the latter returns at once unless the bound fell)
             with self._timed("step_stats" if phase == 0 else "step_stats_retry"):
-                check(lib.gpc_loop_step_stats(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, phase, self.N, self.K, self._KP,
-                                              self._DP, self._grid, st), "gpc_loop_step_stats")
+                check(lib.gpc_loop_step_stats_px(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, phase, self.N, self.K,
+                                                 self._KP, self._DP, self._grid, st), "gpc_loop_step_stats")
             with self._timed("posterior" if phase == 0 else "posterior_retry"):
                 self._loop_posterior(phase)
         self.kernel_launches += 3

@@ -168,11 +168,18 @@ int gpc_natgrad(const double *F, const double *x, const double *lse, const doubl
   a.DP = DP;
   a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
   a.loop = nullptr;
+  a.peers = nullptr;
   return dispatch_natgrad(a, KP, grid, as_stream(stream));
 }
 
 int gpc_loop_natgrad(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
                      double *dots, const gpc_loop_t *loop, long long N, int K, int KP, int DP, int grid, void *stream) {
+  return gpc_loop_natgrad_px(F, bufs, Wt, bias, partials, counter, dots, loop, nullptr, N, K, KP, DP, grid, stream);
+}
+
+int gpc_loop_natgrad_px(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                        double *dots, const gpc_loop_t *loop, const gpc_peers_t *peers, long long N, int K, int KP, int DP, int grid,
+                        void *stream) {
   if (!F || !bufs_ok(bufs) || !Wt || !bias || !partials || !counter || !dots || !loop) return GPC_EINVAL;
   if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
   NatgradArgs a{};
@@ -188,6 +195,7 @@ int gpc_loop_natgrad(const double *F, const gpc_bufs_t *bufs, const double *Wt, 
   a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
   a.loop = loop;
   a.bufs = *bufs;
+  a.peers = peers;
   return dispatch_natgrad(a, KP, grid, as_stream(stream));
 }
 
@@ -224,6 +232,11 @@ int gpc_step_stats(const double *F, const double *x_base, const double *ng, cons
 
 int gpc_loop_step_stats(const double *F, const gpc_bufs_t *bufs, const double *dots, double *beta_out, double *partials,
                         const gpc_loop_t *loop, int phase, long long N, int K, int KP, int DP, int grid, void *stream) {
+  return gpc_loop_step_stats_px(F, bufs, const_cast<double *>(dots), beta_out, partials, loop, nullptr, phase, N, K, KP, DP, grid, stream);
+}
+
+int gpc_loop_step_stats_px(const double *F, const gpc_bufs_t *bufs, double *dots, double *beta_out, double *partials, const gpc_loop_t *loop,
+                           const gpc_peers_t *peers, int phase, long long N, int K, int KP, int DP, int grid, void *stream) {
   if (!F || !bufs_ok(bufs) || !dots || !beta_out || !partials || !loop) return GPC_EINVAL;
   if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
   if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL) return GPC_EINVAL;
@@ -239,12 +252,25 @@ int gpc_loop_step_stats(const double *F, const gpc_bufs_t *bufs, const double *d
   a.loop = loop;
   a.bufs = *bufs;
   a.phase = phase;
+  a.peers = peers;
+  a.dots_sum = peers ? dots : nullptr;
   return dispatch_step_stats(a, KP, grid, as_stream(stream));
 }
 
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
   if (!partials || !out || num_parts < 1 || len < 1) return GPC_EINVAL;
   k_reduce_partials<<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, num_parts, len, out);
+  return launch_rc();
+}
+
+long long gpc_xchg_doubles(int world, int stats_len) {
+  return (world < 1 || world > GPC_MAX_PEERS || stats_len < 1) ? -1 : xchg_doubles(world, stats_len);
+}
+
+int gpc_reduce_push(const double *partials, int num_parts, int len, const gpc_peers_t *peers, unsigned int *counter, const gpc_loop_t *loop,
+                    int phase, void *stream) {
+  if (!partials || !peers || !counter || num_parts < 1 || len < 1) return GPC_EINVAL;
+  k_reduce_push<<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, num_parts, len, peers, counter, loop, phase);
   return launch_rc();
 }
 
@@ -321,7 +347,26 @@ int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, co
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpPostArgs a{partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
-                  counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase};
+                  counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, nullptr};
+  k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
+  return launch_rc();
+}
+
+int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                           const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias,
+                           double *scalars, double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D,
+                           int KP, int DP, const double *dots, const double *beta, gpc_loop_t *loop, int phase, void *stream) {
+  if (!peers || world < 1 || world > GPC_MAX_PEERS || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !Wt || !muk_t || !per_k || !bias ||
+      !scalars || !counter || !info || !dots || !beta || !loop)
+    return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > GPC_MAX_KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+  if (e != cudaSuccess) return cuda_rc(e);
+  MohgpPostArgs a{stats, world, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
+                  counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, peers};
   k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
   return launch_rc();
 }

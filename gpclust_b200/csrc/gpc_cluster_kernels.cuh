@@ -659,6 +659,7 @@ struct MohgpPostArgs {
   const double *beta;  // loop mode: beta of the conjugate S pass
   gpc_loop_t *loop;    // nullable
   int phase;
+  const gpc_peers_t *peers;  // nullable: statistics = the W inbox vectors of the peer exchange (partials / num_parts ignored)
 };
 
 // partial of y[r] = sum_j Mt[j*D + r] x[j] over j == pg (mod 4), for r < D; x in shared memory.  Sixteen independent
@@ -695,6 +696,17 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
   const int r = tid & 63, pg = tid >> 6;
   const int len = KP * DP + KP + 2;
+  const double *partials = a.partials;
+  int num_parts = a.num_parts;
+  __shared__ int xchg_ok;
+  if (a.peers != nullptr) {
+    const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
+    if (tid == 0) xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
+    __syncthreads();
+    if (!xchg_ok && tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);  // a peer never arrived: surfaces as a failed evaluation
+    partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
+    num_parts = a.peers->world;
+  }
   const double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
   // the two N-sized passes have swept the L2 since the last evaluation: pull the replicated D x D operands back in
   // while the statistics are being reduced (fire-and-forget bulk prefetches, 16-B granular)
@@ -707,11 +719,11 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   {
     double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     {
-      const double *src = a.partials + (size_t)k * DP + (r < DP ? r : DP - 1);
-      const int last = a.num_parts - 1;
+      const double *src = partials + (size_t)k * DP + (r < DP ? r : DP - 1);
+      const int last = num_parts - 1;
       // up to 160 partial vectors (one per SM and then some): all 40 loads of this thread are issued before the first
       // use -- clamped, unconditional addresses, because a predicated load is not hoisted above its use
-      for (int p0 = pg; p0 < a.num_parts; p0 += 160) {
+      for (int p0 = pg; p0 < num_parts; p0 += 160) {
         double w[40];
 #pragma unroll
         for (int u = 0; u < 40; ++u) {
@@ -727,9 +739,9 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   double phi_hat = 0.0;
   if (tid < 32) {
     double q0 = 0.0, q1 = 0.0;
-    for (int p = tid; p < a.num_parts; p += 64) {
-      q0 += __ldcg(a.partials + (size_t)p * len + (size_t)KP * DP + k);
-      if (p + 32 < a.num_parts) q1 += __ldcg(a.partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
+    for (int p = tid; p < num_parts; p += 64) {
+      q0 += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + k);
+      if (p + 32 < num_parts) q1 += __ldcg(partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
     }
     phi_hat = warp_sum(q0 + q1);
     if (tid == 0) red_s[0] = phi_hat;
@@ -869,7 +881,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   {
     // every load of this serial tail is issued by a different thread (one L2 round trip, not num_parts of them)
     double H = 0.0;
-    for (int p = tid; p < a.num_parts; p += blockDim.x) H += __ldcg(a.partials + (size_t)p * len + (size_t)KP * DP + KP);
+    for (int p = tid; p < num_parts; p += blockDim.x) H += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + KP);
     H = block_sum(H, red_s);
     if (tid == 0) a.stats[(size_t)KP * DP + KP] = H;
     __shared__ double phi_hat_sh[kMaxMixK];

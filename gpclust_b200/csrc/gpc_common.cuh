@@ -75,6 +75,37 @@ __device__ __forceinline__ bool loop_skip(const gpc_loop_t *loop, int phase) {
 template <typename T>
 __device__ __forceinline__ T sel3(T p0, T p1, T p2, int i) { return i == 0 ? p0 : (i == 1 ? p1 : p2); }
 
+// ---------------------------------------------------------------- peer-memory exchange (gpc_peers_t)
+__host__ __device__ inline long long xchg_l2(int len) { return (len + 1) & ~1; }
+__host__ __device__ inline long long xchg_off_stats(int W, int len, int slot, int sender) { return ((long long)slot * W + sender) * xchg_l2(len); }
+__host__ __device__ inline long long xchg_off_dots(int W, int len, int slot, int sender) { return 2LL * W * xchg_l2(len) + ((long long)slot * W + sender) * 4; }
+__host__ __device__ inline long long xchg_off_flags(int W, int len, int which, int slot, int sender) {  // in doubles (= u64 words)
+  return 2LL * W * xchg_l2(len) + 2LL * W * 4 + ((long long)which * 2 + slot) * W + sender;
+}
+__host__ __device__ inline long long xchg_doubles(int W, int len) { return 2LL * W * xchg_l2(len) + 2LL * W * 4 + 4LL * W; }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// one thread: wait until every rank's flag of exchange `which` (0 statistics, 1 dots) in `slot` of MY inbox has reached
+// `epoch`.  Bounded (a few seconds): returns false if a peer never shows up.
+__device__ inline bool xchg_wait(const gpc_peers_t *P, int which, int slot, unsigned long long epoch) {
+  const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(P->inbox[P->rank]) + xchg_off_flags(P->world, P->stats_len, which, slot, 0);
+  for (int r = 0; r < P->world; ++r) {
+    long long spins = 0;
+    while (ld_acquire_sys(flags + r) < epoch) {
+      if (++spins > (1LL << 23)) return false;
+      __nanosleep(64);
+    }
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------- vector global access (16 B)
 __device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ double2 ldg2_stream(const double *p) {

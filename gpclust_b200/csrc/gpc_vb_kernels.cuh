@@ -61,6 +61,7 @@ struct NatgradArgs {
   int N, K, DP, num_groups, stages;
   const gpc_loop_t *loop;  // nullable: device-resident loop state; the N x K operands then come from `bufs`
   gpc_bufs_t bufs;
+  const gpc_peers_t *peers;  // nullable: push the three dots into every peer's inbox (rows sharded over GPUs)
 };
 
 // ring stage: [F group | x group | lse (8) | lse_old (8)]; the previous-point operands x_old / ng_old go straight
@@ -280,9 +281,27 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       for (int c = lane; c < (int)gridDim.x; c += 32) v += __ldcg(a.partials + (size_t)c * 4 + warp);
       // fixed lane->CTA assignment and fixed shuffle tree => run-to-run deterministic
       v = warp_sum(v);
-      if (lane == 0) a.dots_out[warp] = v;
+      if (lane == 0) {
+        a.dots_out[warp] = v;
+        if (a.peers != nullptr) {  // this rank's contribution -> slot of the NEXT dots exchange in every inbox
+          const gpc_peers_t *P = a.peers;
+          const unsigned long long e = P->epochs[1] + 1;
+          for (int r = 0; r < P->world; ++r) P->inbox[r][xchg_off_dots(P->world, P->stats_len, (int)(e & 1), P->rank) + warp] = v;
+        }
+      }
     }
-    if (threadIdx.x == 0) *a.counter = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *a.counter = 0u;
+      if (a.peers != nullptr) {
+        const gpc_peers_t *P = a.peers;
+        const unsigned long long e = P->epochs[1] + 1;
+        __threadfence_system();
+        for (int r = 0; r < P->world; ++r)
+          st_release_sys(reinterpret_cast<unsigned long long *>(P->inbox[r]) + xchg_off_flags(P->world, P->stats_len, 1, (int)(e & 1), P->rank), e);
+        P->epochs[1] = e;
+      }
+    }
   }
 }
 
@@ -309,6 +328,8 @@ struct StepStatsArgs {
   const gpc_loop_t *loop;  // nullable: device-resident loop state (operands from `bufs`, beta mode / step / sq_old from it)
   gpc_bufs_t bufs;
   int phase;               // GPC_PHASE_CONJ / GPC_PHASE_RETRY
+  const gpc_peers_t *peers;  // nullable: the dots are the rank-ordered sum of the W inbox contributions
+  double *dots_sum;          // peers != NULL: CTA 0 stores the summed dots here (the loop tail and the host read them)
 };
 
 __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
@@ -358,9 +379,26 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
     sq_old = a.loop->sq_old;
     step = a.loop->step;
   }
+  __shared__ double dots_sh[4];
+  if (a.peers != nullptr) {
+    if (threadIdx.x == 0) {
+      const gpc_peers_t *P = a.peers;
+      const unsigned long long e = P->epochs[1];  // the G pass of this rank has pushed exchange e
+      const bool ok = xchg_wait(P, 1, (int)(e & 1), e);
+      double d[3] = {0.0, 0.0, 0.0};
+      for (int r = 0; r < P->world; ++r) {
+        const double *src = P->inbox[P->rank] + xchg_off_dots(P->world, P->stats_len, (int)(e & 1), r);
+        for (int q = 0; q < 3; ++q) d[q] += __ldcg(src + q);
+      }
+      for (int q = 0; q < 3; ++q) dots_sh[q] = ok ? d[q] : nan("");
+      if (blockIdx.x == 0 && a.dots_sum)
+        for (int q = 0; q < 3; ++q) a.dots_sum[q] = dots_sh[q];
+    }
+    __syncthreads();
+  }
   double beta = 0.0;
   if (beta_mode != GPC_BETA_ZERO) {
-    const double sq = a.dots[0], num = a.dots[1], den = a.dots[2];
+    const double sq = a.peers ? dots_sh[0] : a.dots[0], num = a.peers ? dots_sh[1] : a.dots[1], den = a.peers ? dots_sh[2] : a.dots[2];
     if (beta_mode == GPC_BETA_HS) beta = num / den;
     else if (beta_mode == GPC_BETA_PR) beta = num / sq_old;
     else beta = sq / sq_old;
@@ -556,6 +594,45 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
   __syncthreads();
   if (q == 0 && j < len)
     out[j] = ((red[0][c] + red[1][c]) + (red[2][c] + red[3][c])) + ((red[4][c] + red[5][c]) + (red[6][c] + red[7][c]));
+}
+
+// The same reduction, but the result goes straight into every peer's inbox (this rank's slot of the next statistics
+// exchange) over NVLink; the last CTA raises the flags.  Replaces reduce -> NCCL all-reduce between the S pass and the
+// posterior kernel: the consumer sums the W inbox vectors in rank order.
+__global__ void __launch_bounds__(256) k_reduce_push(const double *__restrict__ partials, int num_parts, int len, const gpc_peers_t *P,
+                                                     unsigned int *counter, const gpc_loop_t *loop, int phase) {
+  if (loop_skip(loop, phase)) return;
+  __shared__ double red[8][33];
+  __shared__ bool is_last;
+  const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
+  const unsigned long long e = P->epochs[0] + 1;
+  double v0 = 0.0, v1 = 0.0;
+  if (j < len) {
+    int p = q;
+    for (; p + 8 < num_parts; p += 16) {
+      v0 += partials[(size_t)p * len + j];
+      v1 += partials[(size_t)(p + 8) * len + j];
+    }
+    if (p < num_parts) v0 += partials[(size_t)p * len + j];
+  }
+  red[q][c] = v0 + v1;
+  __syncthreads();
+  if (q < P->world && j < len) {  // warp q stores to peer q, q + 8, ...: coalesced 256-byte rows over NVLink
+    const double v = ((red[0][c] + red[1][c]) + (red[2][c] + red[3][c])) + ((red[4][c] + red[5][c]) + (red[6][c] + red[7][c]));
+    for (int r = q; r < P->world; r += 8) P->inbox[r][xchg_off_stats(P->world, len, (int)(e & 1), P->rank) + j] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < P->world; ++r)
+      st_release_sys(reinterpret_cast<unsigned long long *>(P->inbox[r]) + xchg_off_flags(P->world, len, 0, (int)(e & 1), P->rank), e);
+    P->epochs[0] = e;
+    *counter = 0u;
+  }
 }
 
 }  // namespace gpc

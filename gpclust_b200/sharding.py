@@ -6,7 +6,14 @@ Per bound evaluation the ranks exchange ONE all-reduce of the statistics vector
 dot products.  The backend is whatever the group was created with: NCCL over NVLink on the GPU box, gloo in
 the CPU tests of this host logic (tests/test_sharding_gloo.py).
 """
+import ctypes
+import os
+import warnings
+
 import numpy as np
+
+
+_PEER_CACHE = {}  # (group id, world, stats_len, device index) -> exchange; models of one process run one at a time on a stream
 
 
 class RowShards(object):
@@ -53,6 +60,40 @@ class RowShards(object):
             pos += n
         out = np.concatenate(keep, 0) if keep else np.zeros((0, K))
         return out
+
+    def setup_peers(self, stats_len, device):
+        """Peer-memory exchange descriptor (gpc_peers_t, include/gpclust_b200.h) for the device-resident loop: one
+        symmetric-memory inbox per rank, mapped into every process of the box.  Collective.  -> dict or None (single
+        process, more than 8 ranks, symmetric memory unavailable, or GPCLUST_B200_PEER=0: the NCCL path is used)."""
+        if self.world == 1 or self.world > 8 or os.environ.get("GPCLUST_B200_PEER", "1") == "0":
+            return None
+        from . import _cabi
+        key = (id(self.group), self.world, int(stats_len), getattr(device, "index", None))
+        if key in _PEER_CACHE:
+            return _PEER_CACHE[key]
+        try:
+            import torch
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            n = int(_cabi.lib.gpc_xchg_doubles(self.world, int(stats_len)))
+            buf = symm.empty(n, dtype=torch.float64, device=device)
+            hdl = symm.rendezvous(buf, group)
+            buf.zero_()
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)  # nobody pushes before every inbox has been cleared
+            epochs = torch.zeros(2, dtype=torch.int64, device=device)
+            P = _cabi.GpcPeers()
+            P.world, P.rank, P.stats_len = self.world, self.rank, int(stats_len)
+            ptrs = list(hdl.buffer_ptrs)
+            for r in range(self.world):
+                P.inbox[r] = ptrs[r]
+            P.epochs = epochs.data_ptr()
+            raw = torch.frombuffer(bytearray(bytes(P)), dtype=torch.uint8).to(device)
+            _PEER_CACHE[key] = {"desc": raw, "buf": buf, "handle": hdl, "epochs": epochs}
+            return _PEER_CACHE[key]
+        except Exception as e:  # pragma: no cover - depends on the box
+            warnings.warn("gpclust_b200: peer-memory exchange unavailable (%s: %s); using NCCL all-reduces" % (type(e).__name__, e))
+            return None
 
     def allreduce(self, t):
         """In-place sum over ranks (no-op for a single process)."""

@@ -90,6 +90,23 @@ typedef struct {
   double *sd;     /* search direction (updated in place)                                */
 } gpc_bufs_t;
 
+/* ---- peer-memory exchange (rows sharded over the GPUs of one NVSwitch box) -------------------------------
+ * Instead of an NCCL all-reduce between kernels, the kernel that PRODUCES a small replicated vector (the reduced
+ * statistics, the three CG dots) stores it straight into every peer's inbox over NVLink and raises a flag; the
+ * kernel that CONSUMES it waits for the W flags and sums the W contributions in rank order (bit-identical on all
+ * ranks).  inbox[r] is rank r's exchange buffer mapped into this process (symmetric memory / CUDA IPC); its layout
+ * for W ranks and statistics length L (gpc_xchg_doubles gives the size):
+ *   [2][W][L2] statistics | [2][W][4] dots | [2][W] statistics flags (u64) | [2][W] dots flags (u64),  L2 = L rounded up to 2
+ * Two slots: a rank can be at most one exchange ahead of the slowest.  `epochs` (2 local u64: statistics, dots)
+ * count the exchanges this rank has pushed.                                                                   */
+#define GPC_MAX_PEERS 8
+typedef struct {
+  int world, rank, stats_len, pad;
+  double *inbox[GPC_MAX_PEERS];
+  unsigned long long *epochs; /* local: [0] statistics exchanges pushed, [1] dots exchanges pushed */
+} gpc_peers_t;
+long long gpc_xchg_doubles(int world, int stats_len);
+
 /* ---- library / geometry queries (host only, no GPU needed) ---------------------------------- */
 int gpc_abi_version(void);
 int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
@@ -130,6 +147,16 @@ int gpc_loop_natgrad(const double *F, const gpc_bufs_t *bufs, const double *Wt, 
 int gpc_loop_step_stats(const double *F, const gpc_bufs_t *bufs, const double *dots, double *beta_out, double *partials,
                         const gpc_loop_t *loop, int phase, long long N, int K, int KP, int DP, int grid, void *stream);
 
+/* peer-exchange variants: `peers` is a DEVICE pointer to a gpc_peers_t (NULL = single GPU / NCCL outside)    */
+int gpc_loop_natgrad_px(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                        double *dots, const gpc_loop_t *loop, const gpc_peers_t *peers, long long N, int K, int KP, int DP, int grid,
+                        void *stream);
+int gpc_loop_step_stats_px(const double *F, const gpc_bufs_t *bufs, double *dots, double *beta_out, double *partials, const gpc_loop_t *loop,
+                           const gpc_peers_t *peers, int phase, long long N, int K, int KP, int DP, int grid, void *stream);
+/* fixed-order reduction of the per-CTA statistics, pushed into every peer's inbox (+ flag)                  */
+int gpc_reduce_push(const double *partials, int num_parts, int len, const gpc_peers_t *peers, unsigned int *counter, const gpc_loop_t *loop,
+                    int phase, void *stream);
+
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);
 
@@ -167,6 +194,11 @@ int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, co
                         const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
                         double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP,
                         const double *dots, const double *beta, gpc_loop_t *loop, int phase, void *stream);
+/* as gpc_loop_mohgp_post, the statistics coming from the W inbox vectors of the peer exchange                  */
+int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
+                           const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias,
+                           double *scalars, double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D,
+                           int KP, int DP, const double *dots, const double *beta, gpc_loop_t *loop, int phase, void *stream);
 /* mixing-proportion bound and gradient (collapsed_mixture.py:66-94), bound assembly, G-pass bias.
  * scalars: [0] bound, [1] mixing_prop_bound, [2] H.  mixgrad_out (K doubles) may be NULL.             */
 int gpc_mohgp_finalize(const double *stats, const double *per_k, const double *const_term, double *bias, double *scalars,
