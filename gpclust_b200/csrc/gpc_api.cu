@@ -70,6 +70,15 @@ template <typename Kern>
 int tile_attr(Kern kern) {
   return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
 }
+int launch_post(const MohgpPostArgs &a, int KP, int D, cudaStream_t st) {
+  // dynamic shared memory: eigen workspace + Sy_inv staged by bulk copy (sizes must be multiples of 16 bytes)
+  const size_t smem = sizeof(double) * (size_t)eig_ws_len(D);
+  cudaError_t e = cudaFuncSetAttribute(k_mohgp_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  k_mohgp_post<<<KP, kClusterThreads, smem, st>>>(a);
+  return launch_rc();
+}
+
 bool make_kern_spec(int nparts, const int *kinds, const double *variances, const double *lengthscales, KernSpec &spec) {
   if (nparts < 1 || nparts > kMaxKernParts || !kinds || !variances || !lengthscales) return false;
   spec.nparts = nparts;
@@ -348,8 +357,7 @@ int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, co
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpPostArgs a{partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                   counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, nullptr};
-  k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
-  return launch_rc();
+  return launch_post(a, KP, D, st);
 }
 
 int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
@@ -367,8 +375,7 @@ int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, c
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpPostArgs a{stats, world, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                   counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, peers};
-  k_mohgp_post<<<KP, kClusterThreads, 0, st>>>(a);
-  return launch_rc();
+  return launch_post(a, KP, D, st);
 }
 
 int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,

@@ -516,8 +516,9 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_finalize(const MohgpF
 // i.e. five D x D matrix-vector products per cluster instead of a Cholesky, a D x D triangular solve and a SYRK.
 // phi_hat_k <= 1e-6 takes the reference's Lambda_inv := Sf branch.
 
-// workspace layout (doubles): [lam 64 | U D*D | Ut D*D | Vt D*D | tr(Sy_inv), sum(Sf o Sy_inv), sweeps, off-norm, 4 spare]
-__host__ __device__ inline int eig_ws_len(int D) { return GPC_MAX_DP + 3 * D * D + 8; }
+// workspace layout (doubles): [lam 64 | U D*D | Ut D*D | Vt D*D | Sy_inv D*D | tr(Sy_inv), sum(Sf o Sy_inv), sweeps, off-norm, 4 spare],
+// length rounded up to an even number of doubles so that the whole block is one 16-byte-granular bulk copy
+__host__ __device__ inline int eig_ws_len(int D) { return (GPC_MAX_DP + 4 * D * D + 8 + 1) & ~1; }
 
 struct MohgpEigArgs {
   const double *A, *Ly, *Ly_inv, *Sy_inv, *Sf;
@@ -609,8 +610,9 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_eig(const MohgpEigArg
       __syncthreads();
     }
   }
-  double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
+  double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *SyI = Vt + D * D, *scal = SyI + D * D;
   for (int i = tid; i < GPC_MAX_DP; i += nth) lam[i] = (i < D) ? As[i * ld + i] : 0.0;
+  for (int e = tid; e < D * D; e += nth) SyI[e] = a.Sy_inv[e];
   // U = Ly^-T Q ; V = Ly Q   (Ly, Ly_inv lower triangular with zero strict upper)
   for (int e = tid; e < D * D; e += nth) {
     const int i = e / D, j = e % D;
@@ -662,9 +664,9 @@ struct MohgpPostArgs {
   const gpc_peers_t *peers;  // nullable: statistics = the W inbox vectors of the peer exchange (partials / num_parts ignored)
 };
 
-// partial of y[r] = sum_j Mt[j*D + r] x[j] over j == pg (mod 4), for r < D; x in shared memory.  Sixteen independent
-// loads are in flight per thread: these matrices live in L2 and the kernel is latency-, not bandwidth-bound.
-__device__ __forceinline__ double matvec_t_part(const double *__restrict__ Mt, const double *x_s, int D, int r, int pg) {
+// partial of y[r] = sum_j Mt[j*D + r] x[j] over j == pg (mod 4), for r < D; x in shared memory, Mt in shared memory
+// (staged by bulk copy) or global memory.
+__device__ __forceinline__ double matvec_t_part(const double *Mt, const double *x_s, int D, int r, int pg) {
   // unconditional loads from clamped addresses (a predicated load is not hoisted above its use by the compiler)
   const int rc = r < D ? r : D - 1;
   double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -673,7 +675,7 @@ __device__ __forceinline__ double matvec_t_part(const double *__restrict__ Mt, c
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int jj = j + 4 * u;
-      m[u] = __ldg(Mt + (jj < D ? jj : D - 1) * D + rc);
+      m[u] = Mt[(jj < D ? jj : D - 1) * D + rc];
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
@@ -707,13 +709,20 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
     partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
     num_parts = a.peers->world;
   }
-  const double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *scal = Vt + D * D;
-  // the two N-sized passes have swept the L2 since the last evaluation: pull the replicated D x D operands back in
-  // while the statistics are being reduced (fire-and-forget bulk prefetches, 16-B granular)
+  // the two N-sized passes have swept the L2 since the last evaluation: the replicated D x D operands (eigen
+  // workspace incl. a copy of Sy_inv: <= 132 KB) are pulled into shared memory by one bulk copy while the statistics are being
+  // reduced, so that the five dependent matrix-vector products below never wait on HBM
+  extern __shared__ __align__(128) double post_dyn[];
+  __shared__ uint64_t stage_bar;
+  double *ws_s = post_dyn;
   if (tid == 0) {
-    bulk_prefetch_l2(a.ws, (uint32_t)((eig_ws_len(D) * 8) & ~15));
-    bulk_prefetch_l2(a.Sy_inv, (uint32_t)((D * D * 8) & ~15));
+    mbar_init(&stage_bar, 1);
+    mbar_fence_init();
+    const uint32_t bytes = (uint32_t)eig_ws_len(D) * 8u;  // even number of doubles: a multiple of 16 bytes
+    mbar_arrive_expect_tx(&stage_bar, bytes);
+    bulk_g2s(ws_s, a.ws, bytes, &stage_bar);
   }
+  const double *lam = ws_s, *U = ws_s + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *syi_s = Vt + D * D, *scal = syi_s + D * D;
 
   // ---- this cluster's statistics: fixed-order sum over the per-CTA partials (8 independent loads in flight)
   {
@@ -756,6 +765,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   if (tid == 0) a.stats[(size_t)KP * DP + k] = phi_hat;
   __syncthreads();
 
+  mbar_wait(&stage_bar, 0);
   if (k < a.K) {
     // ---- den_i = 1 + jitter + phi_hat lam_i with GPy's jitchol retry: a failed factorisation <=> some den_i <= 0
     double jitter = 0.0;
@@ -822,12 +832,12 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
         __syncthreads();
         if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
         __syncthreads();
-        red[pg][r] = matvec_t_part(a.Sy_inv, mu_s, D, r, pg);  // w = Sy_inv mu (Sy_inv symmetric)
+        red[pg][r] = matvec_t_part(syi_s, mu_s, D, r, pg);  // w = Sy_inv mu (Sy_inv symmetric)
         __syncthreads();
         if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
         __syncthreads();
       } else {
-        red[pg][r] = matvec_t_part(a.Sy_inv, s_s, D, r, pg);  // h = Sy_inv s
+        red[pg][r] = matvec_t_part(syi_s, s_s, D, r, pg);  // h = Sy_inv s
         __syncthreads();
         if (tid < D) {
           const double h = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);

@@ -45,7 +45,7 @@ def test_geometry_queries_without_gpu():
     assert lib.gpc_padded_rows(1) == 64 and lib.gpc_padded_rows(1000000) == 1000000 and lib.gpc_padded_rows(65) == 128
     assert lib.gpc_stats_len(64, 64) == 64 * 64 + 64 + 2
     assert lib.gpc_stats_len(16, 8) % 2 == 0
-    assert lib.gpc_omgp_padded_n(65) == 128 and lib.gpc_mohgp_eig_ws_len(64) == 64 + 3 * 64 * 64 + 8
+    assert lib.gpc_omgp_padded_n(65) == 128 and lib.gpc_mohgp_eig_ws_len(64) == 64 + 4 * 64 * 64 + 8 and lib.gpc_mohgp_eig_ws_len(3) % 2 == 0
 
 
 def test_bad_arguments_are_rejected_without_touching_the_gpu():
