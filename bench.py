@@ -214,8 +214,8 @@ def run_gpu(args):
     hi = (rank + 1) * N_TOTAL // world
     Y_loc, phi_loc = Y[lo:hi], phi0[lo:hi]
     n_loc = hi - lo
-    kF = lambda: kern.RBF(1, 1.0, 2.0)
-    kY = lambda: kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)
+    kF = lambda: kern.RBF(1, 1.0, 2.0).fix()  # the metric holds the kernel hyper-parameters fixed
+    kY = lambda: (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix()
 
     steps, warm = max(1, args.steps), max(3, args.warmup)
     method = args.method

@@ -90,8 +90,8 @@ class MOHGP(CollapsedMixture):
         self._YTY.copy_(full.view(DP, DP)[:self.D, :self.D])
 
     def parameters_changed(self):
-        """MOHGP.py:58-67: refresh the kernel matrices and their factorisation, then recompute.
-        (update_kern_grads, MOHGP.py:92-122, belongs to the hyper-parameter 'next' row.)"""
+        """MOHGP.py:58-67: refresh the kernel matrices and their factorisation, then recompute (and, when kernel parameters
+        are free, their gradients: update_kern_grads, MOHGP.py:92-122)."""
         D = self.D
         self._Sf.copy_(cov_to_device(self.kernF, self.X, self._X_dev))
         self._Sy.copy_(cov_to_device(self.kernY, self.X, self._X_dev))
@@ -106,6 +106,44 @@ class MOHGP(CollapsedMixture):
         if failed:
             raise np.linalg.LinAlgError("not positive definite, even with jitter.")
         self.do_computations()
+        self._kern_grads_valid = False
+
+    def _kernel_param_list(self):
+        out = []
+        for k in (self.kernF, self.kernY):  # link order of MOHGP.py:44
+            if hasattr(k, "param_list"):
+                out.extend(k.param_list())
+        return out
+
+    def _kernel_gradients(self):
+        if not getattr(self, "_kern_grads_valid", False):
+            self.update_kern_grads()
+        return CollapsedMixture._kernel_gradients(self)
+
+    def update_kern_grads(self):
+        """MOHGP.py:92-122: derivative of the bound w.r.t. the kernel parameters through dL/dSf and dL/dSy.  K x D x D
+        host algebra on the device-computed posterior (C_chols from the literal Cholesky route), once per hyper-parameter
+        objective evaluation -- not part of the VB iteration."""
+        from scipy.linalg import solve_triangular
+        D = self.D
+        Sy_chol_inv, Sf, Sy_inv, phi_hat = self.Sy_chol_inv, self.Sf, self.Sy_inv, self.phi_hat
+        Syi_ybark, ybark, YTY = self.Syi_ybark, self.ybark, self.YTY
+        tmp = [solve_triangular(L, Sy_chol_inv, lower=True) for L in self._C_chols]
+        B_invs = [ph * np.dot(t.T, t) for ph, t in zip(phi_hat, tmp)]
+        LiSfi = [np.eye(D) - np.dot(Sf, Bi) for Bi in B_invs]
+        tmp1 = [np.dot(L.T, s) for L, s in zip(LiSfi, Syi_ybark.T)]
+        dL_dSf = 0.5 * sum([np.dot(t[:, None], t[None, :]) for t in tmp1]) - 0.5 * sum(B_invs)
+        self.kernF.update_gradients_full(dL_dK=dL_dSf, X=self.X)
+        Byks = [np.dot(Bi, yk) for Bi, yk in zip(B_invs, ybark.T)]
+        SyyS = self.Syi_ybarkybarkT_Syi
+        dL_dSy = sum([np.dot(Byk[:, None], Byk[None, :]) / np.power(ph, 3) - S_k / ph - Bi / ph
+                      for Bi, Byk, ph, S_k in zip(B_invs, Byks, phi_hat, SyyS) if ph > 1e-6])
+        dL_dSy = dL_dSy + (self.K - self.N_total) * Sy_inv
+        dL_dSy = dL_dSy + Sy_inv.dot(YTY).dot(Sy_inv)
+        dL_dSy = dL_dSy / 2.0
+        self.kernY.update_gradients_full(dL_dK=dL_dSy, X=self.X)
+        self._dL_dSf, self._dL_dSy = dL_dSf, dL_dSy
+        self._kern_grads_valid = True
 
     def _launch_posterior(self):
         """Statistics -> posterior -> bound in one launch (two + an all-reduce when rows are sharded)."""

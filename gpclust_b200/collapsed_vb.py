@@ -49,13 +49,74 @@ class CollapsedVB(object):
     def log_likelihood(self):
         return self.bound()  # collapsed_vb.py:56-61
 
+    # ---- non-variational (kernel) parameters: the slice of GPy / paramz the reference leans on (collapsed_vb.py:313-323).
+    # Every kernel parameter is positive-constrained through paramz's Logexp transform f(x) = log(1 + e^x); the
+    # optimiser works on x.  `_kernel_param_list()` -> [(object, attribute), ...] of the FREE parameters.
+    _LIM = 36.0
+
+    def _kernel_param_list(self):
+        return []
+
+    @staticmethod
+    def _logexp_finv(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f > CollapsedVB._LIM, f, np.log(np.expm1(np.minimum(f, CollapsedVB._LIM))))
+
+    @staticmethod
+    def _logexp_f(x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.where(x > CollapsedVB._LIM, x, np.log1p(np.exp(np.clip(x, -745.0, CollapsedVB._LIM))))
+
     @property
     def optimizer_array(self):
-        return np.zeros(0)
+        """Untransformed free parameters (GPy Model.optimizer_array)."""
+        plist = self._kernel_param_list()
+        if not plist:
+            return np.zeros(0)
+        return self._logexp_finv([getattr(o, n) for o, n in plist])
+
+    @optimizer_array.setter
+    def optimizer_array(self, x):
+        plist = self._kernel_param_list()
+        vals = self._logexp_f(x)
+        changed = False
+        for (o, n), v in zip(plist, vals):
+            if getattr(o, n) != float(v):
+                setattr(o, n, float(v))
+                changed = True
+        if changed:
+            self.parameters_changed()
+
+    def parameters_changed(self):
+        pass
+
+    def _kernel_gradients(self):
+        """d bound / d (free kernel parameter), constrained space, same order as _kernel_param_list()."""
+        return np.array([getattr(o, n + "_gradient") for o, n in self._kernel_param_list()])
+
+    def _objective_grads(self, x):
+        """GPy Model._objective_grads: (-log_likelihood, -transformed gradients); a failed factorisation counts as +inf."""
+        try:
+            self.optimizer_array = x
+            f = np.asarray([getattr(o, n) for o, n in self._kernel_param_list()])
+            g = self._kernel_gradients() * np.where(f > self._LIM, 1.0, -np.expm1(-f))  # Logexp.gradfactor
+            return -float(self.log_likelihood()), -g
+        except LinAlgError:
+            return np.inf, np.zeros(len(x))
 
     def optimize_parameters(self):
-        """collapsed_vb.py:313-323. No free (kernel) parameters are exposed by this build => 0."""
-        return 0.0
+        """collapsed_vb.py:313-323: optimise the non-variational parameters with GPy's default optimiser (L-BFGS-B,
+        `hyperparam_opt_args['max_iters']` function evaluations); returns the increment of the bound."""
+        if self.optimizer_array.size > 0:
+            from scipy.optimize import fmin_l_bfgs_b
+            start = self.bound()
+            x0 = self.optimizer_array.copy()
+            max_iters = int(self.hyperparam_opt_args.get("max_iters", 20))
+            x_opt, f_opt, info = fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters, maxiter=max_iters)
+            self.optimizer_array = x_opt
+            return self.bound() - start
+        else:
+            return 0.0
 
     # ---- device hooks
     def _cg_gradient(self, with_old):

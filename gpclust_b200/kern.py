@@ -49,7 +49,32 @@ class Kern(object):
     def copy(self):
         return _copy.deepcopy(self)
 
-    # GPy API surface used by the reference's constructors / hyper-parameter hooks
+    # ---- hyper-parameter interface (GPy: every kernel parameter is a positive-constrained Param; `fix()` removes it
+    # from the optimiser's vector).  param_list() -> [(object, attribute name), ...] in GPy's link order.
+    fixed = False
+
+    def fix(self):
+        self.fixed = True
+        for p in getattr(self, "parts", []):
+            p.fix()
+        return self
+
+    def unfix(self):
+        self.fixed = False
+        for p in getattr(self, "parts", []):
+            p.unfix()
+        return self
+
+    constrain_fixed = fix
+    unconstrain_fixed = unfix
+
+    def param_list(self):
+        return []
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        """Set `<name>_gradient` for every parameter from dL/dK (GPy Kern.update_gradients_full; D x D host algebra)."""
+        raise NotImplementedError
+
     def parameters_changed(self):
         pass
 
@@ -77,17 +102,56 @@ class _Stationary(Kern):
     def parts_spec(self):
         return [(self.kind, self.variance, self.lengthscale)]
 
+    def param_list(self):
+        return [] if self.fixed else [(self, "variance"), (self, "lengthscale")]
+
+    def _scaled_dist(self, X, X2=None):
+        # GPy kern/src/stationary.py: r^2 = -2 X X2^T + |x|^2 + |x2|^2, diagonal zeroed when X2 is None, clipped at 0
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        if X2 is None:
+            Xsq = np.sum(np.square(X), 1)
+            r2 = -2.0 * np.dot(X, X.T) + (Xsq[:, None] + Xsq[None, :])
+            r2[np.diag_indices(X.shape[0])] = 0.0
+        else:
+            X2 = np.atleast_2d(np.asarray(X2, dtype=np.float64))
+            r2 = -2.0 * np.dot(X, X2.T) + (np.sum(np.square(X), 1)[:, None] + np.sum(np.square(X2), 1)[None, :])
+        return np.sqrt(np.clip(r2, 0.0, np.inf)) / self.lengthscale
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        # GPy Stationary.update_gradients_full (non-ARD)
+        r = self._scaled_dist(X, X2)
+        self.variance_gradient = float(np.sum(self._K_of_r(r) * dL_dK) / self.variance)
+        self.lengthscale_gradient = float(-np.sum(self._dK_dr(r) * dL_dK * r) / self.lengthscale)
+
 
 class RBF(_Stationary):
     kind = "rbf"
+
+    def _K_of_r(self, r):
+        return self.variance * np.exp(-0.5 * r ** 2)
+
+    def _dK_dr(self, r):
+        return -r * self._K_of_r(r)
 
 
 class Matern32(_Stationary):
     kind = "matern32"
 
+    def _K_of_r(self, r):
+        return self.variance * (1.0 + np.sqrt(3.0) * r) * np.exp(-np.sqrt(3.0) * r)
+
+    def _dK_dr(self, r):
+        return -3.0 * self.variance * r * np.exp(-np.sqrt(3.0) * r)
+
 
 class Matern52(_Stationary):
     kind = "matern52"
+
+    def _K_of_r(self, r):
+        return self.variance * (1.0 + np.sqrt(5.0) * r + 5.0 / 3.0 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
+
+    def _dK_dr(self, r):
+        return self.variance * (10.0 / 3.0 * r - 5.0 * r - 5.0 * np.sqrt(5.0) / 3.0 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
 
 
 class Bias(Kern):
@@ -97,6 +161,12 @@ class Bias(Kern):
     def parts_spec(self):
         return [("bias", self.variance, 1.0)]
 
+    def param_list(self):
+        return [] if self.fixed else [(self, "variance")]
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance_gradient = float(np.sum(dL_dK))
+
 
 class White(Kern):
     def __init__(self, input_dim=1, variance=1.0, active_dims=None, name="white"):
@@ -104,6 +174,12 @@ class White(Kern):
 
     def parts_spec(self):
         return [("white", self.variance, 1.0)]
+
+    def param_list(self):
+        return [] if self.fixed else [(self, "variance")]
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance_gradient = float(np.trace(dL_dK)) if X2 is None else 0.0
 
 
 class Add(Kern):
@@ -121,6 +197,16 @@ class Add(Kern):
         for p in self.parts:
             s.extend(p.parts_spec())
         return s
+
+    def param_list(self):
+        out = []
+        for p in self.parts:
+            out.extend(p.param_list())
+        return out
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        for p in self.parts:  # every part of a sum receives the same dL_dK
+            p.update_gradients_full(dL_dK, X, X2)
 
 
 def cov_to_device(kern, X_host, X_dev):

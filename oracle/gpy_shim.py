@@ -142,6 +142,16 @@ class _Stationary(Kern):
     def K(self, X, X2=None):
         return self.K_of_r(self._scaled_dist(X, X2))
 
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        # GPy Stationary.update_gradients_full (non-ARD): variance.gradient = sum(K o dL_dK)/variance,
+        # lengthscale.gradient = -sum(dK_dr o dL_dK o r)/lengthscale
+        r = self._scaled_dist(X, X2)
+        self.variance_gradient = float(np.sum(self.K_of_r(r) * dL_dK) / self.variance)
+        self.lengthscale_gradient = float(-np.sum(self.dK_dr(r) * dL_dK * r) / self.lengthscale)
+
+    def param_list(self):
+        return [(self, "variance"), (self, "lengthscale")]
+
     def spec(self):
         return [(self.kind, self.variance, self.lengthscale)]
 
@@ -152,6 +162,9 @@ class RBF(_Stationary):
     def K_of_r(self, r):
         return self.variance * np.exp(-0.5 * r ** 2)
 
+    def dK_dr(self, r):
+        return -r * self.K_of_r(r)
+
 
 class Matern32(_Stationary):
     kind = "matern32"
@@ -159,12 +172,18 @@ class Matern32(_Stationary):
     def K_of_r(self, r):
         return self.variance * (1.0 + np.sqrt(3.0) * r) * np.exp(-np.sqrt(3.0) * r)
 
+    def dK_dr(self, r):
+        return -3.0 * self.variance * r * np.exp(-np.sqrt(3.0) * r)
+
 
 class Matern52(_Stationary):
     kind = "matern52"
 
     def K_of_r(self, r):
         return self.variance * (1.0 + np.sqrt(5.0) * r + 5.0 / 3.0 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
+
+    def dK_dr(self, r):
+        return self.variance * (10.0 / 3.0 * r - 5.0 * r - 5.0 * np.sqrt(5.0) / 3.0 * r ** 2) * np.exp(-np.sqrt(5.0) * r)
 
 
 class Bias(Kern):
@@ -177,6 +196,12 @@ class Bias(Kern):
     def K(self, X, X2=None):
         n2 = X.shape[0] if X2 is None else X2.shape[0]
         return np.full((X.shape[0], n2), self.variance)
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance_gradient = float(np.sum(dL_dK))
+
+    def param_list(self):
+        return [(self, "variance")]
 
     def spec(self):
         return [(self.kind, self.variance, 1.0)]
@@ -194,6 +219,12 @@ class White(Kern):
             return np.eye(X.shape[0]) * self.variance
         return np.zeros((X.shape[0], X2.shape[0]))
 
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        self.variance_gradient = float(np.trace(dL_dK)) if X2 is None else 0.0
+
+    def param_list(self):
+        return [(self, "variance")]
+
     def spec(self):
         return [(self.kind, self.variance, 1.0)]
 
@@ -209,6 +240,16 @@ class Add(Kern):
         out = self.parts[0].K(X, X2)
         for p in self.parts[1:]:
             out = out + p.K(X, X2)
+        return out
+
+    def update_gradients_full(self, dL_dK, X, X2=None):
+        for p in self.parts:  # every part of a sum receives the same dL_dK
+            p.update_gradients_full(dL_dK, X, X2)
+
+    def param_list(self):
+        out = []
+        for p in self.parts:
+            out.extend(p.param_list())
         return out
 
     def spec(self):

@@ -435,6 +435,71 @@ class MOHGPOracle(MixtureOracle):
         self.Syi_ybarkybarkT_Syi = self.Syi_ybark.T[:, None, :] * self.Syi_ybark.T[:, :, None]
         self.muk = (self.Lambda_inv * self.Syi_ybark.T[:, :, None]).sum(1).T
 
+    def update_kern_grads(self):
+        # MOHGP.py:92-122 -- derivative of the bound w.r.t. the kernel parameters, through dL/dSf and dL/dSy
+        tmp = [G.dtrtrs(L, self.Sy_chol_inv, lower=1)[0] for L in self._C_chols]
+        B_invs = [ph * np.dot(t.T, t) for ph, t in zip(self.phi_hat, tmp)]
+        LiSfi = [np.eye(self.D) - np.dot(self.Sf, Bi) for Bi in B_invs]
+        tmp1 = [np.dot(L.T, s) for L, s in zip(LiSfi, self.Syi_ybark.T)]
+        tmp = 0.5 * sum([np.dot(t[:, None], t[None, :]) for t in tmp1])
+        tmp += -0.5 * sum(B_invs)
+        self.dL_dSf = tmp
+        self.kernF.update_gradients_full(dL_dK=tmp, X=self.X)
+        Byks = [np.dot(Bi, yk) for Bi, yk in zip(B_invs, self.ybark.T)]
+        tmp = sum([np.dot(Byk[:, None], Byk[None, :]) / np.power(ph, 3) - SyyS / ph - Bi / ph
+                   for Bi, Byk, ph, SyyS in zip(B_invs, Byks, self.phi_hat, self.Syi_ybarkybarkT_Syi) if ph > 1e-6])
+        tmp = tmp + (self.K - self.N) * self.Sy_inv
+        tmp = tmp + G.mdot(self.Sy_inv, self.YTY, self.Sy_inv)
+        tmp = tmp / 2.0
+        self.dL_dSy = tmp
+        self.kernY.update_gradients_full(dL_dK=tmp, X=self.X)
+
+    hyper_free = False  # True: the kernel parameters are free, optimize() interleaves their optimisation (collapsed_vb.py:300-301)
+    hyperparam_max_iters = 20  # collapsed_vb.py:32-35
+
+    def kernel_param_list(self):
+        return self.kernF.param_list() + self.kernY.param_list()
+
+    # paramz Logexp transform + GPy Model.optimize (default optimiser: scipy L-BFGS-B on -log_likelihood), collapsed_vb.py:313-323
+    @staticmethod
+    def _finv(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f > 36.0, f, np.log(np.expm1(np.minimum(f, 36.0))))
+
+    @staticmethod
+    def _f(x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.where(x > 36.0, x, np.log1p(np.exp(np.clip(x, -745.0, 36.0))))
+
+    def _set_x(self, x):
+        for (k, name), v in zip(self.kernel_param_list(), self._f(x)):
+            setattr(k, name, float(v))
+        self.parameters_changed()
+
+    def _objective_grads(self, x):
+        try:
+            self._set_x(x)
+            f = np.array([getattr(k, name) for k, name in self.kernel_param_list()])
+            g = self.kernel_gradients() * np.where(f > 36.0, 1.0, -np.expm1(-f))
+            return -float(self.bound()), -g
+        except LinAlgError:
+            return np.inf, np.zeros(len(x))
+
+    def optimize_parameters(self):
+        if not self.hyper_free:
+            return 0.0
+        from scipy.optimize import fmin_l_bfgs_b
+        start = self.bound()
+        x0 = self._finv([getattr(k, name) for k, name in self.kernel_param_list()])
+        x_opt, _, _ = fmin_l_bfgs_b(self._objective_grads, x0, maxfun=self.hyperparam_max_iters, maxiter=self.hyperparam_max_iters)
+        self._set_x(x_opt)
+        return self.bound() - start
+
+    def kernel_gradients(self):
+        """d bound / d (kernel parameter), in link order kernF then kernY (what GPy hands to its optimiser, untransformed)."""
+        self.update_kern_grads()
+        return np.array([getattr(k, name + "_gradient") for k, name in self.kernel_param_list()])
+
     def bound(self):
         # MOHGP.py:124-135
         return (-0.5 * (self.N * self.D * np.log(2.0 * np.pi)

@@ -36,9 +36,11 @@ def oracle_kernels():
     return G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
 
 
-def product_kernels():
+def product_kernels(fixed=True):
+    """fixed=True: kernel hyper-parameters held fixed (the oracle's default; the reference would need kern.fix())."""
     from gpclust_b200 import kern
-    return kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)
+    kF, kY = kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)
+    return (kF.fix(), kY.fix()) if fixed else (kF, kY)
 
 
 def load_golden():

@@ -158,7 +158,7 @@ def test_matern_dp_drosophila_like():
     np.random.seed(2)
     mo = MOHGPOracle(X, kF, kY, Y, K=K, prior_Z="DP", alpha=1.0)
     np.random.seed(2)
-    mp = MOHGP(X, kern.Matern52(1, 1.0, 12.0), kern.Matern52(1, 0.1, 12.0) + kern.White(1, 0.05), Y, K=K, prior_Z="DP", alpha=1.0)
+    mp = MOHGP(X, kern.Matern52(1, 1.0, 12.0).fix(), (kern.Matern52(1, 0.1, 12.0) + kern.White(1, 0.05)).fix(), Y, K=K, prior_Z="DP", alpha=1.0)
     assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
     mo.out = io.StringIO()
     mo.optimize(maxiter=30, verbose=False)
@@ -195,7 +195,7 @@ def test_duplicate_time_points_singular_Sf():
     np.random.seed(4)
     mo = MOHGPOracle(X, kF, kY, Y, K=K, prior_Z="DP", alpha=2.0)
     np.random.seed(4)
-    mp = MOHGP(X, kern.Matern52(1, 1.0, 12.0), kern.Matern52(1, 0.1, 12.0) + kern.White(1, 0.05), Y, K=K, prior_Z="DP", alpha=2.0)
+    mp = MOHGP(X, kern.Matern52(1, 1.0, 12.0).fix(), (kern.Matern52(1, 0.1, 12.0) + kern.White(1, 0.05)).fix(), Y, K=K, prior_Z="DP", alpha=2.0)
     assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
     assert relerr(mp.muk, mo.muk) < TOL
     g_p, ng_p = mp.vb_grad_natgrad()

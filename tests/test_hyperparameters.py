@@ -1,0 +1,105 @@
+"""Kernel hyper-parameter row: MOHGP.update_kern_grads (MOHGP.py:92-122), the Logexp-transformed
+optimizer array and optimize_parameters (collapsed_vb.py:313-323, GPy Model.optimize = L-BFGS-B, max_iters=20).
+
+CPU: the oracle's restatement of update_kern_grads agrees with finite differences of its own bound (an identity that does not
+depend on the oracle being right about anything else).  GPU: the product's gradients, optimiser vector and hyper-parameter
+step agree with the oracle's on the same inputs."""
+import io
+
+import numpy as np
+import pytest
+
+from helpers import mohgp_problem, relerr
+from oracle import gpy_shim as G
+from oracle.vb_oracle import MOHGPOracle
+
+
+def _oracle(N=200, D=12, K=4, seed=0):
+    X, Y, _ = mohgp_problem(N, D, K, seed)
+    np.random.seed(seed + 1)
+    kF = G.RBF(1, 1.0, 2.0) + G.Bias(1, 0.3)
+    kY = G.Matern52(1, 0.1, 1.0) + G.White(1, 0.05) + G.Matern32(1, 0.2, 3.0)
+    m = MOHGPOracle(X, kF, kY, Y, K=K, prior_Z="DP", alpha=2.0)
+    m.out = io.StringIO()
+    return X, Y, m
+
+
+def test_oracle_kernel_gradients_match_finite_differences():
+    X, Y, m = _oracle()
+    m.optimize(maxiter=5, verbose=False)
+    g = m.kernel_gradients()
+    fd = []
+    for k, name in m.kernel_param_list():
+        v = getattr(k, name)
+        h = 1e-6 * max(1.0, abs(v))
+        setattr(k, name, v + h)
+        m.parameters_changed()
+        bp = m.bound()
+        setattr(k, name, v - h)
+        m.parameters_changed()
+        bm = m.bound()
+        setattr(k, name, v)
+        m.parameters_changed()
+        fd.append((bp - bm) / (2 * h))
+    # the reference's formulas ignore the 1e-6 jitter that separates Sy from chol(Sy + 1e-6 I): exact to ~1e-3 relative
+    assert np.max(np.abs(g - np.array(fd)) / np.maximum(1e-6, np.abs(fd))) < 2e-3
+
+
+def test_oracle_hyperparameter_step_increases_the_bound():
+    X, Y, m = _oracle()
+    m.hyper_free = True
+    m.optimize(maxiter=8, verbose=False)
+    b0 = m.bound()
+    inc = m.optimize_parameters()
+    assert inc > 0 and abs((m.bound() - b0) - inc) < 1e-9 * abs(b0)
+
+
+@pytest.mark.gpu
+def test_gpu_kernel_gradients_and_hyperparameter_step_match_the_oracle():
+    from gpclust_b200 import MOHGP, kern
+    X, Y, mo = _oracle()
+    np.random.seed(1)
+    kF = kern.RBF(1, 1.0, 2.0) + kern.Bias(1, 0.3)
+    kY = kern.Matern52(1, 0.1, 1.0) + kern.White(1, 0.05) + kern.Matern32(1, 0.2, 3.0)
+    mp = MOHGP(X, kF, kY, Y, K=4, prior_Z="DP", alpha=2.0)
+    assert np.array_equal(mp.phi_, mo.phi_)
+    assert mp.optimizer_array.size == 8  # (variance, lengthscale) + variance | (v, l) + variance + (v, l)
+    mp.update_kern_grads()
+    assert relerr(mp._kernel_gradients(), mo.kernel_gradients()) < 1e-7
+    assert relerr(mp._dL_dSf, mo.dL_dSf) < 1e-7 and relerr(mp._dL_dSy, mo.dL_dSy) < 1e-7
+    # optimiser vector round trip through the Logexp transform
+    x = mp.optimizer_array.copy()
+    mp.optimizer_array = x
+    assert relerr(mp.optimizer_array, x) < 1e-14
+    # one hyper-parameter step (L-BFGS-B, 20 evaluations) from the same point
+    mo.hyper_free = True
+    inc_o = mo.optimize_parameters()
+    inc_p = mp.optimize_parameters()
+    assert inc_p > 0 and abs(inc_p - inc_o) < 1e-5 * abs(inc_o)
+    po = np.array([getattr(k, n) for k, n in mo.kernel_param_list()])
+    pp = np.array([getattr(k, n) for k, n in mp._kernel_param_list()])
+    assert np.allclose(pp, po, rtol=1e-5, atol=1e-8)
+    assert abs(mp.bound() - mo.bound()) < 1e-8 * abs(mo.bound())
+
+
+@pytest.mark.gpu
+def test_gpu_optimize_interleaves_hyperparameter_steps_like_the_reference():
+    """optimize() with free kernel parameters: the host-driven loop runs optimize_parameters() at convergence
+    (collapsed_vb.py:248,270) exactly as the oracle does; fixed kernels select the device-resident loop."""
+    from gpclust_b200 import MOHGP, kern
+    X, Y, _ = mohgp_problem(150, 10, 3, 2)
+    np.random.seed(3)
+    mo = MOHGPOracle(X, G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05), Y, K=3)
+    mo.hyper_free = True
+    mo.out = io.StringIO()
+    np.random.seed(3)
+    mp = MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05), Y, K=3)
+    mo.optimize(maxiter=60, verbose=False)
+    mp.optimize(maxiter=60, verbose=False)
+    to, tp = np.array(mo.trace), np.array(mp.optimize_trace)
+    assert to.shape == tp.shape and np.array_equal(to[:, 0], tp[:, 0])
+    assert np.max(np.abs(to[:, 1] - tp[:, 1]) / np.abs(to[:, 1])) < 1e-6
+    po = np.array([getattr(k, n) for k, n in mo.kernel_param_list()])
+    pp = np.array([getattr(k, n) for k, n in mp._kernel_param_list()])
+    assert np.allclose(pp, po, rtol=1e-4)
+    assert not np.allclose(pp, [1.0, 2.0, 0.1, 1.0, 0.05])  # the kernels did move

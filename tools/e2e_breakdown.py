@@ -26,7 +26,7 @@ def T(label, t0):
 for rep in range(2):
     print("rep", rep)
     t = time.perf_counter()
-    m = MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05), Y, K=bench.K, phi_init=phi0)
+    m = MOHGP(X, kern.RBF(1, 1.0, 2.0).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=bench.K, phi_init=phi0)
     t = T("construct", t)
     m.optimize(method="HS", maxiter=30, ftol=-1.0, gtol=-1.0, verbose=False)
     t = T("optimize(30)", t)

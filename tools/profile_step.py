@@ -16,7 +16,7 @@ nrows = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 method = sys.argv[3] if len(sys.argv) > 3 else "HS"
 X, Y, phi0 = bench.synth(nrows, bench.D, bench.K)
-m = MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05), Y, K=bench.K, phi_init=phi0)
+m = MOHGP(X, kern.RBF(1, 1.0, 2.0).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=bench.K, phi_init=phi0)
 m.bound()
 m.run_passes(2, method=method)
 torch.cuda.synchronize()
