@@ -201,3 +201,42 @@ def test_duplicate_time_points_singular_Sf():
     g_p, ng_p = mp.vb_grad_natgrad()
     g_o, ng_o = mo.vb_grad_natgrad()
     assert relerr(ng_p, ng_o) < TOL and relerr(g_p, g_o) < TOL
+
+
+@pytest.mark.parametrize("method", ["HS", "PR", "FR", "steepest"])
+def test_device_resident_loop_equals_host_driven_loop(method):
+    """optimize() runs the loop from the device-resident state (accept / reject, rotation, termination on the device);
+    a callback forces the host-driven loop that follows collapsed_vb.py:147-303 line by line.  Same trace, same state."""
+    mo, m_dev = _pair(900, 20, 7, seed=5)
+    _, m_host = _pair(900, 20, 7, seed=5)
+    n_dev = m_dev.optimize(method=method, maxiter=35, verbose=False)
+    n_host = m_host.optimize(method=method, maxiter=35, verbose=False, callback=lambda: None)
+    assert n_dev == n_host
+    td, th = np.array(m_dev.optimize_trace), np.array(m_host.optimize_trace)
+    assert td.shape == th.shape and np.array_equal(td[:, 0], th[:, 0])
+    assert np.max(np.abs(td[:, 1] - th[:, 1]) / np.abs(th[:, 1])) < 1e-13
+    assert np.allclose(td[:, 2:], th[:, 2:], rtol=1e-9, atol=1e-12)
+    assert relerr(m_dev.phi_, m_host.phi_) < 1e-12 and relerr(m_dev.phi, m_host.phi) < 1e-12
+    assert abs(m_dev.bound() - m_host.bound()) < 1e-13 * abs(m_host.bound())
+    # a second optimize() continues from the adopted state on either path
+    m_dev.optimize(method=method, maxiter=6, verbose=False, callback=lambda: None)
+    m_host.optimize(method=method, maxiter=6, verbose=False)
+    assert abs(m_dev.bound() - m_host.bound()) < 1e-12 * abs(m_host.bound())
+
+
+def test_device_loop_terminates_on_ftol_and_reports_it(capsys):
+    mo, mp = _pair(300, 12, 3, seed=7)
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=400, ftol=1e-3, verbose=False)
+    n = mp.optimize(maxiter=400, ftol=1e-3, verbose=True)
+    out = capsys.readouterr().out
+    assert "vb converged (ftol)" in out and out.count("iteration ") == len(mp.optimize_trace)
+    assert [r[0] for r in mp.optimize_trace] == [r[0] for r in mo.trace] and n == mo.trace[-1][0]
+
+
+def test_unsupported_sizes_fail_loudly():
+    from gpclust_b200 import MOHGP
+    X, Y, _ = mohgp_problem(100, 8, 2, 0)
+    pF, pY = product_kernels()
+    with pytest.raises(ValueError):
+        MOHGP(X, pF, pY, Y, K=65)
