@@ -40,6 +40,10 @@ PROTOTYPES = {
     "gpc_loop_step_stats_px": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_push": [_p, _i, _i, _p, _p, _p, _i, _p],
     "gpc_xchg_doubles": [_i, _i],
+    "gpc_natgrad_chunk": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _i, _i, _ll, _i, _p],
+    "gpc_natgrad_finish": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
+    "gpc_step_lse": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _p],
+    "gpc_stats_chunk": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _ll, _i, _i, _ll, _i, _p],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],
@@ -137,8 +141,13 @@ def ptr(t):
 def padded_k(K):
     kp = lib.gpc_padded_k(int(K))
     if kp < 0:
-        raise ValueError("gpclust_b200: K=%d is outside the supported range 1..64" % K)
+        raise ValueError("gpclust_b200: K=%d is outside the supported range 1..512" % K)
     return kp
+
+
+def ptr_off(t, n_doubles):
+    """Device pointer n_doubles into a float64 tensor."""
+    return ctypes.c_void_p(t.data_ptr() + 8 * int(n_doubles))
 
 
 def padded_d(D):

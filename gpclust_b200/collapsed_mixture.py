@@ -21,7 +21,7 @@ import numpy as np
 from numpy.linalg import LinAlgError
 
 from . import _cabi
-from ._cabi import lib, check, ptr
+from ._cabi import lib, check, ptr, ptr_off
 from .collapsed_vb import CollapsedVB
 from .sharding import RowShards
 
@@ -77,7 +77,7 @@ class CollapsedMixture(CollapsedVB):
         self._ctrl = torch.zeros(_CTRL_LEN, dtype=torch.float64, device=self.device)
         self._ctrl_host = torch.zeros(_CTRL_LEN, dtype=torch.float64).pin_memory()
         self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self._gpart = torch.zeros(self._grid * 4, dtype=torch.float64, device=self.device)
+        self._gpart = torch.zeros(self._grid * 16, dtype=torch.float64, device=self.device)  # 4 doubles per CTA, up to 4 CTAs per SM
         self._state_valid = False
         self._bound_value = None
         self._peers = None      # peer-memory exchange descriptor (rows sharded over the GPUs of one box), see sharding.py
@@ -125,6 +125,11 @@ class CollapsedMixture(CollapsedVB):
         self._bias = z(KP)
         self._per_k = z(KP, 4)
         self._mixgrad = z(KP)
+        self._chunks = (KP + 63) // 64 if KP > 64 else 1   # K > 64: clusters in chunks of 64 (gpc_*_chunk entry points)
+        if self._chunks > 1:
+            self._sa_vec = z(self._Npad)
+            self._hpart = z(self._grid)
+            self._dots_scratch = z(4)
         self._alloc_kd()
 
     def _alloc_kd(self):
@@ -137,7 +142,7 @@ class CollapsedMixture(CollapsedVB):
         self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
         self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
         self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
-        self._peers = self._shards.setup_peers(self._stats_len, self.device) if self._use_peer_exchange() else None
+        self._peers = self._shards.setup_peers(self._stats_len, self.device) if (self._use_peer_exchange() and self._chunks == 1) else None
         self._alloc_model()
 
     def _alloc_model(self):
@@ -276,10 +281,42 @@ class CollapsedMixture(CollapsedVB):
             self._launch_posterior()
 
     def _launch_step_stats(self, x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old):
+        if self._chunks > 1:
+            return self._launch_step_stats_chunked(x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old)
         check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(lse_new), ptr(self._ctrl[_C_SQ:]),
                                  float(sq_old), ptr(self._ctrl[_C_BETA:]), ptr(self._spart), float(step), _cabi.BETA[beta_mode], self.N,
                                  self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_step_stats")
         self.kernel_launches += 1
+
+    def _launch_step_stats_chunked(self, x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old):
+        """K > 64: CG step + row logsumexp + entropy over whole rows, then the statistics of one 64-cluster chunk per launch."""
+        KP, DP, st = self._KP, self._DP, self._stream()
+        check(lib.gpc_step_lse(ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(lse_new), ptr(self._ctrl[_C_SQ:]), float(sq_old),
+                               ptr(self._ctrl[_C_BETA:]), ptr(self._hpart), float(step), _cabi.BETA[beta_mode], self.N, self.K, KP, self._grid, st),
+              "gpc_step_lse")
+        x_at = x_new if ng is not None else x_base
+        for c in range(self._chunks):
+            kc = min(64, self.K - 64 * c)
+            if kc <= 0:
+                break
+            check(lib.gpc_stats_chunk(ptr(self._F), ptr_off(x_at, 512 * c), ptr(lse_new), ptr(self._hpart) if c == 0 else None, ptr(self._spart),
+                                      self._stats_len, 64 * c * DP, KP * DP + 64 * c, KP * DP + KP, 1 if c == 0 else 0, self.N, kc, DP, 8 * KP,
+                                      self._grid, st), "gpc_stats_chunk")
+        self.kernel_launches += 1 + self._chunks
+
+    def _launch_natgrad_chunked(self, x, lse, x_old, lse_old, ng_old, ng_out, grad_out, dots):
+        """K > 64: a = F.W + bias - x per chunk (row sums of phi*a accumulated), then centring, gradient and dots over whole rows."""
+        KP, DP, st = self._KP, self._DP, self._stream()
+        for c in range(self._chunks):
+            kc = min(64, self.K - 64 * c)
+            if kc <= 0:
+                break
+            check(lib.gpc_natgrad_chunk(ptr(self._F), ptr_off(x, 512 * c), ptr(lse), ptr_off(self._Wt, 64 * c * DP), ptr_off(self._bias, 64 * c),
+                                        ptr_off(ng_out, 512 * c), ptr(self._sa_vec), 1 if c == 0 else 0, ptr(self._gpart), ptr(self._counter),
+                                        ptr(self._dots_scratch), self.N, kc, DP, 8 * KP, self._grid, st), "gpc_natgrad_chunk")
+        check(lib.gpc_natgrad_finish(ptr(ng_out), ptr(x), ptr(lse), ptr(self._sa_vec), ptr(x_old), ptr(lse_old), ptr(ng_old), ptr(grad_out),
+                                     ptr(self._gpart), ptr(self._counter), dots, self.N, self.K, KP, self._grid * 4, st), "gpc_natgrad_finish")
+        self.kernel_launches += 1 + self._chunks
 
     def _launch_posterior(self):
         check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
@@ -321,9 +358,13 @@ class CollapsedMixture(CollapsedVB):
             self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
 
     def _launch_natgrad(self, have_old):
-        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias),
-                              ptr(self._xbuf[self._xprev]) if have_old else None, ptr(self._lsebuf[self._xprev]) if have_old else None,
-                              ptr(self._ngbuf[1 - self._ngi]) if have_old else None,
+        x, lse = self._xbuf[self._xi], self._lsebuf[self._xi]
+        x_old = self._xbuf[self._xprev] if have_old else None
+        lse_old = self._lsebuf[self._xprev] if have_old else None
+        ng_old = self._ngbuf[1 - self._ngi] if have_old else None
+        if self._chunks > 1:
+            return self._launch_natgrad_chunked(x, lse, x_old, lse_old, ng_old, self._ngbuf[self._ngi], None, ptr(self._ctrl[_C_SQ:]))
+        check(lib.gpc_natgrad(ptr(self._F), ptr(x), ptr(lse), ptr(self._Wt), ptr(self._bias), ptr(x_old), ptr(lse_old), ptr(ng_old),
                               ptr(self._ngbuf[self._ngi]), None, ptr(self._gpart), ptr(self._counter), ptr(self._ctrl[_C_SQ:]), self.N,
                               self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_natgrad")
         self.kernel_launches += 1
@@ -360,7 +401,7 @@ class CollapsedMixture(CollapsedVB):
     _BATCH = 16       # loop-body passes enqueued per read-back
 
     def _device_loop_ok(self):
-        return True
+        return self._chunks == 1  # K > 64 runs the chunked passes under the host-driven loop
 
     def _bufs(self):
         b = _cabi.GpcBufs()
@@ -482,11 +523,14 @@ class CollapsedMixture(CollapsedVB):
         ng = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
         gr = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
         dots = torch.zeros(4, dtype=torch.float64, device=self.device)
-        check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None,
-                              None, ptr(ng), ptr(gr),
-                              ptr(self._gpart), ptr(self._counter), ptr(dots), self.N, self.K, self._KP, self._DP, self._grid,
-                              self._stream()), "gpc_natgrad")
-        self.kernel_launches += 1
+        if self._chunks > 1:
+            self._launch_natgrad_chunked(self._xbuf[self._xi], self._lsebuf[self._xi], None, None, None, ng, gr, ptr(dots))
+        else:
+            check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None,
+                                  None, ptr(ng), ptr(gr),
+                                  ptr(self._gpart), ptr(self._counter), ptr(dots), self.N, self.K, self._KP, self._DP, self._grid,
+                                  self._stream()), "gpc_natgrad")
+            self.kernel_launches += 1
         return _cabi.to_host(self._unpad(gr)).reshape(-1), _cabi.to_host(self._unpad(ng)).reshape(-1)
 
     # ------------------------------------------------------------------ merge / split search (host control)

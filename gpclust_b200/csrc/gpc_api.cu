@@ -92,7 +92,7 @@ bool make_kern_spec(int nparts, const int *kinds, const double *variances, const
 }
 
 bool geometry_ok(long long N, int K, int KP, int DP, int grid) {
-  return N >= 1 && K >= 1 && K <= KP && KP == gpc_padded_k(K) && DP >= 8 && DP <= GPC_MAX_DP && (DP % 8) == 0 && grid >= 1 &&
+  return N >= 1 && K >= 1 && K <= KP && KP <= GPC_MAX_KP && KP == gpc_padded_k(K) && DP >= 8 && DP <= GPC_MAX_DP && (DP % 8) == 0 && grid >= 1 &&
          gpc_padded_rows(N) / GPC_ROW_TILE < 0x7fffffffLL;
 }
 
@@ -103,7 +103,8 @@ extern "C" {
 int gpc_abi_version(void) { return 1; }
 
 int gpc_padded_k(int K) {
-  if (K < 1 || K > GPC_MAX_KP) return -1;
+  if (K < 1 || K > GPC_MAX_KTOT) return -1;
+  if (K > GPC_MAX_KP) return (K + GPC_MAX_KP - 1) / GPC_MAX_KP * GPC_MAX_KP;  // chunks of 64 clusters
   int kp = 8;
   while (kp < K) kp *= 2;
   return kp;
@@ -266,6 +267,84 @@ int gpc_loop_step_stats_px(const double *F, const gpc_bufs_t *bufs, double *dots
   return dispatch_step_stats(a, KP, grid, as_stream(stream));
 }
 
+// ------------------------------------------------------------------------------------------------ K > 64: chunks of 64 clusters
+int gpc_natgrad_chunk(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, double *a_out, double *sa_vec,
+                      int first, double *partials, unsigned int *counter, double *dots_scratch, long long N, int Kc, int DP, long long xg_stride,
+                      int grid, void *stream) {
+  if (!F || !x || !lse || !Wt || !bias || !a_out || !sa_vec || !partials || !counter || !dots_scratch) return GPC_EINVAL;
+  if (N < 1 || N > 0x7fffffffLL || Kc < 1 || Kc > GPC_MAX_KP || DP < 8 || DP > GPC_MAX_DP || (DP % 8) || grid < 1 || xg_stride < 8 * GPC_MAX_KP)
+    return GPC_EINVAL;
+  NatgradArgs a{};
+  a.F = F;
+  a.x = x;
+  a.lse = lse;
+  a.Wt = Wt;
+  a.bias = bias;
+  a.ng_out = a_out;
+  a.partials = partials;
+  a.counter = counter;
+  a.dots_out = dots_scratch;
+  a.N = (int)N;
+  a.K = Kc;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.xg_stride = xg_stride;
+  a.sa_vec = sa_vec;
+  a.sa_first = first;
+  return dispatch_natgrad(a, GPC_MAX_KP, grid, as_stream(stream));
+}
+
+int gpc_natgrad_finish(double *ng, const double *x, const double *lse, const double *sa_vec, const double *x_old, const double *lse_old,
+                       const double *ng_old, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
+                       int grid, void *stream) {
+  if (!ng || !x || !lse || !sa_vec || !partials || !counter || !dots) return GPC_EINVAL;
+  if ((x_old == nullptr) != (ng_old == nullptr) || (x_old == nullptr) != (lse_old == nullptr)) return GPC_EINVAL;
+  if (N < 1 || N > 0x7fffffffLL || K < 1 || K > KP || KP != gpc_padded_k(K) || grid < 1) return GPC_EINVAL;
+  NatgradFinishArgs a{ng, x, lse, sa_vec, x_old, lse_old, ng_old, grad_out, partials, counter, dots, (int)N, K, KP,
+                      (int)(gpc_padded_rows(N) / kGroupRows)};
+  k_natgrad_finish<<<grid, 256, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_step_lse(const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new, double *lse_new, const double *dots,
+                 double sq_old, double *beta_out, double *hpart, double step, int beta_mode, long long N, int K, int KP, int grid, void *stream) {
+  if (!x_base || !lse_new || !hpart) return GPC_EINVAL;
+  if (ng && !x_new) return GPC_EINVAL;
+  if (beta_mode != GPC_BETA_ZERO && (!dots || !ng)) return GPC_EINVAL;
+  if (beta_mode < GPC_BETA_ZERO || beta_mode > GPC_BETA_FR) return GPC_EINVAL;
+  if (N < 1 || N > 0x7fffffffLL || K < 1 || K > KP || KP != gpc_padded_k(K) || grid < 1) return GPC_EINVAL;
+  StepLseArgs a{x_base, ng, sd_old, sd_new, x_new, lse_new, dots, beta_out, hpart, step, sq_old, beta_mode, (int)N, K, KP,
+                (int)(gpc_padded_rows(N) / kGroupRows)};
+  k_step_lse<<<grid, 256, 0, as_stream(stream)>>>(a);
+  return launch_rc();
+}
+
+int gpc_stats_chunk(const double *F, const double *x, const double *lse, const double *h_in, double *partials, long long part_stride, int t_off,
+                    int ph_off, int h_off, int write_h, long long N, int Kc, int DP, long long xg_stride, int grid, void *stream) {
+  if (!F || !x || !lse || !partials || part_stride < 1) return GPC_EINVAL;
+  if (N < 1 || N > 0x7fffffffLL || Kc < 1 || Kc > GPC_MAX_KP || DP < 8 || DP > GPC_MAX_DP || (DP % 8) || grid < 1 || xg_stride < 8 * GPC_MAX_KP)
+    return GPC_EINVAL;
+  StepStatsArgs a{};
+  a.F = F;
+  a.x_base = x;
+  a.partials = partials;
+  a.beta_mode = GPC_BETA_ZERO;
+  a.N = (int)N;
+  a.K = Kc;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.phase = GPC_PHASE_CONJ;
+  a.xg_stride = xg_stride;
+  a.lse_in = lse;
+  a.h_in = h_in;
+  a.part_stride = part_stride;
+  a.t_off = t_off;
+  a.ph_off = ph_off;
+  a.h_off = h_off;
+  a.write_h = write_h;
+  return dispatch_step_stats(a, GPC_MAX_KP, grid, as_stream(stream));
+}
+
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
   if (!partials || !out || num_parts < 1 || len < 1) return GPC_EINVAL;
   k_reduce_partials<<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, num_parts, len, out);
@@ -348,7 +427,7 @@ int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, co
   if (!partials || num_parts < 1 || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !Wt || !muk_t || !per_k || !bias || !scalars ||
       !counter || !info)
     return GPC_EINVAL;
-  if (K < 1 || K > KP || KP > GPC_MAX_KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > GPC_MAX_KTOT || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
   if (loop && (!dots || !beta || (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY))) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);

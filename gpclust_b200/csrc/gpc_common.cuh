@@ -10,7 +10,8 @@
 
 #include "../../include/gpclust_b200.h"  // GPC_ROW_TILE (rows per CTA tile; every N-sized device array is
                                          // allocated with roundup(N, GPC_ROW_TILE) rows, pad rows zero) and enums
-#define GPC_MAX_KP 64            // padded cluster count handled by the tensor kernels (8 n-tiles)
+#define GPC_MAX_KP 64            // padded cluster count handled by one launch of the tensor kernels (8 n-tiles)
+#define GPC_MAX_KTOT 512         // more clusters are processed in chunks of GPC_MAX_KP
 #define GPC_MAX_DP 64            // padded feature count (time points / MOG features)
 
 namespace gpc {

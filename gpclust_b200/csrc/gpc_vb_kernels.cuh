@@ -62,6 +62,13 @@ struct NatgradArgs {
   const gpc_loop_t *loop;  // nullable: device-resident loop state; the N x K operands then come from `bufs`
   gpc_bufs_t bufs;
   const gpc_peers_t *peers;  // nullable: push the three dots into every peer's inbox (rows sharded over GPUs)
+  // K > 64: the clusters are processed in chunks of 64, one launch per chunk (pointers pre-offset to the chunk).
+  // xg_stride: doubles between consecutive 8-row groups of the N x K operands (0 = 8*KP: single chunk).
+  // sa_vec != NULL selects sweep 1 of the chunked pass: ng_out receives a = F.W + bias - x (not yet centred) and
+  // sa_vec[row] accumulates sum_k phi*a over the chunks (sa_first: this launch initialises it); no dots.
+  long long xg_stride;
+  double *sa_vec;
+  int sa_first;
 };
 
 // ring stage: [F group | x group | lse (8) | lse_old (8)]; the previous-point operands x_old / ng_old go straight
@@ -112,6 +119,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
     p_ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) : nullptr;
   }
   const bool has_old = (p_ng_old != nullptr);
+  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;  // global group stride of the N x K operands
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       double *st = ustages + (size_t)slot * stage_doubles;
       mbar_arrive_expect_tx(&ubar[slot], bytes);
       bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &ubar[slot]);
-      bulk_g2s(st + FG, p_x + (size_t)grp * XG, XG * 8u, &ubar[slot]);
+      bulk_g2s(st + FG, p_x + (size_t)grp * GS, XG * 8u, &ubar[slot]);
       bulk_g2s(st + FG + XG, p_lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
       if (has_old) bulk_g2s(st + FG + XG + kGroupRows, p_lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
     };
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       const double *st = ustages + (size_t)slot * stage_doubles;
       const int row = grp * kGroupRows + g;
       const bool row_ok = row < a.N;
-      const size_t goff = (size_t)grp * XG + (size_t)nt0 * 64 + 2 * lane;
+      const size_t goff = (size_t)grp * GS + (size_t)nt0 * 64 + 2 * lane;
 
       // previous-point operands: HBM -> registers, in flight behind the DMMA loop and pass 1
       double2 xo[NTW], ngo[NTW];
@@ -219,6 +227,15 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       if (h == 0 && lane == 0) {
         const long long nxt = (long long)grp + (long long)R * gstride;
         if (nxt < a.num_groups) feed(slot, (int)nxt);
+      }
+
+      if (a.sa_vec != nullptr) {
+        // sweep 1 of the chunked pass (K > 64): leave a = F.W + bias - x behind, accumulate the row sums over the chunks
+        if (h == 0 && t == 0 && row_ok) a.sa_vec[row] = a.sa_first ? sa : a.sa_vec[row] + sa;
+        double *a_g = p_ng_out + goff;
+#pragma unroll
+        for (int q = 0; q < NTW; ++q) stg2(a_g + q * 64, acc[q][0], acc[q][1]);
+        continue;
       }
 
       // ---- pass 2: natural gradient, gradient, dots
@@ -330,6 +347,16 @@ struct StepStatsArgs {
   int phase;               // GPC_PHASE_CONJ / GPC_PHASE_RETRY
   const gpc_peers_t *peers;  // nullable: the dots are the rank-ordered sum of the W inbox contributions
   double *dots_sum;          // peers != NULL: CTA 0 stores the summed dots here (the loop tail and the host read them)
+  // K > 64: statistics of one 64-cluster chunk per launch (x_base pre-offset to the chunk, ng == NULL).
+  // lse_in != NULL: phi = exp(x - lse_in[row]) with the row logsumexp over ALL clusters (from k_step_lse) instead of a
+  // softmax over the chunk.  part_stride / t_off / ph_off / h_off place the chunk's [T | phi_hat | H] inside the
+  // per-CTA block of the full statistics vector (0 / 0 / 0 / 0 = single chunk).  h_in: per-CTA entropy partials of
+  // k_step_lse, added into the H slot when write_h.
+  long long xg_stride;
+  const double *lse_in;
+  const double *h_in;
+  long long part_stride;
+  int t_off, ph_off, h_off, write_h;
 };
 
 __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
@@ -407,7 +434,12 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   if (blockIdx.x == 0 && threadIdx.x == 0 && p_beta_out) *p_beta_out = beta;
   const bool has_ng = (p_ng != nullptr);
   const bool use_old = has_ng && (beta != 0.0) && (p_sd_old != nullptr);
-  double *part = a.partials + (size_t)blockIdx.x * (KP * DP + KP + 2);
+  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
+  const bool chunked = (a.part_stride != 0);
+  double *part = a.partials + (size_t)blockIdx.x * (chunked ? (size_t)a.part_stride : (size_t)(KP * DP + KP + 2));
+  double *part_t = part + (chunked ? a.t_off : 0);              // T rows of this chunk
+  double *part_ph = part + (chunked ? a.ph_off : KP * DP);       // phi_hat of this chunk
+  double *part_h = part + (chunked ? a.h_off : KP * DP + KP);    // H (+ pad)
 
   if (warp == kSSoftmaxWarps + kSStatWarps) {
     // ---------------- producer
@@ -420,9 +452,9 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         double *st = stages + (size_t)s * stage_doubles;
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
-        bulk_g2s(st + FG, p_x_base + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        if (has_ng) bulk_g2s(st + FG + XG, p_ng + (size_t)grp * XG, XG * 8u, &full_bar[s]);
-        if (use_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * XG, XG * 8u, &full_bar[s]);
+        bulk_g2s(st + FG, p_x_base + (size_t)grp * GS, XG * 8u, &full_bar[s]);
+        if (has_ng) bulk_g2s(st + FG + XG, p_ng + (size_t)grp * GS, XG * 8u, &full_bar[s]);
+        if (use_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * GS, XG * 8u, &full_bar[s]);
       }
     }
   } else if (warp < kSSoftmaxWarps) {
@@ -444,8 +476,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         x[nt][1] = v.y;
       }
       if (has_ng) {
-        double *sdo_g = p_sd_new ? p_sd_new + (size_t)grp * XG + 2 * lane : nullptr;
-        double *xn_g = p_x_new + (size_t)grp * XG + 2 * lane;
+        double *sdo_g = p_sd_new ? p_sd_new + (size_t)grp * GS + 2 * lane : nullptr;
+        double *xn_g = p_x_new + (size_t)grp * GS + 2 * lane;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const double2 ngv = *reinterpret_cast<const double2 *>(xs + XG + nt * 64);
@@ -460,6 +492,28 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
           if (sdo_g) stg2(sdo_g + nt * 64, s0, s1);
           stg2(xn_g + nt * 64, x[nt][0], x[nt][1]);
         }
+      }
+      if (a.lse_in != nullptr) {
+        // chunk of a wider row: phi = exp(x - logsumexp over all clusters); entropy and lse come from k_step_lse
+        const double l = a.lse_in[row];
+        double ex[2 * NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          ex[2 * nt] = x[nt][0] - l;
+          ex[2 * nt + 1] = x[nt][1] - l;
+        }
+        exp_batch<2 * NT>(ex);
+        __syncwarp();
+        double *psl = st + FG + (g >> 2) * 32 + (g & 3);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = 8 * nt + 2 * t;
+          psl[nt * 64 + (2 * t) * 4] = ((FULLK || c < a.K) && row_ok) ? ex[2 * nt] : 0.0;
+          psl[nt * 64 + (2 * t + 1) * 4] = ((FULLK || c + 1 < a.K) && row_ok) ? ex[2 * nt + 1] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&phi_bar[s]);
+        continue;
       }
       // row softmax: max, exp, sum   (np_utilities.py:25-40)
       double m = -INFINITY;
@@ -556,22 +610,24 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
 #pragma unroll
     for (int i = 0; i < TPW; ++i) {
       const int mt = i >> 1, dt = ((i & 1) << 2) + q;
-      if (dt < DT) stg2(part + (size_t)(8 * mt + g) * DP + 8 * dt + 2 * t, acc[i][0], acc[i][1]);
+      if (dt < DT) stg2(part_t + (size_t)(8 * mt + g) * DP + 8 * dt + 2 * t, acc[i][0], acc[i][1]);
     }
     if (q == 0) {
 #pragma unroll
       for (int mt = 0; mt < NT; ++mt) {
         const double cs = quad_sum(colsum[mt]);
-        if (t == 0) part[(size_t)KP * DP + 8 * mt + g] = cs;
+        if (t == 0) part_ph[8 * mt + g] = cs;
       }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && (!chunked || a.write_h)) {
     double v = 0.0;
-    for (int w = 0; w < kSSoftmaxWarps; ++w) v += red_s[w];
-    part[(size_t)KP * DP + KP] = v;
-    part[(size_t)KP * DP + KP + 1] = 0.0;
+    if (a.lse_in == nullptr)
+      for (int w = 0; w < kSSoftmaxWarps; ++w) v += red_s[w];
+    if (a.h_in != nullptr) v += a.h_in[blockIdx.x];
+    part_h[0] = v;
+    part_h[1] = 0.0;
   }
 }
 
@@ -594,6 +650,195 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
   __syncthreads();
   if (q == 0 && j < len)
     out[j] = ((red[0][c] + red[1][c]) + (red[2][c] + red[3][c])) + ((red[4][c] + red[5][c]) + (red[6][c] + red[7][c]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K > 64 (clusters processed in chunks of 64): the two row-coupled steps that span all chunks.
+// ------------------------------------------------------------------------------------------------
+// S1: CG step on whole rows + row logsumexp + entropy.  One warp per 8-row group, lane (g, t) walks the n-tiles of
+// row g; two sweeps (max, then sum of exponentials) exactly as np_utilities.py:25-40, the second one re-reading the
+// x_new this lane has just written (L1/L2 hits).
+struct StepLseArgs {
+  const double *x_base, *ng, *sd_old;
+  double *sd_new, *x_new, *lse_new;
+  const double *dots;
+  double *beta_out;
+  double *hpart;  // gridDim.x entropy partials
+  double step, sq_old;
+  int beta_mode, N, K, KP, num_groups;
+};
+__global__ void __launch_bounds__(256) k_step_lse(const StepLseArgs a) {
+  __shared__ double red_s[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int NTT = a.KP / 8;
+  const size_t GS = (size_t)kGroupRows * a.KP;
+  double beta = 0.0;
+  if (a.beta_mode != GPC_BETA_ZERO) {
+    const double sq = a.dots[0], num = a.dots[1], den = a.dots[2];
+    if (a.beta_mode == GPC_BETA_HS) beta = num / den;
+    else if (a.beta_mode == GPC_BETA_PR) beta = num / a.sq_old;
+    else beta = sq / a.sq_old;
+    if (isnan(beta) || beta < 0.0) beta = 0.0;  // collapsed_vb.py:165-166
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.beta_out) *a.beta_out = beta;
+  const bool has_ng = (a.ng != nullptr);
+  const bool use_old = has_ng && beta != 0.0 && a.sd_old != nullptr;
+  double Hpart = 0.0;
+  for (int grp = blockIdx.x * 8 + warp; grp < a.num_groups; grp += gridDim.x * 8) {
+    const int row = grp * kGroupRows + g;
+    const bool row_ok = row < a.N;
+    const size_t off = (size_t)grp * GS + 2 * lane;
+    const double *xsrc = has_ng ? a.x_new : a.x_base;
+    double m = -INFINITY;
+    for (int nt = 0; nt < NTT; ++nt) {
+      const int c = 8 * nt + 2 * t;
+      double2 xv = ldg2(a.x_base + off + nt * 64);
+      if (has_ng) {
+        const double2 nv = ldg2_stream(a.ng + off + nt * 64);
+        double s0 = nv.x, s1 = nv.y;
+        if (use_old) {
+          const double2 sv = ldg2(a.sd_old + off + nt * 64);
+          s0 += beta * sv.x;  // collapsed_vb.py:167
+          s1 += beta * sv.y;
+        }
+        xv.x += a.step * s0;  // collapsed_vb.py:172
+        xv.y += a.step * s1;
+        if (a.sd_new) stg2(a.sd_new + off + nt * 64, s0, s1);
+        stg2(a.x_new + off + nt * 64, xv.x, xv.y);
+      }
+      if (c < a.K) m = fmax(m, xv.x);
+      if (c + 1 < a.K) m = fmax(m, xv.y);
+    }
+    m = quad_max(m);
+    double ssum = 0.0, px = 0.0;
+    for (int nt0 = 0; nt0 < NTT; nt0 += 4) {
+      double z[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 xv = (nt0 + q < NTT) ? ldg2(xsrc + off + (nt0 + q) * 64) : make_double2(m, m);
+        z[2 * q] = xv.x - m;
+        z[2 * q + 1] = xv.y - m;
+      }
+      double e[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) e[q] = z[q];
+      exp_batch<8>(e);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = 8 * (nt0 + (q >> 1)) + 2 * t + (q & 1);
+        if (c < a.K) {
+          ssum += e[q];
+          px += e[q] * z[q];
+        }
+      }
+    }
+    ssum = quad_sum(ssum);
+    px = quad_sum(px);
+    const double lognorm = log(ssum);
+    if (row_ok && t == 0) Hpart += lognorm - px / ssum;
+    if (a.lse_new && t == 0) a.lse_new[row] = m + lognorm;
+  }
+  Hpart = warp_sum(Hpart);
+  if (lane == 0) red_s[warp] = Hpart;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red_s[w];
+    a.hpart[blockIdx.x] = v;
+  }
+}
+
+// G2: a (left in the natural-gradient buffer by the per-chunk sweep) -> natural gradient, gradient and the CG dots over
+// whole rows: natgrad = a - sa[row], grad = natgrad * exp(x - lse)   (MOHGP.py:150-151, collapsed_vb.py:154,160-164)
+struct NatgradFinishArgs {
+  double *ng;             // in: a ; out: natural gradient
+  const double *x, *lse, *sa_vec;
+  const double *x_old, *lse_old, *ng_old;  // nullable together
+  double *grad_out;       // nullable
+  double *partials;       // gridDim.x * 4
+  unsigned int *counter;
+  double *dots_out;
+  int N, K, KP, num_groups;
+};
+__global__ void __launch_bounds__(256) k_natgrad_finish(const NatgradFinishArgs a) {
+  __shared__ double red_s[8 * 4];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int NTT = a.KP / 8;
+  const size_t GS = (size_t)kGroupRows * a.KP;
+  const bool has_old = (a.ng_old != nullptr);
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  for (int grp = blockIdx.x * 8 + warp; grp < a.num_groups; grp += gridDim.x * 8) {
+    const int row = grp * kGroupRows + g;
+    const bool row_ok = row < a.N;
+    const size_t off = (size_t)grp * GS + 2 * lane;
+    const double sa = a.sa_vec[row], lse = a.lse[row], lse_o = has_old ? a.lse_old[row] : 0.0;
+    for (int nt0 = 0; nt0 < NTT; nt0 += 4) {
+      double phi[8], po[8];
+      double2 av[4], ngo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool in = nt0 + q < NTT;
+        const double2 xv = in ? ldg2_stream(a.x + off + (nt0 + q) * 64) : make_double2(0.0, 0.0);
+        av[q] = in ? ldg2(a.ng + off + (nt0 + q) * 64) : make_double2(0.0, 0.0);
+        phi[2 * q] = xv.x - lse;
+        phi[2 * q + 1] = xv.y - lse;
+        if (has_old) {
+          const double2 xo = in ? ldg2_stream(a.x_old + off + (nt0 + q) * 64) : make_double2(0.0, 0.0);
+          ngo[q] = in ? ldg2_stream(a.ng_old + off + (nt0 + q) * 64) : make_double2(0.0, 0.0);
+          po[2 * q] = xo.x - lse_o;
+          po[2 * q + 1] = xo.y - lse_o;
+        }
+      }
+      exp_batch<8>(phi);
+      if (has_old) exp_batch<8>(po);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (nt0 + q >= NTT) continue;
+        const int c = 8 * (nt0 + q) + 2 * t;
+        const bool ok0 = c < a.K && row_ok, ok1 = c + 1 < a.K && row_ok;
+        const double n0 = ok0 ? av[q].x - sa : 0.0, n1 = ok1 ? av[q].y - sa : 0.0;
+        const double p0 = ok0 ? phi[2 * q] : 0.0, p1 = ok1 ? phi[2 * q + 1] : 0.0;
+        const double g0 = n0 * p0, g1 = n1 * p1;
+        stg2(a.ng + off + (nt0 + q) * 64, n0, n1);
+        if (a.grad_out) stg2(a.grad_out + off + (nt0 + q) * 64, g0, g1);
+        d0 += n0 * g0 + n1 * g1;
+        if (has_old) {
+          const double e0 = n0 - ngo[q].x, e1 = n1 - ngo[q].y;
+          d1 += e0 * g0 + e1 * g1;
+          d2 += e0 * (ngo[q].x * (ok0 ? po[2 * q] : 0.0)) + e1 * (ngo[q].y * (ok1 ? po[2 * q + 1] : 0.0));
+        }
+      }
+    }
+  }
+  d0 = warp_sum(d0);
+  d1 = warp_sum(d1);
+  d2 = warp_sum(d2);
+  if (lane == 0) {
+    red_s[warp * 4 + 0] = d0;
+    red_s[warp * 4 + 1] = d1;
+    red_s[warp * 4 + 2] = d2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red_s[w * 4 + threadIdx.x];
+    a.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp < 3) {
+      double v = 0.0;
+      for (int c = lane; c < (int)gridDim.x; c += 32) v += __ldcg(a.partials + (size_t)c * 4 + warp);
+      v = warp_sum(v);
+      if (lane == 0) a.dots_out[warp] = v;
+    }
+    if (threadIdx.x == 0) *a.counter = 0u;
+  }
 }
 
 // The same reduction, but the result goes straight into every peer's inbox (this rank's slot of the next statistics

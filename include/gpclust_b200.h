@@ -109,7 +109,7 @@ long long gpc_xchg_doubles(int world, int stats_len);
 
 /* ---- library / geometry queries (host only, no GPU needed) ---------------------------------- */
 int gpc_abi_version(void);
-int gpc_padded_k(int K);           /* 8,16,32,64; -1 when K is unsupported (K < 1 or K > 64)        */
+int gpc_padded_k(int K);           /* 8,16,32,64, then multiples of 64 up to 512; -1 when K < 1 or K > 512 */
 int gpc_padded_d(int D);           /* roundup(D, 8);  -1 when D < 1 or D > 64                      */
 long long gpc_padded_rows(long long N);
 int gpc_stats_len(int KP, int DP); /* KP*DP + KP + 2 (one pad double keeps blocks 16-B aligned)    */
@@ -156,6 +156,25 @@ int gpc_loop_step_stats_px(const double *F, const gpc_bufs_t *bufs, double *dots
 /* fixed-order reduction of the per-CTA statistics, pushed into every peer's inbox (+ flag)                  */
 int gpc_reduce_push(const double *partials, int num_parts, int len, const gpc_peers_t *peers, unsigned int *counter, const gpc_loop_t *loop,
                     int phase, void *stream);
+
+/* ---- K > 64: the clusters are processed in chunks of 64 (one launch of the tensor kernels per chunk) ----------
+ * N x K arrays keep the fragment-major layout with KP/8 n-tiles per 8-row group (xg_stride = 8*KP doubles between
+ * groups); a chunk's slice starts 512*c doubles into the group.  Pointers named x / a_out / Wt / bias are PRE-OFFSET to
+ * the chunk by the caller (x + 512*c, Wt + 64*c*DP, bias + 64*c).
+ * S pass = gpc_step_lse (CG step on whole rows, row logsumexp, entropy partials; collapsed_vb.py:167,172 +
+ *          np_utilities.py:25-40) followed by gpc_stats_chunk per chunk (phi = exp(x - lse), T_c = phi_c^T F, phi_hat_c).
+ * G pass = gpc_natgrad_chunk per chunk (a_c = F.W_c + bias_c - x_c into the natural-gradient buffer, sa[row] += sum phi*a)
+ *          followed by gpc_natgrad_finish (natgrad = a - sa, gradient, the CG dots).                                    */
+int gpc_natgrad_chunk(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, double *a_out, double *sa_vec,
+                      int first, double *partials, unsigned int *counter, double *dots_scratch, long long N, int Kc, int DP, long long xg_stride,
+                      int grid, void *stream);
+int gpc_natgrad_finish(double *ng, const double *x, const double *lse, const double *sa_vec, const double *x_old, const double *lse_old,
+                       const double *ng_old, double *grad_out, double *partials, unsigned int *counter, double *dots, long long N, int K, int KP,
+                       int grid, void *stream);
+int gpc_step_lse(const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new, double *lse_new, const double *dots,
+                 double sq_old, double *beta_out, double *hpart, double step, int beta_mode, long long N, int K, int KP, int grid, void *stream);
+int gpc_stats_chunk(const double *F, const double *x, const double *lse, const double *h_in, double *partials, long long part_stride, int t_off,
+                    int ph_off, int h_off, int write_h, long long N, int Kc, int DP, long long xg_stride, int grid, void *stream);
 
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);

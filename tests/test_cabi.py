@@ -40,7 +40,8 @@ def test_geometry_queries_without_gpu():
     lib = _cabi.lib
     assert lib.gpc_abi_version() >= 1
     assert [lib.gpc_padded_k(k) for k in (1, 8, 9, 16, 17, 33, 64)] == [8, 8, 16, 16, 32, 64, 64]
-    assert lib.gpc_padded_k(0) == -1 and lib.gpc_padded_k(65) == -1
+    assert lib.gpc_padded_k(0) == -1 and lib.gpc_padded_k(513) == -1
+    assert [lib.gpc_padded_k(k) for k in (65, 128, 129, 500, 512)] == [128, 128, 192, 512, 512]  # chunks of 64
     assert [lib.gpc_padded_d(d) for d in (1, 8, 56, 64)] == [8, 8, 56, 64] and lib.gpc_padded_d(65) == -1
     assert lib.gpc_padded_rows(1) == 64 and lib.gpc_padded_rows(1000000) == 1000000 and lib.gpc_padded_rows(65) == 128
     assert lib.gpc_stats_len(64, 64) == 64 * 64 + 64 + 2
@@ -56,7 +57,7 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     with pytest.raises(ValueError):
         _cabi.check(rc, "gpc_reduce_partials")
     with pytest.raises(ValueError):
-        _cabi.padded_k(65)
+        _cabi.padded_k(513)
 
 
 def test_no_cpu_fallback():

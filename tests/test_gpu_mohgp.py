@@ -239,4 +239,28 @@ def test_unsupported_sizes_fail_loudly():
     X, Y, _ = mohgp_problem(100, 8, 2, 0)
     pF, pY = product_kernels()
     with pytest.raises(ValueError):
-        MOHGP(X, pF, pY, Y, K=65)
+        MOHGP(X, pF, pY, Y, K=513)
+
+
+@pytest.mark.parametrize("N,D,K,prior_Z", [(700, 24, 65, "symmetric"), (1500, 64, 128, "DP"), (900, 40, 200, "symmetric"), (8000, 32, 512, "symmetric")])
+def test_more_than_64_clusters(N, D, K, prior_Z):
+    """Config 5 of BASELINE.json uses K up to 512: clusters are processed in chunks of 64 (gpc_step_lse / gpc_stats_chunk /
+    gpc_natgrad_chunk / gpc_natgrad_finish).  Same parity bar as the single-chunk path."""
+    mo, mp = _pair(N, D, K, prior_Z, alpha=1.0 if prior_Z == "symmetric" else 2.0)
+    assert relerr(mp.phi, mo.phi) < 1e-13
+    assert relerr(mp.phi_hat, mo.phi_hat) < 1e-12
+    assert abs(mp.H - mo.H) <= 1e-11 * abs(mo.H)
+    assert relerr(mp.ybark, mo.ybark) < 1e-12
+    assert relerr(mp.muk, mo.muk) < TOL
+    assert abs(mp.bound() - mo.bound()) < TOL * abs(mo.bound())
+    g_p, ng_p = mp.vb_grad_natgrad()
+    g_o, ng_o = mo.vb_grad_natgrad()
+    assert relerr(ng_p, ng_o) < TOL and relerr(g_p, g_o) < TOL
+    mo.out = io.StringIO()
+    iters = 12 if K < 512 else 6  # few data per cluster make the trajectory chaotic: keep the comparison short
+    mo.optimize(maxiter=iters, verbose=False)
+    mp.optimize(maxiter=iters, verbose=False)
+    to, tp = np.array(mo.trace), np.array(mp.optimize_trace)
+    assert to.shape == tp.shape and np.array_equal(to[:, 0], tp[:, 0])
+    assert np.max(np.abs(to[:, 1] - tp[:, 1]) / np.abs(to[:, 1])) < TOL
+    assert relerr(mp.phi, mo.phi) < 1e-7
