@@ -73,6 +73,8 @@ PROTOTYPES = {
     "gpc_multiple_mahalanobis": [_p, _p, _p, _ll, _i, _i, _p, _p],
     "gpc_multiple_pdinv": [_p, _i, _i, _p, _p, _p, _p],
     "gpc_gram_partials": [_p, _ll, _i, _p, _i, _p],
+    "gpc_normalise_rows": [_p, _ll, _i, _p, _p],
+    "gpc_replicate_scores": [_p, _ll, _i, _p, _i, _p, _p],
     "gpc_pack_rows": [_p, _ll, _i, _i, _i, _p, _p],
     "gpc_unpack_rows": [_p, _ll, _i, _i, _i, _p, _p],
     "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],

@@ -575,6 +575,19 @@ int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, voi
   return launch_rc();
 }
 
+int gpc_normalise_rows(const double *src, long long N, int D, double *dst, void *stream) {
+  if (!src || !dst || N < 1 || D < 1 || N > 0x7fffffffLL) return GPC_EINVAL;
+  const long long blocks = (N + 7) / 8;
+  k_normalise_rows<<<(unsigned)(blocks > 65536 ? 65536 : blocks), 256, 0, as_stream(stream)>>>(src, (int)N, D, dst);
+  return launch_rc();
+}
+
+int gpc_replicate_scores(const double *Y, long long N, int D, const int *group, int G, double *score, void *stream) {
+  if (!Y || !group || !score || N < 1 || D < 1 || G < 1 || G > 64 || N > 0x7fffffffLL) return GPC_EINVAL;
+  k_replicate_scores<<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(Y, (int)N, D, group, G, score);
+  return launch_rc();
+}
+
 int gpc_pack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream) {
   if (!src || !dst || N < 1 || C < 1 || CP < C || (CP % 8) || N > 0x7fffffffLL) return GPC_EINVAL;
   const long long total = gpc_padded_rows(N) * CP;

@@ -142,6 +142,55 @@ __global__ void k_unpad_rows(const double *__restrict__ src, int N, int K, int l
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ingest (the step before the path; drosophila.ipynb cells [2] and [4]).
+// Row-wise normalisation  y <- (y - mean(y)) / std(y)   (population std, as numpy's .std(1)); one warp per row.
+__global__ void __launch_bounds__(256) k_normalise_rows(const double *__restrict__ src, int N, int D, double *__restrict__ dst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < N; row += (long long)gridDim.x * 8) {
+    const double *y = src + (size_t)row * D;
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) s += y[d];
+    const double mean = warp_sum(s) / D;
+    double v = 0.0;
+    for (int d = lane; d < D; d += 32) v += (y[d] - mean) * (y[d] - mean);
+    const double sd = sqrt(warp_sum(v) / D);
+    for (int d = lane; d < D; d += 32) dst[(size_t)row * D + d] = (y[d] - mean) / sd;
+  }
+}
+// Replicate score of a series: std over time points of the replicate means / mean over time points of the replicate stds
+// (drosophila.ipynb cell [4]).  group[d] in [0, G) is the time-point index of column d; one thread per row, G <= 64.
+__global__ void k_replicate_scores(const double *__restrict__ Y, int N, int D, const int *__restrict__ group, int G, double *__restrict__ score) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  const double *y = Y + (size_t)row * D;
+  double sum[64], sq[64];
+  int cnt[64];
+  for (int q = 0; q < G; ++q) {
+    sum[q] = sq[q] = 0.0;
+    cnt[q] = 0;
+  }
+  for (int d = 0; d < D; ++d) {
+    sum[group[d]] += y[d];
+    cnt[group[d]] += 1;
+  }
+  for (int q = 0; q < G; ++q) sum[q] /= cnt[q];  // replicate means
+  for (int d = 0; d < D; ++d) {
+    const double e = y[d] - sum[group[d]];
+    sq[group[d]] += e * e;
+  }
+  double mm = 0.0, ms = 0.0;
+  for (int q = 0; q < G; ++q) {
+    mm += sum[q];
+    ms += sqrt(sq[q] / cnt[q]);
+  }
+  mm /= G;
+  ms /= G;
+  double vm = 0.0;
+  for (int q = 0; q < G; ++q) vm += (sum[q] - mm) * (sum[q] - mm);
+  score[row] = sqrt(vm / G) / ms;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row softmax read-out: one warp per row.  x has leading dimension ldx; phi / logphi (nullable) are
 // written with leading dimension ldo; Hpart[blockIdx.x] = sum over this CTA's rows of -sum_k phi log phi.
 constexpr int kSoftmaxWarps = 8;

@@ -291,6 +291,12 @@ int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, 
 /* Y^T Y (MOHGP.py:53) of the feature rows F (fragment-major): partials grid x DP x DP, then
  * gpc_reduce_partials(len = DP*DP).                                                                    */
 int gpc_gram_partials(const double *F, long long Npad, int DP, double *partials, int grid, void *stream);
+/* ---- ingest helpers (drosophila.ipynb cells [2], [4]) ------------------------------------------------- */
+/* dst = (src - rowmean) / rowstd  (population std), N x D row-major                                   */
+int gpc_normalise_rows(const double *src, long long N, int D, double *dst, void *stream);
+/* score[n] = std_t(mean over replicates) / mean_t(std over replicates); group[d] = time-point index of column d (device int array), G <= 64 */
+int gpc_replicate_scores(const double *Y, long long N, int D, const int *group, int G, double *score, void *stream);
+
 /* contiguous N x C row-major  <->  the fragment-major device layout (Npad rows, CP columns, pad = 0)   */
 int gpc_pack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream);
 int gpc_unpack_rows(const double *src, long long N, int C, int CP, int layout, double *dst, void *stream);

@@ -1,0 +1,42 @@
+"""Ingest helpers: loaders for the reference's data files and the notebook's preparation steps."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+
+def test_loaders_read_the_reference_files():
+    from gpclust_b200 import io
+    X, Y, z = io.load_split_data(os.path.join(GOLDEN, "split_data_test.csv"))
+    assert X.shape == Y.shape == (z.shape[0], 1) and set(np.unique(z)) <= {0, 1} and X.shape[0] > 100
+    sp, rep, t = io.load_kalinka_pdata(os.path.join(GOLDEN, "kalinka09_pdata.csv"))
+    assert len(sp) == len(rep) == len(t) and len(t) > 50
+    sp1, rep1, t1 = io.load_kalinka_pdata(os.path.join(GOLDEN, "kalinka09_pdata.csv"), species=sp[0])
+    assert len(t1) < len(t) and np.all(np.diff(np.sort(np.unique(t1))) > 0)
+    a = io.load_numpy_fixture(os.path.join(GOLDEN, "twoD_clustering_example.npy"))
+    assert a.shape == (506, 2)
+
+
+@pytest.mark.gpu
+def test_normalisation_and_replicate_scores_match_numpy():
+    from gpclust_b200 import io
+    rng = np.random.RandomState(0)
+    times = np.repeat(np.arange(2.0, 16.0, 2.0), 8)  # 7 time points x 8 replicates
+    Y = rng.randn(3000, times.size) * rng.rand(3000, 1) * 3 + rng.randn(3000, 1)
+    e = Y - Y.mean(1)[:, None]
+    e /= e.std(1)[:, None]
+    got = io.normalise_rows(Y)
+    assert np.max(np.abs(got - e)) < 1e-13
+    means, stds = [], []
+    for t in np.unique(times):
+        idx = times == t
+        means.append(e[:, idx].mean(1))
+        stds.append(e[:, idx].std(1))
+    means, stds = np.vstack(means).T, np.vstack(stds).T
+    scores = means.std(1) / stds.mean(1)
+    got = io.replicate_scores(e, times)
+    assert np.max(np.abs(got - scores) / scores) < 1e-12
+    top, index = io.select_top_series(e, times, n=500)
+    assert np.array_equal(index, np.argsort(scores)[::-1][:500]) and top.shape == (500, times.size)
