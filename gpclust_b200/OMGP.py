@@ -27,6 +27,7 @@ from . import kern as _kern
 from ._cabi import lib, check, ptr
 from .collapsed_mixture import CollapsedMixture
 from .collapsed_vb import CollapsedVB
+from .sharding import RowShards
 
 
 class _Point(object):
@@ -57,6 +58,7 @@ class OMGP(CollapsedMixture):
         self.prior_Z, self.alpha = prior_Z, alpha
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._world, self._rank, self.N_total = 1, 0, self.N
+        self._shards = RowShards.solo()  # N does not shard (dense coupling between all points of a component)
         self.kernel_launches = 0
         self._kernel_events = None
 

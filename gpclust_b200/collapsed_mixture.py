@@ -548,21 +548,24 @@ class CollapsedMixture(CollapsedVB):
         self.set_vb_param(phi_)
 
     def try_split(self, indexK=None, threshold=0.9, verbose=True, maxiter=100, optimize_params=None):
-        """collapsed_mixture.py:112-189 (single-rank: the row gather / scatter is done on the host copy)."""
-        if self._world > 1:
-            raise NotImplementedError("try_split over sharded rows is a 'next' row (SURVEY.md section 8 f-1)")
+        """collapsed_mixture.py:112-189.  With rows sharded over ranks the membership count and the `special` point are
+        taken over ALL rows: every rank draws the same legacy-RNG values, the owner of the special row is found from the
+        all-gathered per-rank counts, everything else is local to the rank's rows."""
+        verbose = verbose and self._is_root()
         if indexK is None:
-            indexK = np.random.multinomial(1, self.phi_hat / self.N).argmax()
+            indexK = np.random.multinomial(1, self.phi_hat / self.N_total).argmax()
         if indexK > (self.K - 1):
             return False  # index exceed no. of clusters
         elif self.phi_hat[indexK] < 1:
             return False  # no data to split
         phi = self.phi
-        if np.sum(phi[:, indexK] > threshold) < 2:
+        indexN = np.nonzero(phi[:, indexK] > threshold)[0]
+        counts = self._shards.allgather_int(len(indexN), self.device)
+        n_members = int(counts.sum())
+        if n_members < 2:
             return False  # only one data point
         if verbose:
             print("\nattempting to split cluster ", indexK)
-
         bound_old = self.bound()
         phi_old = self.get_vb_param().copy()
         old_K = self.K
@@ -570,10 +573,13 @@ class CollapsedMixture(CollapsedVB):
         # re-initalize
         logits = phi_old.reshape(self.N, old_K)
         logits = np.hstack((logits, logits.min(1)[:, None]))
-        indexN = np.nonzero(phi[:, indexK] > threshold)[0]
-        special = np.random.permutation(indexN)[0]
+        # np.random.permutation(indexN)[0] of the reference: the first entry of a shuffle depends on the length only
+        j = int(np.random.permutation(n_members)[0])
+        before = int(counts[:self._rank].sum())
         logits[indexN, -1] = logits[indexN, indexK].copy()
-        logits[special, -1] = np.max(logits[special]) + 10
+        if before <= j < before + len(indexN):
+            special = indexN[j - before]
+            logits[special, -1] = np.max(logits[special]) + 10
         self.K = old_K + 1
         self.set_vb_param(logits)
 

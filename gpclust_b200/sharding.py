@@ -30,6 +30,13 @@ class RowShards(object):
         except ImportError:
             pass
 
+    @classmethod
+    def solo(cls):
+        """A single-process instance regardless of any initialised process group (models that do not shard rows)."""
+        self = cls.__new__(cls)
+        self.group, self.dist, self.world, self.rank = None, None, 1, 0
+        return self
+
     def partition(self, n_local, device=None):
         """-> (row_start, N_total) for this rank given its local row count."""
         if self.world == 1:
@@ -94,6 +101,16 @@ class RowShards(object):
         except Exception as e:  # pragma: no cover - depends on the box
             warnings.warn("gpclust_b200: peer-memory exchange unavailable (%s: %s); using NCCL all-reduces" % (type(e).__name__, e))
             return None
+
+    def allgather_int(self, value, device=None):
+        """-> int64 numpy array of `value` on every rank (rank order)."""
+        if self.world == 1:
+            return np.array([int(value)], dtype=np.int64)
+        import torch
+        t = torch.zeros(self.world, dtype=torch.int64, device=device)
+        t[self.rank] = int(value)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
 
     def allreduce(self, t):
         """In-place sum over ranks (no-op for a single process)."""

@@ -45,6 +45,29 @@ for (N, D, K, prior) in [(5000, 64, 64, "symmetric"), (3001, 24, 7, "DP")]:
         print("MOHGP N=%d D=%d K=%d %s: init bound rel diff %.2e, trace rel diff %.2e, iters equal %s, assignments equal %s -> %s"
               % (N, D, K, prior, abs(b_s - b_1) / abs(b_1), rel, same_iters, assign, "OK" if good else "FAIL"))
 
+# sharded merge-split search (collapsed_mixture.py:112-189): same decisions, same K, same bound as the single-rank run
+N, D, K = 1200, 16, 3
+X, Y, _ = mohgp_problem(N, D, 6, seed=3)
+np.random.seed(9)
+phi0 = np.random.randn(N, K)
+lo, hi = RowShards.even_split(N, world, rank)
+kF, kY = product_kernels()
+ms = MOHGP(X, kF, kY, Y[lo:hi], K=K, phi_init=phi0[lo:hi])
+kF, kY = product_kernels()
+m1 = MOHGP(X, kF, kY, Y, K=K, phi_init=phi0, group=solo)
+ms.optimize(maxiter=60, verbose=False)
+m1.optimize(maxiter=60, verbose=False)
+res = []
+for m in (ms, m1):
+    np.random.seed(11)
+    r = [m.try_split(k, verbose=False, maxiter=20, optimize_params={"maxiter": 30, "verbose": False}) for k in range(3)]
+    res.append((r, m.K, m.bound()))
+good = res[0][0] == res[1][0] and res[0][1] == res[1][1] and abs(res[0][2] - res[1][2]) < 1e-9 * abs(res[1][2])
+ok = ok and good
+if rank == 0:
+    print("sharded try_split: decisions %s vs %s, K %d vs %d, bound rel diff %.2e -> %s"
+          % (res[0][0], res[1][0], res[0][1], res[1][1], abs(res[0][2] - res[1][2]) / abs(res[1][2]), "OK" if good else "FAIL"))
+
 # MOG shard check
 rng = np.random.RandomState(0)
 Xm = rng.randn(4000, 2) * 0.3 + rng.randint(0, 3, (4000, 1)) * 2.0
