@@ -431,9 +431,12 @@ int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, co
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
   if (loop && (!dots || !beta || (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY))) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
-  // the flag word is cleared by a tiny kernel-ordered memset; in loop mode a skipped evaluation leaves it cleared too
-  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
-  if (e != cudaSuccess) return cuda_rc(e);
+  // the flag word is cleared by a tiny stream-ordered memset; in loop mode the kernel's last CTA consumes and re-arms it
+  // (the first loop evaluation follows a synchronous one that left it clear unless it failed -- and then raised)
+  if (!loop) {
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+  }
   MohgpPostArgs a{partials, num_parts, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                   counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, nullptr};
   return launch_post(a, KP, D, st);
@@ -450,8 +453,6 @@ int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, c
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
   if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
-  if (e != cudaSuccess) return cuda_rc(e);
   MohgpPostArgs a{stats, world, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                   counter, info, alpha, prior, K, D, KP, DP, dots, beta, loop, phase, peers};
   return launch_post(a, KP, D, st);

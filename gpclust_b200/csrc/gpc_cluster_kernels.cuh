@@ -911,7 +911,10 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
       a.scalars[1] = mix_s;
       a.scalars[2] = H;
       *a.counter = 0u;
-      if (a.loop) cg_decide(a.loop, a.phase, bound, atomicOr(a.info, 0) != 0, a.dots[0], a.beta[0]);
+      if (a.loop) {
+        // loop mode: the flag word is consumed here and re-armed for the next evaluation (no memset between kernels)
+        cg_decide(a.loop, a.phase, bound, atomicExch(a.info, 0) != 0, a.dots[0], a.beta[0]);
+      }
     }
     for (int kk = tid; kk < KP; kk += blockDim.x)
       a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
