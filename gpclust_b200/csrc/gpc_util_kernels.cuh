@@ -253,42 +253,45 @@ __global__ void __launch_bounds__(128) k_mahalanobis_pairs(const double *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP); F fragment-major
-constexpr int kGramRows = 32;
-__global__ void __launch_bounds__(256) k_gram_partials(const double *__restrict__ F, int Npad, int DP, double *__restrict__ partials) {
-  extern __shared__ __align__(16) double tile[];  // kGramRows x DP, row-major
-  const int tid = threadIdx.x;
-  const int nout = DP * DP;
-  // each thread owns outputs tid, tid+256, ... (at most 16 for DP = 64)
-  double acc[16];
+// Gram matrix partials: part[c][i][j] = sum over CTA c's rows of F[n][i] F[n][j]   (i, j < DP); F fragment-major.
+// On the FP64 tensor pipe: for one 8-row group the A fragment of F^T for (m-tile mt, k-step ks) and the B fragment of F for
+// (n-tile dt, ks) are the SAME shared-memory word pattern  base[tile*64 + ks*16]  (gpc_vb_kernels.cuh, statistics warps),
+// so a 64-row slab (8 groups, copied verbatim) feeds 2*8 k-steps; warp w owns the output tiles (mt = w, dt = 0..7).
+constexpr int kGramRows = 64;
+__global__ void __launch_bounds__(256, 2) k_gram_partials(const double *__restrict__ F, int Npad, int DP, double *__restrict__ partials) {
+  extern __shared__ __align__(16) double slab[];  // kGramRows x DP, fragment-major (8 groups)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int DT = DP / 8;
+  double acc[8][2];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) acc[q] = 0.0;
-  const int num_tiles = Npad / kGramRows;
-  for (int tix = blockIdx.x; tix < num_tiles; tix += gridDim.x) {
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+  const int num_slabs = Npad / kGramRows, slab_doubles = kGramRows * DP;
+  const double *fb = slab + (g >> 2) * 32 + t * 4 + (g & 3);
+  for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x) {
     __syncthreads();
-    const double *src = F + (size_t)tix * kGramRows * DP;  // 4 consecutive groups
-    for (int e = tid; e < kGramRows * DP; e += blockDim.x) {
-      const int grp = e / (8 * DP), o = e % (8 * DP);
-      const int d = ((o >> 5) << 2) + (o & 3), r = (o >> 2) & 7;
-      tile[(grp * 8 + r) * DP + d] = src[e];
-    }
+    const double2 *src = reinterpret_cast<const double2 *>(F + (size_t)sl * slab_doubles);
+    double2 *dst = reinterpret_cast<double2 *>(slab);
+    for (int e = tid; e < slab_doubles / 2; e += 256) dst[e] = src[e];
     __syncthreads();
+    if (warp < DT) {
+#pragma unroll 2
+      for (int grp = 0; grp < kGramRows / 8; ++grp) {
+        const double *gb = fb + grp * 8 * DP;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int o = tid + q * 256;
-      if (o < nout) {
-        const int i = o / DP, j = o % DP;
-        double v = acc[q];
-        for (int r = 0; r < kGramRows; ++r) v += tile[r * DP + i] * tile[r * DP + j];
-        acc[q] = v;
+        for (int ks = 0; ks < 2; ++ks) {
+          const double af = gb[warp * 64 + ks * 16];
+#pragma unroll
+          for (int dt = 0; dt < 8; ++dt)
+            if (dt < DT) dmma884(acc[dt][0], acc[dt][1], af, gb[dt * 64 + ks * 16]);
+        }
       }
     }
   }
-  double *part = partials + (size_t)blockIdx.x * nout;
+  double *part = partials + (size_t)blockIdx.x * DP * DP;
+  if (warp < DT) {
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const int o = tid + q * 256;
-    if (o < nout) part[o] = acc[q];
+    for (int dt = 0; dt < 8; ++dt)
+      if (dt < DT) stg2(part + (size_t)(8 * warp + g) * DP + 8 * dt + 2 * t, acc[dt][0], acc[dt][1]);
   }
 }
 
