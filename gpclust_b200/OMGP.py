@@ -14,8 +14,12 @@ set_vb_param; bound() and vb_grad_natgrad() read the cached per-component result
     gpc_omgp_finalize               bound + mixing-proportion terms                OMGP.py:123
     gpc_dense_natgrad, gpc_cg_axpy  natural gradient, CG dots, search direction    OMGP.py:142-147, collapsed_vb.py:152-172
 
+    gpc_omgp_kern_grads             kernel / noise-variance gradients (update_kern_grads)   OMGP.py:55-94
+
 N does not shard (dense coupling between all points of a component); components are independent.
-`update_kern_grads` (OMGP.py:55-94, kernel hyper-parameter gradients) is a "next" row.
+The noise variance and the kernel parameters are free (Logexp-constrained) as in the reference (OMGP.py:31-32):
+`optimize()` interleaves `optimize_parameters()` (collapsed_vb.py:248,270,300-301); `kern.fix()` / `variance_fixed = True`
+hold them.
 """
 import ctypes
 
@@ -51,6 +55,9 @@ class OMGP(CollapsedMixture):
         else:
             self.kern = list(kernels)
         self.variance = float(np.asarray(variance).reshape(-1)[0])
+        self.variance_fixed = False  # GPy: m.variance.fix()
+        self.variance_gradient = 0.0
+        self._kern_grads_valid = False
 
         # CollapsedMixture.__init__ (collapsed_mixture.py:24-47) without the feature-row machinery of MOHGP / MOG
         self.N, self.K = int(N), int(K)
@@ -152,9 +159,54 @@ class OMGP(CollapsedMixture):
         if len(self.kern) > self.K:
             self.kern = self.kern[:self.K]
         self._cur = self._evaluate(self._x)
+        self._kern_grads_valid = False
 
     def parameters_changed(self):
+        """OMGP.py:35-38.  The reference recomputes everything inside bound(); here the cached point is refreshed."""
         self.do_computations()
+
+    # ------------------------------------------------------------------ kernel hyper-parameters (OMGP.py:31-32, 55-94)
+    def _kernel_param_list(self):
+        out = [] if self.variance_fixed else [(self, "variance")]  # link order: variance, then the kernels
+        for k in self.kern:
+            if hasattr(k, "param_list"):
+                out.extend(k.param_list())
+        return out
+
+    def _kernel_gradients(self):
+        if not self._kern_grads_valid:
+            self.update_kern_grads()
+        return CollapsedMixture._kernel_gradients(self)
+
+    def update_kern_grads(self):
+        """OMGP.py:55-94.  Per component: B = K + diag(variance / phi) (no 1e-6 here, appendix A.11), factor and
+        triangular inverse on the device, then gpc_omgp_kern_grads contracts dL_dB = alpha alpha^T - B^-1 (formed tile by
+        tile, never stored) with the parameter derivatives of every covariance part."""
+        torch = self.torch
+        p, N, Np = self._cur, self.N, self._Npad
+        if getattr(self, "_kg_tiles", None) is None:
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+            self._kg_alpha, self._kg_diag = z(Np, self.D), z(Np)
+            self._kg_tiles = z(int(lib.gpc_omgp_kgrad_tiles(Np)) * 16)
+            self._kg_out = z(16)
+        grad_variance = 0.0
+        for i, k in enumerate(self.kern):
+            self._factor_component(p.phi, i, 0.0)
+            nparts, kinds, var, ls, _ = self._kern_arrays(k)
+            check(lib.gpc_omgp_kern_grads(ptr(self._W), ptr(self._Xd), self._Xd.shape[1], ptr(self._Yd), N, self.D, nparts, kinds, var, ls,
+                                          ptr(self._tbuf), ptr(self._part), ptr(self._kg_alpha), ptr(self._kg_diag), ptr(self._kg_tiles),
+                                          ptr(self._kg_out), self._stream()), "gpc_omgp_kern_grads")
+            self.kernel_launches += 5
+            out = self._kg_out.cpu().numpy()
+            for j, part in enumerate(getattr(k, "parts", [k])):  # GPy update_gradients_full with dL_dK = 0.5 dL_dB
+                part.variance_gradient = 0.5 * float(out[2 * j])
+                if hasattr(part, "lengthscale"):
+                    part.lengthscale_gradient = -0.5 * float(out[2 * j + 1]) / part.lengthscale
+            phi_i = p.phi[:, i]
+            grad_variance += 0.5 * float((self._kg_diag[:N] / (phi_i + 1e-6)).sum().item())  # OMGP.py:88-91
+            grad_variance -= 0.5 * self.D * float(phi_i.sum().item()) / self.variance    # OMGP.py:92
+        self.variance_gradient = grad_variance
+        self._kern_grads_valid = True
 
     def set_vb_param(self, phi_):
         torch = self.torch
@@ -254,6 +306,7 @@ class OMGP(CollapsedMixture):
         self._cur = self._trial
         self._x = self._trial.x
         self._trial = None
+        self._kern_grads_valid = False
         self._ng_old, self._grad_old, self._sd = self._ng, self._grad, self._sd_trial
 
     # ------------------------------------------------------------------ prediction (OMGP.py:149-193): read-out algebra

@@ -66,6 +66,8 @@ PROTOTYPES = {
     "gpc_chol_blocked": [_p, _ll, _p, _p, _p, _p],
     "gpc_tri_inverse_blocked": [_p, _ll, _p, _p, _p],
     "gpc_omgp_component": [_p, _p, _p, _p, _i, _ll, _i, _d, _p, _p, _p, _i, _p, _p],
+    "gpc_omgp_kgrad_tiles": [_ll],
+    "gpc_omgp_kern_grads": [_p, _p, _i, _p, _ll, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _p, _p, _p, _p, _p, _p, _p],
     "gpc_omgp_finalize": [_p, _p, _i, _p, _p, _p, _d, _d, _i, _i, _i, _p],
     "gpc_dense_natgrad": [_p, _p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p],
     "gpc_cg_axpy": [_p, _p, _p, _d, _d, _ll, _p, _p, _p],
@@ -79,8 +81,12 @@ PROTOTYPES = {
     "gpc_unpack_rows": [_p, _ll, _i, _i, _i, _p, _p],
     "gpc_pad_rows": [_p, _ll, _i, _i, _p, _p],
     "gpc_unpad_rows": [_p, _ll, _i, _i, _p, _p],
+    "gpc_graph_begin": [_p],
+    "gpc_graph_end": [_p, ctypes.POINTER(_p)],
+    "gpc_graph_launch": [_p, _p],
+    "gpc_graph_destroy": [_p],
 }
-_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_xchg_doubles": _ll}
+_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_omgp_kgrad_tiles": _ll, "gpc_xchg_doubles": _ll}
 
 
 class GpcBufs(ctypes.Structure):

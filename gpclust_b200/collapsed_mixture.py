@@ -15,6 +15,7 @@ every rank holds a contiguous block of rows, the statistics vector and the three
 all-reduced; everything K- or D-sized is replicated.
 """
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -47,6 +48,25 @@ class _EventPair(object):
             self.pair[1].record()
             ev.setdefault(self.name, []).append(self.pair)
         return False
+
+
+class _PassGraph(object):
+    """A captured batch of loop-body passes (gpc_graph_* of the C-ABI): one launch replays n passes."""
+
+    def __init__(self, handle, passes, launches):
+        self.handle, self.passes, self.launches = handle, passes, launches
+
+    _retired = []  # handles of dropped graphs, destroyed at the next safe point (never from inside a capture / the GC)
+
+    def __del__(self):
+        if self.handle:
+            _PassGraph._retired.append(self.handle)
+        self.handle = None
+
+    @staticmethod
+    def reap():
+        while _PassGraph._retired:
+            lib.gpc_graph_destroy(_PassGraph._retired.pop())
 
 
 class CollapsedMixture(CollapsedVB):
@@ -83,6 +103,8 @@ class CollapsedMixture(CollapsedVB):
         self._peers = None      # peer-memory exchange descriptor (rows sharded over the GPUs of one box), see sharding.py
         self._loop_dev = None   # gpc_loop_t + trace rows (device-resident loop state), allocated on first optimize()
         self._loop_host = None
+        self._graphs = {}       # captured pass batches, keyed by (passes, K, alpha, prior); dropped whenever a buffer is re-allocated
+        self._cap_stream = None
         self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
         self._kernel_events = None  # bench.py: {"natgrad": [(start, end), ...], "step_stats": [...]} CUDA events
 
@@ -115,6 +137,7 @@ class CollapsedMixture(CollapsedVB):
             return
         self._KP = KP
         self._kbuf_K = K
+        self._graphs = {}
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
         self._xbuf = [z(self._Npad, KP) for _ in range(3)]
         self._lsebuf = [z(self._Npad) for _ in range(3)]  # row logsumexp of the matching logits buffer
@@ -138,6 +161,7 @@ class CollapsedMixture(CollapsedVB):
             return
         torch = self.torch
         KP, DP = self._KP, self._DP
+        self._graphs = {}
         self._stats_len = lib.gpc_stats_len(KP, DP)
         self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
         self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
@@ -417,6 +441,7 @@ class CollapsedMixture(CollapsedVB):
         torch = self.torch
         nbytes = ctypes.sizeof(_cabi.GpcLoop) + self._TRACE_CAP * 32
         if self._loop_dev is None:
+            self._graphs = {}
             self._loop_dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._loop_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
         ctypes.memmove(self._loop_host.data_ptr(), ctypes.addressof(L), ctypes.sizeof(_cabi.GpcLoop))
@@ -453,6 +478,51 @@ class CollapsedMixture(CollapsedVB):
                 self._loop_posterior(phase)
         self.kernel_launches += 3
 
+    _GRAPH_PASSES = 16  # passes per captured graph (plus a single-pass graph for the remainder)
+
+    def _graphs_ok(self):
+        if os.environ.get("GPCLUST_B200_GRAPH", "1") == "0" or self._kernel_events is not None:
+            return False
+        return self._world == 1 or self._peers is not None  # the NCCL exchange stays on the eager path
+
+    def _pass_graph(self, bufs, n):
+        """The launch sequence of n passes, captured once (every argument is invariant: the kernels pick their
+        operands from the device-resident loop state)."""
+        key = (n, self.K, float(self.alpha), self.prior_Z)
+        g = self._graphs.get(key)
+        if g is None:
+            torch = self.torch
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(device=self.device)
+            launches0 = self.kernel_launches
+            _PassGraph.reap()
+            with torch.cuda.stream(self._cap_stream):
+                st = self._stream()
+                check(lib.gpc_graph_begin(st), "gpc_graph_begin")
+                handle = ctypes.c_void_p()
+                try:
+                    for _ in range(n):
+                        self._enqueue_pass(bufs)
+                finally:
+                    rc = lib.gpc_graph_end(st, ctypes.byref(handle))
+                check(rc, "gpc_graph_end")
+            g = _PassGraph(handle, n, self.kernel_launches - launches0)
+            self.kernel_launches = launches0  # nothing ran during the capture
+            self._graphs[key] = g
+        return g
+
+    def _enqueue_passes(self, bufs, n):
+        if not self._graphs_ok():
+            for _ in range(n):
+                self._enqueue_pass(bufs)
+            return
+        st = self._stream()
+        while n > 0:
+            g = self._pass_graph(bufs, self._GRAPH_PASSES if n >= self._GRAPH_PASSES else 1)
+            check(lib.gpc_graph_launch(g.handle, st), "gpc_graph_launch")
+            self.kernel_launches += g.launches
+            n -= g.passes
+
     def _loop_sync_host(self, L):
         """Adopt the device loop state on the host side (buffer selectors, bound, control block)."""
         self._xi, self._xprev, self._xtrial, self._ngi = L.xi, (None if L.xprev < 0 else L.xprev), L.xtrial, L.ngi
@@ -479,8 +549,7 @@ class CollapsedMixture(CollapsedVB):
             n = min(self._BATCH, remaining)
             if max_passes is not None:
                 n = min(n, max_passes - passes)
-            for _ in range(n):
-                self._enqueue_pass(bufs)
+            self._enqueue_passes(bufs, n)
             passes += n
             L, rows = self._loop_download()
             rows_all.extend(rows)
@@ -568,6 +637,7 @@ class CollapsedMixture(CollapsedVB):
             print("\nattempting to split cluster ", indexK)
         bound_old = self.bound()
         phi_old = self.get_vb_param().copy()
+        param_old = self.optimizer_array.copy()  # collapsed_mixture.py:143-144
         old_K = self.K
 
         # re-initalize
@@ -591,6 +661,8 @@ class CollapsedMixture(CollapsedVB):
         if bound_increase < 1e-3:
             self.K = old_K
             self.set_vb_param(phi_old)
+            if param_old.size:
+                self.optimizer_array = param_old  # collapsed_mixture.py:174
             if verbose:
                 print("split failed, bound changed by: ", bound_increase, "(K=%s)" % self.K)
             return False

@@ -686,6 +686,41 @@ int gpc_omgp_component(const double *W, const double *Y, const double *ldsum, co
   return launch_rc();
 }
 
+long long gpc_omgp_kgrad_tiles(long long Npad) {
+  const long long nb = Npad / kOB;
+  return nb * (nb + 1) / 2;
+}
+
+int gpc_omgp_kern_grads(const double *W, const double *X, int q, const double *Y, long long N, int Dy, int nparts, const int *kinds,
+                        const double *variances, const double *lengthscales, double *tbuf, double *part, double *alpha, double *dldb_diag,
+                        double *tile_part, double *out, void *stream) {
+  if (!W || !X || !Y || !tbuf || !part || !alpha || !dldb_diag || !tile_part || !out) return GPC_EINVAL;
+  if (N < 1 || N > 0x3fffffffLL || q < 1 || Dy < 1 || Dy > kOmgpMaxDy) return GPC_EINVAL;
+  OmgpKgradArgs a{};
+  if (!make_kern_spec(nparts, kinds, variances, lengthscales, a.spec)) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  const int Npad = (int)gpc_omgp_padded_n(N), nslab = gpc_omgp_slabs(Npad);
+  const long long tiles = gpc_omgp_kgrad_tiles(Npad);
+  if (tiles > 0x7fffffffLL) return GPC_EINVAL;
+  k_omgp_wy<<<(Npad + 7) / 8, 256, 0, st>>>(W, Npad, Y, Dy, tbuf);
+  k_omgp_colstats<<<dim3(Npad / 64, nslab), 256, 0, st>>>(W, Npad, tbuf, Dy, kOmgpSlabRows, part);
+  k_omgp_alpha<<<(Npad + 255) / 256, 256, 0, st>>>(part, nslab, (int)N, Npad, Dy, alpha, dldb_diag);
+  a.W = W;
+  a.X = X;
+  a.alpha = alpha;
+  a.part = tile_part;
+  a.N = (int)N;
+  a.Npad = Npad;
+  a.q = q;
+  a.Dy = Dy;
+  constexpr size_t smem = sizeof(double) * 2 * kOB * kOStrideN;
+  int rc = cuda_rc(cudaFuncSetAttribute(k_omgp_kgrad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (rc) return rc;
+  k_omgp_kgrad_tiles<<<(unsigned)tiles, 256, smem, st>>>(a);
+  k_reduce_partials<<<1, 256, 0, st>>>(tile_part, (int)tiles, 2 * kMaxKernParts, out);
+  return launch_rc();
+}
+
 int gpc_omgp_finalize(const double *comp, const double *Hpart, int n_hpart, double *scalars, double *phi_hat, double *mixgrad, double variance,
                       double alpha, int prior, int K, int Dy, void *stream) {
   if (!comp || !Hpart || !scalars || !phi_hat || !mixgrad || K < 1 || K > kMaxMixK || n_hpart < 1) return GPC_EINVAL;
@@ -709,6 +744,35 @@ int gpc_cg_axpy(const double *x, const double *ng, const double *sd_old, double 
   if (!x || !ng || !sd_new || !x_new || len < 1) return GPC_EINVAL;
   k_cg_axpy<<<(unsigned)((len + 255) / 256), 256, 0, as_stream(stream)>>>(x, ng, sd_old, beta, step, len, sd_new, x_new);
   return launch_rc();
+}
+
+// ---- launch-sequence replay (CUDA graph of a batch of loop-body passes)
+int gpc_graph_begin(void *stream) {
+  if (!stream) return GPC_EINVAL;  // the legacy default stream cannot be captured
+  return cuda_rc(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed));
+}
+
+int gpc_graph_end(void *stream, void **exec) {
+  if (!stream || !exec) return GPC_EINVAL;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(as_stream(stream), &graph);
+  if (e != cudaSuccess || graph == nullptr) return e != cudaSuccess ? cuda_rc(e) : GPC_EINVAL;
+  cudaGraphExec_t ge = nullptr;
+  e = cudaGraphInstantiate(&ge, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_rc(e);
+  *exec = reinterpret_cast<void *>(ge);
+  return 0;
+}
+
+int gpc_graph_launch(void *exec, void *stream) {
+  if (!exec) return GPC_EINVAL;
+  return cuda_rc(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), as_stream(stream)));
+}
+
+int gpc_graph_destroy(void *exec) {
+  if (!exec) return GPC_EINVAL;
+  return cuda_rc(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec)));
 }
 
 }  // extern "C"

@@ -293,6 +293,141 @@ __global__ void __launch_bounds__(1024) k_omgp_component(const OmgpCompArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel hyper-parameter gradients (OMGP.update_kern_grads, OMGP.py:55-94).  For one component, with
+//   B = K(X) + diag(variance / phi)   (no 1e-6 here -- quirk of OMGP.py:63),  W = L^-1,  alpha = B^-1 Y:
+//   dL_dB = alpha alpha^T - B^-1                                              (OMGP.py:71-75)
+// k_omgp_alpha turns the column statistics of W (k_omgp_colstats) into alpha and diag(dL_dB).
+__global__ void __launch_bounds__(256) k_omgp_alpha(const double *__restrict__ part, int nslab, int N, int Npad, int Dy, double *__restrict__ alpha,
+                                                    double *__restrict__ dldb_diag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Npad) return;
+  double v[kOmgpMaxDy + 1];
+#pragma unroll
+  for (int d = 0; d <= kOmgpMaxDy; ++d) v[d] = 0.0;
+  for (int s = 0; s < nslab; ++s) {
+    const double *p = part + ((size_t)s * Npad + j) * (kOmgpMaxDy + 1);
+#pragma unroll
+    for (int d = 0; d <= kOmgpMaxDy; ++d) v[d] += p[d];
+  }
+  double a2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < kOmgpMaxDy; ++d)
+    if (d < Dy) {
+      const double a = (j < N) ? v[1 + d] : 0.0;
+      alpha[(size_t)j * Dy + d] = a;
+      a2 += a * a;
+    }
+  dldb_diag[j] = (j < N) ? a2 - v[0] : 0.0;
+}
+
+// Tile (ib >= jb) of B^-1 = W^T W on the FP64 tensor pipe (k-loop over the row tiles kb >= ib of the lower-triangular W),
+// contracted in the epilogue against the parameter derivatives of every covariance part (GPy Stationary /
+// Bias / White update_gradients_full with dL_dK = 0.5 dL_dB -- the 0.5 and the 1/lengthscale are applied by the host):
+//   part[cta][2p]   = sum_ij w_ij dL_dB_ij k_p(r_ij) / variance_p
+//   part[cta][2p+1] = sum_ij w_ij dL_dB_ij dk_p/dr (r_ij) r_ij            (stationary parts; 0 otherwise)
+// w_ij = 2 for off-diagonal tiles (the symmetric partner is not visited), 1 on diagonal tiles.  Nothing N x N is stored.
+struct OmgpKgradArgs {
+  const double *W;      // Npad x Npad, lower triangular
+  const double *X;      // N x q
+  const double *alpha;  // Npad x Dy (zero pad rows)
+  double *part;         // gridDim.x x 16
+  KernSpec spec;
+  int N, Npad, q, Dy;
+};
+__global__ void __launch_bounds__(256) k_omgp_kgrad_tiles(const OmgpKgradArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  double *Ps = sm, *Qs = sm + kOB * kOStrideN;
+  __shared__ double red_s[32];
+  int ta = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((ta + 1) * (ta + 2) / 2 <= (int)blockIdx.x) ++ta;
+  while (ta * (ta + 1) / 2 > (int)blockIdx.x) --ta;
+  const int ib = ta, jb = blockIdx.x - ta * (ta + 1) / 2;
+  const int nb = a.Npad / kOB, ld = a.Npad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  double acc[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  for (int kb = ib; kb < nb; ++kb) {
+    const double *P = a.W + (size_t)kb * kOB * ld + (size_t)ib * kOB;
+    const double *Q = a.W + (size_t)kb * kOB * ld + (size_t)jb * kOB;
+    __syncthreads();
+    for (int e = tid; e < kOB * kOB / 2; e += blockDim.x) {
+      const int r = e >> 5, c2 = (e & 31) * 2;
+      *reinterpret_cast<double2 *>(Ps + r * kOStrideN + c2) = ldg2(P + (size_t)r * ld + c2);
+      *reinterpret_cast<double2 *>(Qs + r * kOStrideN + c2) = ldg2(Q + (size_t)r * ld + c2);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int ks = 0; ks < kOB / 4; ++ks) {
+      const double af = Ps[(4 * ks + t) * kOStrideN + warp * 8 + g];  // A[m][k] = P[k][m]
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], af, Qs[(4 * ks + t) * kOStrideN + 8 * nt + g]);
+    }
+  }
+  // epilogue: lane (g, t) of warp w holds (row 8w+g, cols 8nt+2t, +1) of the tile
+  double sums[2 * kMaxKernParts];
+#pragma unroll
+  for (int p = 0; p < 2 * kMaxKernParts; ++p) sums[p] = 0.0;
+  const int i = ib * kOB + warp * 8 + g;
+  const double wgt = (ib == jb) ? 1.0 : 2.0;
+  if (i < a.N) {
+    double ai[kOmgpMaxDy];
+#pragma unroll
+    for (int d = 0; d < kOmgpMaxDy; ++d) ai[d] = (d < a.Dy) ? a.alpha[(size_t)i * a.Dy + d] : 0.0;
+    const double *xi = a.X + (size_t)i * a.q;
+    double si = 0.0;
+    for (int c = 0; c < a.q; ++c) si += xi[c] * xi[c];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = jb * kOB + 8 * nt + 2 * t + e;
+        if (j >= a.N) continue;
+        double aa = 0.0;
+#pragma unroll
+        for (int d = 0; d < kOmgpMaxDy; ++d)
+          if (d < a.Dy) aa += ai[d] * a.alpha[(size_t)j * a.Dy + d];
+        const double dl = wgt * (aa - acc[nt][e]);
+        const double *xj = a.X + (size_t)j * a.q;
+        double dot = 0.0, sj = 0.0;
+        for (int c = 0; c < a.q; ++c) {
+          dot += xi[c] * xj[c];
+          sj += xj[c] * xj[c];
+        }
+        double r2 = -2.0 * dot + (si + sj);  // GPy Stationary._unscaled_dist (see kern_value)
+        if (i == j) r2 = 0.0;
+        const double r_un = sqrt(fmax(r2, 0.0));
+#pragma unroll
+        for (int p = 0; p < kMaxKernParts; ++p) {
+          if (p >= a.spec.nparts) continue;
+          const double r = r_un / a.spec.lengthscale[p], var = a.spec.variance[p];
+          double f, dr;  // k_p / variance, dk_p/dr * r
+          switch (a.spec.kind[p]) {
+            case GPC_KERN_RBF: f = exp(-0.5 * (r * r)); dr = -r * (var * f) * r; break;
+            case GPC_KERN_MATERN32: { const double ex = exp(-sqrt(3.0) * r); f = (1.0 + sqrt(3.0) * r) * ex; dr = (-3.0 * var * r * ex) * r; } break;
+            case GPC_KERN_MATERN52: {
+              const double ex = exp(-sqrt(5.0) * r);
+              f = (1.0 + sqrt(5.0) * r + 5.0 / 3.0 * (r * r)) * ex;
+              dr = (var * (10.0 / 3.0 * r - 5.0 * r - 5.0 * sqrt(5.0) / 3.0 * (r * r)) * ex) * r;
+            } break;
+            case GPC_KERN_BIAS: f = 1.0; dr = 0.0; break;
+            default: f = (i == j) ? 1.0 : 0.0; dr = 0.0; break;  // white: trace(dL_dK)
+          }
+          sums[2 * p] += dl * f;
+          sums[2 * p + 1] += dl * dr;
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 2 * kMaxKernParts; ++p) {
+    const double v = block_sum(sums[p], red_s);
+    if (tid == 0) a.part[(size_t)blockIdx.x * 2 * kMaxKernParts + p] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Bound assembly (OMGP.py:96-123) + mixing-proportion gradient.  comp: K x 4 from k_omgp_component.
 struct OmgpFinalizeArgs {
   const double *comp;

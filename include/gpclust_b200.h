@@ -267,6 +267,18 @@ int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv,
  * Y: Npad x Dy (pad rows zero), Dy <= 8.  tbuf: Npad x Dy.  part: see gpc_omgp_slabs.                       */
 int gpc_omgp_component(const double *W, const double *Y, const double *ldsum, const double *phi_col, int phi_stride, long long N, int Dy,
                        double variance, double *tbuf, double *part, double *grad_col, int grad_stride, double *comp, void *stream);
+/* Kernel hyper-parameter gradients of one component (OMGP.update_kern_grads, OMGP.py:55-94).  W = L^-1 of
+ * B = K + diag(variance / phi) (built with eps = 0: OMGP.py:63 has no 1e-6).  With dL_dB = alpha alpha^T - B^-1:
+ *   out[2p]   = sum_ij dL_dB_ij k_p(x_i,x_j) / variance_p         (-> GPy variance.gradient = 0.5 * out[2p])
+ *   out[2p+1] = sum_ij dL_dB_ij dk_p/dr r_ij                      (-> lengthscale.gradient = -0.5 * out[2p+1] / lengthscale_p)
+ * for part p of the covariance (White: trace; Bias: plain sum), and dldb_diag[j] = diag(dL_dB) (OMGP.py:88-91).
+ * B^-1 = W^T W is formed tile by tile on the FP64 tensor pipe and contracted in the epilogue; nothing N x N is stored.
+ * Scratch: tbuf Npad x Dy, part as gpc_omgp_component, alpha Npad x Dy, dldb_diag Npad,
+ * tile_part gpc_omgp_kgrad_tiles(Npad) x 16, out 16 doubles.                                                */
+long long gpc_omgp_kgrad_tiles(long long Npad);
+int gpc_omgp_kern_grads(const double *W, const double *X, int q, const double *Y, long long N, int Dy, int nparts, const int *kinds,
+                        const double *variances, const double *lengthscales, double *tbuf, double *part, double *alpha, double *dldb_diag,
+                        double *tile_part, double *out, void *stream);
 /* bound (OMGP.py:96-123) from comp (K x 4) + entropy partials; phi_hat, mixing-proportion gradient (K each) */
 int gpc_omgp_finalize(const double *comp, const double *Hpart, int n_hpart, double *scalars, double *phi_hat, double *mixgrad, double variance,
                       double alpha, int prior, int K, int Dy, void *stream);
@@ -303,6 +315,16 @@ int gpc_unpack_rows(const double *src, long long N, int C, int CP, int layout, d
 /* layout helpers: contiguous N x D  <->  row-major padded Npad x ld                                  */
 int gpc_pad_rows(const double *src, long long N, int D, int DP, double *dst, void *stream);
 int gpc_unpad_rows(const double *src, long long N, int K, int ld, double *dst, void *stream);
+
+/* ---- launch-sequence replay -------------------------------------------------------------------
+ * The device-resident loop (gpc_loop_t above) makes every launch of a loop-body pass argument-invariant, so a batch of
+ * passes is captured once into a CUDA graph and replayed with a single launch (no per-kernel host work).
+ * gpc_graph_begin starts a (relaxed-mode) capture on `stream` (must not be the legacy default stream); every gpc_* launch
+ * issued on that stream until gpc_graph_end is recorded instead of executed.  *exec is an opaque handle.       */
+int gpc_graph_begin(void *stream);
+int gpc_graph_end(void *stream, void **exec);
+int gpc_graph_launch(void *exec, void *stream);
+int gpc_graph_destroy(void *exec);
 
 #ifdef __cplusplus
 }

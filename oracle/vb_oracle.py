@@ -287,6 +287,8 @@ class MixtureOracle(object):
 
         bound_old = self.bound()
         phi_old = self.get_vb_param().copy()
+        hyper = getattr(self, "hyper_free", False)  # collapsed_mixture.py:143-144: param_old = self.optimizer_array.copy()
+        param_old = [getattr(o, n) for o, n in self.kernel_param_list()] if hyper else []
         old_K = self.K
 
         self.K += 1
@@ -304,6 +306,10 @@ class MixtureOracle(object):
         if bound_increase < 1e-3:
             self.K = old_K
             self.set_vb_param(phi_old)
+            if hyper:  # collapsed_mixture.py:174: self.optimizer_array = param_old
+                for (o, n), v in zip(self.kernel_param_list(), param_old):
+                    setattr(o, n, v)
+                self.parameters_changed()
             if verbose:
                 self.out.write("split failed, bound changed by:  %.12g (K=%s)\n" % (bound_increase, self.K))
             return False
@@ -399,7 +405,52 @@ class MOGOracle(MixtureOracle):
 
 
 # --------------------------------------------------------------------------- L4: MOHGP
-class MOHGPOracle(MixtureOracle):
+class HyperOracle(object):
+    """The slice of GPy / paramz the reference leans on for the non-variational parameters (collapsed_vb.py:313-323):
+    Logexp-transformed optimiser vector and Model.optimize = L-BFGS-B on -log_likelihood.  Mixed into MOHGPOracle / OMGPOracle,
+    which provide kernel_param_list(), kernel_gradients() and parameters_changed()."""
+
+    hyper_free = False  # True: the kernel parameters are free, optimize() interleaves their optimisation (collapsed_vb.py:300-301)
+    hyperparam_max_iters = 20  # collapsed_vb.py:32-35
+
+    # paramz Logexp transform + GPy Model.optimize (default optimiser: scipy L-BFGS-B on -log_likelihood), collapsed_vb.py:313-323
+    @staticmethod
+    def _finv(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f > 36.0, f, np.log(np.expm1(np.minimum(f, 36.0))))
+
+    @staticmethod
+    def _f(x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.where(x > 36.0, x, np.log1p(np.exp(np.clip(x, -745.0, 36.0))))
+
+    def _set_x(self, x):
+        for (k, name), v in zip(self.kernel_param_list(), self._f(x)):
+            setattr(k, name, float(v))
+        self.parameters_changed()
+
+    def _objective_grads(self, x):
+        try:
+            self._set_x(x)
+            f = np.array([getattr(k, name) for k, name in self.kernel_param_list()])
+            g = self.kernel_gradients() * np.where(f > 36.0, 1.0, -np.expm1(-f))
+            return -float(self.bound()), -g
+        except LinAlgError:
+            return np.inf, np.zeros(len(x))
+
+    def optimize_parameters(self):
+        if not self.hyper_free:
+            return 0.0
+        from scipy.optimize import fmin_l_bfgs_b
+        start = self.bound()
+        x0 = self._finv([getattr(k, name) for k, name in self.kernel_param_list()])
+        x_opt, _, _ = fmin_l_bfgs_b(self._objective_grads, x0, maxfun=self.hyperparam_max_iters, maxiter=self.hyperparam_max_iters)
+        self._set_x(x_opt)
+        return self.bound() - start
+
+
+
+class MOHGPOracle(HyperOracle, MixtureOracle):
     """MOHGP.py:33-90, :124-153.  `mahalanobis` selects the pairwise form: the weave substitution
     (default, utilities.py:147-170), the Python-3 fallback solve, or the whitened GEMM."""
 
@@ -454,46 +505,8 @@ class MOHGPOracle(MixtureOracle):
         self.dL_dSy = tmp
         self.kernY.update_gradients_full(dL_dK=tmp, X=self.X)
 
-    hyper_free = False  # True: the kernel parameters are free, optimize() interleaves their optimisation (collapsed_vb.py:300-301)
-    hyperparam_max_iters = 20  # collapsed_vb.py:32-35
-
     def kernel_param_list(self):
         return self.kernF.param_list() + self.kernY.param_list()
-
-    # paramz Logexp transform + GPy Model.optimize (default optimiser: scipy L-BFGS-B on -log_likelihood), collapsed_vb.py:313-323
-    @staticmethod
-    def _finv(f):
-        f = np.asarray(f, dtype=np.float64)
-        return np.where(f > 36.0, f, np.log(np.expm1(np.minimum(f, 36.0))))
-
-    @staticmethod
-    def _f(x):
-        x = np.asarray(x, dtype=np.float64)
-        return np.where(x > 36.0, x, np.log1p(np.exp(np.clip(x, -745.0, 36.0))))
-
-    def _set_x(self, x):
-        for (k, name), v in zip(self.kernel_param_list(), self._f(x)):
-            setattr(k, name, float(v))
-        self.parameters_changed()
-
-    def _objective_grads(self, x):
-        try:
-            self._set_x(x)
-            f = np.array([getattr(k, name) for k, name in self.kernel_param_list()])
-            g = self.kernel_gradients() * np.where(f > 36.0, 1.0, -np.expm1(-f))
-            return -float(self.bound()), -g
-        except LinAlgError:
-            return np.inf, np.zeros(len(x))
-
-    def optimize_parameters(self):
-        if not self.hyper_free:
-            return 0.0
-        from scipy.optimize import fmin_l_bfgs_b
-        start = self.bound()
-        x0 = self._finv([getattr(k, name) for k, name in self.kernel_param_list()])
-        x_opt, _, _ = fmin_l_bfgs_b(self._objective_grads, x0, maxfun=self.hyperparam_max_iters, maxiter=self.hyperparam_max_iters)
-        self._set_x(x_opt)
-        return self.bound() - start
 
     def kernel_gradients(self):
         """d bound / d (kernel parameter), in link order kernF then kernY (what GPy hands to its optimiser, untransformed)."""
@@ -520,7 +533,7 @@ class MOHGPOracle(MixtureOracle):
 
 
 # --------------------------------------------------------------------------- L4: OMGP
-class OMGPOracle(MixtureOracle):
+class OMGPOracle(HyperOracle, MixtureOracle):
     """OMGP.py:14-53, :96-147 (bound and approximate natural gradient; appendix A.11 quirks kept)."""
 
     def __init__(self, X, Y, K=2, kernels=None, variance=1.0, alpha=1.0, prior_Z="symmetric"):
@@ -562,3 +575,35 @@ class OMGPOracle(MixtureOracle):
             grad_Lm[:, i] = -0.5 * self.variance * dL_dB_diag / (self.phi[:, i] ** 2 + 1e-6)
         grad_phi = grad_Lm + self.mixing_prop_bound_grad() + self.Hgrad
         return self._natural(grad_phi)
+
+    def parameters_changed(self):
+        pass  # OMGP.py:35-38 only refreshes the gradients; bound() / vb_grad_natgrad() recompute everything from the kernels
+
+    def update_kern_grads(self):
+        """OMGP.py:55-94: gradients of the bound w.r.t. the kernel parameters of every component and the noise variance.
+        Quirk kept (appendix A.11): the kernel gradients use B = K + diag(variance / phi) with NO 1e-6, and the same
+        dL_dB then enters the variance gradient together with 1 / (phi + 1e-6)."""
+        grad_Lm_variance = 0.0
+        for i, kern in enumerate(self.kern):
+            Kmat = kern.K(self.X)
+            B_inv = np.diag(1.0 / (self.phi[:, i] / self.variance))
+            Bi, LB, LBi, Blogdet = G.pdinv(Kmat + B_inv)
+            tmp = G.dpotrs(LB, self.YYT)[0]
+            tmp[np.diag_indices(self.N)] -= 1.0  # GPy.util.diag.subtract(tmp, 1)
+            dL_dB = G.dpotrs(LB, tmp.T)[0]
+            kern.update_gradients_full(dL_dK=0.5 * dL_dB, X=self.X)
+            grad_B_inv = np.diag(1.0 / (self.phi[:, i] + 1e-6))
+            grad_Lm_variance += 0.5 * np.trace(np.dot(dL_dB, grad_B_inv))
+            grad_Lm_variance -= 0.5 * self.D * np.einsum("j,j->", self.phi[:, i], (1.0 / self.variance) * np.ones(self.N))
+        self.variance_gradient = float(grad_Lm_variance)
+
+    def kernel_param_list(self):
+        """GPy link order (OMGP.py:31-32): the noise variance first, then the kernels of the components."""
+        out = [(self, "variance")]
+        for k in self.kern:
+            out.extend(k.param_list())
+        return out
+
+    def kernel_gradients(self):
+        self.update_kern_grads()
+        return np.array([getattr(o, n + "_gradient") for o, n in self.kernel_param_list()])

@@ -142,9 +142,19 @@ def omgp_case(GPclust, name, N, Dy, K, prior_Z, alpha, seed, variance, kernels, 
            "kernels": json.dumps([k.spec() for k in m.kern])}
     g, ng = m.vb_grad_natgrad()
     out.update(bound0=m.bound(), grad0=g, natgrad0=ng, phi_init=m.phi.copy())
+
+    def kgrads():
+        # the reference's own update_kern_grads (OMGP.py:55-94): [d/d variance, then (variance, lengthscale) per component]
+        m.update_kern_grads()
+        v = [float(np.asarray(m.variance.gradient).reshape(-1)[0])]
+        for k in m.kern:
+            v.extend([k.variance_gradient, k.lengthscale_gradient])
+        return np.array(v)
+
+    out.update(kgrad0=kgrads())
     out["trace"] = run_optimize(m, method="HS", maxiter=maxiter)
     g, ng = m.vb_grad_natgrad()
-    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy())
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy(), kgrad1=kgrads())
     Xnew = np.linspace(0, 10, 7)[:, None]
     mu, va = m.predict(Xnew, 0)
     out.update(Xnew=Xnew, pred_mu0=mu, pred_va0=va)

@@ -27,14 +27,22 @@ def _data(N, Dy, K, seed):
     return X, Y
 
 
-def _pair(N, Dy, K, prior_Z="symmetric", alpha=1.0, variance=0.01, seed=0, lengthscales=None):
+def _pair(N, Dy, K, prior_Z="symmetric", alpha=1.0, variance=0.01, seed=0, lengthscales=None, free=False, kernels=None):
+    """free=False: noise variance and kernel parameters held fixed on both sides (the oracle's default; the reference
+    would need .fix()).  free=True: both sides optimise them (OMGP.py:31-32, collapsed_vb.py:313-323)."""
     from gpclust_b200 import OMGP, kern
     X, Y = _data(N, Dy, K, seed)
     ls = lengthscales or [1.0 + 0.5 * i for i in range(K)]
+    ko = kernels(G) if kernels else [G.RBF(1, 1.0, l) for l in ls]
+    kp = kernels(kern) if kernels else [kern.RBF(1, 1.0, l) for l in ls]
+    if not free:
+        kp = [k.fix() for k in kp]
     np.random.seed(seed + 1)
-    mo = OMGPOracle(X, Y, K=K, kernels=[G.RBF(1, 1.0, l) for l in ls], variance=variance, alpha=alpha, prior_Z=prior_Z)
+    mo = OMGPOracle(X, Y, K=K, kernels=ko, variance=variance, alpha=alpha, prior_Z=prior_Z)
+    mo.hyper_free = free
     np.random.seed(seed + 1)
-    mp = OMGP(X, Y, K=K, kernels=[kern.RBF(1, 1.0, l) for l in ls], variance=variance, alpha=alpha, prior_Z=prior_Z)
+    mp = OMGP(X, Y, K=K, kernels=kp, variance=variance, alpha=alpha, prior_Z=prior_Z)
+    mp.variance_fixed = not free
     assert np.array_equal(mp.phi_, mo.phi_)
     return mo, mp
 
@@ -119,3 +127,49 @@ def test_split_and_predict():
     va0 = mo.variance + k.K(Xnew, Xnew) - kx.T.dot(KBi.dot(kx))
     m0, v0 = mp.predict(Xnew, 0)
     assert relerr(m0, mu0) < 1e-6 and relerr(v0, va0) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ kernel hyper-parameters
+def _mixed_kernels(mod):
+    return [mod.RBF(1, 1.2, 0.8) + mod.White(1, 0.02), mod.Matern32(1, 0.7, 1.5) + mod.Bias(1, 0.3), mod.Matern52(1, 1.0, 2.5)]
+
+
+@pytest.mark.parametrize("N,Dy,K,kernels", [(50, 1, 2, None), (130, 2, 3, _mixed_kernels), (333, 1, 3, _mixed_kernels), (700, 2, 2, None)])
+def test_kernel_gradients(N, Dy, K, kernels):
+    """OMGP.update_kern_grads (OMGP.py:55-94): gradients of the noise variance and of every covariance parameter; B^-1 is formed
+    tile by tile on the tensor pipe and contracted on the fly (gpc_omgp_kern_grads)."""
+    mo, mp = _pair(N, Dy, K, free=True, kernels=kernels, variance=0.05)
+    g_o, g_p = mo.kernel_gradients(), mp._kernel_gradients()
+    assert [n for _, n in mo.kernel_param_list()] == [n for _, n in mp._kernel_param_list()]
+    assert g_o.shape == g_p.shape and np.max(np.abs(g_p - g_o) / np.maximum(1e-3 * np.max(np.abs(g_o)), np.abs(g_o))) < TOL
+    # after a few iterations of the loop (responsibilities close to 0 / 1: the variance / phi diagonal spans many decades)
+    mo.hyper_free = False
+    mp.variance_fixed = True
+    for k in mp.kern:
+        k.fix()
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=6, verbose=False)
+    mp.optimize(maxiter=6, verbose=False)
+    mp.variance_fixed = False
+    for k in mp.kern:
+        k.unfix()
+    g_o, g_p = mo.kernel_gradients(), mp._kernel_gradients()
+    assert np.max(np.abs(g_p - g_o) / np.maximum(1e-3 * np.max(np.abs(g_o)), np.abs(g_o))) < 1e-6
+
+
+def test_hyperparameter_step():
+    """optimize_parameters (collapsed_vb.py:313-323) with the noise variance and the kernels free: same optimiser vector,
+    same bound increment as the oracle's restatement of GPy's L-BFGS-B step."""
+    mo, mp = _pair(120, 1, 2, free=True, variance=0.05, seed=3)
+    assert relerr(mp.optimizer_array, mo._finv([getattr(o, n) for o, n in mo.kernel_param_list()])) < 1e-14
+    b0 = mp.bound()
+    inc_o, inc_p = mo.optimize_parameters(), mp.optimize_parameters()
+    assert inc_p > 0 and abs(inc_p - inc_o) < 1e-6 * abs(b0)
+    assert abs(mp.bound() - mo.bound()) < 1e-6 * abs(mo.bound())
+    assert abs(mp.variance - mo.variance) < 1e-5 * mo.variance
+    # the loop interleaves the step at convergence (collapsed_vb.py:248,270)
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=40, verbose=False)
+    mp.optimize(maxiter=40, verbose=False)
+    assert [r[0] for r in mp.optimize_trace] == [r[0] for r in mo.trace]
+    assert abs(mp.bound() - mo.bound()) < 1e-5 * abs(mo.bound())

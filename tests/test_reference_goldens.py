@@ -111,9 +111,11 @@ def test_oracle_omgp_matches_reference(path):
                    prior_Z=str(d["prior_Z"]))
     m.set_vb_param(d["phi0"].flatten())
     _check_start(m, d)
+    assert relerr(m.kernel_gradients(), d["kgrad0"]) < TOL  # OMGP.update_kern_grads (OMGP.py:55-94) at the initial point
     m.out = io.StringIO()
     m.optimize(method="HS", maxiter=12, verbose=False)
     _check_model(m, d, m.trace)
+    assert relerr(m.kernel_gradients(), d["kgrad1"]) < 1e-7  # after 8 accepted steps (rounding of the loop amplified)
 
 
 @pytest.mark.parametrize("path", _cases("mog"))
@@ -172,7 +174,20 @@ def test_gpu_omgp_matches_reference(path):
              alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]))
     m.set_vb_param(d["phi0"].flatten())
     _check_start(m, d)
+
+    def kgrads():  # gradient vector with every parameter free; the loop itself runs with them fixed, as in the fixture
+        m.variance_fixed = False
+        for k in m.kern:
+            k.unfix()
+        g = m._kernel_gradients()
+        m.variance_fixed = True
+        for k in m.kern:
+            k.fix()
+        return g
+
+    assert relerr(kgrads(), d["kgrad0"]) < TOL  # OMGP.update_kern_grads (OMGP.py:55-94)
     m.optimize(method="HS", maxiter=12, verbose=False)
     _check_model(m, d, m.optimize_trace)
+    assert relerr(kgrads(), d["kgrad1"]) < 1e-7
     mu, va = m.predict(d["Xnew"], 0)
     assert relerr(mu, d["pred_mu0"]) < 1e-7 and relerr(va, d["pred_va0"]) < 1e-7
