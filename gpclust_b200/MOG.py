@@ -89,7 +89,7 @@ class MOG(CollapsedMixture):
         self.kernel_launches += 1
 
     def _loop_posterior(self, phase):
-        check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+        check(lib.gpc_reduce_partials(ptr(self._spart), self._nparts, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
         self._allreduce(self._stats)
         check(lib.gpc_loop_mog_post(ptr(self._stats), ptr(self._m0c_dev), ptr(self._S0_dev), ptr(self._Wt), ptr(self._per_k), ptr(self._mun_c),
                                     ptr(self._Sns), ptr(self._Sns_inv), self._info_ptr(), float(self.k0), float(self.v0), ptr(self._bias),

@@ -148,12 +148,12 @@ class MOHGP(CollapsedMixture):
     def _launch_posterior(self):
         """Statistics -> posterior -> bound in one launch (two + an all-reduce when rows are sharded)."""
         if self._world > 1:
-            check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+            check(lib.gpc_reduce_partials(ptr(self._spart), self._nparts, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
             self.kernel_launches += 1
             self._allreduce(self._stats)
             parts, nparts = self._stats, 1
         else:
-            parts, nparts = self._spart, self._grid
+            parts, nparts = self._spart, self._nparts
         check(lib.gpc_mohgp_post(ptr(parts), nparts, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
                                  ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias), ptr(self._ctrl),
                                  ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z],
@@ -178,12 +178,12 @@ class MOHGP(CollapsedMixture):
             self.kernel_launches += 2
             return
         if self._world > 1:
-            check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+            check(lib.gpc_reduce_partials(ptr(self._spart), self._nparts, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
             self.kernel_launches += 1
             self._allreduce(self._stats)
             parts, nparts = self._stats, 1
         else:
-            parts, nparts = self._spart, self._grid
+            parts, nparts = self._spart, self._nparts
         check(lib.gpc_loop_mohgp_post(ptr(parts), nparts, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
                                       ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias), ptr(self._ctrl),
                                       ptr(self._mixgrad), ptr(self._counter[1:]), self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z],

@@ -44,6 +44,9 @@ PROTOTYPES = {
     "gpc_natgrad_finish": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "gpc_step_lse": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _p],
     "gpc_stats_chunk": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _ll, _i, _i, _ll, _i, _p],
+    "gpc_wide_clusters": [_i, _i],
+    "gpc_natgrad_wide": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_step_stats_wide": [_p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_partials": [_p, _i, _i, _p, _p],
     "gpc_mohgp_setup": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "gpc_mohgp_const": [_p, _p, _p, _d, _i, _p, _p],

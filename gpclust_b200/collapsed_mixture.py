@@ -165,6 +165,15 @@ class CollapsedMixture(CollapsedVB):
         self._stats_len = lib.gpc_stats_len(KP, DP)
         self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
         self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
+        # K > 64: one launch per pass by thread-block clusters of KP/64 CTAs (gpc_*_wide); GPCLUST_B200_WIDE=0 keeps the
+        # per-chunk launches (gpc_*_chunk) for comparison
+        self._wide = self._chunks > 1 and os.environ.get("GPCLUST_B200_WIDE", "1") != "0"
+        self._nparts = self._grid  # per-CTA (per-cluster in wide mode) blocks of partial statistics
+        if self._wide:
+            self._ncl = int(lib.gpc_wide_clusters(KP, DP))
+            if self._ncl < 1:
+                check(self._ncl or -1, "gpc_wide_clusters")
+            self._nparts = self._ncl
         self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
         self._peers = self._shards.setup_peers(self._stats_len, self.device) if (self._use_peer_exchange() and self._chunks == 1) else None
         self._alloc_model()
@@ -305,6 +314,13 @@ class CollapsedMixture(CollapsedVB):
             self._launch_posterior()
 
     def _launch_step_stats(self, x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old):
+        if self._wide:
+            check(lib.gpc_step_stats_wide(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(lse_new),
+                                          ptr(self._ctrl[_C_SQ:]), float(sq_old), ptr(self._ctrl[_C_BETA:]), ptr(self._spart), float(step),
+                                          _cabi.BETA[beta_mode], self.N, self.K, self._KP, self._DP, self._ncl, self._stream()),
+                  "gpc_step_stats_wide")
+            self.kernel_launches += 1
+            return
         if self._chunks > 1:
             return self._launch_step_stats_chunked(x_base, ng, sd_old, sd_new, x_new, lse_new, beta_mode, step, sq_old)
         check(lib.gpc_step_stats(ptr(self._F), ptr(x_base), ptr(ng), ptr(sd_old), ptr(sd_new), ptr(x_new), ptr(lse_new), ptr(self._ctrl[_C_SQ:]),
@@ -328,6 +344,14 @@ class CollapsedMixture(CollapsedVB):
                                       self._grid, st), "gpc_stats_chunk")
         self.kernel_launches += 1 + self._chunks
 
+    def _launch_natgrad_wide_or_chunked(self, x, lse, x_old, lse_old, ng_old, ng_out, grad_out, dots):
+        if not self._wide:
+            return self._launch_natgrad_chunked(x, lse, x_old, lse_old, ng_old, ng_out, grad_out, dots)
+        check(lib.gpc_natgrad_wide(ptr(self._F), ptr(x), ptr(lse), ptr(self._Wt), ptr(self._bias), ptr(x_old), ptr(lse_old), ptr(ng_old),
+                                   ptr(ng_out), ptr(grad_out), ptr(self._gpart), ptr(self._counter), dots, self.N, self.K, self._KP, self._DP,
+                                   self._ncl, self._stream()), "gpc_natgrad_wide")
+        self.kernel_launches += 1
+
     def _launch_natgrad_chunked(self, x, lse, x_old, lse_old, ng_old, ng_out, grad_out, dots):
         """K > 64: a = F.W + bias - x per chunk (row sums of phi*a accumulated), then centring, gradient and dots over whole rows."""
         KP, DP, st = self._KP, self._DP, self._stream()
@@ -343,7 +367,7 @@ class CollapsedMixture(CollapsedVB):
         self.kernel_launches += 1 + self._chunks
 
     def _launch_posterior(self):
-        check(lib.gpc_reduce_partials(ptr(self._spart), self._grid, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
+        check(lib.gpc_reduce_partials(ptr(self._spart), self._nparts, self._stats_len, ptr(self._stats), self._stream()), "gpc_reduce_partials")
         self.kernel_launches += 1
         self._allreduce(self._stats)
         self._launch_cluster()
@@ -387,7 +411,7 @@ class CollapsedMixture(CollapsedVB):
         lse_old = self._lsebuf[self._xprev] if have_old else None
         ng_old = self._ngbuf[1 - self._ngi] if have_old else None
         if self._chunks > 1:
-            return self._launch_natgrad_chunked(x, lse, x_old, lse_old, ng_old, self._ngbuf[self._ngi], None, ptr(self._ctrl[_C_SQ:]))
+            return self._launch_natgrad_wide_or_chunked(x, lse, x_old, lse_old, ng_old, self._ngbuf[self._ngi], None, ptr(self._ctrl[_C_SQ:]))
         check(lib.gpc_natgrad(ptr(self._F), ptr(x), ptr(lse), ptr(self._Wt), ptr(self._bias), ptr(x_old), ptr(lse_old), ptr(ng_old),
                               ptr(self._ngbuf[self._ngi]), None, ptr(self._gpart), ptr(self._counter), ptr(self._ctrl[_C_SQ:]), self.N,
                               self.K, self._KP, self._DP, self._grid, self._stream()), "gpc_natgrad")
@@ -593,7 +617,7 @@ class CollapsedMixture(CollapsedVB):
         gr = torch.empty((self._Npad, self._KP), dtype=torch.float64, device=self.device)
         dots = torch.zeros(4, dtype=torch.float64, device=self.device)
         if self._chunks > 1:
-            self._launch_natgrad_chunked(self._xbuf[self._xi], self._lsebuf[self._xi], None, None, None, ng, gr, ptr(dots))
+            self._launch_natgrad_wide_or_chunked(self._xbuf[self._xi], self._lsebuf[self._xi], None, None, None, ng, gr, ptr(dots))
         else:
             check(lib.gpc_natgrad(ptr(self._F), ptr(self._xbuf[self._xi]), ptr(self._lsebuf[self._xi]), ptr(self._Wt), ptr(self._bias), None, None,
                                   None, ptr(ng), ptr(gr),

@@ -65,6 +65,67 @@ int launch_step_stats(StepStatsArgs &a, int grid, cudaStream_t st) {
                    : launch_vb(k_step_stats<KP, false>, a, smem, grid, kSThreads, st);
 }
 
+// ---- wide mode (K > 64): clusters of KP/64 CTAs, one 64-cluster chunk per CTA (gpc_vb_kernels.cuh)
+int natgrad_stages_wide(int DP) {
+  const int units = kGConsumers / 2;
+  const size_t fixed = sizeof(double) * ((size_t)g_fixed_doubles(GPC_MAX_KP, DP) + g_cl_doubles()) + 64;
+  const size_t per = sizeof(double) * (size_t)g_stage_doubles(GPC_MAX_KP, DP) + sizeof(uint64_t);
+  int r = (int)((kSmemBudget - fixed) / per) / units;
+  if (r > kMaxUnitSlots) r = kMaxUnitSlots;
+  return r * units;
+}
+size_t natgrad_smem_wide(int DP, int S) { return natgrad_smem(GPC_MAX_KP, DP, S) + sizeof(double) * g_cl_doubles(); }
+int step_stats_stages_wide(int DP) {
+  const size_t fixed = sizeof(double) * ((size_t)kSSoftmaxWarps + s_cl_doubles()) + 64;
+  const size_t per = sizeof(double) * (size_t)s_stage_doubles(GPC_MAX_KP, DP) + 3 * sizeof(uint64_t);
+  const int s = (int)((kSmemBudget - fixed) / per);
+  return s > kMaxStages ? kMaxStages : s;
+}
+size_t step_stats_smem_wide(int DP, int S) { return step_stats_smem(GPC_MAX_KP, DP, S) + sizeof(double) * s_cl_doubles(); }
+
+template <typename Kern, typename Args>
+int launch_wide(Kern kern, const Args &a, size_t smem, int csize, int nclusters, int threads, cudaStream_t st, int *max_clusters) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_rc(e);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters != nullptr) {  // query only: how many clusters of this shape are co-resident
+    cfg.gridDim = dim3((unsigned)csize);
+    e = cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
+    return cuda_rc(e);
+  }
+  cfg.gridDim = dim3((unsigned)(csize * nclusters));
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  return e == cudaSuccess ? launch_rc() : cuda_rc(e);
+}
+int dispatch_natgrad_wide(NatgradArgs &a, int csize, int nclusters, cudaStream_t st, int *max_clusters) {
+  a.stages = natgrad_stages_wide(a.DP);
+  a.csize = csize;
+  const size_t smem = natgrad_smem_wide(a.DP, a.stages);
+  return a.K == csize * GPC_MAX_KP ? launch_wide(k_natgrad<GPC_MAX_KP, true, true>, a, smem, csize, nclusters, kGThreads, st, max_clusters)
+                                   : launch_wide(k_natgrad<GPC_MAX_KP, false, true>, a, smem, csize, nclusters, kGThreads, st, max_clusters);
+}
+int dispatch_step_stats_wide(StepStatsArgs &a, int csize, int nclusters, cudaStream_t st, int *max_clusters) {
+  a.stages = step_stats_stages_wide(a.DP);
+  a.csize = csize;
+  const size_t smem = step_stats_smem_wide(a.DP, a.stages);
+  return a.K == csize * GPC_MAX_KP ? launch_wide(k_step_stats<GPC_MAX_KP, true, true>, a, smem, csize, nclusters, kSThreads, st, max_clusters)
+                                   : launch_wide(k_step_stats<GPC_MAX_KP, false, true>, a, smem, csize, nclusters, kSThreads, st, max_clusters);
+}
+bool wide_geometry_ok(long long N, int K, int KP, int DP, int nclusters) {
+  return N >= 1 && N <= 0x7fffffffLL && K > GPC_MAX_KP && K <= KP && KP <= GPC_MAX_KTOT && KP == gpc_padded_k(K) && DP >= 8 && DP <= GPC_MAX_DP &&
+         (DP % 8) == 0 && nclusters >= 1;
+}
+
 constexpr size_t kTileSmem = sizeof(double) * (size_t)kOB * (kOStrideT + kOStrideN);
 template <typename Kern>
 int tile_attr(Kern kern) {
@@ -343,6 +404,84 @@ int gpc_stats_chunk(const double *F, const double *x, const double *lse, const d
   a.h_off = h_off;
   a.write_h = write_h;
   return dispatch_step_stats(a, GPC_MAX_KP, grid, as_stream(stream));
+}
+
+// ---- wide mode entry points (K > 64)
+int gpc_wide_clusters(int KP, int DP) {
+  if (KP <= GPC_MAX_KP || KP > GPC_MAX_KTOT || (KP % GPC_MAX_KP) || DP < 8 || DP > GPC_MAX_DP || (DP % 8)) return GPC_EINVAL;
+  const int csize = KP / GPC_MAX_KP;
+  NatgradArgs g{};
+  g.DP = DP;
+  g.K = KP;
+  StepStatsArgs s{};
+  s.DP = DP;
+  s.K = KP;
+  int ng = 0, ns = 0;
+  int rc = dispatch_natgrad_wide(g, csize, 1, nullptr, &ng);
+  if (rc) return rc;
+  rc = dispatch_step_stats_wide(s, csize, 1, nullptr, &ns);
+  if (rc) return rc;
+  const int n = ng < ns ? ng : ns;
+  return n >= 1 ? n : -(int)cudaErrorLaunchOutOfResources;
+}
+
+int gpc_natgrad_wide(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, const double *x_old,
+                     const double *lse_old, const double *ng_old, double *ng_out, double *grad_out, double *partials, unsigned int *counter,
+                     double *dots, long long N, int K, int KP, int DP, int nclusters, void *stream) {
+  if (!F || !x || !lse || !Wt || !bias || !ng_out || !partials || !counter || !dots) return GPC_EINVAL;
+  if ((x_old == nullptr) != (ng_old == nullptr) || (x_old == nullptr) != (lse_old == nullptr)) return GPC_EINVAL;
+  if (!wide_geometry_ok(N, K, KP, DP, nclusters)) return GPC_EINVAL;
+  NatgradArgs a{};
+  a.F = F;
+  a.x = x;
+  a.lse = lse;
+  a.Wt = Wt;
+  a.bias = bias;
+  a.x_old = x_old;
+  a.lse_old = lse_old;
+  a.ng_old = ng_old;
+  a.ng_out = ng_out;
+  a.grad_out = grad_out;
+  a.partials = partials;
+  a.counter = counter;
+  a.dots_out = dots;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.xg_stride = (long long)kGroupRows * KP;
+  return dispatch_natgrad_wide(a, KP / GPC_MAX_KP, nclusters, as_stream(stream), nullptr);
+}
+
+int gpc_step_stats_wide(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
+                        double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode,
+                        long long N, int K, int KP, int DP, int nclusters, void *stream) {
+  if (!F || !x_base || !partials) return GPC_EINVAL;
+  if (ng && !x_new) return GPC_EINVAL;
+  if (beta_mode != GPC_BETA_ZERO && (!dots || !ng)) return GPC_EINVAL;
+  if (beta_mode < GPC_BETA_ZERO || beta_mode > GPC_BETA_FR) return GPC_EINVAL;
+  if (!wide_geometry_ok(N, K, KP, DP, nclusters)) return GPC_EINVAL;
+  StepStatsArgs a{};
+  a.F = F;
+  a.x_base = x_base;
+  a.ng = ng;
+  a.sd_old = sd_old;
+  a.sd_new = sd_new;
+  a.x_new = x_new;
+  a.lse_new = lse_new;
+  a.dots = dots;
+  a.sq_old = sq_old;
+  a.beta_out = beta_out;
+  a.partials = partials;
+  a.step = step;
+  a.beta_mode = beta_mode;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.phase = GPC_PHASE_CONJ;
+  a.xg_stride = (long long)kGroupRows * KP;
+  return dispatch_step_stats_wide(a, KP / GPC_MAX_KP, nclusters, as_stream(stream), nullptr);
 }
 
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {

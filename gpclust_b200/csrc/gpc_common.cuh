@@ -60,6 +60,52 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block clusters (distributed shared memory)
+// K > 64: the CTAs of a cluster share the same row groups, CTA `rank` owning the clusters [64 rank, 64 rank + 64); the
+// row-coupled scalars (softmax max / sum, sum_k phi*a) are exchanged through each other's shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory"); }
+// arrive (release at cluster scope: this thread's earlier remote stores are visible to the waiter) on a peer's mbarrier
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "DONE_C:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
 // bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");

@@ -40,6 +40,7 @@ constexpr int kSSoftmaxWarps = 7;                  // S pass (7 + 4 + 1 = 12 war
 constexpr int kSStatWarps = 4;
 constexpr int kSThreads = (kSSoftmaxWarps + kSStatWarps + 1) * 32;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kMaxCl = GPC_MAX_KTOT / GPC_MAX_KP;  // CTAs per cluster in the wide (K > 64) mode: one 64-cluster chunk each
 
 // ------------------------------------------------------------------------------------------------
 // G pass
@@ -69,12 +70,18 @@ struct NatgradArgs {
   long long xg_stride;
   double *sa_vec;
   int sa_first;
+  // wide mode (template CL): launched with clusters of `csize` CTAs; K is the total cluster count, Wt / bias / the N x K
+  // operands are the full KPtot = 64*csize wide arrays (xg_stride = 8*KPtot) and CTA `rank` of a cluster works on the
+  // columns [64 rank, 64 rank + 64) of the row groups of its cluster.
+  int csize;
 };
 
 // ring stage: [F group | x group | lse (8) | lse_old (8)]; the previous-point operands x_old / ng_old go straight
 // from HBM to registers (the fragment-major layout makes those loads 512 contiguous bytes per warp instruction)
 __host__ __device__ inline int g_stage_doubles(int KP, int DP) { return kGroupRows * DP + kGroupRows * KP + 2 * kGroupRows; }
 __host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP + KP + kGConsumers * 4 + 2 * kGConsumers * kGroupRows; }
+// wide mode: mailbox [2 parities][units][kMaxCl ranks][8 rows] + 2*units mbarriers
+__host__ __device__ inline int g_cl_doubles() { return 2 * kGConsumers * kMaxCl * kGroupRows + 2 * kGConsumers; }
 
 // FULLK: K == KP, no column masking.
 // All 12 warps compute.  They work in units of NSPLIT warps that share one group: warp h of a unit owns the n-tiles
@@ -83,7 +90,7 @@ __host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP 
 // slot it has just finished with the unit's group R visits ahead (cp.async.bulk + mbarrier complete_tx) -- no
 // producer warp, no empty barriers (the unit's own exchange barrier orders "both warps are done reading" before
 // the refill), and the four schedulers carry three compute warps each.
-template <int KP, bool FULLK>
+template <int KP, bool FULLK, bool CL = false>
 __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   constexpr int NT = KP / 8;
   constexpr int NSPLIT = (NT >= 2) ? 2 : 1;
@@ -100,39 +107,51 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   double *red_s = bias_s + KP;                               // kGConsumers * 4
   double *sax_s = red_s + kGConsumers * 4;                   // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sax_s + 2 * kGConsumers * kGroupRows);
+  uint64_t *mb_bar = full_bar + a.stages;                                  // wide mode: [2][UNITS]
+  double *sa_mb = reinterpret_cast<double *>(mb_bar + 2 * kGConsumers);    // wide mode: [2][UNITS][kMaxCl][8]
   __shared__ bool is_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const double *p_x = a.x, *p_lse = a.lse, *p_x_old = a.x_old, *p_lse_old = a.lse_old, *p_ng_old = a.ng_old;
-  double *p_ng_out = a.ng_out;
+  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
+  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
+  const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);  // real clusters among this CTA's KP columns
+  const size_t coff = (size_t)crank * XG;                              // this CTA's chunk inside a group of the N x K operands
+  const double *p_x = a.x + coff, *p_lse = a.lse, *p_x_old = a.x_old ? a.x_old + coff : nullptr, *p_lse_old = a.lse_old;
+  const double *p_ng_old = a.ng_old ? a.ng_old + coff : nullptr;
+  double *p_ng_out = a.ng_out + coff;
+  double *p_grad_out = a.grad_out ? a.grad_out + coff : nullptr;
+  const double *p_Wt = a.Wt + (size_t)crank * KP * a.DP, *p_bias = a.bias + crank * KP;
   if (a.loop != nullptr) {
     if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
     const int xi = a.loop->xi, xp = a.loop->xprev, ngi = a.loop->ngi, method = a.loop->method;
-    p_x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi);
+    p_x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
     p_lse = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xi);
-    p_ng_out = ngi ? a.bufs.ng[1] : a.bufs.ng[0];
+    p_ng_out = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
     // HS / PR need the previous accepted point (collapsed_vb.py:159-164); none on the first pass
     const bool ho = (a.loop->first == 0) && xp >= 0 && (method == GPC_BETA_HS || method == GPC_BETA_PR);
-    p_x_old = ho ? sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xp) : nullptr;
+    p_x_old = ho ? sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xp) + coff : nullptr;
     p_lse_old = ho ? sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xp) : nullptr;
-    p_ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) : nullptr;
+    p_ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) + coff : nullptr;
   }
   const bool has_old = (p_ng_old != nullptr);
   const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;  // global group stride of the N x K operands
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
+    if (CL)
+      for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&mb_bar[s], (uint32_t)(kGroupRows * csize));
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
     const int ln = i & 31, f = i >> 5;  // f = ks*NT + nt
     const int nt = f % NT, ks = f / NT;
-    w_s[i] = a.Wt[(size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3)];
+    w_s[i] = p_Wt[(size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3)];
   }
-  for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = a.bias[i];
+  for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = p_bias[i];
   for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) red_s[i] = 0.0;
-  __syncthreads();
+  if (CL) cluster_sync_all();  // every peer's mailbox barriers exist before the first remote arrive
+  else __syncthreads();
 
   {
     const int unit = warp / NSPLIT, h = warp % NSPLIT, nt0 = h * NTW;
@@ -140,8 +159,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
     const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? kGroupRows : 0)) * 8u;
     double *ustages = stages + (size_t)unit * R * stage_doubles;
     uint64_t *ubar = full_bar + unit * R;
-    const int gstride = UNITS * gridDim.x;
-    const int grp0 = blockIdx.x + unit * gridDim.x;
+    const int gstride = UNITS * ncl;
+    const int grp0 = cid + unit * ncl;
     // arm ring slot `slot` with group `grp` (one elected lane of the unit)
     auto feed = [&](int slot, int grp) {
       double *st = ustages + (size_t)slot * stage_doubles;
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
 #pragma unroll
       for (int q = 0; q < NTW; ++q) {
         const int c = 8 * (nt0 + q) + 2 * t;
-        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
         const double2 xv = *reinterpret_cast<const double2 *>(xs + q * 64);
         const double2 bb = *reinterpret_cast<const double2 *>(bias_s + c);
         acc[q][0] = ok0 ? (acc[q][0] + bb.x) - xv.x : 0.0;
@@ -209,8 +228,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
 #pragma unroll
       for (int q = 0; q < NTW; ++q) {
         const int c = 8 * (nt0 + q) + 2 * t;
-        if (!(FULLK || c < a.K)) phi[2 * q] = 0.0;
-        if (!(FULLK || c + 1 < a.K)) phi[2 * q + 1] = 0.0;
+        if (!(FULLK || c < Kc)) phi[2 * q] = 0.0;
+        if (!(FULLK || c + 1 < Kc)) phi[2 * q + 1] = 0.0;
         sa += phi[2 * q] * acc[q][0] + phi[2 * q + 1] * acc[q][1];
       }
       sa = quad_sum(sa);
@@ -229,6 +248,41 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
         if (nxt < a.num_groups) feed(slot, (int)nxt);
       }
 
+      // previous-point responsibilities (independent of the row sums: in wide mode they hide the cluster exchange)
+      double po[2 * NTW];
+      auto old_point = [&]() {
+        if (has_old) {
+#pragma unroll
+          for (int q = 0; q < NTW; ++q) {
+            po[2 * q] = xo[q].x - lse_o;
+            po[2 * q + 1] = xo[q].y - lse_o;
+          }
+          exp_batch<2 * NTW>(po);
+        }
+      };
+      if (CL) {
+        // the row sums of this CTA's 64 clusters -> every CTA of the cluster (remote shared-memory stores + arrive on the
+        // peer's mailbox barrier); total = sum over ranks in rank order (identical on every CTA).  Two parities: a peer can
+        // post visit i+2 only after it has consumed MY visit i+1, which this unit posts after both its warps finished visit i.
+        const int par = i & 1;
+        double *mb = sa_mb + (size_t)((par * UNITS + unit) * kMaxCl) * kGroupRows;
+        uint64_t *mbb = mb_bar + par * UNITS + unit;
+        {
+          // every lane of the unit holds the row sum: lane (h, g, t) posts row g to peer NSPLIT-interleaved rank h*4 + t, so
+          // the (release) round trips to the peers run in parallel instead of one after the other
+          const uint32_t la = smem_u32(mb + crank * kGroupRows + g), lb = smem_u32(mbb);
+          for (int rc = h * 4 + t; rc < csize; rc += 4 * NSPLIT) {
+            st_cluster_f64(cluster_map(la, (uint32_t)rc), sa);
+            mbar_arrive_remote(cluster_map(lb, (uint32_t)rc));
+          }
+        }
+        old_point();
+        mbar_wait_cluster(mbb, (uint32_t)((i >> 1) & 1));
+        double tot = 0.0;
+        for (int rc = 0; rc < csize; ++rc) tot += mb[rc * kGroupRows + g];
+        sa = tot;
+      }
+
       if (a.sa_vec != nullptr) {
         // sweep 1 of the chunked pass (K > 64): leave a = F.W + bias - x behind, accumulate the row sums over the chunks
         if (h == 0 && t == 0 && row_ok) a.sa_vec[row] = a.sa_first ? sa : a.sa_vec[row] + sa;
@@ -239,21 +293,13 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       }
 
       // ---- pass 2: natural gradient, gradient, dots
-      double po[2 * NTW];
-      if (has_old) {
-#pragma unroll
-        for (int q = 0; q < NTW; ++q) {
-          po[2 * q] = xo[q].x - lse_o;
-          po[2 * q + 1] = xo[q].y - lse_o;
-        }
-        exp_batch<2 * NTW>(po);
-      }
+      if (!CL) old_point();
       double *ngo_g = p_ng_out + goff;
-      double *gro_g = a.grad_out ? a.grad_out + goff : nullptr;
+      double *gro_g = p_grad_out ? p_grad_out + goff : nullptr;
 #pragma unroll
       for (int q = 0; q < NTW; ++q) {
         const int c = 8 * (nt0 + q) + 2 * t;
-        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
         const double n0 = (ok0 && row_ok) ? acc[q][0] - sa : 0.0;
         const double n1 = (ok1 && row_ok) ? acc[q][1] - sa : 0.0;
         const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
@@ -277,7 +323,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       red_s[warp * 4 + 2] = d2;
     }
   }
-  __syncthreads();
+  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
+  else __syncthreads();
   // deterministic two-level reduction: per-CTA partial, last CTA sums all partials in index order
   if (threadIdx.x < 3) {
     double v = 0.0;
@@ -357,11 +404,16 @@ struct StepStatsArgs {
   const double *h_in;
   long long part_stride;
   int t_off, ph_off, h_off, write_h;
+  // wide mode (template CL): clusters of `csize` CTAs, see NatgradArgs.  K is the total cluster count; partials holds one
+  // full [T KPtot x DP | phi_hat KPtot | H | pad] block PER CLUSTER (rank r fills rows / entries [64 r, 64 r + 64), rank 0 H).
+  int csize;
 };
 
 __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
+// wide mode: mailbox [softmax warps][2 parities][kMaxCl ranks][8 rows][max, sum, sum e*(x-max)] + 2 mbarriers per softmax warp
+__host__ __device__ inline int s_cl_doubles() { return kSSoftmaxWarps * 2 * kMaxCl * kGroupRows * 3 + 2 * kSSoftmaxWarps; }
 
-template <int KP, bool FULLK>
+template <int KP, bool FULLK, bool CL = false>
 __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs a) {
   constexpr int NT = KP / 8;
   constexpr int XG = kGroupRows * KP;
@@ -374,9 +426,15 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + kSSoftmaxWarps);
   uint64_t *phi_bar = full_bar + S;
   uint64_t *empty_bar = phi_bar + S;
+  uint64_t *mb_bar = empty_bar + S;                                           // wide mode: [softmax warp][2]
+  double *sm_mb = reinterpret_cast<double *>(mb_bar + 2 * kSSoftmaxWarps);    // wide mode: [softmax warp][2][kMaxCl][8][3]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
+  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
+  const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);
+  const size_t coff = (size_t)crank * XG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -384,22 +442,26 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       mbar_init(&phi_bar[s], 1);
       mbar_init(&empty_bar[s], kSStatWarps);
     }
+    if (CL)
+      for (int s = 0; s < 2 * kSSoftmaxWarps; ++s) mbar_init(&mb_bar[s], (uint32_t)(kGroupRows * csize));
     mbar_fence_init();
   }
-  __syncthreads();
+  if (CL) cluster_sync_all();
+  else __syncthreads();
 
-  const double *p_x_base = a.x_base, *p_ng = a.ng, *p_sd_old = a.sd_old;
-  double *p_sd_new = a.sd_new, *p_x_new = a.x_new, *p_lse_new = a.lse_new, *p_beta_out = a.beta_out;
+  const double *p_x_base = a.x_base + coff, *p_ng = a.ng ? a.ng + coff : nullptr, *p_sd_old = a.sd_old ? a.sd_old + coff : nullptr;
+  double *p_sd_new = a.sd_new ? a.sd_new + coff : nullptr, *p_x_new = a.x_new ? a.x_new + coff : nullptr, *p_lse_new = a.lse_new;
+  double *p_beta_out = a.beta_out;
   int beta_mode = a.beta_mode;
   double sq_old = a.sq_old, step = a.step;
   if (a.loop != nullptr) {
     if (loop_skip(a.loop, a.phase)) return;
     const int xi = a.loop->xi, xt = a.loop->xtrial, ngi = a.loop->ngi;
-    p_x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi);
-    p_x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt);
+    p_x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
+    p_x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt) + coff;
     p_lse_new = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xt);
-    p_ng = ngi ? a.bufs.ng[1] : a.bufs.ng[0];
-    p_sd_old = p_sd_new = a.bufs.sd;
+    p_ng = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
+    p_sd_old = p_sd_new = a.bufs.sd + coff;
     // collapsed_vb.py:157-158 (first pass / steepest) and :182-184 (retry with searchDir = -natgrad)
     beta_mode = (a.phase == GPC_PHASE_RETRY || a.loop->first != 0) ? GPC_BETA_ZERO : a.loop->method;
     if (a.phase == GPC_PHASE_RETRY) p_beta_out = nullptr;  // the trace reports the conjugate beta
@@ -436,17 +498,19 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   const bool use_old = has_ng && (beta != 0.0) && (p_sd_old != nullptr);
   const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
   const bool chunked = (a.part_stride != 0);
-  double *part = a.partials + (size_t)blockIdx.x * (chunked ? (size_t)a.part_stride : (size_t)(KP * DP + KP + 2));
-  double *part_t = part + (chunked ? a.t_off : 0);              // T rows of this chunk
-  double *part_ph = part + (chunked ? a.ph_off : KP * DP);       // phi_hat of this chunk
-  double *part_h = part + (chunked ? a.h_off : KP * DP + KP);    // H (+ pad)
+  const int KPT = KP * csize;  // total padded cluster count
+  double *part = CL ? a.partials + (size_t)cid * (size_t)(KPT * DP + KPT + 2)
+                    : a.partials + (size_t)blockIdx.x * (chunked ? (size_t)a.part_stride : (size_t)(KP * DP + KP + 2));
+  double *part_t = part + (CL ? crank * KP * DP : (chunked ? a.t_off : 0));           // T rows of this chunk
+  double *part_ph = part + (CL ? KPT * DP + crank * KP : (chunked ? a.ph_off : KP * DP));  // phi_hat of this chunk
+  double *part_h = part + (CL ? KPT * DP + KPT : (chunked ? a.h_off : KP * DP + KP));      // H (+ pad)
 
   if (warp == kSSoftmaxWarps + kSStatWarps) {
     // ---------------- producer
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (use_old ? XG : 0)) * 8u;
       int j = 0;
-      for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
+      for (int grp = cid; grp < a.num_groups; grp += ncl, ++j) {
         const int s = j % S;
         if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
         double *st = stages + (size_t)s * stage_doubles;
@@ -460,8 +524,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   } else if (warp < kSSoftmaxWarps) {
     // ---------------- softmax warps: CG step + softmax statistics of one group each
     double Hpart = 0.0;
-    int j = warp;
-    for (int grp = blockIdx.x + warp * gridDim.x; grp < a.num_groups; grp += kSSoftmaxWarps * gridDim.x, j += kSSoftmaxWarps) {
+    int j = warp, iw = 0;
+    for (int grp = cid + warp * ncl; grp < a.num_groups; grp += kSSoftmaxWarps * ncl, j += kSSoftmaxWarps, ++iw) {
       const int s = j % S;
       double *st = stages + (size_t)s * stage_doubles;
       const int row = grp * kGroupRows + g;
@@ -508,8 +572,88 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int c = 8 * nt + 2 * t;
-          psl[nt * 64 + (2 * t) * 4] = ((FULLK || c < a.K) && row_ok) ? ex[2 * nt] : 0.0;
-          psl[nt * 64 + (2 * t + 1) * 4] = ((FULLK || c + 1 < a.K) && row_ok) ? ex[2 * nt + 1] : 0.0;
+          psl[nt * 64 + (2 * t) * 4] = ((FULLK || c < Kc) && row_ok) ? ex[2 * nt] : 0.0;
+          psl[nt * 64 + (2 * t + 1) * 4] = ((FULLK || c + 1 < Kc) && row_ok) ? ex[2 * nt + 1] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&phi_bar[s]);
+        continue;
+      }
+      if (CL) {
+        // softmax over a row spread across the CTAs of the cluster: local (max, sum e, sum e*(x - max)) of this CTA's 64 columns,
+        // exchanged through every peer's mailbox; all ranks then combine the csize triples in the same order.
+        double m = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = 8 * nt + 2 * t;
+          if (FULLK || c < Kc) m = fmax(m, x[nt][0]);
+          if (FULLK || c + 1 < Kc) m = fmax(m, x[nt][1]);
+        }
+        m = quad_max(m);
+        double ex[2 * NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          x[nt][0] -= m;
+          x[nt][1] -= m;
+          ex[2 * nt] = x[nt][0];
+          ex[2 * nt + 1] = x[nt][1];
+        }
+        exp_batch<2 * NT>(ex);
+        double ssum = 0.0, px = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = 8 * nt + 2 * t;
+          const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
+          ex[2 * nt] = ok0 ? ex[2 * nt] : 0.0;
+          ex[2 * nt + 1] = ok1 ? ex[2 * nt + 1] : 0.0;
+          ssum += ex[2 * nt] + ex[2 * nt + 1];
+          if (ok0) px += ex[2 * nt] * x[nt][0];
+          if (ok1) px += ex[2 * nt + 1] * x[nt][1];
+        }
+        ssum = quad_sum(ssum);
+        px = quad_sum(px);
+        const int par = iw & 1;
+        double *mb = sm_mb + (size_t)((warp * 2 + par) * kMaxCl) * (kGroupRows * 3);
+        uint64_t *mbb = mb_bar + warp * 2 + par;
+        {
+          // all four lanes of a quad hold the row's triple: lane t posts to the ranks t and t + 4 (parallel round trips)
+          const uint32_t la = smem_u32(mb + (crank * kGroupRows + g) * 3), lb = smem_u32(mbb);
+          for (int rc = t; rc < csize; rc += 4) {
+            const uint32_t ra = cluster_map(la, (uint32_t)rc);
+            st_cluster_f64(ra, m);
+            st_cluster_f64(ra + 8, ssum);
+            st_cluster_f64(ra + 16, px);
+            mbar_arrive_remote(cluster_map(lb, (uint32_t)rc));
+          }
+        }
+        mbar_wait_cluster(mbb, (uint32_t)((iw >> 1) & 1));
+        // lane t of the quad combines the ranks t and t + 4
+        double mm[2], ss[2], pp[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int rc = t + 4 * q;
+          const bool v = rc < csize;
+          const double *src = mb + ((v ? rc : 0) * kGroupRows + g) * 3;
+          mm[q] = v ? src[0] : -INFINITY;
+          ss[q] = v ? src[1] : 0.0;
+          pp[q] = v ? src[2] : 0.0;
+        }
+        const double M = quad_max(fmax(mm[0], mm[1]));
+        double ee[3] = {mm[0] - M, mm[1] - M, m - M};
+        const double dm0 = (t < csize) ? ee[0] : 0.0, dm1 = (t + 4 < csize) ? ee[1] : 0.0;
+        exp_batch<3>(ee);
+        const double Ssum = quad_sum(ss[0] * ee[0] + ss[1] * ee[1]);
+        const double Psum = quad_sum(ee[0] * (pp[0] + dm0 * ss[0]) + ee[1] * (pp[1] + dm1 * ss[1]));
+        const double inv = row_ok ? ee[2] / Ssum : 0.0;
+        const double lognorm = log(Ssum);
+        if (crank == 0 && row_ok && t == 0) Hpart += lognorm - Psum / Ssum;
+        if (crank == 0 && p_lse_new && t == 0) p_lse_new[row] = M + lognorm;
+        __syncwarp();
+        double *ps = st + FG + (g >> 2) * 32 + (g & 3);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          ps[nt * 64 + (2 * t) * 4] = ex[2 * nt] * inv;
+          ps[nt * 64 + (2 * t + 1) * 4] = ex[2 * nt + 1] * inv;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&phi_bar[s]);
@@ -520,8 +664,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        if (FULLK || c < a.K) m = fmax(m, x[nt][0]);
-        if (FULLK || c + 1 < a.K) m = fmax(m, x[nt][1]);
+        if (FULLK || c < Kc) m = fmax(m, x[nt][0]);
+        if (FULLK || c + 1 < Kc) m = fmax(m, x[nt][1]);
       }
       m = quad_max(m);
       double ssum = 0.0, px = 0.0;
@@ -537,7 +681,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int c = 8 * nt + 2 * t;
-        const bool ok0 = FULLK || c < a.K, ok1 = FULLK || c + 1 < a.K;
+        const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
         const double e0 = ok0 ? ex[2 * nt] : 0.0, e1 = ok1 ? ex[2 * nt + 1] : 0.0;
         ssum += e0 + e1;
         if (ok0) px += e0 * x[nt][0];
@@ -577,7 +721,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt) colsum[mt] = 0.0;
     int j = 0;
-    for (int grp = blockIdx.x; grp < a.num_groups; grp += gridDim.x, ++j) {
+    for (int grp = cid; grp < a.num_groups; grp += ncl, ++j) {
       const int s = j % S;
       const double *st = stages + (size_t)s * stage_doubles;
       mbar_wait(&phi_bar[s], (uint32_t)((j / S) & 1));
@@ -620,8 +764,9 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       }
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && (!chunked || a.write_h)) {
+  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
+  else __syncthreads();
+  if (threadIdx.x == 0 && (CL ? crank == 0 : (!chunked || a.write_h))) {
     double v = 0.0;
     if (a.lse_in == nullptr)
       for (int w = 0; w < kSSoftmaxWarps; ++w) v += red_s[w];

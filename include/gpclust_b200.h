@@ -176,6 +176,22 @@ int gpc_step_lse(const double *x_base, const double *ng, const double *sd_old, d
 int gpc_stats_chunk(const double *F, const double *x, const double *lse, const double *h_in, double *partials, long long part_stride, int t_off,
                     int ph_off, int h_off, int write_h, long long N, int Kc, int DP, long long xg_stride, int grid, void *stream);
 
+/* ---- wide mode: K > 64 in ONE launch per pass ---------------------------------------------------
+ * The kernels run as thread-block clusters of KP/64 CTAs: the CTAs of a cluster walk the same 8-row groups, CTA r owning the
+ * clusters [64r, 64r+64) (its own slice of Wt / bias / the N x K operands, F re-read from L2), and the row-coupled scalars --
+ * (max, sum e, sum e*(x-max)) of the softmax (np_utilities.py:25-40) and sum_k phi*a of the natural gradient
+ * (MOHGP.py:150) -- are exchanged through each other's shared memory.  Same arguments and meaning as gpc_natgrad /
+ * gpc_step_stats with KP = gpc_padded_k(K) in (64, 512]; N x K operands in the fragment-major layout of width KP.
+ * nclusters = gpc_wide_clusters(KP, DP) (co-resident clusters on this device); `partials` of the S pass holds nclusters
+ * blocks of gpc_stats_len(KP, DP) doubles, of the G pass nclusters*(KP/64)*4 doubles.                            */
+int gpc_wide_clusters(int KP, int DP);
+int gpc_natgrad_wide(const double *F, const double *x, const double *lse, const double *Wt, const double *bias, const double *x_old,
+                     const double *lse_old, const double *ng_old, double *ng_out, double *grad_out, double *partials, unsigned int *counter,
+                     double *dots, long long N, int K, int KP, int DP, int nclusters, void *stream);
+int gpc_step_stats_wide(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
+                        double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode,
+                        long long N, int K, int KP, int DP, int nclusters, void *stream);
+
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);
 
