@@ -168,7 +168,7 @@ class MOHGP(CollapsedMixture):
             # rows sharded over the GPUs of one box: the reduced statistics go straight into every peer's inbox over
             # NVLink (no NCCL call, no host involvement); the posterior kernel sums the W inbox vectors in rank order
             px = ptr(self._peers["desc"])
-            check(lib.gpc_reduce_push(ptr(self._spart), self._grid, self._stats_len, px, ptr(self._counter[2:]), ptr(self._loop_dev), phase,
+            check(lib.gpc_reduce_push(ptr(self._spart), self._nparts, self._stats_len, px, ptr(self._counter[2:]), ptr(self._loop_dev), phase,
                                       self._stream()), "gpc_reduce_push")
             check(lib.gpc_loop_mohgp_post_px(px, self._world, ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf), ptr(self._const),
                                              ptr(self._Wt), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._bias),

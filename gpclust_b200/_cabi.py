@@ -38,6 +38,8 @@ PROTOTYPES = {
     "gpc_loop_step_stats": [_p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_loop_natgrad_px": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "gpc_loop_step_stats_px": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_natgrad_wide": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "gpc_loop_step_stats_wide": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_push": [_p, _i, _i, _p, _p, _p, _i, _p],
     "gpc_xchg_doubles": [_i, _i],
     "gpc_natgrad_chunk": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _i, _i, _ll, _i, _p],

@@ -174,8 +174,9 @@ class CollapsedMixture(CollapsedVB):
             if self._ncl < 1:
                 check(self._ncl or -1, "gpc_wide_clusters")
             self._nparts = self._ncl
+        self._peers = self._shards.setup_peers(self._stats_len, self.device) if (self._use_peer_exchange() and (self._chunks == 1 or self._wide)) else None
         self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
-        self._peers = self._shards.setup_peers(self._stats_len, self.device) if (self._use_peer_exchange() and self._chunks == 1) else None
+
         self._alloc_model()
 
     def _alloc_model(self):
@@ -449,7 +450,7 @@ class CollapsedMixture(CollapsedVB):
     _BATCH = 16       # loop-body passes enqueued per read-back
 
     def _device_loop_ok(self):
-        return self._chunks == 1  # K > 64 runs the chunked passes under the host-driven loop
+        return self._chunks == 1 or self._wide  # the per-chunk launches (GPCLUST_B200_WIDE=0) run under the host-driven loop
 
     def _bufs(self):
         b = _cabi.GpcBufs()
@@ -489,15 +490,18 @@ class CollapsedMixture(CollapsedVB):
         lp, st = ptr(self._loop_dev), self._stream()
         dots, beta = ptr(self._ctrl[_C_SQ:]), ptr(self._ctrl[_C_BETA:])
         px = ptr(self._peers["desc"]) if self._peers is not None else None
+        g_pass = lib.gpc_loop_natgrad_wide if self._wide else lib.gpc_loop_natgrad_px
+        s_pass = lib.gpc_loop_step_stats_wide if self._wide else lib.gpc_loop_step_stats_px
+        ctas = self._ncl if self._wide else self._grid  # clusters of KP/64 CTAs in wide mode
         with self._timed("natgrad"):
-            check(lib.gpc_loop_natgrad_px(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._counter), dots,
-                                          lp, px, self.N, self.K, self._KP, self._DP, self._grid, st), "gpc_loop_natgrad")
+            check(g_pass(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._counter), dots,
+                         lp, px, self.N, self.K, self._KP, self._DP, ctas, st), "gpc_loop_natgrad")
         if self._world > 1 and px is None:
             self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
         for phase in (0, 1):  # GPC_PHASE_CONJ, GPC_PHASE_RETRY (the latter returns at once unless the bound fell)
             with self._timed("step_stats" if phase == 0 else "step_stats_retry"):
-                check(lib.gpc_loop_step_stats_px(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, phase, self.N, self.K,
-                                                 self._KP, self._DP, self._grid, st), "gpc_loop_step_stats")
+                check(s_pass(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, phase, self.N, self.K,
+                             self._KP, self._DP, ctas, st), "gpc_loop_step_stats")
             with self._timed("posterior" if phase == 0 else "posterior_retry"):
                 self._loop_posterior(phase)
         self.kernel_launches += 3

@@ -484,6 +484,52 @@ int gpc_step_stats_wide(const double *F, const double *x_base, const double *ng,
   return dispatch_step_stats_wide(a, KP / GPC_MAX_KP, nclusters, as_stream(stream), nullptr);
 }
 
+int gpc_loop_natgrad_wide(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                          double *dots, const gpc_loop_t *loop, const gpc_peers_t *peers, long long N, int K, int KP, int DP, int nclusters,
+                          void *stream) {
+  if (!F || !bufs_ok(bufs) || !Wt || !bias || !partials || !counter || !dots || !loop) return GPC_EINVAL;
+  if (!wide_geometry_ok(N, K, KP, DP, nclusters)) return GPC_EINVAL;
+  NatgradArgs a{};
+  a.F = F;
+  a.Wt = Wt;
+  a.bias = bias;
+  a.partials = partials;
+  a.counter = counter;
+  a.dots_out = dots;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.loop = loop;
+  a.bufs = *bufs;
+  a.peers = peers;
+  a.xg_stride = (long long)kGroupRows * KP;
+  return dispatch_natgrad_wide(a, KP / GPC_MAX_KP, nclusters, as_stream(stream), nullptr);
+}
+
+int gpc_loop_step_stats_wide(const double *F, const gpc_bufs_t *bufs, double *dots, double *beta_out, double *partials, const gpc_loop_t *loop,
+                             const gpc_peers_t *peers, int phase, long long N, int K, int KP, int DP, int nclusters, void *stream) {
+  if (!F || !bufs_ok(bufs) || !dots || !beta_out || !partials || !loop) return GPC_EINVAL;
+  if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
+  if (!wide_geometry_ok(N, K, KP, DP, nclusters)) return GPC_EINVAL;
+  StepStatsArgs a{};
+  a.F = F;
+  a.dots = dots;
+  a.beta_out = beta_out;
+  a.partials = partials;
+  a.N = (int)N;
+  a.K = K;
+  a.DP = DP;
+  a.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.loop = loop;
+  a.bufs = *bufs;
+  a.phase = phase;
+  a.peers = peers;
+  a.dots_sum = peers ? dots : nullptr;
+  a.xg_stride = (long long)kGroupRows * KP;
+  return dispatch_step_stats_wide(a, KP / GPC_MAX_KP, nclusters, as_stream(stream), nullptr);
+}
+
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream) {
   if (!partials || !out || num_parts < 1 || len < 1) return GPC_EINVAL;
   k_reduce_partials<<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, num_parts, len, out);
@@ -588,7 +634,7 @@ int gpc_loop_mohgp_post_px(const gpc_peers_t *peers, int world, double *stats, c
   if (!peers || world < 1 || world > GPC_MAX_PEERS || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !Wt || !muk_t || !per_k || !bias ||
       !scalars || !counter || !info || !dots || !beta || !loop)
     return GPC_EINVAL;
-  if (K < 1 || K > KP || KP > GPC_MAX_KP || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > GPC_MAX_KTOT || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
   if (phase != GPC_PHASE_CONJ && phase != GPC_PHASE_RETRY) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);

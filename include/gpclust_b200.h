@@ -191,6 +191,12 @@ int gpc_natgrad_wide(const double *F, const double *x, const double *lse, const 
 int gpc_step_stats_wide(const double *F, const double *x_base, const double *ng, const double *sd_old, double *sd_new, double *x_new,
                         double *lse_new, const double *dots, double sq_old, double *beta_out, double *partials, double step, int beta_mode,
                         long long N, int K, int KP, int DP, int nclusters, void *stream);
+/* the wide passes driven by a device-resident gpc_loop_t (as gpc_loop_natgrad_px / gpc_loop_step_stats_px)       */
+int gpc_loop_natgrad_wide(const double *F, const gpc_bufs_t *bufs, const double *Wt, const double *bias, double *partials, unsigned int *counter,
+                          double *dots, const gpc_loop_t *loop, const gpc_peers_t *peers, long long N, int K, int KP, int DP, int nclusters,
+                          void *stream);
+int gpc_loop_step_stats_wide(const double *F, const gpc_bufs_t *bufs, double *dots, double *beta_out, double *partials, const gpc_loop_t *loop,
+                             const gpc_peers_t *peers, int phase, long long N, int K, int KP, int DP, int nclusters, void *stream);
 
 /* out[j] = sum_c partials[c*len + j], c in fixed order (bit-reproducible).                          */
 int gpc_reduce_partials(const double *partials, int num_parts, int len, double *out, void *stream);

@@ -38,7 +38,7 @@ for K in Ks:
     phi0 = torch.randn((N, K), dtype=torch.float64, device="cuda")  # device RNG: the host stream would take minutes at K=512
     m = MOHGP(X, kern.RBF(1, 1.0, 2.0).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=K, phi_init=phi0)
     del phi0
-    passes, warm = 12, 3
+    passes, warm = 32, 16
     if m._device_loop_ok():
         m.run_passes(warm)
         torch.cuda.synchronize()

@@ -22,7 +22,7 @@ from gpclust_b200 import MOHGP, MOG
 from gpclust_b200.sharding import RowShards
 
 ok = True
-for (N, D, K, prior) in [(5000, 64, 64, "symmetric"), (3001, 24, 7, "DP")]:
+for (N, D, K, prior) in [(5000, 64, 64, "symmetric"), (3001, 24, 7, "DP"), (4000, 32, 130, "symmetric")]:
     X, Y, _ = mohgp_problem(N, D, K, seed=1)
     np.random.seed(4)
     phi0 = np.random.randn(N, K)
