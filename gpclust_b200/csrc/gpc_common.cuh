@@ -87,23 +87,11 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory"); }
-// arrive (release at cluster scope: this thread's earlier remote stores are visible to the waiter) on a peer's mbarrier
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP_C:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra DONE_C;\n"
-      "bra WAIT_LOOP_C;\n"
-      "DONE_C:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)
-      : "memory");
+// asynchronous remote store whose completion is counted (complete_tx, 8 bytes) on the RECEIVER's mbarrier: the
+// receiver arms its barrier with arrive.expect_tx(total bytes) and waits on it like on a bulk copy -- no MEMBAR on the
+// sender, no L1 invalidation (CCTL.IVALL) on the receiver, which is what a release/acquire pair at cluster scope costs
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(remote_addr), "d"(v), "r"(remote_bar) : "memory");
 }
 
 // bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
     if (CL)
-      for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&mb_bar[s], (uint32_t)(kGroupRows * csize));
+      for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&mb_bar[s], 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
@@ -261,23 +261,21 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
         }
       };
       if (CL) {
-        // the row sums of this CTA's 64 clusters -> every CTA of the cluster (remote shared-memory stores + arrive on the
-        // peer's mailbox barrier); total = sum over ranks in rank order (identical on every CTA).  Two parities: a peer can
+        // the row sums of this CTA's 64 clusters -> every CTA of the cluster (st.async into the peers' mailboxes, counted on
+        // the peers' mailbox barriers); total = sum over ranks in rank order (identical on every CTA).  Two parities: a peer can
         // post visit i+2 only after it has consumed MY visit i+1, which this unit posts after both its warps finished visit i.
         const int par = i & 1;
         double *mb = sa_mb + (size_t)((par * UNITS + unit) * kMaxCl) * kGroupRows;
         uint64_t *mbb = mb_bar + par * UNITS + unit;
         {
-          // every lane of the unit holds the row sum: lane (h, g, t) posts row g to peer NSPLIT-interleaved rank h*4 + t, so
-          // the (release) round trips to the peers run in parallel instead of one after the other
+          // arm this CTA's mailbox barrier for the csize x 8 doubles of this visit, then every lane of the unit (all hold the
+          // row sum) posts row g to ONE peer, rank h*4 + t: asynchronous remote stores that complete on the peer's barrier
+          if (h == 0 && lane == 0) mbar_arrive_expect_tx(mbb, (uint32_t)(csize * kGroupRows * 8));
           const uint32_t la = smem_u32(mb + crank * kGroupRows + g), lb = smem_u32(mbb);
-          for (int rc = h * 4 + t; rc < csize; rc += 4 * NSPLIT) {
-            st_cluster_f64(cluster_map(la, (uint32_t)rc), sa);
-            mbar_arrive_remote(cluster_map(lb, (uint32_t)rc));
-          }
+          for (int rc = h * 4 + t; rc < csize; rc += 4 * NSPLIT) st_async_f64(cluster_map(la, (uint32_t)rc), sa, cluster_map(lb, (uint32_t)rc));
         }
         old_point();
-        mbar_wait_cluster(mbb, (uint32_t)((i >> 1) & 1));
+        mbar_wait(mbb, (uint32_t)((i >> 1) & 1));
         double tot = 0.0;
         for (int rc = 0; rc < csize; ++rc) tot += mb[rc * kGroupRows + g];
         sa = tot;
@@ -443,7 +441,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       mbar_init(&empty_bar[s], kSStatWarps);
     }
     if (CL)
-      for (int s = 0; s < 2 * kSSoftmaxWarps; ++s) mbar_init(&mb_bar[s], (uint32_t)(kGroupRows * csize));
+      for (int s = 0; s < 2 * kSSoftmaxWarps; ++s) mbar_init(&mb_bar[s], 1);
     mbar_fence_init();
   }
   if (CL) cluster_sync_all();
@@ -616,17 +614,18 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         double *mb = sm_mb + (size_t)((warp * 2 + par) * kMaxCl) * (kGroupRows * 3);
         uint64_t *mbb = mb_bar + warp * 2 + par;
         {
-          // all four lanes of a quad hold the row's triple: lane t posts to the ranks t and t + 4 (parallel round trips)
+          // arm this CTA's mailbox barrier for the csize x 8 triples of this visit; all four lanes of a quad hold the row's
+          // triple: lane t posts it to the ranks t and t + 4 (asynchronous remote stores counted on the peer's barrier)
+          if (lane == 0) mbar_arrive_expect_tx(mbb, (uint32_t)(csize * kGroupRows * 24));
           const uint32_t la = smem_u32(mb + (crank * kGroupRows + g) * 3), lb = smem_u32(mbb);
           for (int rc = t; rc < csize; rc += 4) {
-            const uint32_t ra = cluster_map(la, (uint32_t)rc);
-            st_cluster_f64(ra, m);
-            st_cluster_f64(ra + 8, ssum);
-            st_cluster_f64(ra + 16, px);
-            mbar_arrive_remote(cluster_map(lb, (uint32_t)rc));
+            const uint32_t ra = cluster_map(la, (uint32_t)rc), rb = cluster_map(lb, (uint32_t)rc);
+            st_async_f64(ra, m, rb);
+            st_async_f64(ra + 8, ssum, rb);
+            st_async_f64(ra + 16, px, rb);
           }
         }
-        mbar_wait_cluster(mbb, (uint32_t)((iw >> 1) & 1));
+        mbar_wait(mbb, (uint32_t)((iw >> 1) & 1));
         // lane t of the quad combines the ranks t and t + 4
         double mm[2], ss[2], pp[2];
 #pragma unroll
