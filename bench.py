@@ -37,8 +37,8 @@ METRIC = "MOHGP VB iterations/sec (N=1M,D=64,K=64)"
 UNIT = "iterations/s"
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 1M rows, HS, from the ncu --set full capture summarised in
-# profiles/ncu_r01_v3_summary.csv (scaled linearly to the rows this rank holds)
-NCU_DRAM_BYTES_PER_LAUNCH_1M = {"natgrad": 2.064148e9 + 0.480519e9, "step_stats": 2.048132e9 + 1.000140e9}
+# profiles/ncu_r01_v4_summary.csv (scaled linearly to the rows this rank holds)
+NCU_DRAM_BYTES_PER_LAUNCH_1M = {"natgrad": 2.064082e9 + 0.481799e9, "step_stats": 2.048080e9 + 1.000766e9}
 
 
 def synth(n_total, d, k, seed=0):
@@ -328,7 +328,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "MOHGP N=1M D=64 K=64 FP64 %s-CG (config 3)" % method, "N": N_TOTAL, "D": D, "K": K, "method": method,
-                   "rows_per_gpu": n_loc, "parallelism": "rows sharded x%d, NCCL allreduce of stats+dots" % world,
+                   "rows_per_gpu": n_loc, "parallelism": ("rows sharded x%d, statistics + CG dots exchanged over NVLink peer memory inside the kernels" % world) if world > 1 else "1 GPU",
                    "l2": "inputs larger than L2 (11 N x K arrays of %.0f MB per step)" % (n_loc * K * 8 / 1e6),
                    "rejected_steps": rejected, "final_bound": last_bound},
         "clocks": clocks,
@@ -340,7 +340,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_kind": peak_kind,
                      "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_1M[dom] * n_loc / 1e6) if method == "HS" else None,
-                     "traffic_source": "profiles/ncu_r01_v3_summary.csv (ncu --set full, 1M rows, scaled by rows per GPU)",
+                     "traffic_source": "profiles/ncu_r01_v4_summary.csv (ncu --set full, 1M rows, scaled by rows per GPU)",
                      "alg_bytes_per_launch": alg[dom], "ms_per_launch": kernel_ms[dom],
                      "iteration_hbm_frac": iter_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         "kernels_ms": kernel_ms,

@@ -1,0 +1,25 @@
+"""Reduce an `ncu --page raw --csv` export to the columns kept under profiles/ (one row per profiled launch).
+Usage: python tools/ncu_pick.py raw.csv > profiles/ncu_<round>_summary.csv"""
+import csv
+import sys
+
+COLS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_dim_x",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio"]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[0]
+keep = [c for c in COLS if c in hdr]
+w = csv.writer(sys.stdout)
+w.writerow(keep)
+w.writerow([rows[1][hdr.index(c)] for c in keep])
+for r in rows[2:]:
+    if len(r) >= len(hdr):
+        w.writerow([r[hdr.index(c)] for c in keep])
