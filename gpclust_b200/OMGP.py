@@ -16,7 +16,8 @@ set_vb_param; bound() and vb_grad_natgrad() read the cached per-component result
 
     gpc_omgp_kern_grads             kernel / noise-variance gradients (update_kern_grads)   OMGP.py:55-94
 
-N does not shard (dense coupling between all points of a component); components are independent.
+N does not shard (dense coupling between all points of a component); components are independent: with several ranks
+component i is computed by rank i % world and the results are combined by one all-reduce (sharding.ComponentShards).
 The noise variance and the kernel parameters are free (Logexp-constrained) as in the reference (OMGP.py:31-32):
 `optimize()` interleaves `optimize_parameters()` (collapsed_vb.py:248,270,300-301); `kern.fix()` / `variance_fixed = True`
 hold them.
@@ -31,7 +32,7 @@ from . import kern as _kern
 from ._cabi import lib, check, ptr
 from .collapsed_mixture import CollapsedMixture
 from .collapsed_vb import CollapsedVB
-from .sharding import RowShards
+from .sharding import ComponentShards, RowShards
 
 
 class _Point(object):
@@ -40,7 +41,10 @@ class _Point(object):
 
 
 class OMGP(CollapsedMixture):
-    def __init__(self, X, Y, K=2, kernels=None, variance=1.0, alpha=1.0, prior_Z="symmetric", name="OMGP"):
+    def __init__(self, X, Y, K=2, kernels=None, variance=1.0, alpha=1.0, prior_Z="symmetric", name="OMGP", group=None):
+        """Reference signature (OMGP.py:14) + `group`: with torch.distributed initialised (one process per GPU) the components
+        are shared out over the ranks of `group` (component i -> rank i % world); X, Y and the variational parameters must be
+        the same on every rank (same numpy seed)."""
         torch = _cabi.require_cuda()
         self.torch = torch
         CollapsedVB.__init__(self, name)
@@ -64,8 +68,10 @@ class OMGP(CollapsedMixture):
         assert prior_Z in ["symmetric", "DP"]
         self.prior_Z, self.alpha = prior_Z, alpha
         self.device = torch.device("cuda", torch.cuda.current_device())
+        # N does not shard (dense coupling between all points of a component); components do
+        self._cshards = ComponentShards(group)
+        self._shards = RowShards.solo()  # every rank holds ALL rows: the inherited row logic (try_split counts ...) is single-process
         self._world, self._rank, self.N_total = 1, 0, self.N
-        self._shards = RowShards.solo()  # N does not shard (dense coupling between all points of a component)
         self.kernel_launches = 0
         self._kernel_events = None
 
@@ -136,12 +142,24 @@ class OMGP(CollapsedMixture):
         check(lib.gpc_softmax_rows(ptr(x), N, K, K, ptr(p.phi), ptr(p.logphi), K, ptr(p.hpart), grid, self._stream()), "gpc_softmax_rows")
         p.grad_Lm = torch.empty_like(p.phi)
         p.comp = torch.zeros((K, 4), dtype=torch.float64, device=self.device)
+        failed = False
+        if self._cshards.world > 1:
+            p.grad_Lm.zero_()
         for i in range(K):
-            self._factor_component(p.phi, i, 1e-6)
+            if not self._cshards.owns(i) or failed:
+                continue
+            try:
+                self._factor_component(p.phi, i, 1e-6)
+            except LinAlgError:
+                failed = True
+                continue
             check(lib.gpc_omgp_component(ptr(self._W), ptr(self._Yd), ptr(self._ldsum), ptr(p.phi[:, i]), K, N, self.D, float(self.variance),
                                          ptr(self._tbuf), ptr(self._part), ptr(p.grad_Lm[:, i]), K, ptr(p.comp[i]), self._stream()),
                   "gpc_omgp_component")
             self.kernel_launches += 3
+        if self._cshards.any_failed(failed, p.comp):
+            raise LinAlgError("not positive definite, even with jitter.")
+        self._cshards.combine(p.comp, p.grad_Lm)  # the owners' disjoint results -> every rank
         p.scalars = torch.zeros(4, dtype=torch.float64, device=self.device)
         p.phi_hat = torch.zeros(K, dtype=torch.float64, device=self.device)
         p.mixgrad = torch.zeros(K, dtype=torch.float64, device=self.device)
@@ -190,21 +208,35 @@ class OMGP(CollapsedMixture):
             self._kg_tiles = z(int(lib.gpc_omgp_kgrad_tiles(Np)) * 16)
             self._kg_out = z(16)
         grad_variance = 0.0
+        nk = len(self.kern)
+        gtab = torch.zeros((nk, 17), dtype=torch.float64, device=self.device)  # per component: 16 part sums + variance terms
+        failed = False
         for i, k in enumerate(self.kern):
-            self._factor_component(p.phi, i, 0.0)
+            if not self._cshards.owns(i) or failed:
+                continue
+            try:
+                self._factor_component(p.phi, i, 0.0)
+            except LinAlgError:
+                failed = True
+                continue
             nparts, kinds, var, ls, _ = self._kern_arrays(k)
             check(lib.gpc_omgp_kern_grads(ptr(self._W), ptr(self._Xd), self._Xd.shape[1], ptr(self._Yd), N, self.D, nparts, kinds, var, ls,
                                           ptr(self._tbuf), ptr(self._part), ptr(self._kg_alpha), ptr(self._kg_diag), ptr(self._kg_tiles),
                                           ptr(self._kg_out), self._stream()), "gpc_omgp_kern_grads")
             self.kernel_launches += 5
-            out = self._kg_out.cpu().numpy()
-            for j, part in enumerate(getattr(k, "parts", [k])):  # GPy update_gradients_full with dL_dK = 0.5 dL_dB
-                part.variance_gradient = 0.5 * float(out[2 * j])
-                if hasattr(part, "lengthscale"):
-                    part.lengthscale_gradient = -0.5 * float(out[2 * j + 1]) / part.lengthscale
             phi_i = p.phi[:, i]
-            grad_variance += 0.5 * float((self._kg_diag[:N] / (phi_i + 1e-6)).sum().item())  # OMGP.py:88-91
-            grad_variance -= 0.5 * self.D * float(phi_i.sum().item()) / self.variance    # OMGP.py:92
+            gtab[i, :16] = self._kg_out
+            gtab[i, 16] = 0.5 * (self._kg_diag[:N] / (phi_i + 1e-6)).sum() - 0.5 * self.D * phi_i.sum() / self.variance  # OMGP.py:88-92
+        if self._cshards.any_failed(failed, gtab):
+            raise LinAlgError("not positive definite, even with jitter.")
+        self._cshards.combine(gtab)
+        tab = gtab.cpu().numpy()
+        for i, k in enumerate(self.kern):
+            for j, part in enumerate(getattr(k, "parts", [k])):  # GPy update_gradients_full with dL_dK = 0.5 dL_dB
+                part.variance_gradient = 0.5 * float(tab[i, 2 * j])
+                if hasattr(part, "lengthscale"):
+                    part.lengthscale_gradient = -0.5 * float(tab[i, 2 * j + 1]) / part.lengthscale
+            grad_variance += float(tab[i, 16])
         self.variance_gradient = grad_variance
         self._kern_grads_valid = True
 
@@ -347,6 +379,5 @@ class OMGP(CollapsedMixture):
     def _device_loop_ok(self):
         return False  # every bound evaluation needs the host (jitchol retry per component): host-driven loop
 
-    # merge/split over sharded rows is meaningless here (single process)
     def _is_root(self):
-        return True
+        return self._cshards.rank == 0  # messages from one rank only

@@ -122,3 +122,27 @@ class RowShards(object):
     def even_split(n_total, world, rank):
         """Contiguous near-even split used by bench.py: rows [lo, hi) of rank."""
         return rank * n_total // world, (rank + 1) * n_total // world
+
+
+class ComponentShards(RowShards):
+    """OMGP: the dense N x N work of one component does not shard, but the components are
+    independent -- component i is owned by rank i % world.  Data and responsibilities are replicated; the owners'
+    results (per-component bound scalars, the grad_Lm column, kernel gradients) are DISJOINT contributions that one
+    all-reduce(sum) assembles on every rank, and a failed factorisation on any rank is raised on all of them."""
+
+    def owns(self, i):
+        return i % self.world == self.rank
+
+    def combine(self, *tensors):
+        """In-place sum over ranks of tensors that are zero outside this rank's components."""
+        for t in tensors:
+            self.allreduce(t)
+
+    def any_failed(self, failed, like=None):
+        """True on every rank when `failed` is true on at least one."""
+        if self.world == 1:
+            return bool(failed)
+        import torch
+        t = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device=None if like is None else like.device)
+        self.allreduce(t)
+        return bool(t.item() > 0.0)

@@ -59,6 +59,37 @@ def _worker(rank, world, port, q):
         dots = torch.tensor([float((g2 * ng2).sum())], dtype=torch.float64)
         sh.allreduce(dots)
         assert abs(dots.item() - float(np.dot(g, ng))) < 1e-10 * abs(float(np.dot(g, ng)))
+
+        # OMGP: components shared out over the ranks (component i -> rank i % world); the owners' per-component bound terms,
+        # gradient columns and a failure flag combine into the single-process values (OMGP.py:96-147 through the oracle)
+        from gpclust_b200.sharding import ComponentShards
+        from oracle.vb_oracle import OMGPOracle
+        from oracle import gpy_shim as G
+        cs = ComponentShards()
+        assert [cs.owns(i) for i in range(4)] == [(i % world) == rank for i in range(4)]
+        rng = np.random.RandomState(5)
+        Xo = np.sort(rng.uniform(0, 10, 40))[:, None]
+        Yo = np.sin(Xo) + 0.1 * rng.randn(40, 1)
+        np.random.seed(11)
+        mo = OMGPOracle(Xo, Yo, K=3, kernels=[G.RBF(1, 1.0, 1.0 + 0.5 * i) for i in range(3)], variance=0.05)
+        comp = torch.zeros(3, 2, dtype=torch.float64)
+        cols = torch.zeros(40, 3, dtype=torch.float64)
+        for i, kern in enumerate(mo.kern):
+            if not cs.owns(i):
+                continue
+            B = kern.K(Xo) + np.diag(1.0 / ((mo.phi[:, i] + 1e-6) / mo.variance))
+            Bi, LB, _, logdet = G.pdinv(B)
+            comp[i, 0] = -0.5 * G.dpotrs(LB, mo.YYT)[0].trace() - 0.5 * logdet
+            comp[i, 1] = -0.5 * mo.D * mo.phi[:, i].sum() * np.log(2 * np.pi * mo.variance)
+            alpha = G.dpotrs(LB, Yo)[0]
+            cols[:, i] = torch.from_numpy(-0.5 * mo.variance * (np.sum(np.square(alpha), 1) - np.diag(Bi)) / (mo.phi[:, i] ** 2 + 1e-6))
+        cs.combine(comp, cols)
+        bound = float(comp.sum()) + mo.mixing_prop_bound() + mo.H
+        assert abs(bound - mo.bound()) < 1e-12 * abs(mo.bound())
+        g_o, ng_o = mo.vb_grad_natgrad()
+        g_s, ng_s = mo._natural(cols.numpy() + mo.mixing_prop_bound_grad() + mo.Hgrad)
+        assert np.allclose(ng_s, ng_o, rtol=1e-12, atol=1e-12)
+        assert cs.any_failed(rank == 1) is True and cs.any_failed(False) is False
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

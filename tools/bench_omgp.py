@@ -1,7 +1,7 @@
 """Config 4 (BASELINE.json): OMGP synthetic data association, K = 8 overlapping GPs.  Times one bound + gradient evaluation
 (all K components: build, blocked Cholesky, triangular inverse, per-component terms) for growing N and prints one JSON line
 per N, with the oracle (numpy/LAPACK) timed beside it at the sizes it finishes in seconds.
-Usage: python tools/bench_omgp.py [N ...]"""
+Usage: python tools/bench_omgp.py [N ...]      (under torchrun the K components are shared out over the ranks, one per GPU at 8)"""
 import json
 import os
 import sys
@@ -14,6 +14,12 @@ import torch
 
 from gpclust_b200 import OMGP, kern
 
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 K = 8
 sizes = [int(a) for a in sys.argv[1:]] or [2048, 8192, 16384]
 for N in sizes:
@@ -36,10 +42,10 @@ for N in sizes:
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
     flops = K * (2.0 / 3.0) * float(m._Npad) ** 3  # Cholesky N^3/3 + triangular inverse N^3/3 per component
-    line = {"workload": "OMGP bound+gradient evaluation, K=8 RBF components, D=1", "N": N, "Npad": m._Npad, "s_per_evaluation": dt,
+    line = {"workload": "OMGP bound+gradient evaluation, K=8 RBF components, D=1", "n_gpus": world, "N": N, "Npad": m._Npad, "s_per_evaluation": dt,
             "fp64_tflops": flops / dt / 1e12, "first_evaluation_s": t_first, "bound": p.bound,
             "matrix_gb": 2 * 8.0 * m._Npad ** 2 / 1e9}
-    if N <= 4096:
+    if N <= 4096 and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from oracle import gpy_shim as G
         from oracle.vb_oracle import OMGPOracle
@@ -50,6 +56,9 @@ for N in sizes:
         g = mo.vb_grad_natgrad()
         line["cpu_oracle_s_per_evaluation"] = time.perf_counter() - t0
         line["bound_rel_diff_vs_oracle"] = abs(b - m.bound()) / abs(b)
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     del m
     torch.cuda.empty_cache()
+if world > 1:
+    dist.destroy_process_group()

@@ -83,6 +83,34 @@ good = rel < 1e-10 and [r[0] for r in ms.optimize_trace] == [r[0] for r in m1.op
 ok = ok and good
 if rank == 0:
     print("MOG N=4000 D=2 K=6: trace rel diff %.2e -> %s" % (rel, "OK" if good else "FAIL"))
+# OMGP: components shared out over the ranks (component i -> rank i % world) must reproduce the single-rank run
+from gpclust_b200 import OMGP, kern
+rng = np.random.RandomState(2)
+No, Ko = 300, 5
+Xo = np.sort(rng.uniform(0, 10, No))[:, None]
+co = rng.randint(0, Ko, No)
+Yo = (np.sin(Xo[:, 0] * (0.5 + 0.4 * co) + co) * (1.0 + 0.3 * co) + 0.1 * rng.randn(No))[:, None]
+mk = lambda: [kern.RBF(1, 1.0, 1.0 + 0.5 * i) for i in range(Ko)]
+np.random.seed(21)
+ms = OMGP(Xo, Yo, K=Ko, kernels=mk(), variance=0.05)
+np.random.seed(21)
+m1 = OMGP(Xo, Yo, K=Ko, kernels=mk(), variance=0.05, group=solo)
+g_s, g_1 = ms._kernel_gradients(), m1._kernel_gradients()
+ng_s, ng_1 = ms.vb_grad_natgrad()[1], m1.vb_grad_natgrad()[1]
+b_s, b_1 = ms.bound(), m1.bound()
+for m in (ms, m1):
+    m.variance_fixed = True
+    for k in m.kern:
+        k.fix()
+ms.optimize(maxiter=10, verbose=False)
+m1.optimize(maxiter=10, verbose=False)
+rel = max(abs(a[1] - b[1]) / abs(b[1]) for a, b in zip(ms.optimize_trace, m1.optimize_trace))
+good = (abs(b_s - b_1) < 1e-12 * abs(b_1) and np.max(np.abs(ng_s - ng_1)) <= 1e-12 * np.max(np.abs(ng_1)) and
+        np.max(np.abs(g_s - g_1)) <= 1e-10 * np.max(np.abs(g_1)) and rel < 1e-10 and len(ms.optimize_trace) == len(m1.optimize_trace))
+ok = ok and good
+if rank == 0:
+    print("OMGP N=%d K=%d over %d ranks: bound rel diff %.2e, kernel-gradient rel diff %.2e, trace rel diff %.2e -> %s"
+          % (No, Ko, world, abs(b_s - b_1) / abs(b_1), np.max(np.abs(g_s - g_1)) / np.max(np.abs(g_1)), rel, "OK" if good else "FAIL"))
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()
