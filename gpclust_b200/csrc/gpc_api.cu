@@ -601,7 +601,7 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
   cudaError_t e = cudaFuncSetAttribute(k_mohgp_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpEigArgs a{A, Ly, Ly_inv, Sy_inv, Sf, ws, D};
-  k_mohgp_eig<<<1, kClusterThreads, smem, as_stream(stream)>>>(a);
+  k_mohgp_eig<<<1, kEigThreads, smem, as_stream(stream)>>>(a);
   return launch_rc();
 }
 

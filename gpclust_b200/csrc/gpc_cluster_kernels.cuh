@@ -526,8 +526,10 @@ struct MohgpEigArgs {
   int D;
 };
 
-// One CTA.  Two-sided cyclic Jacobi with the round-robin parallel ordering: n/2 disjoint rotations per round.
-__global__ void __launch_bounds__(kClusterThreads) k_mohgp_eig(const MohgpEigArgs a) {
+// One CTA of 1024 threads (every round is three barrier-separated phases of n^2/2 .. n^2 independent element updates: latency,
+// not throughput).  Two-sided cyclic Jacobi with the round-robin parallel ordering: n/2 disjoint rotations per round.
+constexpr int kEigThreads = 1024;
+__global__ void __launch_bounds__(kEigThreads) k_mohgp_eig(const MohgpEigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, n = (D + 1) & ~1, ld = GPC_MAX_DP + 1, tid = threadIdx.x, nth = blockDim.x;
   double *As = sm;                    // n x ld

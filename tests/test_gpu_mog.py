@@ -23,7 +23,7 @@ def _pair(X, K, prior_Z="symmetric", alpha=1.0, seed=0, **kw):
     return mo, mp
 
 
-@pytest.mark.parametrize("N,D,K", [(506, 2, 10), (100, 1, 2), (1000, 3, 7), (333, 5, 20), (2000, 9, 33), (64, 2, 64)])
+@pytest.mark.parametrize("N,D,K", [(506, 2, 10), (100, 1, 2), (1000, 3, 7), (333, 5, 20), (2000, 9, 33), (64, 2, 64), (3000, 2, 70), (4000, 4, 130)])
 @pytest.mark.parametrize("prior_Z", ["symmetric", "DP"])
 def test_state_bound_gradient(N, D, K, prior_Z):
     rng = np.random.RandomState(N + D)
