@@ -127,6 +127,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// Raise this rank's flag of exchange (`which`, `slot`) in every peer's inbox.  Called by ONE WARP after the block-wide barrier
+// that follows the data stores: a single system-scope fence (executed once for the warp), then lane r stores the flag of peer r
+// -- the eight NVLink round trips overlap instead of eight st.release.sys (= fence + store each) issued one after the other.
+__device__ __forceinline__ void xchg_raise_flags(const gpc_peers_t *P, int which, int slot, unsigned long long epoch) {
+  const int lane = threadIdx.x & 31;
+  __threadfence_system();
+  if (lane < P->world)
+    st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + xchg_off_flags(P->world, P->stats_len, which, slot, P->rank), epoch);
+}
 // one thread: wait until every rank's flag of exchange `which` (0 statistics, 1 dots) in `slot` of MY inbox has reached
 // `epoch`.  Bounded (a few seconds): returns false if a peer never shows up.
 __device__ inline bool xchg_wait(const gpc_peers_t *P, int which, int slot, unsigned long long epoch) {

@@ -353,16 +353,15 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      *a.counter = 0u;
+    if (warp == 0) {
       if (a.peers != nullptr) {
         const gpc_peers_t *P = a.peers;
         const unsigned long long e = P->epochs[1] + 1;
-        __threadfence_system();
-        for (int r = 0; r < P->world; ++r)
-          st_release_sys(reinterpret_cast<unsigned long long *>(P->inbox[r]) + xchg_off_flags(P->world, P->stats_len, 1, (int)(e & 1), P->rank), e);
-        P->epochs[1] = e;
+        xchg_raise_flags(P, 1, (int)(e & 1), e);
+        __syncwarp();
+        if (lane == 0) P->epochs[1] = e;
       }
+      if (lane == 0) *a.counter = 0u;
     }
   }
 }
@@ -1015,12 +1014,13 @@ __global__ void __launch_bounds__(256) k_reduce_push(const double *__restrict__ 
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence_system();
-    for (int r = 0; r < P->world; ++r)
-      st_release_sys(reinterpret_cast<unsigned long long *>(P->inbox[r]) + xchg_off_flags(P->world, len, 0, (int)(e & 1), P->rank), e);
-    P->epochs[0] = e;
-    *counter = 0u;
+  if (is_last && threadIdx.x < 32) {
+    xchg_raise_flags(P, 0, (int)(e & 1), e);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      P->epochs[0] = e;
+      *counter = 0u;
+    }
   }
 }
 
