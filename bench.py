@@ -307,13 +307,17 @@ def run_gpu(args):
     rejected2 = int(rows2[-1][0] - it_before2) - steps
     kernel_ms = {name: float(np.mean([a.elapsed_time(b) for a, b in pairs])) for name, pairs in m._kernel_events.items()}
     kernel_n = {name: len(pairs) for name, pairs in m._kernel_events.items()}
-    # skipped RETRY-phase launches return at once: report the mean over the launches that did work
-    for name in ("step_stats_retry", "posterior_retry"):
+    # one bound evaluation per enqueued sequence: the sequence after a rejected conjugate step skips its G pass (returns at
+    # once) and runs S / posterior as the steepest retry -- report the G pass over the launches that did work
+    # (and the sequences enqueued beyond the last accepted step return at once altogether)
+    n_eval = steps + rejected2
+    for name, keep in (("natgrad", steps), ("step_stats", n_eval), ("posterior", n_eval)):
         if name in m._kernel_events:
-            d = sorted(a.elapsed_time(b) for a, b in m._kernel_events[name])
-            work = d[len(d) - rejected2:] if rejected2 else []
-            kernel_ms[name] = float(np.mean(work)) if work else 0.0
-            kernel_ms[name + "_skipped"] = float(np.mean(d[:len(d) - rejected2])) if len(d) > rejected2 else 0.0
+            d = sorted((a.elapsed_time(b) for a, b in m._kernel_events[name]), reverse=True)
+            kernel_ms[name] = float(np.mean(d[:keep]))
+            kernel_n[name] = min(keep, len(d))
+            if len(d) > keep:
+                kernel_ms[name + "_skipped"] = float(np.mean(d[keep:]))
     m._kernel_events = None
     ms_per_step = elapsed_ms / steps
     value = 1e3 / ms_per_step

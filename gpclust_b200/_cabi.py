@@ -103,7 +103,7 @@ class GpcLoop(ctypes.Structure):
     """gpc_loop_t of include/gpclust_b200.h (the trace rows follow it in device memory)"""
     _fields_ = [("bound_old", _d), ("sq_old", _d), ("ftol", _d), ("gtol", _d), ("maxiter", _d), ("step", _d),
                 ("iteration", _i), ("method", _i), ("first", _i), ("xi", _i), ("xprev", _i), ("xtrial", _i), ("ngi", _i),
-                ("need_retry", _i), ("done", _i), ("n_trace", _i), ("trace_cap", _i), ("pad", _i)]
+                ("need_retry", _i), ("done", _i), ("n_trace", _i), ("trace_cap", _i), ("slot_mode", _i), ("pass_budget", _i), ("pad", _i)]
 
 
 class GpcPeers(ctypes.Structure):
@@ -111,7 +111,7 @@ class GpcPeers(ctypes.Structure):
     _fields_ = [("world", _i), ("rank", _i), ("stats_len", _i), ("pad", _i), ("inbox", _p * 8), ("epochs", _p)]
 
 
-DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT = 1, 2, 4, 8
+DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT, DONE_BUDGET = 1, 2, 4, 8, 16
 
 
 class GpclustLibraryError(RuntimeError):

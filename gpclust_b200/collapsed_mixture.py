@@ -486,7 +486,8 @@ class CollapsedMixture(CollapsedVB):
         raise NotImplementedError
 
     def _enqueue_pass(self, bufs):
-        """One pass of the loop body collapsed_vb.py:152-193 as a fixed launch sequence; nothing is read back."""
+        """One bound evaluation of the loop body collapsed_vb.py:152-193 (the conjugate step, or the steepest retry of :182-193 when
+        the previous one was rejected) as a fixed launch sequence; nothing is read back."""
         lp, st = ptr(self._loop_dev), self._stream()
         dots, beta = ptr(self._ctrl[_C_SQ:]), ptr(self._ctrl[_C_BETA:])
         px = ptr(self._peers["desc"]) if self._peers is not None else None
@@ -498,13 +499,14 @@ class CollapsedMixture(CollapsedVB):
                          lp, px, self.N, self.K, self._KP, self._DP, ctas, st), "gpc_loop_natgrad")
         if self._world > 1 and px is None:
             self._allreduce(self._ctrl[_C_SQ:_C_SQ + 3])
-        for phase in (0, 1):  # GPC_PHASE_CONJ, GPC_PHASE_RETRY (the latter returns at once unless the bound fell)
-            with self._timed("step_stats" if phase == 0 else "step_stats_retry"):
-                check(s_pass(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, phase, self.N, self.K,
-                             self._KP, self._DP, ctas, st), "gpc_loop_step_stats")
-            with self._timed("posterior" if phase == 0 else "posterior_retry"):
-                self._loop_posterior(phase)
-        self.kernel_launches += 3
+        # slot mode (gpc_loop_t.slot_mode): ONE bound evaluation per enqueued sequence; after a rejected conjugate step the next
+        # sequence skips its G pass and runs S / posterior in the RETRY phase (the `phase` arguments are ignored)
+        with self._timed("step_stats"):
+            check(s_pass(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, 0, self.N, self.K,
+                         self._KP, self._DP, ctas, st), "gpc_loop_step_stats")
+        with self._timed("posterior"):
+            self._loop_posterior(0)
+        self.kernel_launches += 2
 
     _GRAPH_PASSES = 16  # passes per captured graph (plus a single-pass graph for the remainder)
 
@@ -569,23 +571,26 @@ class CollapsedMixture(CollapsedVB):
         L.xi, L.xprev, L.xtrial, L.ngi = self._xi, (-1 if self._xprev is None else self._xprev), self._xtrial, self._ngi
         L.need_retry = L.done = L.n_trace = 0
         L.trace_cap = self._TRACE_CAP
+        L.slot_mode = 1
+        L.pass_budget = int(max_passes) if max_passes is not None else 0  # the device raises DONE_BUDGET after that many accepted steps
         self._loop_upload(L)
         bufs = self._bufs()
-        rows_all, passes = [], 0
+        rows_all = []
         while True:
+            # every enqueued sequence is one bound evaluation, which is what `iteration` / `maxiter` count (collapsed_vb.py:177,191)
             remaining = max(1, int(np.ceil(float(maxiter) - L.iteration))) if np.isfinite(maxiter) else self._BATCH
             n = min(self._BATCH, remaining)
             if max_passes is not None:
-                n = min(n, max_passes - passes)
+                left = max_passes - len(rows_all)
+                n = min(self._TRACE_CAP, left + max(2, left // 4))  # accepted steps wanted + room for rejected conjugate steps
             self._enqueue_passes(bufs, n)
-            passes += n
             L, rows = self._loop_download()
             rows_all.extend(rows)
             if say:
                 for it, b, sq, beta in rows:
                     sys.stdout.write("\riteration " + str(it) + " bound=" + str(b) + " grad=" + str(sq) + ", beta=" + str(beta) + "\n")
                 sys.stdout.flush()
-            if L.done or (max_passes is not None and passes >= max_passes):
+            if L.done:
                 break
             # rewind the trace cursor for the next batch (a 4-byte field; everything else stays device-owned)
             off = _cabi.GpcLoop.n_trace.offset
@@ -600,7 +605,7 @@ class CollapsedMixture(CollapsedVB):
         st = getattr(self, "_pass_state", None)
         if st is None or st["xi"] != self._xi:
             st = {"iteration": 0, "bound_old": self.bound(), "sq_old": 0.0, "first": True}
-        cap, self._TRACE_CAP = self._TRACE_CAP, max(self._TRACE_CAP, n)
+        cap, self._TRACE_CAP = self._TRACE_CAP, max(self._TRACE_CAP, n + max(2, n // 4))
         if self._loop_dev is not None and self._loop_dev.numel() < ctypes.sizeof(_cabi.GpcLoop) + self._TRACE_CAP * 32:
             self._loop_dev = None
         batch, self._BATCH = self._BATCH, n

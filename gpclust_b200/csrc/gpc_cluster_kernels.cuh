@@ -458,6 +458,10 @@ __device__ inline void cg_decide(gpc_loop_t *L, int phase, double bound_trial, b
   if (fabs(bound_trial - bound_old) <= L->ftol) done |= GPC_DONE_FTOL;
   if (sq <= L->gtol) done |= GPC_DONE_GTOL;
   if ((double)iteration >= L->maxiter) done |= GPC_DONE_MAXITER;
+  if (L->pass_budget > 0) {  // run exactly this many accepted steps (bench / profiling)
+    L->pass_budget -= 1;
+    if (L->pass_budget == 0) done |= GPC_DONE_BUDGET;
+  }
   L->done = done;
   L->sq_old = sq;
   L->bound_old = bound_trial;
@@ -697,6 +701,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   __shared__ double mix_s;
   __shared__ bool is_last;
   if (loop_skip(a.loop, a.phase)) return;
+  const int phase = loop_phase(a.loop, a.phase);  // every CTA reads it here, before the last CTA's decision can change it
   const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
   const int r = tid & 63, pg = tid >> 6;
   const int len = KP * DP + KP + 2;
@@ -915,7 +920,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
       *a.counter = 0u;
       if (a.loop) {
         // loop mode: the flag word is consumed here and re-armed for the next evaluation (no memset between kernels)
-        cg_decide(a.loop, a.phase, bound, atomicExch(a.info, 0) != 0, a.dots[0], a.beta[0]);
+        cg_decide(a.loop, phase, bound, atomicExch(a.info, 0) != 0, a.dots[0], a.beta[0]);
       }
     }
     for (int kk = tid; kk < KP; kk += blockDim.x)
@@ -1104,7 +1109,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mog_finalize(const MogFinal
     a.scalars[2] = H;
   }
   __syncthreads();  // bias / mixgrad below are written before the loop state may flip (same thread order is not needed: next kernel)
-  if (threadIdx.x == 0 && a.loop) cg_decide(a.loop, a.phase, a.scalars[0], *a.info != 0, a.dots[0], a.beta[0]);
+  if (threadIdx.x == 0 && a.loop) cg_decide(a.loop, loop_phase(a.loop, a.phase), a.scalars[0], *a.info != 0, a.dots[0], a.beta[0]);
   __syncthreads();
   for (int k = threadIdx.x; k < a.KP; k += blockDim.x) a.bias[k] = (k < a.K) ? a.per_k[k * 4 + 3] + mixgrad[k] : 0.0;
   if (a.mixgrad_out)

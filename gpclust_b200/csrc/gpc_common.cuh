@@ -105,7 +105,14 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t 
 __device__ __forceinline__ bool loop_skip(const gpc_loop_t *loop, int phase) {
   if (loop == nullptr) return false;
   if (loop->done != 0) return true;
+  if (loop->slot_mode != 0) return false;  // one evaluation per slot: only the G pass ever skips (it checks need_retry itself)
   return phase == GPC_PHASE_RETRY && loop->need_retry == 0;
+}
+// phase of this kernel: the launch argument, or (slot mode) RETRY exactly when the previous slot's conjugate step was rejected.
+// Read at kernel entry by every CTA; need_retry is only written by the last CTA of a posterior kernel after all CTAs are done.
+__device__ __forceinline__ int loop_phase(const gpc_loop_t *loop, int phase) {
+  if (loop != nullptr && loop->slot_mode != 0) return loop->need_retry ? GPC_PHASE_RETRY : GPC_PHASE_CONJ;
+  return phase;
 }
 template <typename T>
 __device__ __forceinline__ T sel3(T p0, T p1, T p2, int i) { return i == 0 ? p0 : (i == 1 ? p1 : p2); }

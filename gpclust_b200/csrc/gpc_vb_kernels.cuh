@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   const double *p_Wt = a.Wt + (size_t)crank * KP * a.DP, *p_bias = a.bias + crank * KP;
   if (a.loop != nullptr) {
     if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
+    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
     const int xi = a.loop->xi, xp = a.loop->xprev, ngi = a.loop->ngi, method = a.loop->method;
     p_x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
     p_lse = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xi);
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   double sq_old = a.sq_old, step = a.step;
   if (a.loop != nullptr) {
     if (loop_skip(a.loop, a.phase)) return;
+    const int phase = loop_phase(a.loop, a.phase);
     const int xi = a.loop->xi, xt = a.loop->xtrial, ngi = a.loop->ngi;
     p_x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
     p_x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt) + coff;
@@ -460,8 +462,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
     p_ng = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
     p_sd_old = p_sd_new = a.bufs.sd + coff;
     // collapsed_vb.py:157-158 (first pass / steepest) and :182-184 (retry with searchDir = -natgrad)
-    beta_mode = (a.phase == GPC_PHASE_RETRY || a.loop->first != 0) ? GPC_BETA_ZERO : a.loop->method;
-    if (a.phase == GPC_PHASE_RETRY) p_beta_out = nullptr;  // the trace reports the conjugate beta
+    beta_mode = (phase == GPC_PHASE_RETRY || a.loop->first != 0) ? GPC_BETA_ZERO : a.loop->method;
+    if (phase == GPC_PHASE_RETRY) p_beta_out = nullptr;  // the trace reports the conjugate beta
     sq_old = a.loop->sq_old;
     step = a.loop->step;
   }

@@ -62,13 +62,18 @@ extern "C" {
  *     gpc_loop_natgrad -> gpc_loop_step_stats(CONJ) -> [reduce, all-reduce] -> gpc_loop_*_post(CONJ)
  *                      -> gpc_loop_step_stats(RETRY) -> [reduce, all-reduce] -> gpc_loop_*_post(RETRY)
  * reads it to pick its buffers or to return at once (`done`, or RETRY without `need_retry`).  The host enqueues a
- * batch of such sequences without synchronising and reads the trace back once per batch.                    */
+ * batch of such sequences without synchronising and reads the trace back once per batch.
+ * slot_mode = 1 shortens the sequence to ONE bound evaluation per slot,
+ *     gpc_loop_natgrad -> gpc_loop_step_stats -> [reduce / push] -> gpc_loop_*_post          (`phase` arguments ignored)
+ * where a slot that follows a rejected conjugate step (need_retry) skips the G pass (same point, same gradient) and
+ * runs the other two in the RETRY phase: no launches that return at once after every accepted step.            */
 #define GPC_PHASE_CONJ 0
 #define GPC_PHASE_RETRY 1
 #define GPC_DONE_FTOL 1
 #define GPC_DONE_GTOL 2
 #define GPC_DONE_MAXITER 4
 #define GPC_DONE_FAULT 8
+#define GPC_DONE_BUDGET 16
 typedef struct {
   double bound_old; /* bound at the accepted point                                   */
   double sq_old;    /* natgrad.grad of the previous iteration (PR / FR)              */
@@ -80,6 +85,8 @@ typedef struct {
   int need_retry;   /* the conjugate step lowered the bound: the RETRY kernels run   */
   int done;         /* GPC_DONE_* bits; once set every later kernel returns at once  */
   int n_trace, trace_cap;
+  int slot_mode;    /* 1: every kernel takes its phase from need_retry (see below)   */
+  int pass_budget;  /* > 0: accepted steps left before GPC_DONE_BUDGET is raised     */
   int pad;
   /* followed by trace_cap rows [iteration, bound, squareNorm, beta] of doubles      */
 } gpc_loop_t;
