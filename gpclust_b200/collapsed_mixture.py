@@ -507,6 +507,15 @@ class CollapsedMixture(CollapsedVB):
         with self._timed("posterior"):
             self._loop_posterior(0)
         self.kernel_launches += 2
+        if not self._slot_mode():
+            # the fixed five-launch pass (slot_mode = 0): the RETRY kernels follow every conjugate evaluation and return at once
+            # unless the bound fell
+            with self._timed("step_stats_retry"):
+                check(s_pass(ptr(self._F), ctypes.byref(bufs), dots, beta, ptr(self._spart), lp, px, 1, self.N, self.K,
+                             self._KP, self._DP, ctas, st), "gpc_loop_step_stats")
+            with self._timed("posterior_retry"):
+                self._loop_posterior(1)
+            self.kernel_launches += 1
 
     _GRAPH_PASSES = 16  # passes per captured graph (plus a single-pass graph for the remainder)
 
@@ -518,7 +527,7 @@ class CollapsedMixture(CollapsedVB):
     def _pass_graph(self, bufs, n):
         """The launch sequence of n passes, captured once (every argument is invariant: the kernels pick their
         operands from the device-resident loop state)."""
-        key = (n, self.K, float(self.alpha), self.prior_Z)
+        key = (n, self.K, float(self.alpha), self.prior_Z, self._slot_mode())
         g = self._graphs.get(key)
         if g is None:
             torch = self.torch
@@ -553,6 +562,10 @@ class CollapsedMixture(CollapsedVB):
             self.kernel_launches += g.launches
             n -= g.passes
 
+    @staticmethod
+    def _slot_mode():
+        return os.environ.get("GPCLUST_B200_SLOT", "1") != "0"
+
     def _loop_sync_host(self, L):
         """Adopt the device loop state on the host side (buffer selectors, bound, control block)."""
         self._xi, self._xprev, self._xtrial, self._ngi = L.xi, (None if L.xprev < 0 else L.xprev), L.xtrial, L.ngi
@@ -571,7 +584,7 @@ class CollapsedMixture(CollapsedVB):
         L.xi, L.xprev, L.xtrial, L.ngi = self._xi, (-1 if self._xprev is None else self._xprev), self._xtrial, self._ngi
         L.need_retry = L.done = L.n_trace = 0
         L.trace_cap = self._TRACE_CAP
-        L.slot_mode = 1
+        L.slot_mode = 1 if self._slot_mode() else 0
         L.pass_budget = int(max_passes) if max_passes is not None else 0  # the device raises DONE_BUDGET after that many accepted steps
         self._loop_upload(L)
         bufs = self._bufs()
@@ -582,7 +595,8 @@ class CollapsedMixture(CollapsedVB):
             n = min(self._BATCH, remaining)
             if max_passes is not None:
                 left = max_passes - len(rows_all)
-                n = min(self._TRACE_CAP, left + max(2, left // 4))  # accepted steps wanted + room for rejected conjugate steps
+                # accepted steps wanted + room for rejected conjugate steps (each costs a sequence of its own in slot mode)
+                n = min(self._TRACE_CAP, left + max(2, left // 4)) if self._slot_mode() else left
             self._enqueue_passes(bufs, n)
             L, rows = self._loop_download()
             rows_all.extend(rows)

@@ -707,18 +707,10 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   const int len = KP * DP + KP + 2;
   const double *partials = a.partials;
   int num_parts = a.num_parts;
-  __shared__ int xchg_ok;
-  if (a.peers != nullptr) {
-    const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
-    if (tid == 0) xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
-    __syncthreads();
-    if (!xchg_ok && tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);  // a peer never arrived: surfaces as a failed evaluation
-    partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
-    num_parts = a.peers->world;
-  }
   // the two N-sized passes have swept the L2 since the last evaluation: the replicated D x D operands (eigen
   // workspace incl. a copy of Sy_inv: <= 132 KB) are pulled into shared memory by one bulk copy while the statistics are being
-  // reduced, so that the five dependent matrix-vector products below never wait on HBM
+  // reduced (and, with rows sharded over GPUs, while the peers' statistics are still on their way), so that the five dependent
+  // matrix-vector products below never wait on HBM
   extern __shared__ __align__(128) double post_dyn[];
   __shared__ uint64_t stage_bar;
   double *ws_s = post_dyn;
@@ -728,6 +720,15 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
     const uint32_t bytes = (uint32_t)eig_ws_len(D) * 8u;  // even number of doubles: a multiple of 16 bytes
     mbar_arrive_expect_tx(&stage_bar, bytes);
     bulk_g2s(ws_s, a.ws, bytes, &stage_bar);
+  }
+  __shared__ int xchg_ok;
+  if (a.peers != nullptr) {
+    const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
+    if (tid == 0) xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
+    __syncthreads();
+    if (!xchg_ok && tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);  // a peer never arrived: surfaces as a failed evaluation
+    partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
+    num_parts = a.peers->world;
   }
   const double *lam = ws_s, *U = ws_s + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *syi_s = Vt + D * D, *scal = syi_s + D * D;
 

@@ -468,7 +468,10 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
     step = a.loop->step;
   }
   __shared__ double dots_sh[4];
-  if (a.peers != nullptr) {
+  // rows sharded over GPUs: the dots of the G pass arrive through the peer inbox.  Only the consumers need them (beta); the
+  // producer warp goes straight to filling the ring, so the exchange latency / rank skew hides behind the first HBM loads
+  const bool is_producer = (warp == kSSoftmaxWarps + kSStatWarps);
+  if (a.peers != nullptr && !is_producer) {
     if (threadIdx.x == 0) {
       const gpc_peers_t *P = a.peers;
       const unsigned long long e = P->epochs[1];  // the G pass of this rank has pushed exchange e
@@ -482,10 +485,10 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       if (blockIdx.x == 0 && a.dots_sum)
         for (int q = 0; q < 3; ++q) a.dots_sum[q] = dots_sh[q];
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;\n" ::"n"((kSSoftmaxWarps + kSStatWarps) * 32) : "memory");
   }
   double beta = 0.0;
-  if (beta_mode != GPC_BETA_ZERO) {
+  if (beta_mode != GPC_BETA_ZERO && !(a.peers != nullptr && is_producer)) {
     const double sq = a.peers ? dots_sh[0] : a.dots[0], num = a.peers ? dots_sh[1] : a.dots[1], den = a.peers ? dots_sh[2] : a.dots[2];
     if (beta_mode == GPC_BETA_HS) beta = num / den;
     else if (beta_mode == GPC_BETA_PR) beta = num / sq_old;
@@ -495,6 +498,9 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   if (blockIdx.x == 0 && threadIdx.x == 0 && p_beta_out) *p_beta_out = beta;
   const bool has_ng = (p_ng != nullptr);
   const bool use_old = has_ng && (beta != 0.0) && (p_sd_old != nullptr);
+  // what the producer stages: with the peer exchange it does not know beta, so the old search direction is staged whenever the
+  // step may use it (beta == 0 then simply leaves it unread)
+  const bool load_old = (a.peers != nullptr) ? (has_ng && beta_mode != GPC_BETA_ZERO && p_sd_old != nullptr) : use_old;
   const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
   const bool chunked = (a.part_stride != 0);
   const int KPT = KP * csize;  // total padded cluster count
@@ -507,7 +513,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
   if (warp == kSSoftmaxWarps + kSStatWarps) {
     // ---------------- producer
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (use_old ? XG : 0)) * 8u;
+      const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (load_old ? XG : 0)) * 8u;
       int j = 0;
       for (int grp = cid; grp < a.num_groups; grp += ncl, ++j) {
         const int s = j % S;
@@ -517,7 +523,7 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &full_bar[s]);
         bulk_g2s(st + FG, p_x_base + (size_t)grp * GS, XG * 8u, &full_bar[s]);
         if (has_ng) bulk_g2s(st + FG + XG, p_ng + (size_t)grp * GS, XG * 8u, &full_bar[s]);
-        if (use_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * GS, XG * 8u, &full_bar[s]);
+        if (load_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * GS, XG * 8u, &full_bar[s]);
       }
     }
   } else if (warp < kSSoftmaxWarps) {
