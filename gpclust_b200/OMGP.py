@@ -88,6 +88,7 @@ class OMGP(CollapsedMixture):
         self._part = z(int(lib.gpc_omgp_slabs(Np)) * Np * int(lib.gpc_omgp_part_stride()))
         self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._dots = z(4)
+        self._aux_stream = None
         self._cur = None
         self._trial = None
         self._ng = self._grad = self._ng_old = self._grad_old = self._sd = self._sd_trial = None
@@ -104,8 +105,9 @@ class OMGP(CollapsedMixture):
                 _cabi.as_c_array([float(s[1]) for s in spec], ctypes.c_double), _cabi.as_c_array([float(s[2]) for s in spec], ctypes.c_double),
                 sum(float(s[1]) for s in spec))  # k(x, x) of a sum of stationary / bias / white parts
 
-    def _factor_component(self, phi, i, eps):
-        """B_i -> L (in self._B), W = L^-1 (self._W), with GPy's jitchol retry (jitter = mean(diag)*1e-6*10^t)."""
+    def _factor_component(self, phi, i, eps, then=None):
+        """B_i -> L (in self._B), W = L^-1 (self._W), with GPy's jitchol retry (jitter = mean(diag)*1e-6*10^t).  `then`: callable that
+        enqueues the consumers of W (run again after a retry)."""
         torch = self.torch
         nparts, kinds, var, ls, kdiag = self._kern_arrays(self.kern[i])
         jitter = 0.0
@@ -119,13 +121,16 @@ class OMGP(CollapsedMixture):
                 break
             check(lib.gpc_omgp_build(ptr(self._Xd), self.N, self._Xd.shape[1], nparts, kinds, var, ls, ptr(phi[:, i]), phi.shape[1],
                                      float(self.variance), float(eps), float(jitter), ptr(self._B), self._stream()), "gpc_omgp_build")
-            check(lib.gpc_chol_blocked(ptr(self._B), self._Npad, ptr(self._dinv), ptr(self._ldsum), ptr(self._info), self._stream()),
-                  "gpc_chol_blocked")
-            self.kernel_launches += 1 + 3 * (self._Npad // 64)
+            # factorisation and triangular inverse pipelined over two streams (the inverse of step j runs underneath the trailing
+            # updates of the factorisation); whatever consumes W is enqueued BEFORE the flag is read, so the device never idles
+            if self._aux_stream is None:
+                self._aux_stream = self.torch.cuda.Stream(device=self.device)
+            check(lib.gpc_chol_inverse(ptr(self._B), self._Npad, ptr(self._dinv), ptr(self._ldsum), ptr(self._info), ptr(self._W),
+                                       self._stream(), ctypes.c_void_p(self._aux_stream.cuda_stream)), "gpc_chol_inverse")
+            self.kernel_launches += 2 + 6 * (self._Npad // 64)
+            if then is not None:
+                then()
             if int(self._info.item()) == 0:
-                check(lib.gpc_tri_inverse_blocked(ptr(self._B), self._Npad, ptr(self._dinv), ptr(self._W), self._stream()),
-                      "gpc_tri_inverse_blocked")
-                self.kernel_launches += 1 + 2 * (self._Npad // 64)
                 return
         raise LinAlgError("not positive definite, even with jitter.")
 
@@ -148,15 +153,16 @@ class OMGP(CollapsedMixture):
         for i in range(K):
             if not self._cshards.owns(i) or failed:
                 continue
+            def stats(i=i):
+                check(lib.gpc_omgp_component(ptr(self._W), ptr(self._Yd), ptr(self._ldsum), ptr(p.phi[:, i]), K, N, self.D, float(self.variance),
+                                             ptr(self._tbuf), ptr(self._part), ptr(p.grad_Lm[:, i]), K, ptr(p.comp[i]), self._stream()),
+                      "gpc_omgp_component")
+                self.kernel_launches += 3
             try:
-                self._factor_component(p.phi, i, 1e-6)
+                self._factor_component(p.phi, i, 1e-6, then=stats)
             except LinAlgError:
                 failed = True
                 continue
-            check(lib.gpc_omgp_component(ptr(self._W), ptr(self._Yd), ptr(self._ldsum), ptr(p.phi[:, i]), K, N, self.D, float(self.variance),
-                                         ptr(self._tbuf), ptr(self._part), ptr(p.grad_Lm[:, i]), K, ptr(p.comp[i]), self._stream()),
-                  "gpc_omgp_component")
-            self.kernel_launches += 3
         if self._cshards.any_failed(failed, p.comp):
             raise LinAlgError("not positive definite, even with jitter.")
         self._cshards.combine(p.comp, p.grad_Lm)  # the owners' disjoint results -> every rank

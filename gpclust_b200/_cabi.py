@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gpc_omgp_build": [_p, _ll, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _p, _i, _d, _d, _d, _p, _p],
     "gpc_chol_blocked": [_p, _ll, _p, _p, _p, _p],
     "gpc_tri_inverse_blocked": [_p, _ll, _p, _p, _p],
+    "gpc_chol_inverse": [_p, _ll, _p, _p, _p, _p, _p, _p],
     "gpc_omgp_component": [_p, _p, _p, _p, _i, _ll, _i, _d, _p, _p, _p, _i, _p, _p],
     "gpc_omgp_kgrad_tiles": [_ll],
     "gpc_omgp_kern_grads": [_p, _p, _i, _p, _ll, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _p, _p, _p, _p, _p, _p, _p],

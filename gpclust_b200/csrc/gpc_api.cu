@@ -837,9 +837,58 @@ int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int
     const int m = nb - jb - 1;
     if (m > 0) {
       k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
-      k_omgp_chol_trail<<<m * (m + 1) / 2, 256, kTileSmem, st>>>(A, ld, jb);
+      k_omgp_chol_trail<<<m * (m + 1) / 2, 256, kTileSmem, st>>>(A, ld, jb, 0);
     }
   }
+  return launch_rc();
+}
+
+// Factorisation and triangular inverse pipelined over two streams: step jb of the inverse needs only the diagonal-tile inverse
+// and column jb of L, both final once the panel of step jb is done, so the inverse chain (aux stream) runs underneath the
+// trailing updates of the factorisation (main stream) instead of after them.  Capturable (the events become graph edges).
+int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int *info, double *W, void *stream, void *aux_stream) {
+  if (!A || !dinv || !ldsum || !info || !W || !aux_stream || stream == aux_stream) return GPC_EINVAL;
+  if (Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream), ax = as_stream(aux_stream);
+  int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (rc) return rc;
+  constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
+  if ((rc = cuda_rc(cudaFuncSetAttribute(k_omgp_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem)))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_row))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_trail))) return rc;
+  const int nb = (int)(Npad / kOB), ld = (int)Npad;
+  const long long total = Npad * Npad;
+  // Main stream = the critical chain  diag(j) -> panel(j) -> trailing update of block column j+1 (look-ahead) -> diag(j+1) ...;
+  // aux stream = the bulk work: inverse step j and the rest of trailing update j, both released by panel(j).
+  // Two event objects re-recorded per step (a wait captures the record that precedes it).
+  cudaEvent_t ev, rest;
+  if ((rc = cuda_rc(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)))) return rc;
+  if ((rc = cuda_rc(cudaEventCreateWithFlags(&rest, cudaEventDisableTiming)))) return rc;
+  cudaEventRecord(ev, st);  // fork: the aux stream starts after everything enqueued on the main stream so far
+  cudaStreamWaitEvent(ax, ev, 0);
+  k_omgp_inv_zero<<<(unsigned)((total / 2 + 255) / 256), 256, 0, ax>>>(W, total);
+  for (int jb = 0; jb < nb; ++jb) {
+    k_omgp_chol_diag<<<1, kClusterThreads, diag_smem, st>>>(A, ld, jb, dinv, ldsum, info);
+    const int m = nb - jb - 1;
+    if (m > 0) k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
+    cudaEventRecord(ev, st);
+    cudaStreamWaitEvent(ax, ev, 0);
+    if (m > 0) {
+      if (jb > 0) cudaStreamWaitEvent(st, rest, 0);  // block column jb+1 was last written by the rest-update of step jb-1
+      k_omgp_chol_trail<<<m, 256, kTileSmem, st>>>(A, ld, jb, 1);
+    }
+    k_omgp_inv_diag<<<1, 256, 0, ax>>>(W, ld, jb, dinv);
+    if (jb > 0) k_omgp_inv_row<<<jb, 256, kTileSmem, ax>>>(W, ld, jb, dinv);
+    if (m > 0) k_omgp_inv_trail<<<dim3(jb + 1, m), 256, kTileSmem, ax>>>(W, ld, A, ld, jb);
+    if (m > 1) k_omgp_chol_trail<<<m * (m + 1) / 2 - m, 256, kTileSmem, ax>>>(A, ld, jb, 2);
+    cudaEventRecord(rest, ax);
+  }
+  cudaEventRecord(ev, ax);  // join
+  cudaStreamWaitEvent(st, ev, 0);
+  cudaEventDestroy(ev);
+  cudaEventDestroy(rest);
   return launch_rc();
 }
 

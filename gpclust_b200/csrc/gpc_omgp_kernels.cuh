@@ -155,13 +155,25 @@ __global__ void __launch_bounds__(256) k_omgp_chol_panel(double *A, int ld, int 
 }
 
 // Trailing update after panel jb: A[i][k] -= A[i][jb] A[k][jb]^T for jb < k <= i (lower tiles only).
-__global__ void __launch_bounds__(256) k_omgp_chol_trail(double *A, int ld, int jb) {
+// part: 0 = all lower tiles; 1 = only block column jb+1 (what the NEXT diagonal tile and panel need -- look-ahead);
+//       2 = everything but block column jb+1.
+__global__ void __launch_bounds__(256) k_omgp_chol_trail(double *A, int ld, int jb, int part) {
   extern __shared__ __align__(16) double sm[];
-  // decode the triangular tile index: blockIdx.x = a(a+1)/2 + b, 0 <= b <= a
-  int a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
-  while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
-  const int b = blockIdx.x - a * (a + 1) / 2;
+  int a, b;
+  if (part == 1) {
+    a = blockIdx.x;
+    b = 0;
+  } else {
+    // decode the triangular tile index: blockIdx.x = a(a+1)/2 + b, 0 <= b <= a
+    a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
+    while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
+    b = blockIdx.x - a * (a + 1) / 2;
+    if (part == 2) {  // the triangle without its first column: shift by one block row / column
+      a += 1;
+      b += 1;
+    }
+  }
   const int ib = jb + 1 + a, kb = jb + 1 + b;
   tile_product_64<true, true>(A + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld, A + (size_t)kb * kOB * ld + (size_t)jb * kOB, ld,
                               A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideT);
@@ -175,6 +187,15 @@ __global__ void k_omgp_inv_init(double *__restrict__ W, int Npad, const double *
   if (e >= (long long)Npad * Npad) return;
   const int i = (int)(e / Npad), j = (int)(e % Npad);
   W[e] = ((i >> 6) == (j >> 6)) ? dinv[(size_t)(i >> 6) * kOB * kOB + (i & 63) * kOB + (j & 63)] : 0.0;
+}
+// the same initialisation split for the pipelined variant (gpc_chol_inverse): all zeros first, diagonal tile ib at step ib
+__global__ void k_omgp_inv_zero(double *__restrict__ W, long long total) {
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (e < total) stg2(W + e, 0.0, 0.0);
+}
+__global__ void __launch_bounds__(256) k_omgp_inv_diag(double *__restrict__ W, int ld, int ib, const double *__restrict__ dinv) {
+  for (int e = threadIdx.x; e < kOB * kOB; e += blockDim.x)
+    W[(size_t)(ib * kOB + (e >> 6)) * ld + ib * kOB + (e & 63)] = dinv[(size_t)ib * kOB * kOB + e];
 }
 // step ib, part (a): W[ib][j] <- Linv_ib * W[ib][j]  for j < ib   (blockIdx.x = j)
 __global__ void __launch_bounds__(256) k_omgp_inv_row(double *W, int ld, int ib, const double *__restrict__ dinv) {

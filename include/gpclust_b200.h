@@ -291,6 +291,10 @@ int gpc_omgp_build(const double *X, long long N, int q, int nparts, const int *k
 int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int *info, void *stream);
 /* W = L^-1 (lower triangular, strict upper zero) -- the dtrtri of GPy pdinv                                */
 int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv, double *W, void *stream);
+/* gpc_chol_blocked + gpc_tri_inverse_blocked pipelined over two streams (same results): step j of the inverse starts as soon as
+ * the panel of step j is factorised and runs underneath the trailing updates.  `aux_stream` is a second stream of the caller; it is
+ * forked from / joined back into `stream`, so the call behaves like one launch sequence on `stream` (and can be captured).    */
+int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int *info, double *W, void *stream, void *aux_stream);
 /* comp[0] = tr(B^-1 Y Y^T), comp[1] = logdet B, comp[2] = sum_n phi_ni; grad_col (stride grad_stride) =
  * -0.5 variance (sum_d alpha^2 - diag(B^-1)) / (phi^2 + 1e-6)  (OMGP.py:113,117,121,138-140).
  * Y: Npad x Dy (pad rows zero), Dy <= 8.  tbuf: Npad x Dy.  part: see gpc_omgp_slabs.                       */

@@ -96,6 +96,15 @@ def test_blocked_cholesky_and_inverse_against_lapack():
     Wh = W.cpu().numpy()
     assert np.allclose(np.triu(Wh, 1), 0.0)
     assert relerr(Wh, np.linalg.inv(L)) < 1e-11
+    # the pipelined variant (inverse chain on a second stream underneath the trailing updates): identical results
+    A2 = torch.from_numpy(A.copy()).cuda()
+    W2 = torch.full((n, n), 7.0, dtype=torch.float64, device="cuda")
+    dinv2, ldsum2 = torch.zeros_like(dinv), torch.zeros_like(ldsum)
+    aux = torch.cuda.Stream()
+    check(lib.gpc_chol_inverse(ptr(A2), n, ptr(dinv2), ptr(ldsum2), ptr(info), ptr(W2), st, ctypes.c_void_p(aux.cuda_stream)), "chol_inverse")
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    assert torch.equal(A2, Ad) and torch.equal(W2, W) and torch.equal(ldsum2, ldsum)
     # not positive definite -> flag
     Bd = torch.from_numpy(A - 2.0 * np.eye(n)).cuda()
     check(lib.gpc_chol_blocked(ptr(Bd), n, ptr(dinv), ptr(ldsum), ptr(info), st), "chol")
