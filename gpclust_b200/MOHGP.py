@@ -13,6 +13,8 @@ bound / vb_grad_natgrad (MOHGP.py:70-90, :124-135, :137-153) runs in the sm_100a
 Y may be a numpy array or a CUDA tensor (N x D; N = the rows this rank holds).  The dead N x D x D
 `YYT` of MOHGP.py:52 is not materialised.
 """
+import os
+
 import numpy as np
 
 from . import _cabi
@@ -28,10 +30,10 @@ class MOHGP(CollapsedMixture):
         self.X = np.asarray(X, dtype=np.float64)
         assert self.X.shape[0] == self.D, "input data don't match observations"
 
-        CollapsedMixture.__init__(self, N, K, prior_Z, alpha, name, phi_init=phi_init, group=group)
-
         self.kernF = kernF
         self.kernY = kernY
+        self._early_setup = None
+        CollapsedMixture.__init__(self, N, K, prior_Z, alpha, name, phi_init=phi_init, group=group, before_upload=self._kernel_setup_early)
 
         # features: F = Y, fragment-major, Npad x DP
         DP = _cabi.padded_d(self.D)
@@ -45,6 +47,18 @@ class MOHGP(CollapsedMixture):
         check(lib.gpc_pack_rows(ptr(Yd), N, self.D, DP, _cabi.LAYOUT["features"], ptr(F), self._stream()), "gpc_pack_rows")
         self.kernel_launches += 1
         del Yd
+        self._set_features(F, DP)
+
+        # Computations that can be done outside the optimisation loop (MOHGP.py:52-53)
+        self._compute_YTY()
+        # initialize kernels (MOHGP.py:47-49) and the first do_computations (MOHGP.py:55)
+        self.parameters_changed()
+
+    def _kernel_setup_early(self):
+        """The covariance fills, pdinv(Sy + 1e-6 I), A and its eigendecomposition (MOHGP.py:47-49) depend on X and the kernels
+        only: they are enqueued on a side stream BEFORE the rows are uploaded, so the 4 ms Jacobi kernel runs while Y and the
+        initial logits are still crossing PCIe.  parameters_changed() joins the side stream."""
+        torch = self.torch
         self._X_dev = torch.from_numpy(self.X).to(self.device)
         D = self.D
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
@@ -53,12 +67,23 @@ class MOHGP(CollapsedMixture):
         self._Sy_logdet, self._const = z(1), z(1)
         self._YTY = z(D, D)
         self._eig_ws = z(int(lib.gpc_mohgp_eig_ws_len(D)))
-        self._set_features(F, DP)
+        if os.environ.get("GPCLUST_B200_EARLY", "1") == "0":
+            return  # parameters_changed() launches the set-up in stream order
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch_kernel_setup()
+        self._early_setup = side
 
-        # Computations that can be done outside the optimisation loop (MOHGP.py:52-53)
-        self._compute_YTY()
-        # initialize kernels (MOHGP.py:47-49) and the first do_computations (MOHGP.py:55)
-        self.parameters_changed()
+    def _launch_kernel_setup(self):
+        D = self.D
+        self._Sf.copy_(cov_to_device(self.kernF, self.X, self._X_dev))
+        self._Sy.copy_(cov_to_device(self.kernY, self.X, self._X_dev))
+        check(lib.gpc_mohgp_setup(ptr(self._Sf), ptr(self._Sy), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._A),
+                                  ptr(self._Sy_logdet), self._info_ptr(), D, self._stream()), "gpc_mohgp_setup")
+        check(lib.gpc_mohgp_eig(ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._Sf), D, ptr(self._eig_ws),
+                                self._stream()), "gpc_mohgp_eig")
+        self.kernel_launches += 4
 
     @property
     def Y(self):
@@ -93,15 +118,14 @@ class MOHGP(CollapsedMixture):
         """MOHGP.py:58-67: refresh the kernel matrices and their factorisation, then recompute (and, when kernel parameters
         are free, their gradients: update_kern_grads, MOHGP.py:92-122)."""
         D = self.D
-        self._Sf.copy_(cov_to_device(self.kernF, self.X, self._X_dev))
-        self._Sy.copy_(cov_to_device(self.kernY, self.X, self._X_dev))
-        check(lib.gpc_mohgp_setup(ptr(self._Sf), ptr(self._Sy), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._A),
-                                  ptr(self._Sy_logdet), self._info_ptr(), D, self._stream()), "gpc_mohgp_setup")
+        if self._early_setup is not None:  # constructor: already enqueued on the side stream (see _kernel_setup_early)
+            self.torch.cuda.current_stream().wait_stream(self._early_setup)
+            self._early_setup = None
+        else:
+            self._launch_kernel_setup()
         check(lib.gpc_mohgp_const(ptr(self._YTY), ptr(self._Sy_inv), ptr(self._Sy_logdet), float(self.N_total), D, ptr(self._const),
                                   self._stream()), "gpc_mohgp_const")
-        check(lib.gpc_mohgp_eig(ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy_inv), ptr(self._Sf), D, ptr(self._eig_ws),
-                                self._stream()), "gpc_mohgp_eig")
-        self.kernel_launches += 5
+        self.kernel_launches += 1
         _, _, _, failed = self._readback()
         if failed:
             raise np.linalg.LinAlgError("not positive definite, even with jitter.")

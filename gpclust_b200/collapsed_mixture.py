@@ -72,7 +72,7 @@ class _PassGraph(object):
 class CollapsedMixture(CollapsedVB):
     """collapsed_mixture.py:15-205.  N is the number of rows held by THIS rank."""
 
-    def __init__(self, N, K, prior_Z="symmetric", alpha=1.0, name="col_mix", phi_init=None, group=None):
+    def __init__(self, N, K, prior_Z="symmetric", alpha=1.0, name="col_mix", phi_init=None, group=None, before_upload=None):
         CollapsedVB.__init__(self, name)
         self.torch = _cabi.require_cuda()
         torch = self.torch
@@ -110,6 +110,8 @@ class CollapsedMixture(CollapsedVB):
 
         # random initial conditions for the vb parameters (collapsed_mixture.py:41): the legacy global
         # numpy stream, drawn for ALL rows so that a sharded run starts from the same point
+        if before_upload is not None:
+            before_upload()  # subclass hook: device work that does not depend on the rows, started before they cross PCIe
         if phi_init is None:
             phi_init = self._draw_rows(self.K)
         self._alloc_k(self.K)
