@@ -8,9 +8,11 @@ delegated to four device hooks that the mixture layer implements with the fused 
                                           -> (bound, squareNorm, beta, failed)
     _cg_accept() / _cg_restore()          buffer rotation / fall back to the accepted point
 
-GPy is not a dependency: the model base class here is a plain object.  Kernel hyper-parameter
-optimisation (collapsed_vb.py:313-323 -> GPy Model.optimize) is a documented "next" row; with no free
-parameters `optimize_parameters()` returns 0. exactly like the reference (:322-323).
+GPy is not a dependency: the model base class here is a plain object that carries the slice of GPy / paramz
+the reference leans on -- the Logexp-transformed `optimizer_array` of the free (kernel, noise) parameters and
+`optimize_parameters()` (collapsed_vb.py:313-323 -> GPy Model.optimize = L-BFGS-B on -bound).  With no free
+parameters `optimize_parameters()` returns 0. exactly like the reference (:322-323) and `optimize()` runs the
+loop from the device-resident state (collapsed_mixture._run_on_device) instead of the host-driven one below.
 """
 import sys
 import warnings

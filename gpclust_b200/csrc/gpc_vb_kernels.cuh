@@ -19,14 +19,21 @@
 // cp.async.bulk lands in shared memory exactly in the order the lanes read it: conflict-free LDS, no padding
 // bytes in HBM, and the global stores of a warp are 512 contiguous bytes.
 //
-// Both kernels are persistent, one CTA per SM, warp-specialised around a ring of group-sized shared-memory
-// stages fed by a producer warp with cp.async.bulk + mbarrier (complete_tx):
-//   G pass: 1 producer warp + 8 consumer warps (one group each, round-robin), W resident in shared memory.
-//   S pass: 1 producer warp + 8 softmax warps (CG step, softmax, entropy; leave phi in the stage in A-fragment
-//           order) + 4 statistics warps (every group: T += phi^T F on the tensor pipe, 16 of the 64 8x8 tiles each).
-// Consumers never wait on HBM, only on the ring; the ring depth (11 / 13 stages of ~16 KB) is what hides the
-// HBM latency.  The S pass leaves lse[n] = logsumexp_k x[n,:] behind so that the G pass gets phi = exp(x - lse)
-// without row reductions.
+// Both kernels are persistent, one CTA per SM (12 warps, 168 registers each), built around rings of group-sized
+// shared-memory stages filled by cp.async.bulk + mbarrier (complete_tx):
+//   G pass: six units of two warps; a unit owns one 8-row group at a time (warp h: clusters [32h, 32h+32)) and feeds
+//           its own 3-4 ring slots [F | x | lse]; the previous-point operands go straight from HBM to registers; W stays
+//           resident in shared memory in B-fragment order.
+//   S pass: 1 producer warp (13-stage ring of [F | x | ng | sd]) + 7 softmax warps (CG step, softmax, entropy; leave phi
+//           in the stage in A-fragment order) + 4 statistics warps (every group: T += phi^T F on the tensor pipe, 16 of the
+//           64 8x8 tiles each).
+// Consumers never wait on HBM, only on the ring.  The S pass leaves lse[n] = logsumexp_k x[n,:] behind so that the G pass
+// gets phi = exp(x - lse) without row reductions.
+// K > 64 ("wide" mode, template parameter CL): the same kernels launched as thread-block clusters of KP/64 CTAs.  The CTAs
+// of a cluster walk the same row groups, CTA r owning clusters [64r, 64r+64); the row-coupled scalars (softmax max / sum /
+// sum e*(x-max); sum_k phi*a) are exchanged through distributed shared memory: st.async into every peer's mailbox, counted
+// by complete_tx on the peer's mbarrier, two mailbox parities per unit / softmax warp.
+// Device-resident loop (gpc_loop_t), peer exchange over NVLink (gpc_peers_t): see include/gpclust_b200.h.
 #pragma once
 #include "gpc_common.cuh"
 

@@ -29,7 +29,7 @@ def _pair(N, D, K, prior_Z="symmetric", alpha=1.0, seed=0):
     return mo, mp
 
 
-SHAPES = [(400, 12, 5), (1000, 64, 64), (777, 56, 20), (64, 8, 2), (130, 3, 1), (5000, 33, 17), (300, 64, 9)]
+SHAPES = [(400, 12, 5), (1000, 64, 64), (777, 56, 20), (64, 8, 2), (130, 3, 1), (5000, 33, 17), (300, 64, 9), (5, 6, 3), (9, 2, 2)]
 
 
 @pytest.mark.parametrize("N,D,K", SHAPES)
