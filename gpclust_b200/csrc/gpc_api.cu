@@ -126,7 +126,7 @@ bool wide_geometry_ok(long long N, int K, int KP, int DP, int nclusters) {
          (DP % 8) == 0 && nclusters >= 1;
 }
 
-constexpr size_t kTileSmem = sizeof(double) * (size_t)kOB * (kOStrideT + kOStrideN);
+constexpr size_t kTileSmem = sizeof(double) * ((size_t)kOB * kOStrideH + (size_t)kOKH * kOStrideN);  // P half + the larger Q half
 template <typename Kern>
 int tile_attr(Kern kern) {
   return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));

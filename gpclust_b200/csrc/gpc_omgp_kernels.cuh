@@ -43,31 +43,47 @@ __global__ void k_omgp_build(const double *__restrict__ X, int N, int Npad, int 
 // ------------------------------------------------------------------------------------------------
 // 64 x 64 x 64 tile product on the FP64 tensor pipe.  256 threads; warp w owns rows 8w..8w+7.
 //   C = (SUB ? C - P*op(Q) : P*op(Q)),  op(Q) = Q^T when QT (Q given as n x k rows), Q otherwise (k x n rows)
-// P may alias C (it is staged in shared memory before anything is written).
+// P may alias C (both k-halves of P are consumed before anything is written).
+// The operands are staged in two k-halves of 32 (36.9 KB of shared memory per CTA instead of 71.7 KB): five CTAs per SM instead of
+// three, which is what overlaps one CTA's global loads / read-modify-write epilogue with the DMMAs of the others.
+constexpr int kOKH = 32;          // k columns staged at a time
+constexpr int kOStrideH = 36;     // row stride of a 32-wide half read along k (bank skew 4)
 template <bool QT, bool SUB>
 __device__ __forceinline__ void tile_product_64(const double *__restrict__ P, int ldp, const double *__restrict__ Q, int ldq, double *C, int ldc,
                                                 double *Ps, double *Qs) {
-  constexpr int QS = QT ? kOStrideT : kOStrideN;
   const int tid = threadIdx.x;
-  __syncthreads();  // previous user of the staging buffers is done
-  for (int e = tid; e < kOB * kOB / 2; e += blockDim.x) {
-    const int r = e >> 5, c2 = (e & 31) * 2;
-    *reinterpret_cast<double2 *>(Ps + r * kOStrideT + c2) = ldg2(P + (size_t)r * ldp + c2);
-    *reinterpret_cast<double2 *>(Qs + r * QS + c2) = ldg2(Q + (size_t)r * ldq + c2);
-  }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   double acc[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-  const double *pa = Ps + (warp * 8 + g) * kOStrideT + t;
+  const double *pa = Ps + (warp * 8 + g) * kOStrideH + t;
+#pragma unroll 1
+  for (int kh = 0; kh < kOB / kOKH; ++kh) {
+    __syncthreads();  // previous user of the staging buffers is done
+    for (int e = tid; e < kOB * kOKH / 2; e += blockDim.x) {  // P rows x 32 columns of this half
+      const int r = e >> 4, c2 = (e & 15) * 2;
+      *reinterpret_cast<double2 *>(Ps + r * kOStrideH + c2) = ldg2(P + (size_t)r * ldp + kh * kOKH + c2);
+    }
+    if (QT) {
+      for (int e = tid; e < kOB * kOKH / 2; e += blockDim.x) {  // Q given as n x k rows: 64 rows x 32 columns
+        const int r = e >> 4, c2 = (e & 15) * 2;
+        *reinterpret_cast<double2 *>(Qs + r * kOStrideH + c2) = ldg2(Q + (size_t)r * ldq + kh * kOKH + c2);
+      }
+    } else {
+      for (int e = tid; e < kOKH * kOB / 2; e += blockDim.x) {  // Q given as k x n rows: 32 rows x 64 columns
+        const int r = e >> 5, c2 = (e & 31) * 2;
+        *reinterpret_cast<double2 *>(Qs + r * kOStrideN + c2) = ldg2(Q + (size_t)(kh * kOKH + r) * ldq + c2);
+      }
+    }
+    __syncthreads();
 #pragma unroll 4
-  for (int ks = 0; ks < kOB / 4; ++ks) {
-    const double af = pa[4 * ks];
+    for (int ks = 0; ks < kOKH / 4; ++ks) {
+      const double af = pa[4 * ks];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const double bf = QT ? Qs[(8 * nt + g) * QS + 4 * ks + t] : Qs[(4 * ks + t) * QS + 8 * nt + g];
-      dmma884(acc[nt][0], acc[nt][1], af, bf);
+      for (int nt = 0; nt < 8; ++nt) {
+        const double bf = QT ? Qs[(8 * nt + g) * kOStrideH + 4 * ks + t] : Qs[(4 * ks + t) * kOStrideN + 8 * nt + g];
+        dmma884(acc[nt][0], acc[nt][1], af, bf);
+      }
     }
   }
   double *crow = C + (size_t)(warp * 8 + g) * ldc + 2 * t;
@@ -151,13 +167,13 @@ __global__ void __launch_bounds__(256) k_omgp_chol_panel(double *A, int ld, int 
   extern __shared__ __align__(16) double sm[];
   const int ib = jb + 1 + blockIdx.x;
   double *T = A + (size_t)ib * kOB * ld + (size_t)jb * kOB;
-  tile_product_64<true, false>(T, ld, dinv + (size_t)jb * kOB * kOB, kOB, T, ld, sm, sm + kOB * kOStrideT);
+  tile_product_64<true, false>(T, ld, dinv + (size_t)jb * kOB * kOB, kOB, T, ld, sm, sm + kOB * kOStrideH);
 }
 
 // Trailing update after panel jb: A[i][k] -= A[i][jb] A[k][jb]^T for jb < k <= i (lower tiles only).
 // part: 0 = all lower tiles; 1 = only block column jb+1 (what the NEXT diagonal tile and panel need -- look-ahead);
 //       2 = everything but block column jb+1.
-__global__ void __launch_bounds__(256) k_omgp_chol_trail(double *A, int ld, int jb, int part) {
+__global__ void __launch_bounds__(256, 4) k_omgp_chol_trail(double *A, int ld, int jb, int part) {
   extern __shared__ __align__(16) double sm[];
   int a, b;
   if (part == 1) {
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(256) k_omgp_chol_trail(double *A, int ld, int 
   }
   const int ib = jb + 1 + a, kb = jb + 1 + b;
   tile_product_64<true, true>(A + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld, A + (size_t)kb * kOB * ld + (size_t)jb * kOB, ld,
-                              A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideT);
+                              A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideH);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,14 +217,14 @@ __global__ void __launch_bounds__(256) k_omgp_inv_diag(double *__restrict__ W, i
 __global__ void __launch_bounds__(256) k_omgp_inv_row(double *W, int ld, int ib, const double *__restrict__ dinv) {
   extern __shared__ __align__(16) double sm[];
   double *T = W + (size_t)ib * kOB * ld + (size_t)blockIdx.x * kOB;
-  tile_product_64<false, false>(dinv + (size_t)ib * kOB * kOB, kOB, T, ld, T, ld, sm, sm + kOB * kOStrideT);
+  tile_product_64<false, false>(dinv + (size_t)ib * kOB * kOB, kOB, T, ld, T, ld, sm, sm + kOB * kOStrideH);
 }
 // step ib, part (b): W[m][j] -= L[m][ib] * W[ib][j]  for m > ib, j <= ib   (grid: x = j, y = m - ib - 1)
-__global__ void __launch_bounds__(256) k_omgp_inv_trail(double *W, int ld, const double *__restrict__ L, int ldl, int ib) {
+__global__ void __launch_bounds__(256, 4) k_omgp_inv_trail(double *W, int ld, const double *__restrict__ L, int ldl, int ib) {
   extern __shared__ __align__(16) double sm[];
   const int jb = blockIdx.x, mb = ib + 1 + blockIdx.y;
   tile_product_64<false, true>(L + (size_t)mb * kOB * ldl + (size_t)ib * kOB, ldl, W + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld,
-                               W + (size_t)mb * kOB * ld + (size_t)jb * kOB, ld, sm, sm + kOB * kOStrideT);
+                               W + (size_t)mb * kOB * ld + (size_t)jb * kOB, ld, sm, sm + kOB * kOStrideH);
 }
 
 // ------------------------------------------------------------------------------------------------
