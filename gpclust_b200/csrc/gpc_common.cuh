@@ -253,6 +253,48 @@ __device__ __forceinline__ void exp_batch(double (&x)[N]) {  // in place: x[i] <
   for (int i = 0; i < N; ++i) x[i] = __hiloint2double(__double2hiint(p[i]) + (k[i] << 20), __double2loint(p[i]));
 }
 
+// exp for the G pass (FP64-issue-bound): table-driven variant of exp_batch.  x = (32 k + j) ln2/32 + r, |r| <= ln2/64, so a
+// degree-6 Taylor polynomial suffices (truncation 3.5e-18) and exp(x) = 2^k * 2^(j/32) * p(r): 11 FP64 instructions per value instead
+// of 15.  2^(j/32) comes from a 32-entry table held one entry per LANE (`tab_lane` = kExpTab[lane]) and fetched with a warp shuffle:
+// no shared memory, no bank conflicts.  Every lane of the warp must be active at the call.  ~1.4 ulp (checked against a
+// 64-bit-mantissa reference over [-708, 3]); arguments clamped at -708 as in exp_batch.
+__constant__ double kExpTab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+template <int N>
+__device__ __forceinline__ void exp_batch_tab(double (&x)[N], double tab_lane) {  // in place: x[i] <- exp(x[i])
+  int k[N];
+  const double l2e32 = kExpC[0] * 32.0, shift = kExpC[1], ln2hi = kExpC[2] * 0.03125, ln2lo = kExpC[3] * 0.03125, lo = kExpC[4];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double xi = (x[i] > lo) ? x[i] : lo;
+    const double t = fma(xi, l2e32, shift);
+    const double n = t - shift;
+    k[i] = __double2loint(t);
+    x[i] = fma(n, ln2lo, fma(n, ln2hi, xi));  // r
+  }
+  double p[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(1.0 / 720.0, x[i], 1.0 / 120.0);
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const double cc = (c == 0) ? 1.0 / 24.0 : (c == 1) ? 1.0 / 6.0 : (c == 2) ? 0.5 : 1.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], x[i], cc);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double v = __shfl_sync(0xffffffffu, tab_lane, k[i] & 31) * p[i];
+    x[i] = __hiloint2double(__double2hiint(v) + ((k[i] >> 5) << 20), __double2loint(v));
+  }
+}
+
 __device__ __forceinline__ void exp_pair(double x0, double x1, double &e0, double &e1) {
   double v[2] = {x0, x1};
   exp_batch<2>(v);

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const double exp_tab = kExpTab[lane];  // this lane's entry of the 2^(j/32) table (exp_batch_tab)
   const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
   const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
   const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);  // real clusters among this CTA's KP columns
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
         phi[2 * q] = xv.x - lse;
         phi[2 * q + 1] = xv.y - lse;
       }
-      exp_batch<2 * NTW>(phi);
+      exp_batch_tab<2 * NTW>(phi, exp_tab);
       double sa = 0.0;
 #pragma unroll
       for (int q = 0; q < NTW; ++q) {
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
             po[2 * q] = xo[q].x - lse_o;
             po[2 * q + 1] = xo[q].y - lse_o;
           }
-          exp_batch<2 * NTW>(po);
+          exp_batch_tab<2 * NTW>(po, exp_tab);
         }
       };
       if (CL) {
