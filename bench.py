@@ -26,6 +26,12 @@ import subprocess
 import sys
 import time
 
+if "reference" in sys.argv[1:]:
+    # --impl reference is a CPU run on ALL host cores at every --gpus N.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would time the OpenMP kernels (and numpy's BLAS) on one core: set the thread counts before numpy / libgomp are loaded.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +41,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 N_TOTAL, D, K = 1000000, 64, 64
 METRIC = "MOHGP VB iterations/sec (N=1M,D=64,K=64)"
 UNIT = "iterations/s"
+
+
+def config_of(method):
+    """`config` of the JSON line -- identical in both arms (the driver compares them key by key)."""
+    return {"workload": "MOHGP N=1M D=64 K=64 FP64 %s-CG (config 3)" % method, "N": N_TOTAL, "D": D, "K": K, "method": method,
+            "l2": "inputs larger than L2: every step streams 11 N x K / N x D arrays (5.6 GB over all GPUs, >= 700 MB per GPU at 8 GPUs) "
+                  "against 126 MB of L2; no flush between steps"}
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 1M rows, HS, from the ncu --set full capture summarised in
 # profiles/ncu_r01_v4_summary.csv (scaled linearly to the rows this rank holds)
@@ -187,6 +200,27 @@ def cpu_reference_rate(X, Y, phi0, k, budget_s, passes=2):
     return rate, cores, sample, t_iter
 
 
+def cpu_other_baselines(X, Y, phi0, k):
+    """The two other CPU lines of BASELINE.md section 3, each on a bounded row sample and scaled linearly in N:
+      vectorised_blas          the oracle with the GEMM form of multiple_mahalanobis (numpy / BLAS on all cores): the "fair CPU" line
+      python3_fallback_loops   what the reference runs AS IS on Python 3: np_utilities.multiple_mahalanobis_numpy_loops, a Python
+                               double loop with one np.linalg.solve per (n, k) pair (np_utilities.py:43-59)"""
+    from oracle.vb_oracle import MOHGPOracle, mahalanobis_whitened_gemm, mahalanobis_pairs_solve
+    from oracle import gpy_shim as G
+    out = {}
+    for name, fn, rows, passes in (("vectorised_blas", mahalanobis_whitened_gemm, 100000, 2), ("python3_fallback_loops", mahalanobis_pairs_solve, 200, 1)):
+        kF, kY = G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+        np.random.seed(0)
+        m = MOHGPOracle(X, kF, kY, Y[:rows], K=k, mahalanobis=fn)
+        m.set_vb_param(phi0[:rows].flatten())
+        t0 = time.perf_counter()
+        m.iterate(passes, method="HS")
+        t_pass = (time.perf_counter() - t0) / passes
+        out[name] = {"value": 1.0 / (t_pass * N_TOTAL / float(rows)), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                     "sample": "%d of %d rows, %d loop passes, %.2f s/pass on the sample, scaled linearly in N" % (rows, N_TOTAL, passes, t_pass)}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be imported --
     GPy / scipy.weave are absent).  Rank 0 only."""
@@ -229,7 +263,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": t_step_full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "MOHGP N=1M D=64 K=64 FP64 HS-CG (config 3)", "N": N_TOTAL, "D": D, "K": K, "method": "HS"},
+        "config": config_of(args.method),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d of %d rows per step, %.3f s/step on the sample, scaled linearly in N" % (rows, N_TOTAL, dt / steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -323,8 +357,8 @@ def run_gpu(args):
     value = 1e3 / ms_per_step
 
     # ---------------- end to end through the public API with host buffers
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    Y_pin, phi_pin = pin(Y_loc), pin(phi_loc)
+    # the caller's arrays are PLAIN (pageable) numpy: whatever staging the library does to move them happens inside the timed region
+    Y_host, phi_host0 = np.ascontiguousarray(Y_loc), np.ascontiguousarray(phi_loc)
     del m
     torch.cuda.empty_cache()
     e2e_steps = steps
@@ -332,12 +366,12 @@ def run_gpu(args):
     # the call a user makes: construct from host arrays, optimize(), read the responsibilities and the bound back.
     # maxiter counts bound evaluations (collapsed_vb.py:177,191), so a rejected step uses two of them.
     def e2e_run():
-        mm = MOHGP(X, kF(), kY(), Y_pin, K=K, phi_init=phi_pin)
+        mm = MOHGP(X, kF(), kY(), Y_host, K=K, phi_init=phi_host0)
         mm.optimize(method=method, maxiter=e2e_steps, ftol=-1.0, gtol=-1.0, verbose=False)
         phi = mm.phi
         return mm.bound(), phi, len(mm.optimize_trace)
 
-    e2e_run()  # warm-up (allocator, pinned staging)
+    e2e_run()  # warm-up (CUDA allocator, the library's own pinned staging buffers)
     barrier()
     t0 = time.perf_counter()
     b_e2e, phi_host, e2e_passes = e2e_run()
@@ -352,6 +386,38 @@ def run_gpu(args):
     e2e_value = e2e_passes / e2e_s
     h2d = (n_loc * D * 8 + n_loc * K * 8) * world / float(e2e_passes)
     d2h = (n_loc * K * 8) * world / float(e2e_passes) + 128.0 * world
+
+    # ---------------- oracle parity at the metric's own shape, on this rank count (outside every timed region)
+    parity = None
+    if not args.no_parity:
+        from helpers import headline_parity
+
+        def gather_rows(a):
+            """Row-concatenation of the ranks' (n_loc x C) arrays on rank 0, over NCCL point-to-point (device tensors)."""
+            if world == 1:
+                return a
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            if rank != 0:
+                dist.send(t, dst=0)
+                return None
+            parts = [a]
+            for r in range(1, world):
+                rows_r = (r + 1) * N_TOTAL // world - r * N_TOTAL // world
+                buf = torch.empty((rows_r, a.shape[1]), dtype=t.dtype, device="cuda")
+                dist.recv(buf, src=r)
+                parts.append(buf.cpu().numpy())
+            return np.concatenate(parts, 0)
+
+        mp_ = MOHGP(X, kF(), kY(), Y_loc, K=K, phi_init=phi_loc)
+        parity = headline_parity(X, Y, phi0, K, mp_, passes=args.parity_passes, method=method, gather=gather_rows, is_root=(rank == 0))
+        del mp_
+        torch.cuda.empty_cache()
+        if parity is not None:
+            parity["ranks"] = world
+            parity["tolerance"] = 1e-9
+            parity["ok"] = bool(parity["bound_rel"] < 1e-9 and parity["natgrad_rel"] < 1e-9 and parity["trace_iterations_equal"] and
+                                parity["bound_rel_after"] < 1e-9 and parity["phi_rel_after"] < 1e-9 and parity["argmax_equal"])
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -375,20 +441,22 @@ def run_gpu(args):
                             "alg_bytes_per_launch": alg[n], "achieved_GBps": alg[n] / (kernel_ms[n] * 1e-3) / 1e9,
                             "frac": alg[n] / (kernel_ms[n] * 1e-3) / 1e9 / hbm_peak} for n in ("natgrad", "step_stats")}
     iter_bytes = g_bytes + s_bytes
-    tensor_tf = 4.0 * n_loc * K * D * world / (ms_per_step * 1e-3) / 1e12
+    tensor_tf = 4.0 * N_TOTAL * K * D / (ms_per_step * 1e-3) / 1e12  # aggregate over the `world` GPUs
 
-    cpu = None
+    cpu, cpu_other = None, None
     if world == 1 and not args.no_cpu:
         rate, cores, sample, _ = cpu_reference_rate(X, Y, phi0, K, budget_s=args.cpu_budget)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu_other = cpu_other_baselines(X, Y, phi0, K)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MOHGP N=1M D=64 K=64 FP64 %s-CG (config 3)" % method, "N": N_TOTAL, "D": D, "K": K, "method": method,
-                   "rows_per_gpu": n_loc, "parallelism": ("rows sharded x%d, statistics + CG dots exchanged over NVLink peer memory inside the kernels" % world) if world > 1 else "1 GPU",
-                   "l2": "inputs larger than L2 (11 N x K arrays of %.0f MB per step)" % (n_loc * K * 8 / 1e6),
-                   "rejected_steps": rejected, "final_bound": last_bound},
+        "config": config_of(method),
+        "run": {"rows_per_gpu": n_loc,
+                "parallelism": ("rows sharded x%d, statistics + CG dots exchanged over NVLink peer memory inside the kernels" % world) if world > 1 else "1 GPU",
+                "rejected_steps": rejected, "final_bound": last_bound},
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_passes,
                 "what": "MOHGP(X,kernF,kernY,Y_host,K,phi_init=host) + optimize(maxiter=%d evaluations = %d passes) + m.phi + m.bound(), "
@@ -403,9 +471,10 @@ def run_gpu(args):
                      "iteration_hbm_frac": iter_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         "roofline_by_kernel": by_kernel,
         "kernels_ms": kernel_ms,
-        "fp64_tensor": {"achieved": tensor_tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tensor_tf / FP64_DMMA_PEAK_TFLOPS,
-                        "flops_per_step": 4.0 * N_TOTAL * K * D},
+        "fp64_tensor": {"achieved": tensor_tf, "achieved_per_gpu": tensor_tf / world, "peak": FP64_DMMA_PEAK_TFLOPS, "peak_is": "per GPU, measured DMMA",
+                        "unit": "TFLOP/s", "frac": tensor_tf / world / FP64_DMMA_PEAK_TFLOPS, "flops_per_step": 4.0 * N_TOTAL * K * D},
         "cpu_baseline": cpu,
+        "cpu_baselines_other": cpu_other,
     }
     print(json.dumps(line))
     if world > 1:
@@ -420,6 +489,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="HS", choices=["HS", "PR", "FR", "steepest"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity record (about a minute of CPU work at N=1M)")
+    ap.add_argument("--parity-passes", type=int, default=5)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("GPCLUST_B200_LIB") or os.path.join(_HERE, "_lib", "li
 GPC_ROW_TILE = 64
 GPC_EINVAL = 2
 GPC_INFO_NOT_PD = 1
+GPC_INFO_PEER_TIMEOUT = 2
 PRIOR = {"symmetric": 0, "DP": 1}
 BETA = {"zero": 0, "HS": 1, "PR": 2, "FR": 3}
 LAYOUT = {"features": 0, "logits": 1}
@@ -112,7 +113,7 @@ class GpcPeers(ctypes.Structure):
     _fields_ = [("world", _i), ("rank", _i), ("stats_len", _i), ("pad", _i), ("inbox", _p * 8), ("epochs", _p)]
 
 
-DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT, DONE_BUDGET = 1, 2, 4, 8, 16
+DONE_FTOL, DONE_GTOL, DONE_MAXITER, DONE_FAULT, DONE_BUDGET, DONE_PEER_TIMEOUT = 1, 2, 4, 8, 16, 32
 
 
 class GpclustLibraryError(RuntimeError):

@@ -24,6 +24,7 @@ from numpy.linalg import LinAlgError
 from . import _cabi
 from ._cabi import lib, check, ptr, ptr_off
 from .collapsed_vb import CollapsedVB
+from . import sharding
 from .sharding import RowShards
 
 # control block layout (doubles)
@@ -382,6 +383,9 @@ class CollapsedMixture(CollapsedVB):
         self.torch.cuda.current_stream().synchronize()
         h = self._ctrl_host
         info = int(h.view(self.torch.int32)[2 * _C_INFO])
+        if info & _cabi.GPC_INFO_PEER_TIMEOUT:
+            self._state_valid = False
+            raise _cabi.GpclustLibraryError("gpclust_b200: a rank of the NVLink peer exchange never arrived (timeout)")
         return float(h[_C_BOUND]), float(h[_C_SQ]), float(h[_C_BETA]), info != 0
 
     def _info_ptr(self):
@@ -438,6 +442,10 @@ class CollapsedMixture(CollapsedVB):
         self._trial_bound = self._bound_value
         self._trial_failed = False
         return self._bound_value
+
+    def _cg_failed_pass_scalars(self):
+        h = self._ctrl_host  # filled by _loop_sync_host: the dots of the G pass and the conjugate beta of the failed pass
+        return float(h[_C_SQ]), float(h[_C_BETA])
 
     def _cg_accept(self):
         free = self._xprev if self._xprev is not None else 3 - self._xi - self._xtrial
@@ -573,7 +581,8 @@ class CollapsedMixture(CollapsedVB):
         self._xi, self._xprev, self._xtrial, self._ngi = L.xi, (None if L.xprev < 0 else L.xprev), L.xtrial, L.ngi
         self._readback()
         self._bound_value = L.bound_old
-        self._state_valid = True
+        # after GPC_DONE_FAULT the statistics / weights / control block belong to the failed trial point, not to x[xi]
+        self._state_valid = not (L.done & _cabi.DONE_FAULT)
         self._cache = {}
 
     def _run_on_device(self, method, maxiter, ftol, gtol, step_length, iteration, bound_old, sq_old, first, say=False, max_passes=None):
@@ -591,6 +600,13 @@ class CollapsedMixture(CollapsedVB):
         self._loop_upload(L)
         bufs = self._bufs()
         rows_all = []
+        sharding.claim(self._peers, self)
+        try:
+            return self._drive_device_loop(L, bufs, rows_all, maxiter, max_passes, say)
+        finally:
+            sharding.release(self._peers, self)
+
+    def _drive_device_loop(self, L, bufs, rows_all, maxiter, max_passes, say):
         while True:
             # every enqueued sequence is one bound evaluation, which is what `iteration` / `maxiter` count (collapsed_vb.py:177,191)
             remaining = max(1, int(np.ceil(float(maxiter) - L.iteration))) if np.isfinite(maxiter) else self._BATCH
@@ -606,6 +622,10 @@ class CollapsedMixture(CollapsedVB):
                 for it, b, sq, beta in rows:
                     sys.stdout.write("\riteration " + str(it) + " bound=" + str(b) + " grad=" + str(sq) + ", beta=" + str(beta) + "\n")
                 sys.stdout.flush()
+            if L.done & _cabi.DONE_PEER_TIMEOUT:
+                self._state_valid = False
+                raise _cabi.GpclustLibraryError("gpclust_b200: a rank of the NVLink peer exchange never arrived (timeout on rank %d of %d); "
+                                                "the optimisation state of this model is invalid" % (self._rank, self._world))
             if L.done:
                 break
             # rewind the trace cursor for the next batch (a 4-byte field; everything else stays device-owned)
@@ -629,7 +649,7 @@ class CollapsedMixture(CollapsedVB):
             it, b, sq, first, done, rows = self._run_on_device(method, np.inf, -1.0, -1.0, step_length, st["iteration"], st["bound_old"], st["sq_old"],
                                                                st["first"], max_passes=n)
         finally:
-            self._BATCH = batch
+            self._BATCH, self._TRACE_CAP = batch, cap
         self._pass_state = {"iteration": it, "bound_old": b, "sq_old": sq, "first": first, "xi": self._xi}
         return rows
 

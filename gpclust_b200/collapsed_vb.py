@@ -133,6 +133,10 @@ class CollapsedVB(object):
     def _cg_restore(self):
         raise NotImplementedError
 
+    def _cg_failed_pass_scalars(self):
+        """(squareNorm, beta) of the pass whose two trial points both failed (device loop, GPC_DONE_FAULT)."""
+        raise NotImplementedError
+
     def _is_root(self):
         return True
 
@@ -174,21 +178,31 @@ class CollapsedVB(object):
         squareNorm_old = 0.0
         first = True
         self.optimize_trace = []
+        pending = None
         if callback is None and self.optimizer_array.size == 0 and self._device_loop_ok():
             # no per-iteration host work is required: accept / reject and the termination tests run on the device,
             # the host enqueues batches of passes and reads the trace back once per batch
             iteration, bound_old, squareNorm_old, first, done, rows = self._run_on_device(method, maxiter, ftol, gtol, step_length, iteration,
                                                                                        bound_old, squareNorm_old, first, say=say)
             self.optimize_trace.extend(rows)
-            if not (done & 8):  # GPC_DONE_FAULT: a factorisation failed twice -> continue below on the host path
+            if not (done & 8):
                 if say:  # the reference tests ftol, gtol, maxiter in this order and breaks at the first hit (collapsed_vb.py:229-291)
                     print("vb converged (ftol)" if done & 1 else ("vb converged (gtol)" if done & 2 else "maxiter exceeded"))
                 return iteration
+            # GPC_DONE_FAULT: the conjugate step AND the steepest retry failed to factorise (collapsed_vb.py:187-190).  The device
+            # state belongs to the failed trial point: warn, recompute at the accepted point (set_vb_param(phi_old); bound =
+            # self.bound()), count the two evaluations and fall through to the termination tests below, as the reference does.
+            warnings.warn("Caught LinalgError in setting variational parameters, trying to continue with old parameter settings",
+                          LinAlgWarning)
+            sq, beta = self._cg_failed_pass_scalars()
+            pending = (self._cg_restore(), sq, beta, 2)
         while True:
-            if callback is not None:
-                callback()
-
-            bound, squareNorm, beta, evals = self._cg_iteration(first, method, step_length, bound_old, squareNorm_old)
+            if pending is not None:
+                (bound, squareNorm, beta, evals), pending = pending, None
+            else:
+                if callback is not None:
+                    callback()
+                bound, squareNorm, beta, evals = self._cg_iteration(first, method, step_length, bound_old, squareNorm_old)
             first = False
             iteration += evals
 

@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "gpc_cluster_kernels.cuh"
 #include "gpc_common.cuh"
 #include "gpc_omgp_kernels.cuh"
@@ -18,6 +22,25 @@ namespace {
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 inline int launch_rc() { return cuda_rc(cudaGetLastError()); }
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is set ONCE per (device, kernel) -- raised only when a launch needs more than
+// what is already granted -- instead of on every launch (pure host overhead on the host-driven loops: callbacks, free
+// hyper-parameters, MOG multi-GPU, OMGP's thousands of tile launches).  A process-wide cache of opt-in sizes; not device state.
+template <typename Kern>
+cudaError_t ensure_dyn_smem(Kern kern, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> granted;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const std::pair<int, const void *> key(dev, reinterpret_cast<const void *>(kern));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = granted.find(key);
+  if (it != granted.end() && it->second >= smem) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) granted[key] = smem;
+  return e;
+}
 
 // ring depth: as many group stages as fit next to the fixed part in the 227 KB of one SM (capped)
 constexpr int kMaxStages = 24;
@@ -46,7 +69,7 @@ size_t step_stats_smem(int KP, int DP, int S) {
 
 template <typename Kern, typename Args>
 int launch_vb(Kern kern, const Args &a, size_t smem, int grid, int threads, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dyn_smem(kern, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   kern<<<grid, threads, smem, st>>>(a);
   return launch_rc();
@@ -85,7 +108,7 @@ size_t step_stats_smem_wide(int DP, int S) { return step_stats_smem(GPC_MAX_KP, 
 
 template <typename Kern, typename Args>
 int launch_wide(Kern kern, const Args &a, size_t smem, int csize, int nclusters, int threads, cudaStream_t st, int *max_clusters) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dyn_smem(kern, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -129,12 +152,12 @@ bool wide_geometry_ok(long long N, int K, int KP, int DP, int nclusters) {
 constexpr size_t kTileSmem = sizeof(double) * ((size_t)kOB * kOStrideH + (size_t)kOKH * kOStrideN);  // P half + the larger Q half
 template <typename Kern>
 int tile_attr(Kern kern) {
-  return cuda_rc(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+  return cuda_rc(ensure_dyn_smem(kern, kTileSmem));
 }
 int launch_post(const MohgpPostArgs &a, int KP, int D, cudaStream_t st) {
   // dynamic shared memory: eigen workspace + Sy_inv staged by bulk copy (sizes must be multiples of 16 bytes)
   const size_t smem = sizeof(double) * (size_t)eig_ws_len(D);
-  cudaError_t e = cudaFuncSetAttribute(k_mohgp_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dyn_smem(k_mohgp_post, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   k_mohgp_post<<<KP, kClusterThreads, smem, st>>>(a);
   return launch_rc();
@@ -554,7 +577,7 @@ int gpc_mohgp_setup(const double *Sf, const double *Sy, double *Ly, double *Ly_i
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
   const size_t smem = sizeof(double) * 3 * (size_t)D * (D + 1);
-  e = cudaFuncSetAttribute(k_mohgp_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = ensure_dyn_smem(k_mohgp_setup, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpSetupArgs a{Sf, Sy, Ly, Ly_inv, Sy_inv, A, Sy_logdet, info, D};
   k_mohgp_setup<<<1, kClusterThreads, smem, st>>>(a);
@@ -585,7 +608,7 @@ int gpc_mohgp_cluster(const double *stats, const double *A, const double *Ly, co
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
   const size_t smem = sizeof(double) * (3 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + 3 * GPC_MAX_DP + 32);
-  e = cudaFuncSetAttribute(k_mohgp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = ensure_dyn_smem(k_mohgp_cluster, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpClusterArgs a{stats, A, Ly, Ly_inv, Sy, Sy_inv, Sf, Wt, muk_t, per_k, Syi_ybark_t, Lambda_inv, C_chols, info, K, D, KP, DP};
   k_mohgp_cluster<<<KP, kClusterThreads, smem, st>>>(a);
@@ -598,7 +621,7 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
                   void *stream) {
   if (!A || !Ly || !Ly_inv || !Sy_inv || !Sf || !ws || D < 1 || D > GPC_MAX_DP) return GPC_EINVAL;
   const size_t smem = sizeof(double) * (2 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + GPC_MAX_DP + 32);
-  cudaError_t e = cudaFuncSetAttribute(k_mohgp_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dyn_smem(k_mohgp_eig, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpEigArgs a{A, Ly, Ly_inv, Sy_inv, Sf, ws, D};
   k_mohgp_eig<<<1, kEigThreads, smem, as_stream(stream)>>>(a);
@@ -729,7 +752,7 @@ int gpc_multiple_mahalanobis(const double *X1, const double *X2, const double *L
                              void *stream) {
   if (!X1 || !X2 || !L || !out || N1 < 1 || N2 < 1 || D < 1 || D > kMahaMaxD) return GPC_EINVAL;
   const size_t smem = sizeof(double) * (size_t)D * D;
-  cudaError_t e = cudaFuncSetAttribute(k_mahalanobis_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dyn_smem(k_mahalanobis_pairs, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   const long long pairs = N1 * N2;
   k_mahalanobis_pairs<<<(unsigned)((pairs + 127) / 128), 128, smem, as_stream(stream)>>>(X1, X2, L, (int)N1, N2, D, out);
@@ -742,7 +765,7 @@ int gpc_multiple_pdinv(const double *A, int D, int K, double *inv, double *hld, 
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return cuda_rc(e);
   const size_t smem = sizeof(double) * ((size_t)D * D + 2 * (size_t)D * (D + 1));
-  e = cudaFuncSetAttribute(k_batched_pdinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = ensure_dyn_smem(k_batched_pdinv, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   k_batched_pdinv<<<K, kClusterThreads, smem, st>>>(A, D, K, inv, hld, info);
   return launch_rc();
@@ -828,7 +851,7 @@ int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int
   int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (rc) return rc;
   constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
-  if ((rc = cuda_rc(cudaFuncSetAttribute(k_omgp_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem)))) return rc;
+  if ((rc = cuda_rc(ensure_dyn_smem(k_omgp_chol_diag, diag_smem)))) return rc;
   if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
   if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
   const int nb = (int)(Npad / kOB), ld = (int)Npad;
@@ -853,7 +876,7 @@ int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int
   int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (rc) return rc;
   constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
-  if ((rc = cuda_rc(cudaFuncSetAttribute(k_omgp_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem)))) return rc;
+  if ((rc = cuda_rc(ensure_dyn_smem(k_omgp_chol_diag, diag_smem)))) return rc;
   if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
   if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
   if ((rc = tile_attr(k_omgp_inv_row))) return rc;
@@ -865,31 +888,39 @@ int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int
   // Two event objects re-recorded per step (a wait captures the record that precedes it).
   cudaEvent_t ev, rest;
   if ((rc = cuda_rc(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)))) return rc;
-  if ((rc = cuda_rc(cudaEventCreateWithFlags(&rest, cudaEventDisableTiming)))) return rc;
-  cudaEventRecord(ev, st);  // fork: the aux stream starts after everything enqueued on the main stream so far
-  cudaStreamWaitEvent(ax, ev, 0);
+  if ((rc = cuda_rc(cudaEventCreateWithFlags(&rest, cudaEventDisableTiming)))) {
+    cudaEventDestroy(ev);
+    return rc;
+  }
+  // every event call is an edge of the two-stream pipeline: the first failure is kept and returned (a lost edge would silently
+  // drop a dependency between the factorisation and the inverse)
+  auto edge = [&rc](cudaError_t e) {
+    if (rc == 0 && e != cudaSuccess) rc = cuda_rc(e);
+  };
+  edge(cudaEventRecord(ev, st));  // fork: the aux stream starts after everything enqueued on the main stream so far
+  edge(cudaStreamWaitEvent(ax, ev, 0));
   k_omgp_inv_zero<<<(unsigned)((total / 2 + 255) / 256), 256, 0, ax>>>(W, total);
-  for (int jb = 0; jb < nb; ++jb) {
+  for (int jb = 0; jb < nb && rc == 0; ++jb) {
     k_omgp_chol_diag<<<1, kClusterThreads, diag_smem, st>>>(A, ld, jb, dinv, ldsum, info);
     const int m = nb - jb - 1;
     if (m > 0) k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
-    cudaEventRecord(ev, st);
-    cudaStreamWaitEvent(ax, ev, 0);
+    edge(cudaEventRecord(ev, st));
+    edge(cudaStreamWaitEvent(ax, ev, 0));
     if (m > 0) {
-      if (jb > 0) cudaStreamWaitEvent(st, rest, 0);  // block column jb+1 was last written by the rest-update of step jb-1
+      if (jb > 0) edge(cudaStreamWaitEvent(st, rest, 0));  // block column jb+1 was last written by the rest-update of step jb-1
       k_omgp_chol_trail<<<m, 256, kTileSmem, st>>>(A, ld, jb, 1);
     }
     k_omgp_inv_diag<<<1, 256, 0, ax>>>(W, ld, jb, dinv);
     if (jb > 0) k_omgp_inv_row<<<jb, 256, kTileSmem, ax>>>(W, ld, jb, dinv);
     if (m > 0) k_omgp_inv_trail<<<dim3(jb + 1, m), 256, kTileSmem, ax>>>(W, ld, A, ld, jb);
     if (m > 1) k_omgp_chol_trail<<<m * (m + 1) / 2 - m, 256, kTileSmem, ax>>>(A, ld, jb, 2);
-    cudaEventRecord(rest, ax);
+    edge(cudaEventRecord(rest, ax));
   }
-  cudaEventRecord(ev, ax);  // join
-  cudaStreamWaitEvent(st, ev, 0);
+  edge(cudaEventRecord(ev, ax));  // join (always attempted: a forked capture must be joined back)
+  edge(cudaStreamWaitEvent(st, ev, 0));
   cudaEventDestroy(ev);
   cudaEventDestroy(rest);
-  return launch_rc();
+  return rc ? rc : launch_rc();
 }
 
 int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv, double *W, void *stream) {
@@ -948,7 +979,7 @@ int gpc_omgp_kern_grads(const double *W, const double *X, int q, const double *Y
   a.q = q;
   a.Dy = Dy;
   constexpr size_t smem = sizeof(double) * 2 * kOB * kOStrideN;
-  int rc = cuda_rc(cudaFuncSetAttribute(k_omgp_kgrad_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = cuda_rc(ensure_dyn_smem(k_omgp_kgrad_tiles, smem));
   if (rc) return rc;
   k_omgp_kgrad_tiles<<<(unsigned)tiles, 256, smem, st>>>(a);
   k_reduce_partials<<<1, 256, 0, st>>>(tile_part, (int)tiles, 2 * kMaxKernParts, out);

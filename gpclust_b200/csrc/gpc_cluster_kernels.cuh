@@ -419,6 +419,7 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
 // accept / reject (collapsed_vb.py:170-193), buffer rotation, iteration count, trace row, termination tests
 // (collapsed_vb.py:229-291 with optimize_parameters() == 0, i.e. no free kernel parameters), carry-over (:294-303).
 __device__ inline void cg_decide(gpc_loop_t *L, int phase, double bound_trial, bool failed, double sq, double beta) {
+  if (L->done & GPC_DONE_PEER_TIMEOUT) return;  // the statistics of this evaluation are incomplete: no decision is taken on them
   const double bound_old = L->bound_old;
   int evals = 1;
   if (phase == GPC_PHASE_CONJ) {
@@ -462,7 +463,7 @@ __device__ inline void cg_decide(gpc_loop_t *L, int phase, double bound_trial, b
     L->pass_budget -= 1;
     if (L->pass_budget == 0) done |= GPC_DONE_BUDGET;
   }
-  L->done = done;
+  L->done = done | (L->done & GPC_DONE_PEER_TIMEOUT);
   L->sq_old = sq;
   L->bound_old = bound_trial;
 }
@@ -726,7 +727,10 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
     const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
     if (tid == 0) xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
     __syncthreads();
-    if (!xchg_ok && tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);  // a peer never arrived: surfaces as a failed evaluation
+    if (!xchg_ok && tid == 0) {  // a peer never arrived: a hard fault of the exchange, reported as such (never as not-PD)
+      atomicOr(a.info, GPC_INFO_PEER_TIMEOUT);
+      if (a.loop != nullptr) atomicOr(&a.loop->done, GPC_DONE_PEER_TIMEOUT);
+    }
     partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
     num_parts = a.peers->world;
   }

@@ -490,6 +490,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         for (int q = 0; q < 3; ++q) d[q] += __ldcg(src + q);
       }
       for (int q = 0; q < 3; ++q) dots_sh[q] = ok ? d[q] : nan("");
+      // a peer that never shows up is a hard fault of the exchange, not a numerical outcome: sticky bit, the host raises
+      if (!ok && a.loop != nullptr) atomicOr(const_cast<int *>(&a.loop->done), GPC_DONE_PEER_TIMEOUT);
       if (blockIdx.x == 0 && a.dots_sum)
         for (int q = 0; q < 3; ++q) a.dots_sum[q] = dots_sh[q];
     }

@@ -13,7 +13,25 @@ import warnings
 import numpy as np
 
 
-_PEER_CACHE = {}  # (group id, world, stats_len, device index) -> exchange; models of one process run one at a time on a stream
+# (group object | "WORLD", world, stats_len, device index) -> exchange.  The group object itself is part of the key (held strongly:
+# an id() could be reused after the group is garbage-collected).  Models of equal geometry share one inbox and one epoch counter, so
+# only one of them may be inside its device loop at a time: `claim` / `release` enforce it.
+_PEER_CACHE = {}
+
+
+def claim(peers, owner):
+    if peers is None:
+        return
+    cur = peers.get("owner")
+    if cur is not None and cur is not owner:
+        raise RuntimeError("gpclust_b200: the NVLink peer exchange of this geometry is in use by another model's device loop; "
+                           "models that share a process group run their optimisations one at a time")
+    peers["owner"] = owner
+
+
+def release(peers, owner):
+    if peers is not None and peers.get("owner") is owner:
+        peers["owner"] = None
 
 
 class RowShards(object):
@@ -75,7 +93,7 @@ class RowShards(object):
         if self.world == 1 or self.world > 8 or os.environ.get("GPCLUST_B200_PEER", "1") == "0":
             return None
         from . import _cabi
-        key = (id(self.group), self.world, int(stats_len), getattr(device, "index", None))
+        key = (self.group if self.group is not None else "WORLD", self.world, int(stats_len), getattr(device, "index", None))
         if key in _PEER_CACHE:
             return _PEER_CACHE[key]
         try:
@@ -96,7 +114,7 @@ class RowShards(object):
                 P.inbox[r] = ptrs[r]
             P.epochs = epochs.data_ptr()
             raw = torch.frombuffer(bytearray(bytes(P)), dtype=torch.uint8).to(device)
-            _PEER_CACHE[key] = {"desc": raw, "buf": buf, "handle": hdl, "epochs": epochs}
+            _PEER_CACHE[key] = {"desc": raw, "buf": buf, "handle": hdl, "epochs": epochs, "owner": None}
             return _PEER_CACHE[key]
         except Exception as e:  # pragma: no cover - depends on the box
             warnings.warn("gpclust_b200: peer-memory exchange unavailable (%s: %s); using NCCL all-reduces" % (type(e).__name__, e))

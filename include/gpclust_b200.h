@@ -37,6 +37,7 @@ extern "C" {
 #define GPC_ROW_TILE 64
 #define GPC_EINVAL 2
 #define GPC_INFO_NOT_PD 1
+#define GPC_INFO_PEER_TIMEOUT 2 /* a peer of the NVLink exchange never raised its flag (distinct from a numerical failure) */
 
 #define GPC_PRIOR_SYMMETRIC 0
 #define GPC_PRIOR_DP 1
@@ -74,6 +75,8 @@ extern "C" {
 #define GPC_DONE_MAXITER 4
 #define GPC_DONE_FAULT 8
 #define GPC_DONE_BUDGET 16
+#define GPC_DONE_PEER_TIMEOUT 32 /* sticky: a peer exchange timed out on this rank; every later kernel returns at once and the
+                                    host raises a hard error (never folded into a numerical outcome) */
 typedef struct {
   double bound_old; /* bound at the accepted point                                   */
   double sq_old;    /* natgrad.grad of the previous iteration (PR / FR)              */

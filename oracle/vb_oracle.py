@@ -532,6 +532,18 @@ class MOHGPOracle(HyperOracle, MixtureOracle):
         return self._natural(grad_phi)
 
 
+    def predict_components(self, Xnew):
+        # MOHGP.py:156-174 (the TypeError branch for hierarchical kernY is GPy-specific and out of scope)
+        tmp = [G.dtrtrs(L, self.Sy_chol_inv, lower=1)[0] for L in self._C_chols]
+        B_invs = [ph * np.dot(t.T, t) for ph, t in zip(self.phi_hat, tmp)]
+        kx = self.kernF.K(self.X, Xnew)
+        kxx = self.kernF.K(Xnew) + self.kernY.K(Xnew)
+        tmp = [np.eye(self.D) - np.dot(Bi, self.Sf) for Bi in B_invs]
+        mu = [G.mdot(kx.T, t, self.Sy_inv, yb) for t, yb in zip(tmp, self.ybark.T)]
+        var = [kxx - G.mdot(kx.T, Bi, kx) for Bi in B_invs]
+        return mu, var
+
+
 # --------------------------------------------------------------------------- L4: OMGP
 class OMGPOracle(HyperOracle, MixtureOracle):
     """OMGP.py:14-53, :96-147 (bound and approximate natural gradient; appendix A.11 quirks kept)."""

@@ -123,6 +123,10 @@ def mohgp_case(GPclust, name, N, D, K, prior_Z, alpha, seed, kernF, kernY, X=Non
     out["trace"] = run_optimize(m, method=method, maxiter=maxiter)
     g, ng = m.vb_grad_natgrad()
     out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy(), muk1=m.muk.copy())
+    # the reference's own MOHGP.predict_components (MOHGP.py:156-174) at the optimised point, inside and outside the design range
+    Xnew = np.linspace(X.min() - 1.0, X.max() + 1.0, 9)[:, None]
+    mu, var = m.predict_components(Xnew)
+    out.update(pred_Xnew=Xnew, pred_mu=np.array(mu), pred_var=np.array(var))
     np.savez_compressed(os.path.join(HERE, "reference_mohgp_%s.npz" % name), **out)
     print("mohgp", name, "bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
 

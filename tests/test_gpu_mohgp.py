@@ -301,3 +301,63 @@ def test_wide_mode_equals_per_chunk_launches(monkeypatch):
     mc.optimize(maxiter=20, verbose=False)
     tc = np.array(mc.optimize_trace)
     assert tc.shape == tw.shape and np.max(np.abs(tc[:, 1] - tw[:, 1]) / np.abs(tw[:, 1])) < 1e-9
+
+
+def test_double_failure_restores_accepted_point():
+    """collapsed_vb.py:170-193 when BOTH the conjugate step and the steepest retry fail to factorise.  kernF = Bias(-c) makes
+    C_k = I + phi_hat_k A indefinite as soon as one cluster grows past 1.5x its initial mass, which the very first step does (beta = 0:
+    the retry is the same step and fails too).  The reference warns, restores phi_old, counts two evaluations and stops on ftol
+    because the bound is unchanged.  The device-resident loop reports GPC_DONE_FAULT; the host must then recompute the state at the
+    accepted point (not keep the failed trial's statistics) and finish exactly like the reference and the host-driven loop."""
+    import warnings
+    from gpclust_b200 import MOHGP, kern
+    from gpclust_b200.collapsed_vb import LinAlgWarning
+    from oracle import gpy_shim as G
+    N, D, K = 500, 16, 5
+    X, Y, _ = mohgp_problem(N, D, K, 2)
+    kY = G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+    L = np.linalg.cholesky(kY.K(X) + 1e-6 * np.eye(D))
+    v = np.sum(np.linalg.solve(L, np.ones(D)) ** 2)
+    np.random.seed(3)
+    phi0 = np.random.randn(N, K)
+    e = np.exp(phi0 - phi0.max(1)[:, None])
+    c = 1.0 / (v * 1.5 * (e / e.sum(1)[:, None]).sum(0).max())
+    np.random.seed(3)
+    mo = MOHGPOracle(X, G.Bias(1, -c), kY, Y, K=K)
+    mo.out = io.StringIO()
+    b0 = mo.bound()
+    mo.optimize(maxiter=30, verbose=False)
+    assert [r[0] for r in mo.trace] == [2] and mo.trace[0][1] == b0  # the oracle takes the double-failure path
+    res = {}
+    for name, kw in (("dev", {}), ("host", {"callback": lambda: None})):
+        m = MOHGP(X, kern.Bias(1, -c).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=K, phi_init=phi0)
+        bp = m.bound()
+        assert abs(bp - b0) < TOL * abs(b0)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            n = m.optimize(maxiter=30, verbose=False, **kw)
+        assert any(issubclass(x.category, LinAlgWarning) for x in w), name
+        assert n == 2 and [r[0] for r in m.optimize_trace] == [2], (name, n, m.optimize_trace)
+        assert m.bound() == bp and m.optimize_trace[0][1] == bp and np.array_equal(m.phi_, phi0)  # at the accepted point, state recomputed
+        assert abs(m.optimize_trace[0][2] - mo.trace[0][2]) < 1e-7 * abs(mo.trace[0][2]) and m.optimize_trace[0][3] == 0.0
+        # the model is usable afterwards: same gradient as the oracle at the (unchanged) point
+        g_p, ng_p = m.vb_grad_natgrad()
+        g_o, ng_o = mo.vb_grad_natgrad()
+        assert relerr(ng_p, ng_o) < TOL and relerr(g_p, g_o) < TOL
+        res[name] = m.optimize_trace
+    assert res["dev"] == res["host"]
+
+
+def test_predict_components_against_oracle():
+    """MOHGP.predict_components (MOHGP.py:156-174) after optimisation, D = 64 time points: K mean vectors and K covariance matrices
+    at new inputs inside and outside the design range."""
+    mo, mp = _pair(1500, 64, 6, seed=4)
+    mo.out = io.StringIO()
+    mo.optimize(maxiter=15, verbose=False)
+    mp.optimize(maxiter=15, verbose=False)
+    Xnew = np.linspace(-2.0, 12.0, 23)[:, None]
+    mu_o, var_o = mo.predict_components(Xnew)
+    mu_p, var_p = mp.predict_components(Xnew)
+    assert len(mu_p) == len(var_p) == 6 and mu_p[0].shape == (23,) and var_p[0].shape == (23, 23)
+    assert relerr(np.array(mu_p), np.array(mu_o)) < 1e-7
+    assert relerr(np.array(var_p), np.array(var_o)) < 1e-7

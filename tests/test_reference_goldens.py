@@ -101,6 +101,17 @@ def test_oracle_mohgp_matches_reference(path):
     m.out = io.StringIO()
     m.optimize(method=str(d["method"]), maxiter=int(d["trace"][-1, 0]) if len(d["trace"]) else 25, verbose=False)
     _check_model(m, d, m.trace)
+    _check_predict(m, d)
+
+
+def _check_predict(m, d, tol=1e-7):
+    """MOHGP.predict_components (MOHGP.py:156-174) at the optimised point against the reference's own output: K mean vectors and
+    K covariance matrices at 9 new inputs (inside and outside the design range).  The tolerance is that of the optimised phi
+    (rounding of ~10-25 loop passes), measured against the largest entry."""
+    mu, var = m.predict_components(d["pred_Xnew"])
+    assert len(mu) == len(var) == int(d["K"])
+    assert relerr(np.array(mu), d["pred_mu"]) < tol
+    assert relerr(np.array(var), d["pred_var"]) < tol
 
 
 @pytest.mark.parametrize("path", _cases("omgp"))
@@ -146,6 +157,7 @@ def test_gpu_mohgp_matches_reference(path):
     m.optimize(method=str(d["method"]), maxiter=int(d["trace"][-1, 0]), verbose=False)
     _check_model(m, d, m.optimize_trace)
     assert relerr(m.muk, d["muk1"]) < 1e-8
+    _check_predict(m, d)
 
 
 @pytest.mark.gpu
