@@ -187,6 +187,23 @@ class MOHGP(CollapsedMixture):
     def _use_peer_exchange(self):
         return True
 
+    def _fused_ok(self):
+        # K <= 64 (one 64-cluster chunk per CTA), every SM's CTA co-resident, the NVLink exchange (or one GPU).  GPCLUST_B200_FUSED=0
+        # keeps the per-evaluation launch sequence (graph replay) for comparison.
+        return (self._chunks == 1 and self._grid >= self._KP and (self._world == 1 or self._peers is not None) and
+                os.environ.get("GPCLUST_B200_FUSED", "1") != "0" and self._kernel_events is None)
+
+    def _launch_fused(self, bufs, n):
+        import ctypes
+        px = ptr(self._peers["desc"]) if self._peers is not None else None
+        check(lib.gpc_mohgp_loop(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._spart),
+                                 ptr(self._ctrl[3:]), ptr(self._ctrl[6:]), ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf),
+                                 ptr(self._const), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._ctrl), ptr(self._mixgrad),
+                                 self._info_ptr(), float(self.alpha), _cabi.PRIOR[self.prior_Z], ptr(self._loop_dev), px, ptr(self._sync_words),
+                                 ptr(self._loop_timing), int(n), self.N, self.K, self.D, self._KP, self._DP, self._grid, self._stream()),
+              "gpc_mohgp_loop")
+        self.kernel_launches += 1
+
     def _loop_posterior(self, phase):
         if self._peers is not None:
             # rows sharded over the GPUs of one box: the reduced statistics go straight into every peer's inbox over

@@ -43,6 +43,9 @@ PROTOTYPES = {
     "gpc_loop_step_stats_wide": [_p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _p],
     "gpc_reduce_push": [_p, _i, _i, _p, _p, _p, _i, _p],
     "gpc_xchg_doubles": [_i, _i],
+    "gpc_xchg_doubles_fused": [_i, _i],
+    "gpc_mohgp_loop": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _p, _p, _p, _p, _i, _ll, _i, _i, _i, _i,
+                       _i, _p],
     "gpc_natgrad_chunk": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _i, _i, _ll, _i, _p],
     "gpc_natgrad_finish": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "gpc_step_lse": [_p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _d, _i, _ll, _i, _i, _i, _p],
@@ -93,7 +96,7 @@ PROTOTYPES = {
     "gpc_graph_launch": [_p, _p],
     "gpc_graph_destroy": [_p],
 }
-_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_omgp_kgrad_tiles": _ll, "gpc_xchg_doubles": _ll}
+_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_omgp_kgrad_tiles": _ll, "gpc_xchg_doubles": _ll, "gpc_xchg_doubles_fused": _ll}
 
 
 class GpcBufs(ctypes.Structure):

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgpclust_b200.so")
 SOURCES = ["gpc_api.cu"]
-HEADERS = ["gpc_common.cuh", "gpc_vb_kernels.cuh", "gpc_cluster_kernels.cuh", "gpc_util_kernels.cuh", "gpc_omgp_kernels.cuh",
+HEADERS = ["gpc_common.cuh", "gpc_vb_kernels.cuh", "gpc_loop_kernel.cuh", "gpc_cluster_kernels.cuh", "gpc_util_kernels.cuh", "gpc_omgp_kernels.cuh",
            os.path.join("..", "..", "include", "gpclust_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]

@@ -106,6 +106,8 @@ class CollapsedMixture(CollapsedVB):
         self._loop_host = None
         self._graphs = {}       # captured pass batches, keyed by (passes, K, alpha, prior); dropped whenever a buffer is re-allocated
         self._cap_stream = None
+        self._sync_words = torch.zeros(4, dtype=torch.int32, device=self.device)  # grid-barrier / exit / ticket counters of the fused loop kernel
+        self._loop_timing = None  # bench.py: 8 x int64 device accumulators filled by the fused loop kernel (ns per phase)
         self.kernel_launches = 0  # launches of this package's own kernels (bench.py reports it)
         self._kernel_events = None  # bench.py: {"natgrad": [(start, end), ...], "step_stats": [...]} CUDA events
 
@@ -560,7 +562,19 @@ class CollapsedMixture(CollapsedVB):
             self._graphs[key] = g
         return g
 
+    def _fused_ok(self):
+        """Subclass switch: True when the whole loop runs as one persistent cooperative kernel (gpc_mohgp_loop)."""
+        return False
+
+    def _launch_fused(self, bufs, n):
+        raise NotImplementedError
+
     def _enqueue_passes(self, bufs, n):
+        if self._fused_ok():
+            # ONE launch for the n evaluations: G rows, S rows and the posterior are phases of a persistent kernel separated by
+            # grid-wide barriers (csrc/gpc_loop_kernel.cuh)
+            self._launch_fused(bufs, n)
+            return
         if not self._graphs_ok():
             for _ in range(n):
                 self._enqueue_pass(bufs)
@@ -595,7 +609,7 @@ class CollapsedMixture(CollapsedVB):
         L.xi, L.xprev, L.xtrial, L.ngi = self._xi, (-1 if self._xprev is None else self._xprev), self._xtrial, self._ngi
         L.need_retry = L.done = L.n_trace = 0
         L.trace_cap = self._TRACE_CAP
-        L.slot_mode = 1 if self._slot_mode() else 0
+        L.slot_mode = 1 if (self._slot_mode() or self._fused_ok()) else 0  # the fused loop kernel works in evaluations (slots) only
         L.pass_budget = int(max_passes) if max_passes is not None else 0  # the device raises DONE_BUDGET after that many accepted steps
         self._loop_upload(L)
         bufs = self._bufs()
@@ -614,7 +628,7 @@ class CollapsedMixture(CollapsedVB):
             if max_passes is not None:
                 left = max_passes - len(rows_all)
                 # accepted steps wanted + room for rejected conjugate steps (each costs a sequence of its own in slot mode)
-                n = min(self._TRACE_CAP, left + max(2, left // 4)) if self._slot_mode() else left
+                n = min(self._TRACE_CAP, left + max(2, left // 4)) if (self._slot_mode() or self._fused_ok()) else left
             self._enqueue_passes(bufs, n)
             L, rows = self._loop_download()
             rows_all.extend(rows)

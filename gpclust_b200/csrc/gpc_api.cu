@@ -11,6 +11,7 @@
 
 #include "gpc_cluster_kernels.cuh"
 #include "gpc_common.cuh"
+#include "gpc_loop_kernel.cuh"
 #include "gpc_omgp_kernels.cuh"
 #include "gpc_util_kernels.cuh"
 #include "gpc_vb_kernels.cuh"
@@ -1012,6 +1013,111 @@ int gpc_cg_axpy(const double *x, const double *ng, const double *sd_old, double 
 }
 
 // ---- launch-sequence replay (CUDA graph of a batch of loop-body passes)
+}  // extern "C"
+
+// ---- the whole conjugate natural-gradient loop of MOHGP as one persistent cooperative kernel (gpc_loop_kernel.cuh)
+namespace {
+struct LoopGeom {
+  int g_stages, s_stages;
+  size_t smem;
+};
+LoopGeom loop_geometry(int KP, int DP, int D) {
+  LoopGeom q;
+  const size_t budget = (size_t)kSmemBudget - kLoopHeaderBytes;
+  {
+    const int units = kGConsumers / ((KP / 8 >= 2) ? 2 : 1);
+    const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;
+    const size_t per = sizeof(double) * (size_t)g_stage_doubles(KP, DP) + sizeof(uint64_t);
+    int r = (int)((budget - fixed) / per) / units;
+    if (r > kMaxUnitSlots) r = kMaxUnitSlots;
+    q.g_stages = r * units;
+  }
+  {
+    const size_t fixed = sizeof(double) * kSSoftmaxWarps + 64;
+    const size_t per = sizeof(double) * (size_t)s_stage_doubles(KP, DP) + 3 * sizeof(uint64_t);
+    const int st = (int)((budget - fixed) / per);
+    q.s_stages = st > kMaxStages ? kMaxStages : st;
+  }
+  const size_t post = (((size_t)eig_ws_len(D) * 8 + 127) & ~(size_t)127) + sizeof(PostSmem);
+  size_t m = natgrad_smem(KP, DP, q.g_stages);
+  if (step_stats_smem(KP, DP, q.s_stages) > m) m = step_stats_smem(KP, DP, q.s_stages);
+  if (post > m) m = post;
+  q.smem = kLoopHeaderBytes + ((m + 127) & ~(size_t)127);
+  return q;
+}
+template <int KP>
+int launch_loop(LoopKernelArgs &a, int D, int grid, cudaStream_t st) {
+  const LoopGeom q = loop_geometry(KP, a.g.DP, D);
+  if (q.smem > (size_t)kSmemBudget) return GPC_EINVAL;
+  a.g.stages = q.g_stages;
+  a.s.stages = q.s_stages;
+  void *params[] = {&a};
+  cudaError_t e;
+  if (a.g.K == KP) {
+    if ((e = ensure_dyn_smem(k_mohgp_loop<KP, true>, q.smem)) != cudaSuccess) return cuda_rc(e);
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_mohgp_loop<KP, true>), dim3(grid), dim3(kGThreads), params, q.smem, st);
+  } else {
+    if ((e = ensure_dyn_smem(k_mohgp_loop<KP, false>, q.smem)) != cudaSuccess) return cuda_rc(e);
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_mohgp_loop<KP, false>), dim3(grid), dim3(kGThreads), params, q.smem, st);
+  }
+  return e == cudaSuccess ? launch_rc() : cuda_rc(e);
+}
+}  // namespace
+
+extern "C" {
+
+long long gpc_xchg_doubles_fused(int world, int stats_len) {
+  if (world < 1 || world > GPC_MAX_PEERS || stats_len < 1) return -1;
+  const long long a = fx_doubles(world, stats_len), b = xchg_doubles(world, stats_len);
+  return a > b ? a : b;  // one buffer serves both exchange layouts (they are never live at the same time)
+}
+
+int gpc_mohgp_loop(const double *F, const gpc_bufs_t *bufs, double *Wt, double *bias, double *gpart, double *spart, double *dots, double *beta,
+                   double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf, const double *const_term, double *muk_t,
+                   double *Syi_ybark_t, double *per_k, double *scalars, double *mixgrad_out, int *info, double alpha, int prior, gpc_loop_t *loop,
+                   const gpc_peers_t *peers, unsigned int *sync, unsigned long long *timing, int max_evals, long long N, int K, int D, int KP,
+                   int DP, int grid, void *stream) {
+  if (!F || !bufs_ok(bufs) || !Wt || !bias || !gpart || !spart || !dots || !beta || !stats || !eig_ws || !Sy_inv || !Sf || !const_term || !muk_t ||
+      !per_k || !scalars || !info || !loop || !sync)
+    return GPC_EINVAL;
+  if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL || D < 1 || D > DP || max_evals < 1) return GPC_EINVAL;
+  if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
+  if (grid < KP) return GPC_EINVAL;  // CTA k computes the posterior of cluster k
+  LoopKernelArgs a{};
+  a.g.F = F;
+  a.g.Wt = Wt;
+  a.g.bias = bias;
+  a.g.partials = gpart;
+  a.g.dots_out = dots;
+  a.g.N = (int)N;
+  a.g.K = K;
+  a.g.DP = DP;
+  a.g.num_groups = (int)(gpc_padded_rows(N) / kGroupRows);
+  a.g.bufs = *bufs;
+  a.s.F = F;
+  a.s.beta_out = beta;
+  a.s.partials = spart;
+  a.s.N = (int)N;
+  a.s.K = K;
+  a.s.DP = DP;
+  a.s.num_groups = a.g.num_groups;
+  a.s.bufs = *bufs;
+  a.p = MohgpPostArgs{spart, grid, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
+                      sync + 2, info, alpha, prior, K, D, KP, DP, dots, beta, loop, GPC_PHASE_CONJ, nullptr};
+  a.peers = peers;
+  a.sync = sync;
+  a.timing = timing;
+  a.max_evals = max_evals;
+  cudaStream_t st = as_stream(stream);
+  switch (KP) {
+    case 8: return launch_loop<8>(a, D, grid, st);
+    case 16: return launch_loop<16>(a, D, grid, st);
+    case 32: return launch_loop<32>(a, D, grid, st);
+    case 64: return launch_loop<64>(a, D, grid, st);
+  }
+  return GPC_EINVAL;
+}
+
 int gpc_graph_begin(void *stream) {
   if (!stream) return GPC_EINVAL;  // the legacy default stream cannot be captured
   return cuda_rc(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed));

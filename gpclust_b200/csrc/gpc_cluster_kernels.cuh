@@ -65,12 +65,24 @@ __device__ inline void potrs_vec_warp0(const double *L, int n, int ld, double *x
   }
 }
 
+// Block-wide barrier of the per-cluster routines.  SUB = false: the whole CTA (__syncthreads).  SUB = true: the routine is run by
+// the first kClusterThreads threads of a LARGER CTA (the fused loop kernel, 384 threads): named barrier 2 over those threads.
+template <bool SUB>
+__device__ __forceinline__ void psync() {
+  if (SUB) asm volatile("bar.sync 2, %0;\n" ::"n"(kClusterThreads) : "memory");
+  else __syncthreads();
+}
+template <bool SUB>
+__device__ __forceinline__ int pthreads() {
+  return SUB ? kClusterThreads : (int)blockDim.x;
+}
+template <bool SUB = false>
 __device__ inline double block_sum(double v, double *red_s) {
   v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = pthreads<SUB>() >> 5;
+  psync<SUB>();
   if (lane == 0) red_s[warp] = v;
-  __syncthreads();
+  psync<SUB>();
   double r = 0.0;
   for (int w = 0; w < nw; ++w) r += red_s[w];
   return r;
@@ -358,15 +370,16 @@ struct MixScratch {
   double a[kMaxMixK], b[kMaxMixK], c[kMaxMixK], da[kMaxMixK], db[kMaxMixK], dc[kMaxMixK];
 };
 
+template <bool SUB = false>
 __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, int prior, MixScratch &w, double *mixgrad, double *mix_out) {
   const int tid = threadIdx.x;
   if (prior == GPC_PRIOR_SYMMETRIC) {
-    for (int k = tid; k < K; k += blockDim.x) {
+    for (int k = tid; k < K; k += pthreads<SUB>()) {
       const double v = alpha + phi_hat[k];
       w.a[k] = lgamma(v);
       mixgrad[k] = digamma_pos(v);  // collapsed_mixture.py:86
     }
-    __syncthreads();
+    psync<SUB>();
     if (tid == 0) {
       // ln_dirichlet_C(alpha*1) - ln_dirichlet_C(alpha + phi_hat)   (np_utilities.py:67-69)
       double sum_a = 0.0, sum_lg = 0.0;
@@ -376,7 +389,7 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
       }
       *mix_out = (lgamma(alpha * K) - K * lgamma(alpha)) - (lgamma(sum_a) - sum_lg);
     }
-    __syncthreads();
+    psync<SUB>();
     return;
   }
   // truncated DP, collapsed_mixture.py:72-77 and :88-92
@@ -387,8 +400,8 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
       w.c[k] = tail;
     }
   }
-  __syncthreads();
-  for (int k = tid; k < K; k += blockDim.x) {
+  psync<SUB>();
+  for (int k = tid; k < K; k += pthreads<SUB>()) {
     const double ph = phi_hat[k], tph = w.c[k], til = tph - ph;
     w.a[k] = lgamma(1.0 + ph);
     w.b[k] = lgamma(alpha + til);
@@ -396,9 +409,9 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
     w.db[k] = digamma_pos(til + alpha);
     w.dc[k] = digamma_pos(tph + alpha + 1.0);
   }
-  __syncthreads();
-  for (int k = tid; k < K; k += blockDim.x) w.c[k] = lgamma(alpha + 1.0 + w.c[k]);
-  __syncthreads();
+  psync<SUB>();
+  for (int k = tid; k < K; k += pthreads<SUB>()) w.c[k] = lgamma(alpha + 1.0 + w.c[k]);
+  psync<SUB>();
   if (tid == 0) {
     double A = 0.0, B = 0.0, C = 0.0, cumB = 0.0, cumC = 0.0;
     for (int k = 0; k < K; ++k) {
@@ -411,7 +424,7 @@ __device__ inline void mixing_terms(const double *phi_hat, int K, double alpha, 
     }
     *mix_out = A + B - C + K * (lgamma(1.0 + alpha) - lgamma(alpha));
   }
-  __syncthreads();
+  psync<SUB>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,50 +706,34 @@ __device__ __forceinline__ double matvec_t_part(const double *Mt, const double *
   return r < D ? (v[0] + v[1]) + (v[2] + v[3]) : 0.0;
 }
 
-__global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostArgs a) {
-  __shared__ double red[4][GPC_MAX_DP];
-  __shared__ double yb_s[GPC_MAX_DP], z_s[GPC_MAX_DP], cz_s[GPC_MAX_DP], s_s[GPC_MAX_DP], mu_s[GPC_MAX_DP], w_s[GPC_MAX_DP], c_s[GPC_MAX_DP];
-  __shared__ double red_s[32];
-  __shared__ double mixgrad[kMaxMixK];
-  __shared__ MixScratch scratch;
-  __shared__ double mix_s;
-  __shared__ bool is_last;
-  if (loop_skip(a.loop, a.phase)) return;
-  const int phase = loop_phase(a.loop, a.phase);  // every CTA reads it here, before the last CTA's decision can change it
-  const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
-  const int r = tid & 63, pg = tid >> 6;
-  const int len = KP * DP + KP + 2;
-  const double *partials = a.partials;
-  int num_parts = a.num_parts;
-  // the two N-sized passes have swept the L2 since the last evaluation: the replicated D x D operands (eigen
-  // workspace incl. a copy of Sy_inv: <= 132 KB) are pulled into shared memory by one bulk copy while the statistics are being
-  // reduced (and, with rows sharded over GPUs, while the peers' statistics are still on their way), so that the five dependent
-  // matrix-vector products below never wait on HBM
-  extern __shared__ __align__(128) double post_dyn[];
-  __shared__ uint64_t stage_bar;
-  double *ws_s = post_dyn;
-  if (tid == 0) {
-    mbar_init(&stage_bar, 1);
-    mbar_fence_init();
-    const uint32_t bytes = (uint32_t)eig_ws_len(D) * 8u;  // even number of doubles: a multiple of 16 bytes
-    mbar_arrive_expect_tx(&stage_bar, bytes);
-    bulk_g2s(ws_s, a.ws, bytes, &stage_bar);
-  }
-  __shared__ int xchg_ok;
-  if (a.peers != nullptr) {
-    const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
-    if (tid == 0) xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
-    __syncthreads();
-    if (!xchg_ok && tid == 0) {  // a peer never arrived: a hard fault of the exchange, reported as such (never as not-PD)
-      atomicOr(a.info, GPC_INFO_PEER_TIMEOUT);
-      if (a.loop != nullptr) atomicOr(&a.loop->done, GPC_DONE_PEER_TIMEOUT);
-    }
-    partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
-    num_parts = a.peers->world;
-  }
-  const double *lam = ws_s, *U = ws_s + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *syi_s = Vt + D * D, *scal = syi_s + D * D;
+// shared memory of the posterior routine: static in k_mohgp_post, carved from the (then idle) dynamic ring memory in the fused loop kernel
+struct PostSmem {
+  double red[4][GPC_MAX_DP];
+  double yb_s[GPC_MAX_DP], z_s[GPC_MAX_DP], cz_s[GPC_MAX_DP], s_s[GPC_MAX_DP], mu_s[GPC_MAX_DP], w_s[GPC_MAX_DP], c_s[GPC_MAX_DP];
+  double red_s[32];
+  double mixgrad[kMaxMixK];
+  double phi_hat_sh[kMaxMixK];
+  MixScratch scratch;
+  double mix_s;
+  uint64_t stage_bar;
+  int xchg_ok;
+  int is_last;
+};
 
-  // ---- this cluster's statistics: fixed-order sum over the per-CTA partials (8 independent loads in flight)
+// the replicated D x D operands (eigen workspace incl. a copy of Sy_inv: <= 132 KB) -> shared memory by one bulk copy (one thread)
+__device__ __forceinline__ void post_stage_ws(const double *ws, int D, PostSmem &sm, double *ws_s) {
+  mbar_init(&sm.stage_bar, 1);
+  mbar_fence_init();
+  const uint32_t bytes = (uint32_t)eig_ws_len(D) * 8u;  // even number of doubles: a multiple of 16 bytes
+  mbar_arrive_expect_tx(&sm.stage_bar, bytes);
+  bulk_g2s(ws_s, ws, bytes, &sm.stage_bar);
+}
+
+// this cluster's statistics: fixed-order sum over `num_parts` vectors of stride `len` -> sm.yb_s[0..DP); returns phi_hat_k on every
+// thread.  Ends with a barrier.  (8 independent loads in flight per thread.)
+template <bool SUB>
+__device__ __forceinline__ double post_reduce_row(const double *partials, int num_parts, int len, int k, int KP, int DP, PostSmem &sm) {
+  const int tid = threadIdx.x, r = tid & 63, pg = tid >> 6;
   {
     double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     {
@@ -755,7 +752,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
         for (int u = 0; u < 40; ++u) v[u & 7] += (p0 + 4 * u <= last) ? w[u] : 0.0;
       }
     }
-    red[pg][r] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    sm.red[pg][r] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
   }
   double phi_hat = 0.0;
   if (tid < 32) {
@@ -765,32 +762,36 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
       if (p + 32 < num_parts) q1 += __ldcg(partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
     }
     phi_hat = warp_sum(q0 + q1);
-    if (tid == 0) red_s[0] = phi_hat;
+    if (tid == 0) sm.red_s[0] = phi_hat;
   }
-  __syncthreads();
-  phi_hat = red_s[0];
-  if (tid < DP) {
-    const double v = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-    yb_s[tid] = v;
-    a.stats[(size_t)k * DP + tid] = v;
-  }
-  if (tid == 0) a.stats[(size_t)KP * DP + k] = phi_hat;
-  __syncthreads();
+  psync<SUB>();
+  phi_hat = sm.red_s[0];
+  if (tid < DP) sm.yb_s[tid] = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
+  psync<SUB>();
+  return phi_hat;
+}
 
-  mbar_wait(&stage_bar, 0);
+// per-cluster posterior of cluster k from sm.yb_s / phi_hat (eigenbasis form, see above); ws_s: the staged workspace
+template <bool SUB>
+__device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k, double phi_hat, PostSmem &sm, const double *ws_s) {
+  const int D = a.D, DP = a.DP, tid = threadIdx.x;
+  const int r = tid & 63, pg = tid >> 6;
+  double (*red)[GPC_MAX_DP] = sm.red;
+  double *yb_s = sm.yb_s, *z_s = sm.z_s, *cz_s = sm.cz_s, *s_s = sm.s_s, *mu_s = sm.mu_s, *w_s = sm.w_s, *c_s = sm.c_s, *red_s = sm.red_s;
+  const double *lam = ws_s, *U = ws_s + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *syi_s = Vt + D * D, *scal = syi_s + D * D;
   if (k < a.K) {
     // ---- den_i = 1 + jitter + phi_hat lam_i with GPy's jitchol retry: a failed factorisation <=> some den_i <= 0
     double jitter = 0.0;
     bool ok = false;
     {
       double lmin = (tid < D) ? lam[tid] : INFINITY, lsum = (tid < D) ? lam[tid] : 0.0;
-      lsum = block_sum(lsum, red_s);
+      lsum = block_sum<SUB>(lsum, red_s);
       lmin = warp_max(-lmin);
-      __syncthreads();
+      psync<SUB>();
       if ((tid & 31) == 0) red_s[tid >> 5] = lmin;
-      __syncthreads();
+      psync<SUB>();
       lmin = -fmax(fmax(red_s[0], red_s[1]), fmax(fmax(red_s[2], red_s[3]), fmax(fmax(red_s[4], red_s[5]), fmax(red_s[6], red_s[7]))));
-      __syncthreads();
+      psync<SUB>();
       const double diag_mean = 1.0 + phi_hat * lsum / D;
       for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
         if (attempt == 1) jitter = diag_mean * 1e-6;
@@ -801,14 +802,14 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
     }
     if (!ok) {
       if (tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
-      for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = 0.0;
+      for (int d = tid; d < DP; d += pthreads<SUB>()) a.Wt[(size_t)k * DP + d] = 0.0;
       if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
     } else {
       const bool tiny = !(phi_hat > 1e-6);
       const double shift = tiny ? 0.0 : 1e-6 / phi_hat;
       // z = U^T ybark
       red[pg][r] = matvec_t_part(U, yb_s, D, r, pg);
-      __syncthreads();
+      psync<SUB>();
       double ldd = 0.0;
       if (tid < D) {
         const double z = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
@@ -820,43 +821,43 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
         cz_s[tid] = c * z;
         ldd = (jitter == 0.0) ? log1p(pl) : log(den);
       }
-      __syncthreads();
+      psync<SUB>();
       // s = U z ; V (c o z) ; U (c o z)
       const double ps = matvec_t_part(Ut, z_s, D, r, pg);
       const double pv = tiny ? 0.0 : matvec_t_part(Vt, cz_s, D, r, pg);
       const double pu = tiny ? 0.0 : matvec_t_part(Ut, cz_s, D, r, pg);
-      __syncthreads();
+      psync<SUB>();
       red[pg][r] = ps;
-      __syncthreads();
+      psync<SUB>();
       if (tid < D) s_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      __syncthreads();
+      psync<SUB>();
       red[pg][r] = pv;
-      __syncthreads();
+      psync<SUB>();
       if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      __syncthreads();
+      psync<SUB>();
       red[pg][r] = pu;
-      __syncthreads();
+      psync<SUB>();
       if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      __syncthreads();
+      psync<SUB>();
       if (tiny) {
         // Lambda_inv := Sf (MOHGP.py:85): mu = Sf^T s
         red[pg][r] = matvec_t_part(a.Sf, s_s, D, r, pg);
-        __syncthreads();
+        psync<SUB>();
         if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        __syncthreads();
+        psync<SUB>();
         red[pg][r] = matvec_t_part(syi_s, mu_s, D, r, pg);  // w = Sy_inv mu (Sy_inv symmetric)
-        __syncthreads();
+        psync<SUB>();
         if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        __syncthreads();
+        psync<SUB>();
       } else {
         red[pg][r] = matvec_t_part(syi_s, s_s, D, r, pg);  // h = Sy_inv s
-        __syncthreads();
+        psync<SUB>();
         if (tid < D) {
           const double h = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
           mu_s[tid] -= shift * s_s[tid];
           w_s[tid] -= shift * h;
         }
-        __syncthreads();
+        psync<SUB>();
       }
       double quad = 0.0, tr = 0.0, m2 = 0.0, ss = 0.0;
       if (tid < D) {
@@ -868,16 +869,16 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
         }
         m2 = mu_s[tid] * w_s[tid];
       }
-      ldd = block_sum(ldd, red_s);
-      quad = block_sum(quad, red_s);
-      ss = block_sum(ss, red_s);
-      tr = block_sum(tr, red_s);
-      m2 = block_sum(m2, red_s);
+      ldd = block_sum<SUB>(ldd, red_s);
+      quad = block_sum<SUB>(quad, red_s);
+      ss = block_sum<SUB>(ss, red_s);
+      tr = block_sum<SUB>(tr, red_s);
+      m2 = block_sum<SUB>(m2, red_s);
       if (tid < D) {
         a.muk_t[(size_t)k * D + tid] = mu_s[tid];
         if (a.Syi_ybark_t) a.Syi_ybark_t[(size_t)k * D + tid] = s_s[tid];
       }
-      for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = (d < D) ? w_s[d] : 0.0;
+      for (int d = tid; d < DP; d += pthreads<SUB>()) a.Wt[(size_t)k * DP + d] = (d < D) ? w_s[d] : 0.0;
       if (tid == 0) {
         a.per_k[k * 4 + 0] = ldd;
         a.per_k[k * 4 + 1] = tiny ? quad : quad - shift * ss;
@@ -886,37 +887,36 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
       }
     }
   } else {  // pad clusters: zero weights so that the G pass sees finite numbers
-    for (int d = tid; d < DP; d += blockDim.x) a.Wt[(size_t)k * DP + d] = 0.0;
+    for (int d = tid; d < DP; d += pthreads<SUB>()) a.Wt[(size_t)k * DP + d] = 0.0;
     if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
   }
 
-  // ---- the last CTA to finish assembles the bound and the G-pass bias (MOHGP.py:124-135, :146-148)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int done = atomicAdd(a.counter, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+}
+
+// the last CTA to finish assembles the bound and the G-pass bias (MOHGP.py:124-135, :146-148) and, in loop mode, takes the
+// accept / reject decision.  `partials` / `num_parts` / `len`: where the entropy partials are.
+template <bool SUB>
+__device__ __forceinline__ void post_tail(const MohgpPostArgs &a, PostSmem &sm, const double *partials, int num_parts, int len, int phase) {
+  const int KP = a.KP, DP = a.DP, tid = threadIdx.x;
+  double *red_s = sm.red_s, *mixgrad = sm.mixgrad, *phi_hat_sh = sm.phi_hat_sh;
+  MixScratch &scratch = sm.scratch;
+  double &mix_s = sm.mix_s;
   {
     // every load of this serial tail is issued by a different thread (one L2 round trip, not num_parts of them)
     double H = 0.0;
-    for (int p = tid; p < num_parts; p += blockDim.x) H += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + KP);
-    H = block_sum(H, red_s);
+    for (int p = tid; p < num_parts; p += pthreads<SUB>()) H += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + KP);
+    H = block_sum<SUB>(H, red_s);
     if (tid == 0) a.stats[(size_t)KP * DP + KP] = H;
-    __shared__ double phi_hat_sh[kMaxMixK];
     double ldd = 0.0, quad = 0.0;
-    for (int kk = tid; kk < a.K; kk += blockDim.x) {
+    for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) {
       phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
       ldd += __ldcg(a.per_k + kk * 4 + 0);
       quad += __ldcg(a.per_k + kk * 4 + 1);
     }
-    ldd = block_sum(ldd, red_s);
-    quad = block_sum(quad, red_s);
-    __syncthreads();
-    mixing_terms(phi_hat_sh, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
+    ldd = block_sum<SUB>(ldd, red_s);
+    quad = block_sum<SUB>(quad, red_s);
+    psync<SUB>();
+    mixing_terms<SUB>(phi_hat_sh, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
     if (tid == 0) {
       const double bound = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
       a.scalars[0] = bound;
@@ -925,14 +925,60 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
       *a.counter = 0u;
       if (a.loop) {
         // loop mode: the flag word is consumed here and re-armed for the next evaluation (no memset between kernels)
-        cg_decide(a.loop, phase, bound, atomicExch(a.info, 0) != 0, a.dots[0], a.beta[0]);
+        cg_decide(a.loop, phase, bound, (atomicExch(a.info, 0) & GPC_INFO_NOT_PD) != 0, __ldcg(a.dots), __ldcg(a.beta));
       }
     }
-    for (int kk = tid; kk < KP; kk += blockDim.x)
+    for (int kk = tid; kk < KP; kk += pthreads<SUB>())
       a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
     if (a.mixgrad_out)
-      for (int kk = tid; kk < a.K; kk += blockDim.x) a.mixgrad_out[kk] = mixgrad[kk];
+      for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) a.mixgrad_out[kk] = mixgrad[kk];
   }
+}
+
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostArgs a) {
+  __shared__ PostSmem sm;
+  if (loop_skip(a.loop, a.phase)) return;
+  const int phase = loop_phase(a.loop, a.phase);  // every CTA reads it here, before the last CTA's decision can change it
+  const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x;
+  const int len = KP * DP + KP + 2;
+  const double *partials = a.partials;
+  int num_parts = a.num_parts;
+  // the two N-sized passes have swept the L2 since the last evaluation: the replicated D x D operands (eigen
+  // workspace incl. a copy of Sy_inv: <= 132 KB) are pulled into shared memory by one bulk copy while the statistics are being
+  // reduced (and, with rows sharded over GPUs, while the peers' statistics are still on their way), so that the five dependent
+  // matrix-vector products below never wait on HBM
+  extern __shared__ __align__(128) double post_dyn[];
+  double *ws_s = post_dyn;
+  if (tid == 0) post_stage_ws(a.ws, D, sm, ws_s);
+  if (a.peers != nullptr) {
+    const unsigned long long e = a.peers->epochs[0];  // gpc_reduce_push of this rank has pushed exchange e
+    if (tid == 0) sm.xchg_ok = xchg_wait(a.peers, 0, (int)(e & 1), e) ? 1 : 0;
+    __syncthreads();
+    if (!sm.xchg_ok && tid == 0) {  // a peer never arrived: a hard fault of the exchange, reported as such (never as not-PD)
+      atomicOr(a.info, GPC_INFO_PEER_TIMEOUT);
+      if (a.loop != nullptr) atomicOr(&a.loop->done, GPC_DONE_PEER_TIMEOUT);
+    }
+    partials = a.peers->inbox[a.peers->rank] + xchg_off_stats(a.peers->world, len, (int)(e & 1), 0);
+    num_parts = a.peers->world;
+  }
+  const double phi_hat = post_reduce_row<false>(partials, num_parts, len, k, KP, DP, sm);
+  if (tid < DP) a.stats[(size_t)k * DP + tid] = sm.yb_s[tid];
+  if (tid == 0) a.stats[(size_t)KP * DP + k] = phi_hat;
+
+  mbar_wait(&sm.stage_bar, 0);
+  post_cluster_math<false>(a, k, phi_hat, sm, ws_s);
+
+  // ---- the last CTA to finish assembles the bound and the G-pass bias (MOHGP.py:124-135, :146-148)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int done = atomicAdd(a.counter, 1u);
+    sm.is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  post_tail<false>(a, sm, partials, num_parts, len, phase);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -94,6 +94,24 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(remote_addr), "d"(v), "r"(remote_bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
+// generic-proxy writes (st.global / st.shared by this thread, or observed by it) ordered before later async-proxy accesses
+// (cp.async.bulk reads of the same bytes)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned int *p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
 // bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src_gmem), "r"(bytes) : "memory");

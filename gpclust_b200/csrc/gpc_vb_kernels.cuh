@@ -90,6 +90,76 @@ __host__ __device__ inline int g_fixed_doubles(int KP, int DP) { return KP * DP 
 // wide mode: mailbox [2 parities][units][kMaxCl ranks][8 rows] + 2*units mbarriers
 __host__ __device__ inline int g_cl_doubles() { return 2 * kGConsumers * kMaxCl * kGroupRows + 2 * kGConsumers; }
 
+// shared-memory carve of the G pass (dynamic shared memory; `stages` ring slots)
+struct GSmem {
+  double *stages, *w_s, *bias_s, *red_s, *sax_s, *sa_mb;
+  uint64_t *full_bar, *mb_bar;
+};
+__device__ __forceinline__ GSmem g_carve(unsigned char *smem_raw, int stages, int KP, int DP) {
+  GSmem m;
+  m.stages = reinterpret_cast<double *>(smem_raw);
+  m.w_s = m.stages + (size_t)stages * g_stage_doubles(KP, DP);  // B fragments: ((ks*NT + nt)*32 + lane)
+  m.bias_s = m.w_s + KP * DP;                                    // KP
+  m.red_s = m.bias_s + KP;                                       // kGConsumers * 4
+  m.sax_s = m.red_s + kGConsumers * 4;                           // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
+  m.full_bar = reinterpret_cast<uint64_t *>(m.sax_s + 2 * kGConsumers * kGroupRows);
+  m.mb_bar = m.full_bar + stages;                                           // wide mode: [2][UNITS]
+  m.sa_mb = reinterpret_cast<double *>(m.mb_bar + 2 * kGConsumers);         // wide mode: [2][UNITS][kMaxCl][8]
+  return m;
+}
+// operands of one G pass, resolved from the launch arguments or from the device-resident loop state
+struct GPtrs {
+  const double *x, *lse, *x_old, *lse_old, *ng_old, *Wt, *bias;
+  double *ng_out, *grad_out;
+};
+// `loop`: the loop state to resolve against (a.loop for the stand-alone kernels; the fused loop kernel passes its per-evaluation
+// snapshot in shared memory)
+__device__ __forceinline__ GPtrs g_resolve(const NatgradArgs &a, int KP, int crank, const gpc_loop_t *loop) {
+  const size_t coff = (size_t)crank * (kGroupRows * KP);  // this CTA's chunk inside a group of the N x K operands (wide mode)
+  GPtrs p;
+  p.x = a.x + coff;
+  p.lse = a.lse;
+  p.x_old = a.x_old ? a.x_old + coff : nullptr;
+  p.lse_old = a.lse_old;
+  p.ng_old = a.ng_old ? a.ng_old + coff : nullptr;
+  p.ng_out = a.ng_out + coff;
+  p.grad_out = a.grad_out ? a.grad_out + coff : nullptr;
+  p.Wt = a.Wt + (size_t)crank * KP * a.DP;
+  p.bias = a.bias + crank * KP;
+  if (loop != nullptr) {
+    const int xi = loop->xi, xp = loop->xprev, ngi = loop->ngi, method = loop->method;
+    p.x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
+    p.lse = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xi);
+    p.ng_out = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
+    // HS / PR need the previous accepted point (collapsed_vb.py:159-164); none on the first pass
+    const bool ho = (loop->first == 0) && xp >= 0 && (method == GPC_BETA_HS || method == GPC_BETA_PR);
+    p.x_old = ho ? sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xp) + coff : nullptr;
+    p.lse_old = ho ? sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xp) : nullptr;
+    p.ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) + coff : nullptr;
+  }
+  return p;
+}
+// barriers, resident weights (B-fragment order) and bias; the caller synchronises the block (cluster) afterwards
+template <int KP, bool CL>
+__device__ __forceinline__ void g_setup(const NatgradArgs &a, const GSmem &m, const GPtrs &p) {
+  constexpr int NT = KP / 8;
+  constexpr int UNITS = kGConsumers / ((NT >= 2) ? 2 : 1);
+  const int DP = a.DP;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&m.full_bar[s], 1);
+    if (CL)
+      for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&m.mb_bar[s], 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
+    const int ln = i & 31, f = i >> 5;  // f = ks*NT + nt
+    const int nt = f % NT, ks = f / NT;
+    m.w_s[i] = __ldcg(p.Wt + (size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3));  // L2: rewritten by other CTAs inside the fused loop kernel
+  }
+  for (int i = threadIdx.x; i < KP; i += blockDim.x) m.bias_s[i] = __ldcg(p.bias + i);
+  for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) m.red_s[i] = 0.0;
+}
+
 // FULLK: K == KP, no column masking.
 // All 12 warps compute.  They work in units of NSPLIT warps that share one group: warp h of a unit owns the n-tiles
 // [h*NTW, (h+1)*NTW) (clusters), so the unit's row reduction sum_k phi*a is exchanged through shared memory once per
@@ -97,71 +167,29 @@ __host__ __device__ inline int g_cl_doubles() { return 2 * kGConsumers * kMaxCl 
 // slot it has just finished with the unit's group R visits ahead (cp.async.bulk + mbarrier complete_tx) -- no
 // producer warp, no empty barriers (the unit's own exchange barrier orders "both warps are done reading" before
 // the refill), and the four schedulers carry three compute warps each.
-template <int KP, bool FULLK, bool CL = false>
-__global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
+// The row loop of one CTA: on return red_s[warp*4 + {0,1,2}] hold the warp's partial dots (the caller synchronises).
+// `cid` / `ncl`: index of this CTA (cluster of CTAs in wide mode) among those that share the row groups.
+template <int KP, bool FULLK, bool CL>
+__device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, const GPtrs &p, int cid, int ncl, int crank, int csize) {
   constexpr int NT = KP / 8;
   constexpr int NSPLIT = (NT >= 2) ? 2 : 1;
   constexpr int NTW = NT / NSPLIT;           // n-tiles per warp
   constexpr int UNITS = kGConsumers / NSPLIT;
   constexpr int XG = kGroupRows * KP;        // doubles of one N x K operand per group
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int DP = a.DP, FG = kGroupRows * DP;
   const int R = a.stages / UNITS;            // ring slots per unit
   const int stage_doubles = g_stage_doubles(KP, DP);
-  double *stages = reinterpret_cast<double *>(smem_raw);
-  double *w_s = stages + (size_t)a.stages * stage_doubles;  // B fragments: ((ks*NT + nt)*32 + lane)
-  double *bias_s = w_s + KP * DP;                            // KP
-  double *red_s = bias_s + KP;                               // kGConsumers * 4
-  double *sax_s = red_s + kGConsumers * 4;                   // [2 buffers][UNITS][NSPLIT][8] row-sum exchange
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sax_s + 2 * kGConsumers * kGroupRows);
-  uint64_t *mb_bar = full_bar + a.stages;                                  // wide mode: [2][UNITS]
-  double *sa_mb = reinterpret_cast<double *>(mb_bar + 2 * kGConsumers);    // wide mode: [2][UNITS][kMaxCl][8]
-  __shared__ bool is_last;
-
+  double *stages = m.stages, *w_s = m.w_s, *bias_s = m.bias_s, *red_s = m.red_s, *sax_s = m.sax_s, *sa_mb = m.sa_mb;
+  uint64_t *full_bar = m.full_bar, *mb_bar = m.mb_bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const double exp_tab = kExpTab[lane];  // this lane's entry of the 2^(j/32) table (exp_batch_tab)
-  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
-  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
   const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);  // real clusters among this CTA's KP columns
-  const size_t coff = (size_t)crank * XG;                              // this CTA's chunk inside a group of the N x K operands
-  const double *p_x = a.x + coff, *p_lse = a.lse, *p_x_old = a.x_old ? a.x_old + coff : nullptr, *p_lse_old = a.lse_old;
-  const double *p_ng_old = a.ng_old ? a.ng_old + coff : nullptr;
-  double *p_ng_out = a.ng_out + coff;
-  double *p_grad_out = a.grad_out ? a.grad_out + coff : nullptr;
-  const double *p_Wt = a.Wt + (size_t)crank * KP * a.DP, *p_bias = a.bias + crank * KP;
-  if (a.loop != nullptr) {
-    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
-    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
-    const int xi = a.loop->xi, xp = a.loop->xprev, ngi = a.loop->ngi, method = a.loop->method;
-    p_x = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
-    p_lse = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xi);
-    p_ng_out = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
-    // HS / PR need the previous accepted point (collapsed_vb.py:159-164); none on the first pass
-    const bool ho = (a.loop->first == 0) && xp >= 0 && (method == GPC_BETA_HS || method == GPC_BETA_PR);
-    p_x_old = ho ? sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xp) + coff : nullptr;
-    p_lse_old = ho ? sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xp) : nullptr;
-    p_ng_old = ho ? (ngi ? a.bufs.ng[0] : a.bufs.ng[1]) + coff : nullptr;
-  }
+  const double *p_x = p.x, *p_lse = p.lse, *p_x_old = p.x_old, *p_lse_old = p.lse_old, *p_ng_old = p.ng_old;
+  double *p_ng_out = p.ng_out, *p_grad_out = p.grad_out;
   const bool has_old = (p_ng_old != nullptr);
   const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;  // global group stride of the N x K operands
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) mbar_init(&full_bar[s], 1);
-    if (CL)
-      for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&mb_bar[s], 1);
-    mbar_fence_init();
-  }
-  for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
-    const int ln = i & 31, f = i >> 5;  // f = ks*NT + nt
-    const int nt = f % NT, ks = f / NT;
-    w_s[i] = p_Wt[(size_t)(8 * nt + (ln >> 2)) * DP + 4 * ks + (ln & 3)];
-  }
-  for (int i = threadIdx.x; i < KP; i += blockDim.x) bias_s[i] = p_bias[i];
-  for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) red_s[i] = 0.0;
-  if (CL) cluster_sync_all();  // every peer's mailbox barriers exist before the first remote arrive
-  else __syncthreads();
-
+  (void)csize;
   {
     const int unit = warp / NSPLIT, h = warp % NSPLIT, nt0 = h * NTW;
     const int ksteps = DP / 4;
@@ -330,14 +358,38 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       red_s[warp * 4 + 2] = d2;
     }
   }
+}
+
+// per-CTA partial of the three dots (fixed order over the warps); call after the block-wide barrier that follows g_rows
+__device__ __forceinline__ void g_cta_partial(const GSmem &m, double *partials) {
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int w = 0; w < kGConsumers; ++w) v += m.red_s[w * 4 + threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+}
+
+template <int KP, bool FULLK, bool CL = false>
+__global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
+  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
+  if (a.loop != nullptr) {
+    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
+    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
+  }
+  const GSmem m = g_carve(smem_raw, a.stages, KP, a.DP);
+  const GPtrs p = g_resolve(a, KP, crank, a.loop);
+  g_setup<KP, CL>(a, m, p);
+  if (CL) cluster_sync_all();  // every peer's mailbox barriers exist before the first remote arrive
+  else __syncthreads();
+  g_rows<KP, FULLK, CL>(a, m, p, cid, ncl, crank, csize);
   if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
   else __syncthreads();
   // deterministic two-level reduction: per-CTA partial, last CTA sums all partials in index order
-  if (threadIdx.x < 3) {
-    double v = 0.0;
-    for (int w = 0; w < kGConsumers; ++w) v += red_s[w * 4 + threadIdx.x];
-    a.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
-  }
+  g_cta_partial(m, a.partials);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -419,109 +471,112 @@ __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRo
 // wide mode: mailbox [softmax warps][2 parities][kMaxCl ranks][8 rows][max, sum, sum e*(x-max)] + 2 mbarriers per softmax warp
 __host__ __device__ inline int s_cl_doubles() { return kSSoftmaxWarps * 2 * kMaxCl * kGroupRows * 3 + 2 * kSSoftmaxWarps; }
 
-template <int KP, bool FULLK, bool CL = false>
-__global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs a) {
-  constexpr int NT = KP / 8;
-  constexpr int XG = kGroupRows * KP;
-  constexpr int TPW = NT * 8 / kSStatWarps;  // 8x8 tiles of T per statistics warp q: tile i -> (mt = i/2, dt = 4*(i%2) + q)
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages, DT = DP / 8;
-  const int stage_doubles = s_stage_doubles(KP, DP);
-  double *stages = reinterpret_cast<double *>(smem_raw);
-  double *red_s = stages + (size_t)S * stage_doubles;  // kSSoftmaxWarps
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(red_s + kSSoftmaxWarps);
-  uint64_t *phi_bar = full_bar + S;
-  uint64_t *empty_bar = phi_bar + S;
-  uint64_t *mb_bar = empty_bar + S;                                           // wide mode: [softmax warp][2]
-  double *sm_mb = reinterpret_cast<double *>(mb_bar + 2 * kSSoftmaxWarps);    // wide mode: [softmax warp][2][kMaxCl][8][3]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
-  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
-  const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);
-  const size_t coff = (size_t)crank * XG;
-
+// shared-memory carve of the S pass (dynamic shared memory; S ring stages)
+struct SSmem {
+  double *stages, *red_s, *sm_mb;
+  uint64_t *full_bar, *phi_bar, *empty_bar, *mb_bar;
+};
+__device__ __forceinline__ SSmem s_carve(unsigned char *smem_raw, int S, int KP, int DP) {
+  SSmem m;
+  m.stages = reinterpret_cast<double *>(smem_raw);
+  m.red_s = m.stages + (size_t)S * s_stage_doubles(KP, DP);  // kSSoftmaxWarps
+  m.full_bar = reinterpret_cast<uint64_t *>(m.red_s + kSSoftmaxWarps);
+  m.phi_bar = m.full_bar + S;
+  m.empty_bar = m.phi_bar + S;
+  m.mb_bar = m.empty_bar + S;                                             // wide mode: [softmax warp][2]
+  m.sm_mb = reinterpret_cast<double *>(m.mb_bar + 2 * kSSoftmaxWarps);    // wide mode: [softmax warp][2][kMaxCl][8][3]
+  return m;
+}
+template <bool CL>
+__device__ __forceinline__ void s_init_barriers(const SSmem &m, int S) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&phi_bar[s], 1);
-      mbar_init(&empty_bar[s], kSStatWarps);
+      mbar_init(&m.full_bar[s], 1);
+      mbar_init(&m.phi_bar[s], 1);
+      mbar_init(&m.empty_bar[s], kSStatWarps);
     }
     if (CL)
-      for (int s = 0; s < 2 * kSSoftmaxWarps; ++s) mbar_init(&mb_bar[s], 1);
+      for (int s = 0; s < 2 * kSSoftmaxWarps; ++s) mbar_init(&m.mb_bar[s], 1);
     mbar_fence_init();
   }
-  if (CL) cluster_sync_all();
-  else __syncthreads();
-
-  const double *p_x_base = a.x_base + coff, *p_ng = a.ng ? a.ng + coff : nullptr, *p_sd_old = a.sd_old ? a.sd_old + coff : nullptr;
-  double *p_sd_new = a.sd_new ? a.sd_new + coff : nullptr, *p_x_new = a.x_new ? a.x_new + coff : nullptr, *p_lse_new = a.lse_new;
-  double *p_beta_out = a.beta_out;
-  int beta_mode = a.beta_mode;
-  double sq_old = a.sq_old, step = a.step;
-  if (a.loop != nullptr) {
-    if (loop_skip(a.loop, a.phase)) return;
-    const int phase = loop_phase(a.loop, a.phase);
-    const int xi = a.loop->xi, xt = a.loop->xtrial, ngi = a.loop->ngi;
-    p_x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
-    p_x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt) + coff;
-    p_lse_new = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xt);
-    p_ng = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
-    p_sd_old = p_sd_new = a.bufs.sd + coff;
+}
+// operands and scalars of one S pass, resolved from the launch arguments or from the device-resident loop state
+struct SPtrs {
+  const double *x_base, *ng, *sd_old;
+  double *sd_new, *x_new, *lse_new, *beta_out;
+  double sq_old, step;
+  int beta_mode;
+};
+__device__ __forceinline__ SPtrs s_resolve(const StepStatsArgs &a, int KP, int crank, const gpc_loop_t *loop, int phase_arg) {
+  const size_t coff = (size_t)crank * (kGroupRows * KP);
+  SPtrs p;
+  p.x_base = a.x_base + coff;
+  p.ng = a.ng ? a.ng + coff : nullptr;
+  p.sd_old = a.sd_old ? a.sd_old + coff : nullptr;
+  p.sd_new = a.sd_new ? a.sd_new + coff : nullptr;
+  p.x_new = a.x_new ? a.x_new + coff : nullptr;
+  p.lse_new = a.lse_new;
+  p.beta_out = a.beta_out;
+  p.beta_mode = a.beta_mode;
+  p.sq_old = a.sq_old;
+  p.step = a.step;
+  if (loop != nullptr) {
+    const int phase = loop_phase(loop, phase_arg);
+    const int xi = loop->xi, xt = loop->xtrial, ngi = loop->ngi;
+    p.x_base = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xi) + coff;
+    p.x_new = sel3(a.bufs.x[0], a.bufs.x[1], a.bufs.x[2], xt) + coff;
+    p.lse_new = sel3(a.bufs.lse[0], a.bufs.lse[1], a.bufs.lse[2], xt);
+    p.ng = (ngi ? a.bufs.ng[1] : a.bufs.ng[0]) + coff;
+    p.sd_old = p.sd_new = a.bufs.sd + coff;
     // collapsed_vb.py:157-158 (first pass / steepest) and :182-184 (retry with searchDir = -natgrad)
-    beta_mode = (phase == GPC_PHASE_RETRY || a.loop->first != 0) ? GPC_BETA_ZERO : a.loop->method;
-    if (phase == GPC_PHASE_RETRY) p_beta_out = nullptr;  // the trace reports the conjugate beta
-    sq_old = a.loop->sq_old;
-    step = a.loop->step;
+    p.beta_mode = (phase == GPC_PHASE_RETRY || loop->first != 0) ? GPC_BETA_ZERO : loop->method;
+    if (phase == GPC_PHASE_RETRY) p.beta_out = nullptr;  // the trace reports the conjugate beta
+    p.sq_old = loop->sq_old;
+    p.step = loop->step;
   }
-  __shared__ double dots_sh[4];
-  // rows sharded over GPUs: the dots of the G pass arrive through the peer inbox.  Only the consumers need them (beta); the
-  // producer warp goes straight to filling the ring, so the exchange latency / rank skew hides behind the first HBM loads
-  const bool is_producer = (warp == kSSoftmaxWarps + kSStatWarps);
-  if (a.peers != nullptr && !is_producer) {
-    if (threadIdx.x == 0) {
-      const gpc_peers_t *P = a.peers;
-      const unsigned long long e = P->epochs[1];  // the G pass of this rank has pushed exchange e
-      const bool ok = xchg_wait(P, 1, (int)(e & 1), e);
-      double d[3] = {0.0, 0.0, 0.0};
-      for (int r = 0; r < P->world; ++r) {
-        const double *src = P->inbox[P->rank] + xchg_off_dots(P->world, P->stats_len, (int)(e & 1), r);
-        for (int q = 0; q < 3; ++q) d[q] += __ldcg(src + q);
-      }
-      for (int q = 0; q < 3; ++q) dots_sh[q] = ok ? d[q] : nan("");
-      // a peer that never shows up is a hard fault of the exchange, not a numerical outcome: sticky bit, the host raises
-      if (!ok && a.loop != nullptr) atomicOr(const_cast<int *>(&a.loop->done), GPC_DONE_PEER_TIMEOUT);
-      if (blockIdx.x == 0 && a.dots_sum)
-        for (int q = 0; q < 3; ++q) a.dots_sum[q] = dots_sh[q];
-    }
-    asm volatile("bar.sync 1, %0;\n" ::"n"((kSSoftmaxWarps + kSStatWarps) * 32) : "memory");
-  }
+  return p;
+}
+// beta of collapsed_vb.py:157-166 from the three dots
+__device__ __forceinline__ double cg_beta(int beta_mode, double sq, double num, double den, double sq_old) {
   double beta = 0.0;
-  if (beta_mode != GPC_BETA_ZERO && !(a.peers != nullptr && is_producer)) {
-    const double sq = a.peers ? dots_sh[0] : a.dots[0], num = a.peers ? dots_sh[1] : a.dots[1], den = a.peers ? dots_sh[2] : a.dots[2];
+  if (beta_mode != GPC_BETA_ZERO) {
     if (beta_mode == GPC_BETA_HS) beta = num / den;
     else if (beta_mode == GPC_BETA_PR) beta = num / sq_old;
     else beta = sq / sq_old;
     if (isnan(beta) || beta < 0.0) beta = 0.0;  // collapsed_vb.py:165-166
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p_beta_out) *p_beta_out = beta;
-  const bool has_ng = (p_ng != nullptr);
-  const bool use_old = has_ng && (beta != 0.0) && (p_sd_old != nullptr);
-  // what the producer stages: with the peer exchange it does not know beta, so the old search direction is staged whenever the
-  // step may use it (beta == 0 then simply leaves it unread)
-  const bool load_old = (a.peers != nullptr) ? (has_ng && beta_mode != GPC_BETA_ZERO && p_sd_old != nullptr) : use_old;
-  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
+  return beta;
+}
+// where this CTA's partial statistics go
+struct SPart {
+  double *t, *ph, *h;
+};
+template <int KP, bool CL>
+__device__ __forceinline__ SPart s_part(const StepStatsArgs &a, int cid, int crank, int csize) {
+  const int DP = a.DP;
   const bool chunked = (a.part_stride != 0);
   const int KPT = KP * csize;  // total padded cluster count
   double *part = CL ? a.partials + (size_t)cid * (size_t)(KPT * DP + KPT + 2)
                     : a.partials + (size_t)blockIdx.x * (chunked ? (size_t)a.part_stride : (size_t)(KP * DP + KP + 2));
-  double *part_t = part + (CL ? crank * KP * DP : (chunked ? a.t_off : 0));           // T rows of this chunk
-  double *part_ph = part + (CL ? KPT * DP + crank * KP : (chunked ? a.ph_off : KP * DP));  // phi_hat of this chunk
-  double *part_h = part + (CL ? KPT * DP + KPT : (chunked ? a.h_off : KP * DP + KP));      // H (+ pad)
+  SPart q;
+  q.t = part + (CL ? crank * KP * DP : (chunked ? a.t_off : 0));                  // T rows of this chunk
+  q.ph = part + (CL ? KPT * DP + crank * KP : (chunked ? a.ph_off : KP * DP));    // phi_hat of this chunk
+  q.h = part + (CL ? KPT * DP + KPT : (chunked ? a.h_off : KP * DP + KP));        // H (+ pad)
+  return q;
+}
 
-  if (warp == kSSoftmaxWarps + kSStatWarps) {
-    // ---------------- producer
+// ---------------- producer (one lane): bulk copies of [F | x | ng | sd] groups into the ring
+template <int KP>
+__device__ __forceinline__ void s_producer(const StepStatsArgs &a, const SSmem &m, const SPtrs &p, int cid, int ncl, bool has_ng, bool load_old) {
+  constexpr int XG = kGroupRows * KP;
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages;
+  const int stage_doubles = s_stage_doubles(KP, DP);
+  double *stages = m.stages;
+  uint64_t *full_bar = m.full_bar, *empty_bar = m.empty_bar;
+  const double *p_x_base = p.x_base, *p_ng = p.ng, *p_sd_old = p.sd_old;
+  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
+  const int lane = threadIdx.x & 31;
+  {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (load_old ? XG : 0)) * 8u;
       int j = 0;
@@ -536,7 +591,27 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
         if (load_old) bulk_g2s(st + FG + 2 * XG, p_sd_old + (size_t)grp * GS, XG * 8u, &full_bar[s]);
       }
     }
-  } else if (warp < kSSoftmaxWarps) {
+  }
+}
+
+// ---------------- softmax warps: CG step + softmax statistics of one group each; red_s[warp] <- entropy partial
+template <int KP, bool FULLK, bool CL>
+__device__ __forceinline__ void s_softmax(const StepStatsArgs &a, const SSmem &m, const SPtrs &p, int cid, int ncl, int crank, int csize, double beta,
+                                          bool has_ng, bool use_old) {
+  constexpr int NT = KP / 8;
+  constexpr int XG = kGroupRows * KP;
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages;
+  const int stage_doubles = s_stage_doubles(KP, DP);
+  double *stages = m.stages, *red_s = m.red_s, *sm_mb = m.sm_mb;
+  uint64_t *full_bar = m.full_bar, *phi_bar = m.phi_bar, *mb_bar = m.mb_bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Kc = FULLK ? KP : (CL ? min(KP, a.K - KP * crank) : a.K);
+  double *p_sd_new = p.sd_new, *p_x_new = p.x_new, *p_lse_new = p.lse_new;
+  const double step = p.step;
+  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
+  (void)csize;
+  {
     // ---------------- softmax warps: CG step + softmax statistics of one group each
     double Hpart = 0.0;
     int j = warp, iw = 0;
@@ -727,7 +802,22 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
     }
     Hpart = warp_sum(Hpart);
     if (lane == 0) red_s[warp] = Hpart;
-  } else {
+  }
+}
+
+// ---------------- statistics warps: T[k][d] += sum_rows phi[row][k] F[row][d] for every group of this CTA
+template <int KP, bool CL>
+__device__ __forceinline__ void s_stats(const StepStatsArgs &a, const SSmem &m, const SPart &part, int cid, int ncl) {
+  constexpr int NT = KP / 8;
+  constexpr int TPW = NT * 8 / kSStatWarps;  // 8x8 tiles of T per statistics warp q: tile i -> (mt = i/2, dt = 4*(i%2) + q)
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages, DT = DP / 8;
+  const int stage_doubles = s_stage_doubles(KP, DP);
+  double *stages = m.stages;
+  uint64_t *phi_bar = m.phi_bar, *empty_bar = m.empty_bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double *part_t = part.t, *part_ph = part.ph;
+  {
     // ---------------- statistics warps: T[k][d] += sum_rows phi[row][k] F[row][d] for every group of this CTA
     const int q = warp - kSSoftmaxWarps;
     double acc[TPW][2];
@@ -780,16 +870,73 @@ __global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs
       }
     }
   }
-  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
-  else __syncthreads();
+}
+// entropy partial of this CTA (+ the chunked-mode carry-in); call after the block-wide barrier that follows the role functions
+template <bool CL>
+__device__ __forceinline__ void s_cta_entropy(const StepStatsArgs &a, const SSmem &m, const SPart &part, int crank) {
+  const bool chunked = (a.part_stride != 0);
   if (threadIdx.x == 0 && (CL ? crank == 0 : (!chunked || a.write_h))) {
     double v = 0.0;
     if (a.lse_in == nullptr)
-      for (int w = 0; w < kSSoftmaxWarps; ++w) v += red_s[w];
+      for (int w = 0; w < kSSoftmaxWarps; ++w) v += m.red_s[w];
     if (a.h_in != nullptr) v += a.h_in[blockIdx.x];
-    part_h[0] = v;
-    part_h[1] = 0.0;
+    part.h[0] = v;
+    part.h[1] = 0.0;
   }
+}
+
+template <int KP, bool FULLK, bool CL = false>
+__global__ void __launch_bounds__(kSThreads, 1) k_step_stats(const StepStatsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
+  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
+  const SSmem m = s_carve(smem_raw, a.stages, KP, a.DP);
+  s_init_barriers<CL>(m, a.stages);
+  if (CL) cluster_sync_all();
+  else __syncthreads();
+
+  if (a.loop != nullptr && loop_skip(a.loop, a.phase)) return;
+  const SPtrs p = s_resolve(a, KP, crank, a.loop, a.phase);
+  __shared__ double dots_sh[4];
+  // rows sharded over GPUs: the dots of the G pass arrive through the peer inbox.  Only the consumers need them (beta); the
+  // producer warp goes straight to filling the ring, so the exchange latency / rank skew hides behind the first HBM loads
+  const bool is_producer = (warp == kSSoftmaxWarps + kSStatWarps);
+  if (a.peers != nullptr && !is_producer) {
+    if (threadIdx.x == 0) {
+      const gpc_peers_t *P = a.peers;
+      const unsigned long long e = P->epochs[1];  // the G pass of this rank has pushed exchange e
+      const bool ok = xchg_wait(P, 1, (int)(e & 1), e);
+      double d[3] = {0.0, 0.0, 0.0};
+      for (int r = 0; r < P->world; ++r) {
+        const double *src = P->inbox[P->rank] + xchg_off_dots(P->world, P->stats_len, (int)(e & 1), r);
+        for (int q = 0; q < 3; ++q) d[q] += __ldcg(src + q);
+      }
+      for (int q = 0; q < 3; ++q) dots_sh[q] = ok ? d[q] : nan("");
+      // a peer that never shows up is a hard fault of the exchange, not a numerical outcome: sticky bit, the host raises
+      if (!ok && a.loop != nullptr) atomicOr(const_cast<int *>(&a.loop->done), GPC_DONE_PEER_TIMEOUT);
+      if (blockIdx.x == 0 && a.dots_sum)
+        for (int q = 0; q < 3; ++q) a.dots_sum[q] = dots_sh[q];
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"((kSSoftmaxWarps + kSStatWarps) * 32) : "memory");
+  }
+  double beta = 0.0;
+  if (p.beta_mode != GPC_BETA_ZERO && !(a.peers != nullptr && is_producer))
+    beta = a.peers ? cg_beta(p.beta_mode, dots_sh[0], dots_sh[1], dots_sh[2], p.sq_old) : cg_beta(p.beta_mode, a.dots[0], a.dots[1], a.dots[2], p.sq_old);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.beta_out) *p.beta_out = beta;
+  const bool has_ng = (p.ng != nullptr);
+  const bool use_old = has_ng && (beta != 0.0) && (p.sd_old != nullptr);
+  // what the producer stages: with the peer exchange it does not know beta, so the old search direction is staged whenever the
+  // step may use it (beta == 0 then simply leaves it unread)
+  const bool load_old = (a.peers != nullptr) ? (has_ng && p.beta_mode != GPC_BETA_ZERO && p.sd_old != nullptr) : use_old;
+  const SPart part = s_part<KP, CL>(a, cid, crank, csize);
+
+  if (is_producer) s_producer<KP>(a, m, p, cid, ncl, has_ng, load_old);
+  else if (warp < kSSoftmaxWarps) s_softmax<KP, FULLK, CL>(a, m, p, cid, ncl, crank, csize, beta, has_ng, use_old);
+  else s_stats<KP, CL>(a, m, part, cid, ncl);
+  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
+  else __syncthreads();
+  s_cta_entropy<CL>(a, m, part, crank);
 }
 
 // out[j] = sum over CTAs of partials[c][j], fixed order (deterministic).  Block = 32 columns x 8 part-groups:

@@ -100,7 +100,7 @@ class RowShards(object):
             import torch
             import torch.distributed._symmetric_memory as symm
             group = self.group if self.group is not None else self.dist.group.WORLD
-            n = int(_cabi.lib.gpc_xchg_doubles(self.world, int(stats_len)))
+            n = int(_cabi.lib.gpc_xchg_doubles_fused(self.world, int(stats_len)))  # serves both exchange layouts (fused loop kernel / launch sequence)
             buf = symm.empty(n, dtype=torch.float64, device=device)
             hdl = symm.rendezvous(buf, group)
             buf.zero_()

@@ -167,6 +167,28 @@ int gpc_loop_step_stats_px(const double *F, const gpc_bufs_t *bufs, double *dots
 int gpc_reduce_push(const double *partials, int num_parts, int len, const gpc_peers_t *peers, unsigned int *counter, const gpc_loop_t *loop,
                     int phase, void *stream);
 
+/* ---- the whole loop as ONE persistent cooperative launch (MOHGP, K <= 64) ------------------------------------------------
+ * Replaces the per-evaluation launch sequence gpc_loop_natgrad_px -> gpc_loop_step_stats_px -> gpc_reduce_push -> gpc_loop_mohgp_post_px
+ * of collapsed_vb.py:147-303 + MOHGP.py:70-153: one launch runs up to `max_evals` bound evaluations (or until the device-side
+ * termination tests of gpc_loop_t fire); the phases are separated by grid-wide barriers instead of kernel boundaries, the statistics
+ * are reduced per cluster by the CTA that computes that cluster's posterior, and with rows sharded over GPUs each cluster's row goes
+ * straight into every peer's inbox with its own flag.  Arguments as for the entry points it replaces.
+ *   grid      = gpc_default_grid(device) (one CTA per SM, all co-resident: cooperative launch); must be >= KP
+ *   gpart     grid*4 doubles, spart grid*gpc_stats_len(KP,DP) doubles
+ *   dots/beta device scalars [3] / [1] (read back by the host with the control block)
+ *   sync      4 zero-initialised unsigned ints (the kernel leaves them zero)
+ *   timing    nullable: 6 unsigned 64-bit accumulators -- ns in G rows / dots barrier + exchange / S rows / posterior incl. barriers,
+ *             evaluations, G phases (measured by CTA 0 with %globaltimer)
+ *   peers     NULL on one GPU; otherwise the inbox must hold gpc_xchg_doubles_fused(world, stats_len) doubles:
+ *             [2][W][L] statistics | [2][W][4] dots | [2][W][64] statistics flags (sender, cluster) | [2][W] dots flags
+ * A peer that never arrives sets GPC_DONE_PEER_TIMEOUT in loop->done (bounded waits, 4 s).                                      */
+long long gpc_xchg_doubles_fused(int world, int stats_len);
+int gpc_mohgp_loop(const double *F, const gpc_bufs_t *bufs, double *Wt, double *bias, double *gpart, double *spart, double *dots, double *beta,
+                   double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf, const double *const_term, double *muk_t,
+                   double *Syi_ybark_t, double *per_k, double *scalars, double *mixgrad_out, int *info, double alpha, int prior, gpc_loop_t *loop,
+                   const gpc_peers_t *peers, unsigned int *sync, unsigned long long *timing, int max_evals, long long N, int K, int D, int KP,
+                   int DP, int grid, void *stream);
+
 /* ---- K > 64: the clusters are processed in chunks of 64 (one launch of the tensor kernels per chunk) ----------
  * N x K arrays keep the fragment-major layout with KP/8 n-tiles per 8-row group (xg_stride = 8*KP doubles between
  * groups); a chunk's slice starts 512*c doubles into the group.  Pointers named x / a_out / Wt / bias are PRE-OFFSET to
