@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -78,12 +79,14 @@ int launch_vb(Kern kern, const Args &a, size_t smem, int grid, int threads, cuda
 template <int KP>
 int launch_natgrad(NatgradArgs &a, int grid, cudaStream_t st) {
   a.stages = natgrad_stages(KP, a.DP);
-  const size_t smem = natgrad_smem(KP, a.DP, a.stages);
+  size_t smem = natgrad_smem(KP, a.DP, a.stages);
+  if (const char *e = getenv("GPC_DEBUG_G_SMEM")) smem = (size_t)atoi(e);  // experiment: L1 carve-out sensitivity of the G pass
   return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, kGThreads, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, kGThreads, st);
 }
 template <int KP>
 int launch_step_stats(StepStatsArgs &a, int grid, cudaStream_t st) {
   a.stages = step_stats_stages(KP, a.DP);
+  if (const char *e = getenv("GPC_DEBUG_S_STAGES")) a.stages = atoi(e);  // experiment: ring depth / L1 carve-out of the S pass
   const size_t smem = step_stats_smem(KP, a.DP, a.stages);
   return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, kSThreads, st)
                    : launch_vb(k_step_stats<KP, false>, a, smem, grid, kSThreads, st);
@@ -1017,13 +1020,19 @@ int gpc_cg_axpy(const double *x, const double *ng, const double *sd_old, double 
 
 // ---- the whole conjugate natural-gradient loop of MOHGP as one persistent cooperative kernel (gpc_loop_kernel.cuh)
 namespace {
+constexpr size_t kLoopRingBudget = 180000;
 struct LoopGeom {
   int g_stages, s_stages;
   size_t smem;
 };
 LoopGeom loop_geometry(int KP, int DP, int D) {
   LoopGeom q;
-  const size_t budget = (size_t)kSmemBudget - kLoopHeaderBytes;
+  // Shared memory deliberately NOT maxed out: the G rows read the previous-point operands and write the natural gradient through
+  // L1, and the carve-out is per launch -- with the 228 KB configuration (what a full-depth S ring would ask for) the G phase
+  // loses 8 % (measured: 580 vs 539 us at 1M rows), while the S ring is insensitive to its depth from 8 stages up.  180 KB of rings
+  // (+ header) selects the 196 KB configuration: two ring slots per G unit, ten S stages.
+  size_t budget = kLoopRingBudget;
+  if (const char *e = getenv("GPC_DEBUG_LOOP_BUDGET")) budget = (size_t)atoi(e);  // experiments (tools/scratch)
   {
     const int units = kGConsumers / ((KP / 8 >= 2) ? 2 : 1);
     const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;

@@ -29,7 +29,7 @@
 
 namespace gpc {
 
-constexpr int kLoopHeaderBytes = 512;  // loop-state snapshot + scalars at the start of dynamic shared memory
+constexpr int kLoopHeaderBytes = 1024;  // loop-state snapshot + scalars at the start of dynamic shared memory
 constexpr long long kSpinLimitNs = 4000000000LL;  // bounded waits (grid barrier, peer flags): 4 s
 
 // ---- inbox layout of the fused exchange (doubles / u64 words), W ranks, statistics length L (even), up to 64 clusters
@@ -54,38 +54,48 @@ struct LoopKernelArgs {
   int max_evals;
 };
 
-struct LoopShared {  // header of dynamic shared memory (long-lived scalars live here, not in registers of the row loops)
+struct LoopShared {  // header of dynamic shared memory: everything that lives across phases is here, not in registers of the row loops
   gpc_loop_t L;      // snapshot of the device loop state, taken once per evaluation through L2
+  MohgpPostArgs p;   // posterior arguments (copied from the kernel parameters once: the out-of-line phases read them from here)
+  const gpc_peers_t *peers;
+  double *inbox_self;
+  unsigned int *sync;
+  unsigned long long *timing;
+  const double *gpart, *spart;
+  double *dots_out;
   double dots[4];
   unsigned long long e_stats, e_dots;  // exchange epochs (uniform over the grid)
   unsigned long long t_acc[4], n_eval, n_g, t[4];
   unsigned int bar_target;
-  int abort;
+  int abort, W, my_rank, len;
+  int ev, max_evals, retry, g_stages, s_stages, KP, DP;
+  const gpc_loop_t *loop_g;  // the loop state in global memory
+  double *spart_mine;        // this CTA's block of partial statistics
 };
 static_assert(sizeof(LoopShared) <= kLoopHeaderBytes, "loop header");
 
-// Grid-wide barrier among all CTAs of the (cooperative) launch.  `nthreads` threads of this CTA take part (named barrier `bar_id`;
-// 0 = the whole CTA).  Monotone counter; `*target_s` (shared memory, thread 0) is the value the counter reaches when everybody arrived.
+// Grid-wide barrier among all CTAs of the (cooperative) launch.  NTHREADS threads of this CTA take part (named barrier BAR_ID;
+// 0 = the whole CTA).  Monotone counter; hs.bar_target (thread 0) is the value the counter reaches when everybody arrived.
 // Returns false when the wait ran into the spin limit (a CTA of this grid is stuck in a peer wait that timed out elsewhere).
 template <int BAR_ID, int NTHREADS>
-__device__ __forceinline__ bool grid_barrier(unsigned int *ctr, unsigned int *target_s, int *abort_s) {
+__device__ __forceinline__ bool grid_barrier(LoopShared &hs) {
   asm volatile("bar.sync %0, %1;\n" ::"n"(BAR_ID), "n"(NTHREADS) : "memory");
-  if (threadIdx.x == 0 && *abort_s == 0) {  // once a wait of this CTA has timed out no further barrier spins: the loop is being left
-    const unsigned int target = *target_s + gridDim.x;
-    *target_s = target;
+  if (threadIdx.x == 0 && hs.abort == 0) {  // once a wait of this CTA has timed out no further barrier spins: the loop is being left
+    const unsigned int target = hs.bar_target + gridDim.x;
+    hs.bar_target = target;
     __threadfence();
-    red_release_gpu_add_u32(ctr, 1u);
+    red_release_gpu_add_u32(hs.sync, 1u);
     const unsigned long long t0 = globaltimer_ns();
     int spins = 0;
-    while ((int)(ld_acquire_gpu_u32(ctr) - target) < 0) {
+    while ((int)(ld_acquire_gpu_u32(hs.sync) - target) < 0) {
       if (((++spins) & 1023) == 0 && (long long)(globaltimer_ns() - t0) > kSpinLimitNs) {
-        *abort_s = 1;
+        hs.abort = 1;
         break;
       }
     }
   }
   asm volatile("bar.sync %0, %1;\n" ::"n"(BAR_ID), "n"(NTHREADS) : "memory");
-  return *reinterpret_cast<volatile int *>(abort_s) == 0;
+  return *reinterpret_cast<volatile int *>(&hs.abort) == 0;
 }
 
 // one thread: wait until the u64 word at `flag` (this rank's own inbox) has reached `epoch`; bounded
@@ -98,23 +108,267 @@ __device__ __forceinline__ bool flag_wait(const unsigned long long *flag, unsign
   return true;
 }
 
+constexpr int kRowThreads = (kSSoftmaxWarps + kSStatWarps) * 32;  // the S phase's consumers (everything but the producer warp)
+
+// The phases between the row loops are OUT OF LINE (their own register allocation, arguments through the shared-memory header):
+// the row loops run at the register limit of the CTA shape (168) and must not share it with anything that lives across phases.
+
+// B1 + the three dots (collapsed_vb.py:154,160-164), run by the S phase's consumer warps.  On return hs.dots holds the dots summed
+// over CTAs (and ranks, in rank order); CTA 0 has stored them for the host.
+__device__ __noinline__ void loop_dots_phase(LoopShared &hs) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cid = (int)blockIdx.x, ncl = (int)gridDim.x;
+  grid_barrier<3, kRowThreads>(hs);  // every CTA's partial dots are in L2 (a timed-out wait sets hs.abort; the loop ends at B2)
+  const gpc_peers_t *P = hs.peers;
+  if (P == nullptr) {
+    if (warp < 3) {
+      double v = 0.0;
+      for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
+      v = warp_sum(v);  // fixed lane -> CTA assignment and fixed shuffle tree: identical on every CTA, run to run
+      if (lane == 0) {
+        hs.dots[warp] = v;
+        if (cid == 0) hs.dots_out[warp] = v;
+      }
+    }
+  } else {
+    const int W = hs.W, my_rank = hs.my_rank, len = hs.len;
+    const unsigned long long e_dots = hs.e_dots + 1;  // uniform; thread 0 stores it back after the last barrier below
+    const int slot = (int)(e_dots & 1);
+    if (cid == 0) {
+      if (warp < 3) {
+        double v = 0.0;
+        for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
+        v = warp_sum(v);
+        if (lane < W) P->inbox[lane][fx_off_dots(W, len, slot, my_rank) + warp] = v;  // lane r -> peer r, over NVLink
+      }
+      asm volatile("bar.sync 3, %0;\n" ::"n"(kRowThreads) : "memory");
+      if (warp == 0) {
+        __threadfence_system();
+        if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_dflag(W, len, slot, my_rank), e_dots);
+      }
+    }
+    if (warp == 0) {
+      bool ok = true;
+      if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_dflag(W, len, slot, lane), e_dots);
+      ok = __all_sync(0xffffffffu, ok);
+      if (lane < 3) {
+        double d = 0.0;
+        for (int r = 0; r < W; ++r) d += __ldcg(hs.inbox_self + fx_off_dots(W, len, slot, r) + lane);  // rank order: identical on all ranks
+        hs.dots[lane] = ok ? d : nan("");
+        if (cid == 0) hs.dots_out[lane] = hs.dots[lane];
+      }
+      if (!ok && lane == 0) atomicOr(&hs.p.loop->done, GPC_DONE_PEER_TIMEOUT);
+    }
+  }
+  asm volatile("bar.sync 3, %0;\n" ::"n"(kRowThreads) : "memory");
+  if (P != nullptr && tid == 0) hs.e_dots += 1;  // every consumer has read the old value before the barrier above
+  if (hs.timing != nullptr && cid == 0 && tid == 0) hs.t[2] = globaltimer_ns();
+}
+
+// B2, the per-cluster posterior (CTA k < KP, first kClusterThreads threads), the decision, B3.  Returns false when a barrier wait
+// timed out.  smem_raw: the (now idle) ring memory.
+__device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem_raw, int phase) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cid = (int)blockIdx.x, ncl = (int)gridDim.x;
+  if (!grid_barrier<0, kGThreads>(hs)) return false;
+  const MohgpPostArgs &pa = hs.p;
+  const int KP = pa.KP, DP = pa.DP, D = pa.D, len = hs.len;
+  const gpc_peers_t *P = hs.peers;
+  const unsigned long long e_stats = hs.e_stats + 1;  // read by every thread here; thread 0 stores it back after B3
+  if (cid < KP && tid < kClusterThreads) {
+    const int k = cid;
+    double *ws_s = reinterpret_cast<double *>(smem_raw);
+    PostSmem &ps = *reinterpret_cast<PostSmem *>(smem_raw + (((size_t)eig_ws_len(D) * 8 + 127) & ~(size_t)127));
+    if (tid == 0) post_stage_ws(pa.ws, D, ps, ws_s);
+    double phi_hat = post_reduce_row<true>(hs.spart, ncl, len, k, KP, DP, ps);
+    const double *hparts = hs.spart;
+    int hnum = ncl;
+    if (P != nullptr) {
+      const int W = hs.W, my_rank = hs.my_rank;
+      const int slot = (int)(e_stats & 1);
+      // this rank's row of cluster k (+ its entropy, with cluster 0) -> every peer's inbox; one flag per (sender, cluster)
+      double Hloc = 0.0;
+      if (k == 0) {
+        for (int c = tid; c < ncl; c += kClusterThreads) Hloc += __ldcg(hs.spart + (size_t)c * len + (size_t)KP * DP + KP);
+        Hloc = block_sum<true>(Hloc, ps.red_s);
+      }
+      const long long base = fx_off_stats(W, len, slot, my_rank);
+      for (int r = 0; r < W; ++r) {
+        double *dst = P->inbox[r] + base;
+        if (tid < DP) dst[(size_t)k * DP + tid] = ps.yb_s[tid];
+        if (tid == 64) dst[(size_t)KP * DP + k] = phi_hat;
+        if (tid == 65 && k == 0) dst[(size_t)KP * DP + KP] = Hloc;
+      }
+      psync<true>();
+      if (warp == 0) {
+        __threadfence_system();
+        if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_sflag(W, len, slot, my_rank, k), e_stats);
+        bool ok = true;
+        if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_sflag(W, len, slot, lane, k), e_stats);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok && lane == 0) {
+          atomicOr(pa.info, GPC_INFO_PEER_TIMEOUT);
+          atomicOr(&pa.loop->done, GPC_DONE_PEER_TIMEOUT);
+        }
+      }
+      psync<true>();
+      hparts = hs.inbox_self + fx_off_stats(W, len, slot, 0);
+      hnum = W;
+      phi_hat = post_reduce_row<true>(hparts, W, len, k, KP, DP, ps);  // sum over the ranks, in rank order
+    }
+    if (tid < DP) pa.stats[(size_t)k * DP + tid] = ps.yb_s[tid];
+    if (tid == 0) pa.stats[(size_t)KP * DP + k] = phi_hat;
+    mbar_wait(&ps.stage_bar, 0);
+    post_cluster_math<true>(pa, k, phi_hat, ps, ws_s);
+    __threadfence();
+    psync<true>();
+    if (tid == 0) {
+      const unsigned int done = atomicAdd(pa.counter, 1u);
+      ps.is_last = (done == (unsigned)KP - 1) ? 1 : 0;
+      mbar_inval(&ps.stage_bar);
+    }
+    psync<true>();
+    if (ps.is_last) {
+      __threadfence();
+      if (P != nullptr && warp == 0) {
+        // the entropies travel with cluster 0's rows: make sure this CTA has observed those flags itself
+        const int slot = (int)(e_stats & 1);
+        if (lane < hs.W) flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_sflag(hs.W, len, slot, lane, 0), e_stats);
+      }
+      psync<true>();
+      post_tail<true>(pa, ps, hparts, hnum, len, phase);  // resets the ticket (pa.counter)
+      __threadfence();
+    }
+  }
+  // B3: the decision and the new weights are visible to every CTA
+  if (!grid_barrier<0, kGThreads>(hs)) return false;
+  if (tid == 0) {
+    hs.e_stats = e_stats;
+    if (hs.timing != nullptr && cid == 0) {
+      const unsigned long long t4 = globaltimer_ns();
+      hs.t_acc[0] += hs.t[1] - hs.t[0];
+      hs.t_acc[1] += hs.t[2] - hs.t[1];
+      hs.t_acc[2] += hs.t[3] - hs.t[2];
+      hs.t_acc[3] += t4 - hs.t[3];
+      hs.n_eval += 1;
+      hs.n_g += (phase == GPC_PHASE_RETRY) ? 0 : 1;
+    }
+  }
+  return true;
+}
+
+#ifndef GPC_LOOP_G_NOINLINE
+#define GPC_LOOP_G_NOINLINE 0
+#endif
+#ifndef GPC_LOOP_S_NOINLINE
+#define GPC_LOOP_S_NOINLINE 0
+#endif
+#if GPC_LOOP_G_NOINLINE
+#define GPC_G_ATTR __noinline__
+#else
+#define GPC_G_ATTR __forceinline__
+#endif
+#if GPC_LOOP_S_NOINLINE
+#define GPC_S_ATTR __noinline__
+#else
+#define GPC_S_ATTR __forceinline__
+#endif
+// the row phases as callable units (kernel parameters are __grid_constant__: their address can be passed on without a local copy)
 template <int KP, bool FULLK>
-__global__ void __launch_bounds__(kGThreads, 1) k_mohgp_loop(const LoopKernelArgs a) {
+__device__ GPC_G_ATTR void loop_g_phase(const NatgradArgs &ga, LoopShared &hs, unsigned char *smem_raw) {
+  const GSmem gm = g_carve(smem_raw, ga.stages, KP, ga.DP);
+  const GPtrs gp = g_resolve(ga, KP, 0, &hs.L);
+  g_setup<KP, false>(ga, gm, gp);
+  __syncthreads();
+  g_rows<KP, FULLK, false>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x, 0, 1);
+  fence_proxy_async();  // this CTA's natural gradient is staged by its own bulk copies in the S phase
+  __syncthreads();
+}
+template <int KP, bool FULLK>
+__device__ GPC_S_ATTR void loop_s_softmax(const StepStatsArgs &sa, LoopShared &hs, unsigned char *smem_raw, double beta) {
+  const SSmem sm = s_carve(smem_raw, sa.stages, KP, sa.DP);
+  const SPtrs sp = s_resolve(sa, KP, 0, &hs.L, hs.retry ? GPC_PHASE_RETRY : GPC_PHASE_CONJ);
+  s_softmax<KP, FULLK, false>(sa, sm, sp, (int)blockIdx.x, (int)gridDim.x, 0, 1, beta, true, beta != 0.0);
+}
+template <int KP>
+__device__ GPC_S_ATTR void loop_s_stats(const StepStatsArgs &sa, unsigned char *smem_raw) {
+  const SSmem sm = s_carve(smem_raw, sa.stages, KP, sa.DP);
+  s_stats<KP, false>(sa, sm, s_part<KP, false>(sa, (int)blockIdx.x, 0, 1), (int)blockIdx.x, (int)gridDim.x);
+}
+
+// start of an evaluation: snapshot of the loop state through L2; false when the loop is over (terminated, or the launch's budget used)
+__device__ __noinline__ bool loop_begin_eval(LoopShared &hs) {
+  __syncthreads();
+  if (threadIdx.x < (int)(sizeof(gpc_loop_t) / 4))
+    reinterpret_cast<int *>(&hs.L)[threadIdx.x] = __ldcg(reinterpret_cast<const int *>(hs.loop_g) + threadIdx.x);
+  __syncthreads();
+  const bool go = hs.L.done == 0 && hs.ev < hs.max_evals;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    hs.ev += 1;
+    hs.retry = hs.L.need_retry != 0;
+    if (hs.timing != nullptr && blockIdx.x == 0) hs.t[0] = hs.t[1] = hs.t[2] = hs.t[3] = globaltimer_ns();
+  }
+  __syncthreads();
+  return go;
+}
+// end of the G rows: per-CTA partial dots, ring barriers invalidated (the memory is re-carved by the S phase)
+__device__ __noinline__ void loop_after_g(LoopShared &hs, unsigned char *smem_raw) {
+  const GSmem gm = g_carve(smem_raw, hs.g_stages, hs.KP, hs.DP);
+  g_cta_partial(gm, const_cast<double *>(hs.gpart));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < hs.g_stages; ++s) mbar_inval(&gm.full_bar[s]);
+    if (hs.timing != nullptr && blockIdx.x == 0) hs.t[1] = hs.t[2] = globaltimer_ns();
+  }
+}
+// end of the S rows: entropy partial of this CTA, ring barriers invalidated
+__device__ __noinline__ void loop_after_s(LoopShared &hs, unsigned char *smem_raw) {
+  const SSmem sm = s_carve(smem_raw, hs.s_stages, hs.KP, hs.DP);
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < kSSoftmaxWarps; ++w) v += sm.red_s[w];
+    double *h = hs.spart_mine + (size_t)hs.KP * hs.DP + hs.KP;
+    h[0] = v;
+    h[1] = 0.0;
+    for (int s = 0; s < hs.s_stages; ++s) {
+      mbar_inval(&sm.full_bar[s]);
+      mbar_inval(&sm.phi_bar[s]);
+      mbar_inval(&sm.empty_bar[s]);
+    }
+    if (hs.timing != nullptr && blockIdx.x == 0) hs.t[3] = globaltimer_ns();
+  }
+}
+
+template <int KP, bool FULLK>
+__global__ void __launch_bounds__(kGThreads, 1) k_mohgp_loop(const __grid_constant__ LoopKernelArgs a) {
   static_assert(kGThreads == kSThreads, "both row phases use the same CTA shape");
   extern __shared__ __align__(128) unsigned char smem_all[];
   LoopShared &hs = *reinterpret_cast<LoopShared *>(smem_all);
   unsigned char *smem_raw = smem_all + kLoopHeaderBytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cid = (int)blockIdx.x, ncl = (int)gridDim.x;
-  const int DP = a.g.DP, D = a.p.D;
-  const int len = KP * DP + KP + 2;
-  constexpr int kRowThreads = (kSSoftmaxWarps + kSStatWarps) * 32;  // the S phase's consumers (everything but the producer warp)
-  const bool is_producer = (warp == kSSoftmaxWarps + kSStatWarps);
-  const gpc_peers_t *P = a.peers;
-  const int W = P ? P->world : 1, my_rank = P ? P->rank : 0;
-  double *inbox_self = P ? P->inbox[my_rank] : nullptr;
-  const bool timekeeper = (a.timing != nullptr) && cid == 0 && tid == 0;
-  if (tid == 0) {
+  const NatgradArgs &ga = a.g;
+  const StepStatsArgs &sa = a.s;
+  if (threadIdx.x == 0) {
+    const gpc_peers_t *P = a.peers;
+    hs.p = a.p;
+    hs.peers = P;
+    hs.W = P ? P->world : 1;
+    hs.my_rank = P ? P->rank : 0;
+    hs.inbox_self = P ? P->inbox[P->rank] : nullptr;
+    hs.sync = a.sync;
+    hs.timing = a.timing;
+    hs.gpart = ga.partials;
+    hs.spart = sa.partials;
+    hs.dots_out = ga.dots_out;
+    hs.len = KP * ga.DP + KP + 2;
+    hs.ev = 0;
+    hs.max_evals = a.max_evals;
+    hs.retry = 0;
+    hs.g_stages = ga.stages;
+    hs.s_stages = sa.stages;
+    hs.KP = KP;
+    hs.DP = ga.DP;
+    hs.loop_g = a.p.loop;
+    hs.spart_mine = sa.partials + (size_t)blockIdx.x * (size_t)(KP * ga.DP + KP + 2);
     hs.abort = 0;
     hs.bar_target = 0u;
     hs.e_stats = P ? __ldcg(P->epochs + 0) : 0ull;
@@ -123,204 +377,52 @@ __global__ void __launch_bounds__(kGThreads, 1) k_mohgp_loop(const LoopKernelArg
     hs.n_eval = hs.n_g = 0ull;
   }
 
-  const NatgradArgs &ga = a.g;
-  const StepStatsArgs &sa = a.s;
-
-  for (int ev = 0; ev < a.max_evals; ++ev) {
-    // ---- loop state of this evaluation (written by the previous evaluation's decision, or by the host), through L2
-    __syncthreads();
-    if (tid < (int)(sizeof(gpc_loop_t) / 4)) reinterpret_cast<int *>(&hs.L)[tid] = __ldcg(reinterpret_cast<const int *>(a.p.loop) + tid);
-    __syncthreads();
-    if (hs.L.done != 0) break;
-    const bool retry = (hs.L.need_retry != 0);
-    const int phase = retry ? GPC_PHASE_RETRY : GPC_PHASE_CONJ;
-    if (timekeeper) hs.t[0] = hs.t[1] = hs.t[2] = hs.t[3] = globaltimer_ns();
-
-    // ------------------------------------------------------------------ G rows
-    if (!retry) {
-      const GSmem gm = g_carve(smem_raw, ga.stages, KP, DP);
-      const GPtrs gp = g_resolve(ga, KP, 0, &hs.L);
-      g_setup<KP, false>(ga, gm, gp);
-      __syncthreads();
-      g_rows<KP, FULLK, false>(ga, gm, gp, cid, ncl, 0, 1);
-      fence_proxy_async();  // this CTA's natural gradient is staged by its own bulk copies in the S phase
-      __syncthreads();
-      g_cta_partial(gm, ga.partials);
-      if (tid == 0)
-        for (int s = 0; s < ga.stages; ++s) mbar_inval(&gm.full_bar[s]);  // the ring memory is re-carved below
-      if (timekeeper) hs.t[1] = hs.t[2] = globaltimer_ns();
+  while (loop_begin_eval(hs)) {
+    // ------------------------------------------------------------------ G rows (skipped in a retry slot: same point, same gradient)
+    if (!hs.retry) {
+      loop_g_phase<KP, FULLK>(ga, hs, smem_raw);
+      loop_after_g(hs, smem_raw);
     }
 
     // ------------------------------------------------------------------ S rows (the producer runs ahead of B1)
-    const SSmem sm = s_carve(smem_raw, sa.stages, KP, DP);
-    const SPtrs sp = s_resolve(sa, KP, 0, &hs.L, phase);  // slot mode: the phase follows need_retry of the snapshot
-    const SPart part = s_part<KP, false>(sa, cid, 0, 1);
-    __syncthreads();  // every warp is done with the G phase's shared memory (and thread 0 with the invalidation)
-    s_init_barriers<false>(sm, sa.stages);
-    __syncthreads();
-    const bool has_ng = true;
-    const bool load_old = (sp.beta_mode != GPC_BETA_ZERO);  // beta is not known yet: stage the old search direction whenever it may be used
-    if (is_producer) {
-      s_producer<KP>(sa, sm, sp, cid, ncl, has_ng, load_old);
-    } else {
-      double beta = 0.0;
-      if (!retry) {
-        // B1 among the consumer warps: every CTA's partial dots are in L2
-        if (!grid_barrier<3, kRowThreads>(a.sync, &hs.bar_target, &hs.abort)) {
-          // fall through to the block barrier below with abort set; the loop ends there
+    {
+      const SSmem sm = s_carve(smem_raw, sa.stages, KP, sa.DP);
+      const SPtrs sp = s_resolve(sa, KP, 0, &hs.L, hs.retry ? GPC_PHASE_RETRY : GPC_PHASE_CONJ);  // slot mode: the phase follows need_retry
+      __syncthreads();  // every warp is done with the G phase's shared memory (and thread 0 with the invalidation)
+      s_init_barriers<false>(sm, sa.stages);
+      __syncthreads();
+      const int warp = threadIdx.x >> 5;
+      if (warp == kSSoftmaxWarps + kSStatWarps) {
+        // beta is not known yet: the old search direction is staged whenever the step may use it
+        s_producer<KP>(sa, sm, sp, (int)blockIdx.x, (int)gridDim.x, true, sp.beta_mode != GPC_BETA_ZERO);
+      } else {
+        double beta = 0.0;
+        if (!hs.retry) {
+          loop_dots_phase(hs);
+          beta = cg_beta(sp.beta_mode, hs.dots[0], hs.dots[1], hs.dots[2], sp.sq_old);
+          if (blockIdx.x == 0 && threadIdx.x == 0 && sp.beta_out) *sp.beta_out = beta;
         }
-        if (P == nullptr) {
-          if (warp < 3) {
-            double v = 0.0;
-            for (int c = lane; c < ncl; c += 32) v += __ldcg(ga.partials + (size_t)c * 4 + warp);
-            v = warp_sum(v);  // fixed lane -> CTA assignment and fixed shuffle tree: identical on every CTA, run to run
-            if (lane == 0) {
-              hs.dots[warp] = v;
-              if (cid == 0) ga.dots_out[warp] = v;
-            }
-          }
-        } else {
-          const unsigned long long e_dots = hs.e_dots + 1;  // uniform: thread 0 stores it back after the barrier below
-          const int slot = (int)(e_dots & 1);
-          if (cid == 0) {
-            if (warp < 3) {
-              double v = 0.0;
-              for (int c = lane; c < ncl; c += 32) v += __ldcg(ga.partials + (size_t)c * 4 + warp);
-              v = warp_sum(v);
-              if (lane < W) P->inbox[lane][fx_off_dots(W, len, slot, my_rank) + warp] = v;  // lane r -> peer r, over NVLink
-            }
-            asm volatile("bar.sync 3, %0;\n" ::"n"(kRowThreads) : "memory");
-            if (warp == 0) {
-              __threadfence_system();
-              if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_dflag(W, len, slot, my_rank), e_dots);
-            }
-          }
-          if (warp == 0) {
-            bool ok = true;
-            if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(inbox_self) + fx_off_dflag(W, len, slot, lane), e_dots);
-            ok = __all_sync(0xffffffffu, ok);
-            if (lane < 3) {
-              double d = 0.0;
-              for (int r = 0; r < W; ++r) d += __ldcg(inbox_self + fx_off_dots(W, len, slot, r) + lane);  // rank order: identical on all ranks
-              hs.dots[lane] = ok ? d : nan("");
-              if (cid == 0) ga.dots_out[lane] = hs.dots[lane];
-            }
-            if (!ok && lane == 0) atomicOr(&a.p.loop->done, GPC_DONE_PEER_TIMEOUT);
-          }
-        }
-        asm volatile("bar.sync 3, %0;\n" ::"n"(kRowThreads) : "memory");
-        if (P != nullptr && tid == 0) hs.e_dots += 1;  // every consumer has read the old value before the barrier above
-        beta = cg_beta(sp.beta_mode, hs.dots[0], hs.dots[1], hs.dots[2], sp.sq_old);
-        if (cid == 0 && tid == 0 && sp.beta_out) *sp.beta_out = beta;
-        if (timekeeper) hs.t[2] = globaltimer_ns();
+        if (warp < kSSoftmaxWarps) loop_s_softmax<KP, FULLK>(sa, hs, smem_raw, beta);
+        else loop_s_stats<KP>(sa, smem_raw);
       }
-      const bool use_old = (beta != 0.0);
-      if (warp < kSSoftmaxWarps) s_softmax<KP, FULLK, false>(sa, sm, sp, cid, ncl, 0, 1, beta, has_ng, use_old);
-      else s_stats<KP, false>(sa, sm, part, cid, ncl);
+      fence_proxy_async();  // x_new / sd written here are staged by this CTA's bulk copies in the next G / S phase
+      __syncthreads();
     }
-    fence_proxy_async();  // x_new / sd written here are staged by this CTA's bulk copies in the next G / S phase
-    __syncthreads();
-    s_cta_entropy<false>(sa, sm, part, 0);
-    if (tid == 0)
-      for (int s = 0; s < sa.stages; ++s) {
-        mbar_inval(&sm.full_bar[s]);
-        mbar_inval(&sm.phi_bar[s]);
-        mbar_inval(&sm.empty_bar[s]);
-      }
-    if (timekeeper) hs.t[3] = globaltimer_ns();
+    loop_after_s(hs, smem_raw);
 
-    // ------------------------------------------------------------------ B2, posterior
-    if (!grid_barrier<0, kGThreads>(a.sync, &hs.bar_target, &hs.abort)) break;
-    const unsigned long long e_stats = hs.e_stats + 1;  // read by every thread before thread 0 bumps it (after the next barrier)
-    if (cid < KP && tid < kClusterThreads) {
-      const int k = cid;
-      double *ws_s = reinterpret_cast<double *>(smem_raw);
-      PostSmem &ps = *reinterpret_cast<PostSmem *>(smem_raw + (((size_t)eig_ws_len(D) * 8 + 127) & ~(size_t)127));
-      if (tid == 0) post_stage_ws(a.p.ws, D, ps, ws_s);
-      double phi_hat = post_reduce_row<true>(sa.partials, ncl, len, k, KP, DP, ps);
-      const double *hparts = sa.partials;
-      int hnum = ncl;
-      if (P != nullptr) {
-        const int slot = (int)(e_stats & 1);
-        // this rank's row of cluster k (+ its entropy, with cluster 0) -> every peer's inbox; one flag per (sender, cluster)
-        double Hloc = 0.0;
-        if (k == 0) {
-          for (int c = tid; c < ncl; c += kClusterThreads) Hloc += __ldcg(sa.partials + (size_t)c * len + (size_t)KP * DP + KP);
-          Hloc = block_sum<true>(Hloc, ps.red_s);
-        }
-        const long long base = fx_off_stats(W, len, slot, my_rank);
-        for (int r = 0; r < W; ++r) {
-          double *dst = P->inbox[r] + base;
-          if (tid < DP) dst[(size_t)k * DP + tid] = ps.yb_s[tid];
-          if (tid == 64) dst[(size_t)KP * DP + k] = phi_hat;
-          if (tid == 65 && k == 0) dst[(size_t)KP * DP + KP] = Hloc;
-        }
-        psync<true>();
-        if (warp == 0) {
-          __threadfence_system();
-          if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_sflag(W, len, slot, my_rank, k), e_stats);
-          bool ok = true;
-          if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(inbox_self) + fx_off_sflag(W, len, slot, lane, k), e_stats);
-          ok = __all_sync(0xffffffffu, ok);
-          if (!ok && lane == 0) {
-            atomicOr(a.p.info, GPC_INFO_PEER_TIMEOUT);
-            atomicOr(&a.p.loop->done, GPC_DONE_PEER_TIMEOUT);
-          }
-        }
-        psync<true>();
-        hparts = inbox_self + fx_off_stats(W, len, slot, 0);
-        hnum = W;
-        phi_hat = post_reduce_row<true>(hparts, W, len, k, KP, DP, ps);  // sum over the ranks, in rank order
-      }
-      if (tid < DP) a.p.stats[(size_t)k * DP + tid] = ps.yb_s[tid];
-      if (tid == 0) a.p.stats[(size_t)KP * DP + k] = phi_hat;
-      mbar_wait(&ps.stage_bar, 0);
-      post_cluster_math<true>(a.p, k, phi_hat, ps, ws_s);
-      __threadfence();
-      psync<true>();
-      if (tid == 0) {
-        const unsigned int done = atomicAdd(a.sync + 2, 1u);
-        ps.is_last = (done == (unsigned)KP - 1) ? 1 : 0;
-        mbar_inval(&ps.stage_bar);
-      }
-      psync<true>();
-      if (ps.is_last) {
-        __threadfence();
-        if (P != nullptr && warp == 0) {
-          // the entropies travel with cluster 0's rows: make sure this CTA has observed those flags itself
-          const int slot = (int)(e_stats & 1);
-          if (lane < W) flag_wait(reinterpret_cast<const unsigned long long *>(inbox_self) + fx_off_sflag(W, len, slot, lane, 0), e_stats);
-        }
-        psync<true>();
-        MohgpPostArgs pa = a.p;
-        pa.counter = a.sync + 2;  // the tail resets the ticket
-        post_tail<true>(pa, ps, hparts, hnum, len, phase);
-        __threadfence();
-      }
-    }
-    // ------------------------------------------------------------------ B3: the decision and the new weights are visible
-    if (!grid_barrier<0, kGThreads>(a.sync, &hs.bar_target, &hs.abort)) break;
-    if (tid == 0) hs.e_stats = e_stats;
-    if (timekeeper) {
-      const unsigned long long t4 = globaltimer_ns();
-      hs.t_acc[0] += hs.t[1] - hs.t[0];
-      hs.t_acc[1] += hs.t[2] - hs.t[1];
-      hs.t_acc[2] += hs.t[3] - hs.t[2];
-      hs.t_acc[3] += t4 - hs.t[3];
-      hs.n_eval += 1;
-      hs.n_g += retry ? 0 : 1;
-    }
+    // ------------------------------------------------------------------ B2, posterior, decision, B3
+    if (!loop_post_phase(hs, smem_raw, hs.retry ? GPC_PHASE_RETRY : GPC_PHASE_CONJ)) break;
   }
 
   // ---- exit: the last CTA to leave re-arms the counters for the next launch; CTA 0 stores the exchange epochs
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     if (hs.abort) atomicOr(&a.p.loop->done, GPC_DONE_PEER_TIMEOUT);
-    if (P != nullptr && cid == 0) {
-      P->epochs[0] = hs.e_stats;
-      P->epochs[1] = hs.e_dots;
+    if (a.peers != nullptr && blockIdx.x == 0) {
+      a.peers->epochs[0] = hs.e_stats;
+      a.peers->epochs[1] = hs.e_dots;
     }
-    if (timekeeper) {
+    if (a.timing != nullptr && blockIdx.x == 0) {
       for (int q = 0; q < 4; ++q) a.timing[q] += hs.t_acc[q];
       a.timing[4] += hs.n_eval;
       a.timing[5] += hs.n_g;

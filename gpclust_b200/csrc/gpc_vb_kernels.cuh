@@ -327,25 +327,51 @@ __device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, con
         continue;
       }
 
-      // ---- pass 2: natural gradient, gradient, dots
-      if (!CL) old_point();
+      // ---- pass 2: natural gradient, gradient, dots.  Outside the wide mode the previous-point responsibilities are evaluated here,
+      // in batches of HB n-tiles, each consumed at once: the peak register demand of the loop is what decides whether the row loop
+      // fits the 168 registers of the CTA shape (it must, also inside the fused loop kernel).
+#ifndef GPC_G_OLD_BATCH
+#define GPC_G_OLD_BATCH 2
+#endif
+      constexpr int HB = (!CL && NTW > GPC_G_OLD_BATCH) ? GPC_G_OLD_BATCH : NTW;
       double *ngo_g = p_ng_out + goff;
       double *gro_g = p_grad_out ? p_grad_out + goff : nullptr;
 #pragma unroll
-      for (int q = 0; q < NTW; ++q) {
-        const int c = 8 * (nt0 + q) + 2 * t;
-        const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
-        const double n0 = (ok0 && row_ok) ? acc[q][0] - sa : 0.0;
-        const double n1 = (ok1 && row_ok) ? acc[q][1] - sa : 0.0;
-        const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
-        stg2(ngo_g + q * 64, n0, n1);
-        if (gro_g) stg2(gro_g + q * 64, g0, g1);
-        d0 += n0 * g0 + n1 * g1;
+      for (int q0 = 0; q0 < NTW; q0 += HB) {
+        double pb[2 * HB];
         if (has_old) {
-          const double po0 = (ok0 && row_ok) ? po[2 * q] : 0.0, po1 = (ok1 && row_ok) ? po[2 * q + 1] : 0.0;
-          const double e0 = n0 - ngo[q].x, e1 = n1 - ngo[q].y;
-          d1 += e0 * g0 + e1 * g1;
-          d2 += e0 * (ngo[q].x * po0) + e1 * (ngo[q].y * po1);
+          if (CL) {
+#pragma unroll
+            for (int q = 0; q < HB; ++q) {
+              pb[2 * q] = po[2 * (q0 + q)];
+              pb[2 * q + 1] = po[2 * (q0 + q) + 1];
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < HB; ++q) {
+              pb[2 * q] = xo[q0 + q].x - lse_o;
+              pb[2 * q + 1] = xo[q0 + q].y - lse_o;
+            }
+            exp_batch_tab<2 * HB>(pb, exp_tab);
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < HB; ++qq) {
+          const int q = q0 + qq;
+          const int c = 8 * (nt0 + q) + 2 * t;
+          const bool ok0 = FULLK || c < Kc, ok1 = FULLK || c + 1 < Kc;
+          const double n0 = (ok0 && row_ok) ? acc[q][0] - sa : 0.0;
+          const double n1 = (ok1 && row_ok) ? acc[q][1] - sa : 0.0;
+          const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
+          stg2(ngo_g + q * 64, n0, n1);
+          if (gro_g) stg2(gro_g + q * 64, g0, g1);
+          d0 += n0 * g0 + n1 * g1;
+          if (has_old) {
+            const double po0 = (ok0 && row_ok) ? pb[2 * qq] : 0.0, po1 = (ok1 && row_ok) ? pb[2 * qq + 1] : 0.0;
+            const double e0 = n0 - ngo[q].x, e1 = n1 - ngo[q].y;
+            d1 += e0 * g0 + e1 * g1;
+            d2 += e0 * (ngo[q].x * po0) + e1 * (ngo[q].y * po1);
+          }
         }
       }
     }
