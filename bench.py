@@ -49,9 +49,26 @@ def config_of(method):
             "l2": "inputs larger than L2: every step streams 11 N x K / N x D arrays (5.6 GB over all GPUs, >= 700 MB per GPU at 8 GPUs) "
                   "against 126 MB of L2; no flush between steps"}
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 1M rows, HS, from the ncu --set full capture summarised in
-# profiles/ncu_r01_v4_summary.csv (scaled linearly to the rows this rank holds)
-NCU_DRAM_BYTES_PER_LAUNCH_1M = {"natgrad": 2.064082e9 + 0.481799e9, "step_stats": 2.048080e9 + 1.000766e9}
+def ncu_traffic(kernel, n_loc, n_evals, n_g):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture of the shipped
+    binary (profiles/ncu_traffic_r02.json, written by tools/ncu_traffic.py next to the capture: bytes per G phase and per S phase at
+    1M rows, and the sha16 of the .so it was taken from), scaled to this launch.  None when there is no capture for this binary."""
+    try:
+        import hashlib
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
+            rec = json.load(f)
+        so = os.path.join(ROOT, "gpclust_b200", "_lib", "libgpclust_b200.so")
+        sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16]
+        per = rec["kernels"].get(kernel)
+        if per is None:
+            return None, "no capture of %s in profiles/ncu_traffic_r02.json" % kernel
+        scale = n_loc / float(rec["rows"])
+        val = (per["dram_bytes_per_g_phase"] * n_g + per["dram_bytes_per_s_phase"] * n_evals) * scale
+        src = "%s (ncu --set full at %d rows, scaled by rows per GPU and evaluations per launch; capture of lib %s, this run %s)" % (
+            rec["source"], rec["rows"], rec["lib_sha16"], "the same binary" if rec["lib_sha16"] == sha else "a DIFFERENT binary " + sha)
+        return val, src
+    except (OSError, KeyError, ValueError) as e:
+        return None, "unavailable (%s)" % type(e).__name__
 
 
 def synth(n_total, d, k, seed=0):
@@ -331,28 +348,46 @@ def run_gpu(args):
     elapsed_ms = float(t.item())
     launches = m.kernel_launches - launches0
 
-    # per-kernel durations: the same K passes continue with a CUDA-event pair around every launch (the pairs cost a
-    # few microseconds per launch, which is why they are kept out of the region `value` is taken from)
-    m._kernel_events = {}
-    it_before2 = m._pass_state["iteration"]
-    rows2 = m.run_passes(steps, method=method)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    rejected2 = int(rows2[-1][0] - it_before2) - steps
-    kernel_ms = {name: float(np.mean([a.elapsed_time(b) for a, b in pairs])) for name, pairs in m._kernel_events.items()}
-    kernel_n = {name: len(pairs) for name, pairs in m._kernel_events.items()}
-    # one bound evaluation per enqueued sequence: the sequence after a rejected conjugate step skips its G pass (returns at
-    # once) and runs S / posterior as the steepest retry -- report the G pass over the launches that did work
-    # (and the sequences enqueued beyond the last accepted step return at once altogether)
-    n_eval = steps + rejected2
-    for name, keep in (("natgrad", steps), ("step_stats", n_eval), ("posterior", n_eval)):
-        if name in m._kernel_events:
-            d = sorted((a.elapsed_time(b) for a, b in m._kernel_events[name]), reverse=True)
-            kernel_ms[name] = float(np.mean(d[:keep]))
-            kernel_n[name] = min(keep, len(d))
-            if len(d) > keep:
-                kernel_ms[name + "_skipped"] = float(np.mean(d[keep:]))
-    m._kernel_events = None
+    fused = bool(m._fused_ok())
+    if fused:
+        # the loop is ONE persistent kernel (k_mohgp_loop): its phases are timed inside the kernel -- CTA 0 reads %globaltimer at the
+        # phase boundaries and accumulates ns per phase -- over the same K passes again (the stamps are kept out of the region
+        # `value` is taken from).  "posterior" = B2 + per-cluster posterior + decision + B3; "dots" = B1 + the dots (+ NVLink exchange).
+        m._loop_timing = torch.zeros(32, dtype=torch.int64, device="cuda")
+        it_before2 = m._pass_state["iteration"]
+        rows2 = m.run_passes(steps, method=method)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        tt = m._loop_timing.cpu().numpy().astype(np.float64)
+        m._loop_timing = None
+        n_eval, n_g = max(1.0, tt[4]), max(1.0, tt[5])
+        kernel_ms = {"natgrad": tt[0] / n_g * 1e-6, "dots": tt[1] / n_g * 1e-6, "step_stats": tt[2] / n_eval * 1e-6, "posterior": tt[3] / n_eval * 1e-6}
+        kernel_n = {"natgrad": int(n_g), "dots": int(n_g), "step_stats": int(n_eval), "posterior": int(n_eval)}
+        for q, nm in enumerate(("post_barrier_wait", "post_row_reduce", "post_exchange", "post_algebra", "post_tail_barrier")):
+            kernel_ms[nm] = tt[6 + q] / n_eval * 1e-6
+    else:
+        # per-kernel durations: the same K passes continue with a CUDA-event pair around every launch (the pairs cost a
+        # few microseconds per launch, which is why they are kept out of the region `value` is taken from)
+        m._kernel_events = {}
+        it_before2 = m._pass_state["iteration"]
+        rows2 = m.run_passes(steps, method=method)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        rejected2 = int(rows2[-1][0] - it_before2) - steps
+        kernel_ms = {name: float(np.mean([a.elapsed_time(b) for a, b in pairs])) for name, pairs in m._kernel_events.items()}
+        kernel_n = {name: len(pairs) for name, pairs in m._kernel_events.items()}
+        # one bound evaluation per enqueued sequence: the sequence after a rejected conjugate step skips its G pass (returns at
+        # once) and runs S / posterior as the steepest retry -- report the G pass over the launches that did work
+        # (and the sequences enqueued beyond the last accepted step return at once altogether)
+        n_eval = steps + rejected2
+        for name, keep in (("natgrad", steps), ("step_stats", n_eval), ("posterior", n_eval)):
+            if name in m._kernel_events:
+                d = sorted((a.elapsed_time(b) for a, b in m._kernel_events[name]), reverse=True)
+                kernel_ms[name] = float(np.mean(d[:keep]))
+                kernel_n[name] = min(keep, len(d))
+                if len(d) > keep:
+                    kernel_ms[name + "_skipped"] = float(np.mean(d[keep:]))
+        m._kernel_events = None
     ms_per_step = elapsed_ms / steps
     value = 1e3 / ms_per_step
 
@@ -432,15 +467,26 @@ def run_gpu(args):
     g_bytes = n_loc * 8.0 * (D + K * (4 if with_old else 2))
     s_bytes = n_loc * 8.0 * (D + K * (5 if method != "steepest" else 4))
     alg = {"natgrad": g_bytes, "step_stats": s_bytes}
-    # the two N-sized kernels share the step almost evenly (the S pass also runs for every rejected conjugate step); `roofline`
-    # reports the one with the longer launch -- the one further from its bound -- and `roofline_by_kernel` both, with their shares
-    dom = max(("natgrad", "step_stats"), key=lambda n: kernel_ms.get(n, 0.0))
-    achieved = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
-    total_ms = sum(kernel_ms.get(n, 0.0) * kernel_n.get(n, 0) for n in ("natgrad", "step_stats", "posterior"))
-    by_kernel = {"k_" + n: {"ms_per_launch": kernel_ms[n], "launches": kernel_n[n], "share_of_step": kernel_ms[n] * kernel_n[n] / total_ms,
-                            "alg_bytes_per_launch": alg[n], "achieved_GBps": alg[n] / (kernel_ms[n] * 1e-3) / 1e9,
-                            "frac": alg[n] / (kernel_ms[n] * 1e-3) / 1e9 / hbm_peak} for n in ("natgrad", "step_stats")}
+    # the two N-sized row phases share the step almost evenly (the S rows also run for every rejected conjugate step)
+    total_ms = sum(kernel_ms.get(n, 0.0) * kernel_n.get(n, 0) for n in ("natgrad", "dots", "step_stats", "posterior"))
+    what = "phase of k_mohgp_loop (in-kernel %globaltimer, CTA 0)" if fused else "kernel (CUDA events around each launch)"
+    by_kernel = {("g_rows" if fused else "k_natgrad") if n == "natgrad" else ("s_rows" if fused else "k_step_stats"):
+                 {"what": what, "ms": kernel_ms[n], "count": kernel_n[n], "share_of_step": kernel_ms[n] * kernel_n[n] / total_ms,
+                  "alg_bytes": alg[n], "achieved_GBps": alg[n] / (kernel_ms[n] * 1e-3) / 1e9, "frac": alg[n] / (kernel_ms[n] * 1e-3) / 1e9 / hbm_peak}
+                 for n in ("natgrad", "step_stats")}
+    if fused:
+        # ONE launch in the timed region: algorithmic bytes of everything it did / its CUDA-event duration
+        n_evals_timed = steps + rejected
+        launch_bytes = steps * g_bytes + n_evals_timed * s_bytes
+        dom, dom_name, dom_ms = None, "k_mohgp_loop", elapsed_ms
+        achieved = launch_bytes / (elapsed_ms * 1e-3) / 1e9
+        dom_bytes = launch_bytes
+    else:
+        dom = max(("natgrad", "step_stats"), key=lambda n: kernel_ms.get(n, 0.0))
+        dom_name, dom_ms, dom_bytes = "k_" + dom, kernel_ms[dom], alg[dom]
+        achieved = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
     iter_bytes = g_bytes + s_bytes
+    traffic, traffic_source = ncu_traffic(dom_name, n_loc, steps + rejected if fused else 1, steps if fused else 1)
     tensor_tf = 4.0 * N_TOTAL * K * D / (ms_per_step * 1e-3) / 1e12  # aggregate over the `world` GPUs
 
     cpu, cpu_other = None, None
@@ -463,11 +509,11 @@ def run_gpu(args):
                         "host numpy in/out" % (e2e_steps, e2e_passes),
                 "bound": b_e2e},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_kind": peak_kind,
-                     "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_1M[dom] * n_loc / 1e6) if method == "HS" else None,
-                     "traffic_source": "profiles/ncu_r01_v4_summary.csv (ncu --set full, 1M rows, scaled by rows per GPU)",
-                     "alg_bytes_per_launch": alg[dom], "ms_per_launch": kernel_ms[dom],
+        "gpu_launches_what": "k_mohgp_loop: the whole timed region is one persistent cooperative launch" if fused else "launches of this package's kernels in the timed region",
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_source,
+                     "alg_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                     "launch": ("one cooperative launch = %d passes (%d bound evaluations); bytes = per-GPU algorithmic bytes of all of them" % (steps, steps + rejected)) if fused else "per launch",
                      "iteration_hbm_frac": iter_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         "roofline_by_kernel": by_kernel,
         "kernels_ms": kernel_ms,

@@ -190,7 +190,7 @@ class MOHGP(CollapsedMixture):
     def _fused_ok(self):
         # K <= 64 (one 64-cluster chunk per CTA), every SM's CTA co-resident, the NVLink exchange (or one GPU).  GPCLUST_B200_FUSED=0
         # keeps the per-evaluation launch sequence (graph replay) for comparison.
-        return (self._chunks == 1 and self._grid >= self._KP and (self._world == 1 or self._peers is not None) and
+        return (self._chunks == 1 and self._grid > self._KP and (self._world == 1 or self._peers is not None) and
                 os.environ.get("GPCLUST_B200_FUSED", "1") != "0" and self._kernel_events is None)
 
     def _launch_fused(self, bufs, n):

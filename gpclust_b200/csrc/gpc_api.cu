@@ -1091,7 +1091,7 @@ int gpc_mohgp_loop(const double *F, const gpc_bufs_t *bufs, double *Wt, double *
     return GPC_EINVAL;
   if (!geometry_ok(N, K, KP, DP, grid) || N > 0x7fffffffLL || D < 1 || D > DP || max_evals < 1) return GPC_EINVAL;
   if (prior != GPC_PRIOR_SYMMETRIC && prior != GPC_PRIOR_DP) return GPC_EINVAL;
-  if (grid < KP) return GPC_EINVAL;  // CTA k computes the posterior of cluster k
+  if (grid <= KP) return GPC_EINVAL;  // CTA k < KP computes the posterior of cluster k, CTA KP the scalar tail of the evaluation
   LoopKernelArgs a{};
   a.g.F = F;
   a.g.Wt = Wt;
@@ -1111,6 +1111,8 @@ int gpc_mohgp_loop(const double *F, const gpc_bufs_t *bufs, double *Wt, double *
   a.s.DP = DP;
   a.s.num_groups = a.g.num_groups;
   a.s.bufs = *bufs;
+  a.s.reverse = 0;  // no measurable gain from the reverse sweep at 125k .. 1M rows per GPU (and it changes the summation order)
+  if (const char *e = getenv("GPC_DEBUG_S_REVERSE")) a.s.reverse = atoi(e);  // experiment
   a.p = MohgpPostArgs{spart, grid, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                       sync + 2, info, alpha, prior, K, D, KP, DP, dots, beta, loop, GPC_PHASE_CONJ, nullptr};
   a.peers = peers;

@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_finalize(const MohgpF
 // i.e. five D x D matrix-vector products per cluster instead of a Cholesky, a D x D triangular solve and a SYRK.
 // phi_hat_k <= 1e-6 takes the reference's Lambda_inv := Sf branch.
 
-// workspace layout (doubles): [lam 64 | U D*D | Ut D*D | Vt D*D | Sy_inv D*D | tr(Sy_inv), sum(Sf o Sy_inv), sweeps, off-norm, 4 spare],
+// workspace layout (doubles): [lam 64 | U D*D | Ut D*D | Vt D*D | Sy_inv D*D | tr(Sy_inv), sum(Sf o Sy_inv), sweeps, off-norm, min lam, sum lam, 2 spare],
 // length rounded up to an even number of doubles so that the whole block is one 16-byte-granular bulk copy
 __host__ __device__ inline int eig_ws_len(int D) { return (GPC_MAX_DP + 4 * D * D + 8 + 1) & ~1; }
 
@@ -655,6 +655,15 @@ __global__ void __launch_bounds__(kEigThreads) k_mohgp_eig(const MohgpEigArgs a)
     scal[1] = t2;
     scal[2] = (double)sweeps;
     scal[3] = sqrt(off / (fro > 0.0 ? fro : 1.0));
+    // smallest eigenvalue and eigenvalue sum (= tr A): the jitchol emulation of the posterior needs them for every cluster and every
+    // evaluation, so they are found once here (same order of operations for every consumer)
+    double lmin = INFINITY, lsum = 0.0;
+    for (int i = 0; i < D; ++i) {
+      lmin = fmin(lmin, As[i * ld + i]);
+      lsum += As[i * ld + i];
+    }
+    scal[4] = lmin;
+    scal[5] = lsum;
   }
 }
 
@@ -686,7 +695,27 @@ struct MohgpPostArgs {
 
 // partial of y[r] = sum_j Mt[j*D + r] x[j] over j == pg (mod 4), for r < D; x in shared memory, Mt in shared memory
 // (staged by bulk copy) or global memory.
+// D == GPC_MAX_DP (= 64, config 3): no clamping, compile-time strides; thread group pg takes the 16 CONSECUTIVE entries
+// j in [16 pg, 16 pg + 16) of x (read as 8 double2), four independent FMA chains.
+__device__ __forceinline__ double matvec_t_part64(const double *Mt, const double *x_s, int r, int pg) {
+  const double *m = Mt + (size_t)(16 * pg) * GPC_MAX_DP + r;
+  const double2 *x2 = reinterpret_cast<const double2 *>(x_s + 16 * pg);
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll
+  for (int u = 0; u < 8; u += 2) {
+    const double2 xa = x2[u], xb = x2[u + 1];
+    v0 = fma(m[(2 * u + 0) * GPC_MAX_DP], xa.x, v0);
+    v1 = fma(m[(2 * u + 1) * GPC_MAX_DP], xa.y, v1);
+    v2 = fma(m[(2 * u + 2) * GPC_MAX_DP], xb.x, v2);
+    v3 = fma(m[(2 * u + 3) * GPC_MAX_DP], xb.y, v3);
+  }
+  return (v0 + v1) + (v2 + v3);
+}
+__device__ __forceinline__ double matvec_t_part_any(const double *Mt, const double *x_s, int D, int r, int pg);
 __device__ __forceinline__ double matvec_t_part(const double *Mt, const double *x_s, int D, int r, int pg) {
+  return D == GPC_MAX_DP ? matvec_t_part64(Mt, x_s, r, pg) : matvec_t_part_any(Mt, x_s, D, r, pg);
+}
+__device__ __forceinline__ double matvec_t_part_any(const double *Mt, const double *x_s, int D, int r, int pg) {
   // unconditional loads from clamped addresses (a predicated load is not hoisted above its use by the compiler)
   const int rc = r < D ? r : D - 1;
   double v[4] = {0.0, 0.0, 0.0, 0.0};
@@ -708,13 +737,14 @@ __device__ __forceinline__ double matvec_t_part(const double *Mt, const double *
 
 // shared memory of the posterior routine: static in k_mohgp_post, carved from the (then idle) dynamic ring memory in the fused loop kernel
 struct PostSmem {
-  double red[4][GPC_MAX_DP];
+  double red[4][GPC_MAX_DP], red1[4][GPC_MAX_DP], red2[4][GPC_MAX_DP];
   double yb_s[GPC_MAX_DP], z_s[GPC_MAX_DP], cz_s[GPC_MAX_DP], s_s[GPC_MAX_DP], mu_s[GPC_MAX_DP], w_s[GPC_MAX_DP], c_s[GPC_MAX_DP];
   double red_s[32];
   double mixgrad[kMaxMixK];
   double phi_hat_sh[kMaxMixK];
   MixScratch scratch;
-  double mix_s;
+  double mix_s, H_s;
+  double xrow[GPC_MAX_PEERS][GPC_MAX_DP + 8];  // fused exchange: the W ranks' rows of this cluster
   uint64_t stage_bar;
   int xchg_ok;
   int is_last;
@@ -729,6 +759,18 @@ __device__ __forceinline__ void post_stage_ws(const double *ws, int D, PostSmem 
   bulk_g2s(ws_s, ws, bytes, &sm.stage_bar);
 }
 
+// phi_hat_k = sum over `num_parts` vectors of their phi_hat entry k, by ONE WARP (all 32 lanes), fixed order.  Every consumer of
+// phi_hat_k (the cluster's own CTA, the CTA that evaluates the mixing-proportion terms) uses this routine: bit-identical values.
+__device__ __forceinline__ double reduce_phi_hat_warp(const double *partials, int num_parts, int len, int KP, int DP, int k) {
+  const int lane = threadIdx.x & 31;
+  double q0 = 0.0, q1 = 0.0;
+  for (int p = lane; p < num_parts; p += 64) {
+    q0 += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + k);
+    if (p + 32 < num_parts) q1 += __ldcg(partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
+  }
+  return warp_sum(q0 + q1);
+}
+
 // this cluster's statistics: fixed-order sum over `num_parts` vectors of stride `len` -> sm.yb_s[0..DP); returns phi_hat_k on every
 // thread.  Ends with a barrier.  (8 independent loads in flight per thread.)
 template <bool SUB>
@@ -740,28 +782,23 @@ __device__ __forceinline__ double post_reduce_row(const double *partials, int nu
       const double *src = partials + (size_t)k * DP + (r < DP ? r : DP - 1);
       const int last = num_parts - 1;
       // up to 160 partial vectors (one per SM and then some): all 40 loads of this thread are issued before the first
-      // use -- clamped, unconditional addresses, because a predicated load is not hoisted above its use
+      // use -- clamped, unconditional addresses, because a predicated load is not hoisted above its use.  32-bit element offsets
+      // (num_parts * len < 2^31): one multiply-add per address.
       for (int p0 = pg; p0 < num_parts; p0 += 160) {
         double w[40];
+        const int nmine = (last - p0) >> 2;  // this thread's partials are p0 + 4u, u = 0 .. nmine
+        const int step4 = 4 * len, off0 = p0 * len;
 #pragma unroll
-        for (int u = 0; u < 40; ++u) {
-          const int pp = p0 + 4 * u;
-          w[u] = __ldcg(src + (size_t)(pp < last ? pp : last) * len);
-        }
+        for (int u = 0; u < 40; ++u) w[u] = __ldcg(src + (off0 + min(u, nmine) * step4));
 #pragma unroll
-        for (int u = 0; u < 40; ++u) v[u & 7] += (p0 + 4 * u <= last) ? w[u] : 0.0;
+        for (int u = 0; u < 40; ++u) v[u & 7] += (u <= nmine) ? w[u] : 0.0;
       }
     }
     sm.red[pg][r] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
   }
   double phi_hat = 0.0;
   if (tid < 32) {
-    double q0 = 0.0, q1 = 0.0;
-    for (int p = tid; p < num_parts; p += 64) {
-      q0 += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + k);
-      if (p + 32 < num_parts) q1 += __ldcg(partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
-    }
-    phi_hat = warp_sum(q0 + q1);
+    phi_hat = reduce_phi_hat_warp(partials, num_parts, len, KP, DP, k);
     if (tid == 0) sm.red_s[0] = phi_hat;
   }
   psync<SUB>();
@@ -771,33 +808,35 @@ __device__ __forceinline__ double post_reduce_row(const double *partials, int nu
   return phi_hat;
 }
 
-// per-cluster posterior of cluster k from sm.yb_s / phi_hat (eigenbasis form, see above); ws_s: the staged workspace
+// per-cluster posterior of cluster k from sm.yb_s / phi_hat (eigenbasis form, see above); ws_s: the staged workspace.
+// Three dependent levels of matrix-vector products (z; then s, V(c o z), U(c o z) together; then Sy_inv s), each level = partial
+// products by 4 thread groups + one barrier + the 4-way sums; one combined block reduction for the five per-cluster scalars.
 template <bool SUB>
-__device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k, double phi_hat, PostSmem &sm, const double *ws_s) {
+__device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k, double phi_hat, PostSmem &sm, const double *ws_s,
+                                                  unsigned long long *dbg = nullptr) {
   const int D = a.D, DP = a.DP, tid = threadIdx.x;
   const int r = tid & 63, pg = tid >> 6;
   double (*red)[GPC_MAX_DP] = sm.red;
-  double *yb_s = sm.yb_s, *z_s = sm.z_s, *cz_s = sm.cz_s, *s_s = sm.s_s, *mu_s = sm.mu_s, *w_s = sm.w_s, *c_s = sm.c_s, *red_s = sm.red_s;
+  double (*red1)[GPC_MAX_DP] = sm.red1;
+  double (*red2)[GPC_MAX_DP] = sm.red2;
+  double *yb_s = sm.yb_s, *z_s = sm.z_s, *cz_s = sm.cz_s, *s_s = sm.s_s, *mu_s = sm.mu_s, *w_s = sm.w_s, *c_s = sm.c_s;
   const double *lam = ws_s, *U = ws_s + GPC_MAX_DP, *Ut = U + D * D, *Vt = Ut + D * D, *syi_s = Vt + D * D, *scal = syi_s + D * D;
+  auto sum4 = [](double (*q)[GPC_MAX_DP], int i) { return (q[0][i] + q[1][i]) + (q[2][i] + q[3][i]); };
   if (k < a.K) {
     // ---- den_i = 1 + jitter + phi_hat lam_i with GPy's jitchol retry: a failed factorisation <=> some den_i <= 0
     double jitter = 0.0;
     bool ok = false;
     {
-      double lmin = (tid < D) ? lam[tid] : INFINITY, lsum = (tid < D) ? lam[tid] : 0.0;
-      lsum = block_sum<SUB>(lsum, red_s);
-      lmin = warp_max(-lmin);
-      psync<SUB>();
-      if ((tid & 31) == 0) red_s[tid >> 5] = lmin;
-      psync<SUB>();
-      lmin = -fmax(fmax(red_s[0], red_s[1]), fmax(fmax(red_s[2], red_s[3]), fmax(fmax(red_s[4], red_s[5]), fmax(red_s[6], red_s[7]))));
-      psync<SUB>();
-      const double diag_mean = 1.0 + phi_hat * lsum / D;
-      for (int attempt = 0; attempt < 6 && !ok; ++attempt) {
-        if (attempt == 1) jitter = diag_mean * 1e-6;
-        else if (attempt > 1) jitter *= 10.0;
-        if (!isfinite(jitter)) break;
-        ok = (1.0 + jitter + phi_hat * lmin > 0.0) && isfinite(phi_hat);
+      const double lmin = scal[4];
+      ok = (1.0 + phi_hat * lmin > 0.0) && isfinite(phi_hat);  // first attempt, no jitter: the only one taken in a healthy run
+      if (!ok && isfinite(phi_hat)) {
+        const double diag_mean = 1.0 + phi_hat * scal[5] / D;
+        for (int attempt = 1; attempt < 6 && !ok; ++attempt) {
+          if (attempt == 1) jitter = diag_mean * 1e-6;
+          else jitter *= 10.0;
+          if (!isfinite(jitter)) break;
+          ok = (1.0 + jitter + phi_hat * lmin > 0.0);
+        }
       }
     }
     if (!ok) {
@@ -807,12 +846,13 @@ __device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k,
     } else {
       const bool tiny = !(phi_hat > 1e-6);
       const double shift = tiny ? 0.0 : 1e-6 / phi_hat;
-      // z = U^T ybark
+      if (dbg) dbg[0] = globaltimer_ns();
+      // level 1: z = U^T ybark
       red[pg][r] = matvec_t_part(U, yb_s, D, r, pg);
       psync<SUB>();
       double ldd = 0.0;
       if (tid < D) {
-        const double z = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        const double z = sum4(red, tid);
         const double pl = phi_hat * lam[tid];
         const double den = (1.0 + jitter) + pl;
         const double c = (jitter == 0.0) ? lam[tid] / den : (jitter + pl) / (den * phi_hat);
@@ -822,43 +862,40 @@ __device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k,
         ldd = (jitter == 0.0) ? log1p(pl) : log(den);
       }
       psync<SUB>();
-      // s = U z ; V (c o z) ; U (c o z)
-      const double ps = matvec_t_part(Ut, z_s, D, r, pg);
-      const double pv = tiny ? 0.0 : matvec_t_part(Vt, cz_s, D, r, pg);
-      const double pu = tiny ? 0.0 : matvec_t_part(Ut, cz_s, D, r, pg);
+      if (dbg) dbg[1] = globaltimer_ns();
+      // level 2: s = U z ; V (c o z) ; U (c o z)
+      red[pg][r] = matvec_t_part(Ut, z_s, D, r, pg);
+      red1[pg][r] = tiny ? 0.0 : matvec_t_part(Vt, cz_s, D, r, pg);
+      red2[pg][r] = tiny ? 0.0 : matvec_t_part(Ut, cz_s, D, r, pg);
       psync<SUB>();
-      red[pg][r] = ps;
+      if (tid < D) {
+        s_s[tid] = sum4(red, tid);
+        mu_s[tid] = sum4(red1, tid);
+        w_s[tid] = sum4(red2, tid);
+      }
       psync<SUB>();
-      if (tid < D) s_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      psync<SUB>();
-      red[pg][r] = pv;
-      psync<SUB>();
-      if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      psync<SUB>();
-      red[pg][r] = pu;
-      psync<SUB>();
-      if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-      psync<SUB>();
+      if (dbg) dbg[2] = globaltimer_ns();
+      // level 3
       if (tiny) {
-        // Lambda_inv := Sf (MOHGP.py:85): mu = Sf^T s
+        // Lambda_inv := Sf (MOHGP.py:85): mu = Sf^T s, then w = Sy_inv mu (Sy_inv symmetric)
         red[pg][r] = matvec_t_part(a.Sf, s_s, D, r, pg);
         psync<SUB>();
-        if (tid < D) mu_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        if (tid < D) mu_s[tid] = sum4(red, tid);
         psync<SUB>();
-        red[pg][r] = matvec_t_part(syi_s, mu_s, D, r, pg);  // w = Sy_inv mu (Sy_inv symmetric)
+        red[pg][r] = matvec_t_part(syi_s, mu_s, D, r, pg);
         psync<SUB>();
-        if (tid < D) w_s[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        psync<SUB>();
+        if (tid < D) w_s[tid] = sum4(red, tid);
       } else {
         red[pg][r] = matvec_t_part(syi_s, s_s, D, r, pg);  // h = Sy_inv s
         psync<SUB>();
         if (tid < D) {
-          const double h = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+          const double h = sum4(red, tid);
           mu_s[tid] -= shift * s_s[tid];
           w_s[tid] -= shift * h;
         }
-        psync<SUB>();
       }
+      if (dbg) dbg[3] = globaltimer_ns();
+      // the five per-cluster scalars in ONE block reduction (each thread < D touches only its own entries of mu_s / w_s above)
       double quad = 0.0, tr = 0.0, m2 = 0.0, ss = 0.0;
       if (tid < D) {
         if (tiny) quad = s_s[tid] * mu_s[tid];
@@ -868,18 +905,32 @@ __device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k,
           tr = c_s[tid];
         }
         m2 = mu_s[tid] * w_s[tid];
-      }
-      ldd = block_sum<SUB>(ldd, red_s);
-      quad = block_sum<SUB>(quad, red_s);
-      ss = block_sum<SUB>(ss, red_s);
-      tr = block_sum<SUB>(tr, red_s);
-      m2 = block_sum<SUB>(m2, red_s);
-      if (tid < D) {
         a.muk_t[(size_t)k * D + tid] = mu_s[tid];
         if (a.Syi_ybark_t) a.Syi_ybark_t[(size_t)k * D + tid] = s_s[tid];
       }
       for (int d = tid; d < DP; d += pthreads<SUB>()) a.Wt[(size_t)k * DP + d] = (d < D) ? w_s[d] : 0.0;
+      ldd = warp_sum(ldd);
+      quad = warp_sum(quad);
+      ss = warp_sum(ss);
+      tr = warp_sum(tr);
+      m2 = warp_sum(m2);
+      if ((tid & 31) == 0 && tid < 64) {  // D <= 64: only the first two warps hold contributions
+        double *q = sm.red_s + (tid >> 5) * 8;
+        q[0] = ldd;
+        q[1] = quad;
+        q[2] = ss;
+        q[3] = tr;
+        q[4] = m2;
+      }
+      psync<SUB>();
+      if (dbg) dbg[4] = globaltimer_ns();
       if (tid == 0) {
+        const double *q = sm.red_s;
+        ldd = q[0] + q[8];
+        quad = q[1] + q[9];
+        ss = q[2] + q[10];
+        tr = q[3] + q[11];
+        m2 = q[4] + q[12];
         a.per_k[k * 4 + 0] = ldd;
         a.per_k[k * 4 + 1] = tiny ? quad : quad - shift * ss;
         a.per_k[k * 4 + 2] = tiny ? scal[1] : tr - shift * scal[0];
@@ -890,49 +941,57 @@ __device__ __forceinline__ void post_cluster_math(const MohgpPostArgs &a, int k,
     for (int d = tid; d < DP; d += pthreads<SUB>()) a.Wt[(size_t)k * DP + d] = 0.0;
     if (tid < 4) a.per_k[k * 4 + tid] = 0.0;
   }
-
 }
 
-// the last CTA to finish assembles the bound and the G-pass bias (MOHGP.py:124-135, :146-148) and, in loop mode, takes the
-// accept / reject decision.  `partials` / `num_parts` / `len`: where the entropy partials are.
+// Tail of a bound evaluation, in two parts.
+// post_tail_prepare: entropy H, mixing-proportion bound and gradient (collapsed_mixture.py:66-94) from sm.phi_hat_sh[0..K) -- needs the
+//   statistics only, not the per-cluster posteriors: the fused loop kernel runs it on a CTA of its own WHILE the cluster CTAs work.
+// post_tail_finish: the per-cluster scalars -> bound (MOHGP.py:124-135), G-pass bias (:146-148), and in loop mode the accept /
+//   reject / termination decision.  `partials` / `num_parts` / `len`: where the entropy partials are.
 template <bool SUB>
-__device__ __forceinline__ void post_tail(const MohgpPostArgs &a, PostSmem &sm, const double *partials, int num_parts, int len, int phase) {
+__device__ __forceinline__ void post_tail_prepare(const MohgpPostArgs &a, PostSmem &sm, const double *partials, int num_parts, int len) {
   const int KP = a.KP, DP = a.DP, tid = threadIdx.x;
-  double *red_s = sm.red_s, *mixgrad = sm.mixgrad, *phi_hat_sh = sm.phi_hat_sh;
-  MixScratch &scratch = sm.scratch;
-  double &mix_s = sm.mix_s;
-  {
-    // every load of this serial tail is issued by a different thread (one L2 round trip, not num_parts of them)
-    double H = 0.0;
-    for (int p = tid; p < num_parts; p += pthreads<SUB>()) H += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + KP);
-    H = block_sum<SUB>(H, red_s);
-    if (tid == 0) a.stats[(size_t)KP * DP + KP] = H;
-    double ldd = 0.0, quad = 0.0;
-    for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) {
-      phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
-      ldd += __ldcg(a.per_k + kk * 4 + 0);
-      quad += __ldcg(a.per_k + kk * 4 + 1);
-    }
-    ldd = block_sum<SUB>(ldd, red_s);
-    quad = block_sum<SUB>(quad, red_s);
-    psync<SUB>();
-    mixing_terms<SUB>(phi_hat_sh, a.K, a.alpha, a.prior, scratch, mixgrad, &mix_s);
-    if (tid == 0) {
-      const double bound = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix_s + H;
-      a.scalars[0] = bound;
-      a.scalars[1] = mix_s;
-      a.scalars[2] = H;
-      *a.counter = 0u;
-      if (a.loop) {
-        // loop mode: the flag word is consumed here and re-armed for the next evaluation (no memset between kernels)
-        cg_decide(a.loop, phase, bound, (atomicExch(a.info, 0) & GPC_INFO_NOT_PD) != 0, __ldcg(a.dots), __ldcg(a.beta));
-      }
-    }
-    for (int kk = tid; kk < KP; kk += pthreads<SUB>())
-      a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
-    if (a.mixgrad_out)
-      for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) a.mixgrad_out[kk] = mixgrad[kk];
+  // every load of this serial tail is issued by a different thread (one L2 round trip, not num_parts of them)
+  double H = 0.0;
+  for (int p = tid; p < num_parts; p += pthreads<SUB>()) H += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + KP);
+  H = block_sum<SUB>(H, sm.red_s);
+  if (tid == 0) sm.H_s = H;
+  psync<SUB>();
+  mixing_terms<SUB>(sm.phi_hat_sh, a.K, a.alpha, a.prior, sm.scratch, sm.mixgrad, &sm.mix_s);
+}
+// the same with sm.H_s already in place
+template <bool SUB>
+__device__ __forceinline__ void post_tail_mixing(const MohgpPostArgs &a, PostSmem &sm) {
+  mixing_terms<SUB>(sm.phi_hat_sh, a.K, a.alpha, a.prior, sm.scratch, sm.mixgrad, &sm.mix_s);
+}
+template <bool SUB>
+__device__ __forceinline__ void post_tail_finish(const MohgpPostArgs &a, PostSmem &sm, int phase) {
+  const int KP = a.KP, DP = a.DP, tid = threadIdx.x;
+  double *mixgrad = sm.mixgrad;
+  double ldd = 0.0, quad = 0.0;
+  for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) {
+    ldd += __ldcg(a.per_k + kk * 4 + 0);
+    quad += __ldcg(a.per_k + kk * 4 + 1);
   }
+  ldd = block_sum<SUB>(ldd, sm.red_s);
+  quad = block_sum<SUB>(quad, sm.red_s);
+  if (tid == 0) {
+    const double H = sm.H_s, mix = sm.mix_s;
+    const double bound = (*a.const_term - 0.5 * ldd) + 0.5 * quad + mix + H;
+    a.stats[(size_t)KP * DP + KP] = H;
+    a.scalars[0] = bound;
+    a.scalars[1] = mix;
+    a.scalars[2] = H;
+    *a.counter = 0u;
+    if (a.loop) {
+      // loop mode: the flag word is consumed here and re-armed for the next evaluation (no memset between kernels)
+      cg_decide(a.loop, phase, bound, (atomicExch(a.info, 0) & GPC_INFO_NOT_PD) != 0, __ldcg(a.dots), __ldcg(a.beta));
+    }
+  }
+  for (int kk = tid; kk < KP; kk += pthreads<SUB>())
+    a.bias[kk] = (kk < a.K) ? (mixgrad[kk] - 0.5 * __ldcg(a.per_k + kk * 4 + 2)) - 0.5 * __ldcg(a.per_k + kk * 4 + 3) : 0.0;
+  if (a.mixgrad_out)
+    for (int kk = tid; kk < a.K; kk += pthreads<SUB>()) a.mixgrad_out[kk] = mixgrad[kk];
 }
 
 __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostArgs a) {
@@ -978,7 +1037,10 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
   __syncthreads();
   if (!sm.is_last) return;
   __threadfence();
-  post_tail<false>(a, sm, partials, num_parts, len, phase);
+  for (int kk = tid; kk < a.K; kk += blockDim.x) sm.phi_hat_sh[kk] = __ldcg(a.stats + (size_t)KP * DP + kk);
+  __syncthreads();
+  post_tail_prepare<false>(a, sm, partials, num_parts, len);
+  post_tail_finish<false>(a, sm, phase);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -32,23 +32,50 @@ namespace gpc {
 constexpr int kLoopHeaderBytes = 1024;  // loop-state snapshot + scalars at the start of dynamic shared memory
 constexpr long long kSpinLimitNs = 4000000000LL;  // bounded waits (grid barrier, peer flags): 4 s
 
-// ---- inbox layout of the fused exchange (doubles / u64 words), W ranks, statistics length L (even), up to 64 clusters
-//   [2][W][L] statistics | [2][W][4] dots | [2][W][64] statistics flags (per sender and cluster) | [2][W] dots flags
-__host__ __device__ inline long long fx_off_stats(int W, int len, int slot, int sender) { return ((long long)slot * W + sender) * xchg_l2(len); }
-__host__ __device__ inline long long fx_off_dots(int W, int len, int slot, int sender) { return 2LL * W * xchg_l2(len) + ((long long)slot * W + sender) * 4; }
-__host__ __device__ inline long long fx_off_sflag(int W, int len, int slot, int sender, int k) {
-  return 2LL * W * xchg_l2(len) + 2LL * W * 4 + ((long long)slot * W + sender) * GPC_MAX_KP + k;
+// ---- inbox layout of the fused exchange: FLAG-IN-DATA messages, no fences and no separate flags.
+// Every double travels as ONE 16-byte store {lo32, epoch32, hi32, epoch32} (the scheme of NCCL's LL protocol): the receiver polls the
+// 16-byte word itself until BOTH epoch fields carry the epoch it expects -- a torn 16-byte write (8-byte atomicity is all that is
+// guaranteed) can then never be taken for a complete one.  The sender fires its stores and moves on: no __threadfence_system, no
+// flag round trip.  Two slots (epoch parity): a rank is at most one exchange ahead of the slowest (every exchange is all-to-all).
+//   in 16-byte units:  [2][W][64 clusters][kLLRow] statistics rows (row k: T[k][0..DP) | phi_hat_k | H (with cluster 0))
+//                      [2][W][4] dots
+constexpr int kLLRow = GPC_MAX_DP + 8;
+__host__ __device__ inline long long ll_off_stats(int W, int slot, int sender, int k) { return (((long long)slot * W + sender) * GPC_MAX_KP + k) * kLLRow; }
+__host__ __device__ inline long long ll_off_dots(int W, int slot, int sender) { return 2LL * W * GPC_MAX_KP * kLLRow + ((long long)slot * W + sender) * 4; }
+__host__ __device__ inline long long ll_units(int W) { return 2LL * W * GPC_MAX_KP * kLLRow + 2LL * W * 4; }
+__host__ __device__ inline long long fx_doubles(int W, int len) { (void)len; return 2 * ll_units(W); }
+
+__device__ __forceinline__ void ll_send(double *inbox_peer, long long unit, double v, unsigned int ep) {
+  const unsigned int lo = (unsigned int)__double2loint(v), hi = (unsigned int)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(reinterpret_cast<uint4 *>(inbox_peer) + unit), "r"(lo), "r"(ep), "r"(hi), "r"(ep)
+               : "memory");
 }
-__host__ __device__ inline long long fx_off_dflag(int W, int len, int slot, int sender) {
-  return 2LL * W * xchg_l2(len) + 2LL * W * 4 + 2LL * W * GPC_MAX_KP + (long long)slot * W + sender;
+// poll one message of this rank's own inbox until it carries epoch `ep`; bounded.  *ok is cleared on a timeout.
+__device__ __forceinline__ double ll_recv(const double *inbox_self, long long unit, unsigned int ep, bool *ok) {
+  const uint4 *p = reinterpret_cast<const uint4 *>(inbox_self) + unit;
+  unsigned int lo, f0, hi, f1;
+  unsigned long long t0 = 0ull;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+    if (f0 == ep && f1 == ep) break;
+    if (((++spins) & 255) == 0) {
+      const unsigned long long t = globaltimer_ns();
+      if (t0 == 0ull) t0 = t;
+      else if ((long long)(t - t0) > kSpinLimitNs) {
+        *ok = false;
+        break;
+      }
+    }
+  }
+  return __hiloint2double((int)hi, (int)lo);
 }
-__host__ __device__ inline long long fx_doubles(int W, int len) { return 2LL * W * xchg_l2(len) + 2LL * W * 4 + 2LL * W * GPC_MAX_KP + 2LL * W; }
 
 struct LoopKernelArgs {
   NatgradArgs g;    // F, Wt, bias, partials (grid x 4), dots_out, N, K, DP, num_groups, stages, bufs      (loop / peers unused)
   StepStatsArgs s;  // F, beta_out, partials (grid x stats_len), N, K, DP, num_groups, stages, bufs         (loop / peers / dots unused)
   MohgpPostArgs p;  // stats, ws, Sy_inv, Sf, const_term, Wt, muk_t, ..., info, alpha, prior, K, D, KP, DP, dots, beta, loop (GLOBAL)
-  const gpc_peers_t *peers;     // nullable; inbox layout fx_* above
+  const gpc_peers_t *peers;     // nullable; inbox layout ll_* above
   unsigned int *sync;           // [0] grid-barrier counter, [1] exit counter, [2] posterior ticket -- all zero between launches
   unsigned long long *timing;   // nullable: [0..3] ns spent in G rows / B1 + dots / S rows / B2 + posterior + B3, [4] evaluations, [5] G phases
   int max_evals;
@@ -66,6 +93,7 @@ struct LoopShared {  // header of dynamic shared memory: everything that lives a
   double dots[4];
   unsigned long long e_stats, e_dots;  // exchange epochs (uniform over the grid)
   unsigned long long t_acc[4], n_eval, n_g, t[4];
+  unsigned long long p_acc[7], pt[7], dbg[8], dbg_acc[8];  // posterior phase in detail (CTA 0): B2 wait / local row reduce / exchange / math + ticket / tail + B3
   unsigned int bar_target;
   int abort, W, my_rank, len;
   int ev, max_evals, retry, g_stages, s_stages, KP, DP;
@@ -131,30 +159,27 @@ __device__ __noinline__ void loop_dots_phase(LoopShared &hs) {
       }
     }
   } else {
-    const int W = hs.W, my_rank = hs.my_rank, len = hs.len;
+    const int W = hs.W, my_rank = hs.my_rank;
     const unsigned long long e_dots = hs.e_dots + 1;  // uniform; thread 0 stores it back after the last barrier below
     const int slot = (int)(e_dots & 1);
-    if (cid == 0) {
-      if (warp < 3) {
-        double v = 0.0;
-        for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
-        v = warp_sum(v);
-        if (lane < W) P->inbox[lane][fx_off_dots(W, len, slot, my_rank) + warp] = v;  // lane r -> peer r, over NVLink
-      }
-      asm volatile("bar.sync 3, %0;\n" ::"n"(kRowThreads) : "memory");
-      if (warp == 0) {
-        __threadfence_system();
-        if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_dflag(W, len, slot, my_rank), e_dots);
-      }
+    const unsigned int ep = (unsigned int)e_dots;
+    if (cid == 0 && warp < 3) {
+      double v = 0.0;
+      for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
+      v = warp_sum(v);
+      if (lane < W) ll_send(P->inbox[lane], ll_off_dots(W, slot, my_rank) + warp, v, ep);  // lane r -> peer r, over NVLink
     }
     if (warp == 0) {
+      // lane (r, q) = (lane / 4, lane % 4) receives dot q of rank r; the W contributions are summed in rank order (identical on all ranks)
       bool ok = true;
-      if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_dflag(W, len, slot, lane), e_dots);
+      const int r = lane >> 2, q = lane & 3;
+      double d = 0.0;
+      if (r < W && q < 3) d = ll_recv(hs.inbox_self, ll_off_dots(W, slot, r) + q, ep, &ok);
       ok = __all_sync(0xffffffffu, ok);
+      double tot = 0.0;
+      for (int rr = 0; rr < W; ++rr) tot += __shfl_sync(0xffffffffu, d, rr * 4 + q);
       if (lane < 3) {
-        double d = 0.0;
-        for (int r = 0; r < W; ++r) d += __ldcg(hs.inbox_self + fx_off_dots(W, len, slot, r) + lane);  // rank order: identical on all ranks
-        hs.dots[lane] = ok ? d : nan("");
+        hs.dots[lane] = ok ? tot : nan("");
         if (cid == 0) hs.dots_out[lane] = hs.dots[lane];
       }
       if (!ok && lane == 0) atomicOr(&hs.p.loop->done, GPC_DONE_PEER_TIMEOUT);
@@ -171,6 +196,8 @@ __device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cid = (int)blockIdx.x, ncl = (int)gridDim.x;
   if (!grid_barrier<0, kGThreads>(hs)) return false;
+  const bool stamp = hs.timing != nullptr && cid == 0 && tid == 0;
+  if (stamp) hs.pt[0] = hs.pt[1] = hs.pt[2] = hs.pt[3] = globaltimer_ns();
   const MohgpPostArgs &pa = hs.p;
   const int KP = pa.KP, DP = pa.DP, D = pa.D, len = hs.len;
   const gpc_peers_t *P = hs.peers;
@@ -181,64 +208,106 @@ __device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem
     PostSmem &ps = *reinterpret_cast<PostSmem *>(smem_raw + (((size_t)eig_ws_len(D) * 8 + 127) & ~(size_t)127));
     if (tid == 0) post_stage_ws(pa.ws, D, ps, ws_s);
     double phi_hat = post_reduce_row<true>(hs.spart, ncl, len, k, KP, DP, ps);
-    const double *hparts = hs.spart;
-    int hnum = ncl;
+    if (stamp) hs.pt[1] = hs.pt[2] = globaltimer_ns();
     if (P != nullptr) {
       const int W = hs.W, my_rank = hs.my_rank;
       const int slot = (int)(e_stats & 1);
-      // this rank's row of cluster k (+ its entropy, with cluster 0) -> every peer's inbox; one flag per (sender, cluster)
+      const unsigned int ep = (unsigned int)e_stats;
+      // this rank's row of cluster k (+ its entropy, with cluster 0) -> every peer's inbox as flag-in-data messages
       double Hloc = 0.0;
       if (k == 0) {
         for (int c = tid; c < ncl; c += kClusterThreads) Hloc += __ldcg(hs.spart + (size_t)c * len + (size_t)KP * DP + KP);
         Hloc = block_sum<true>(Hloc, ps.red_s);
       }
-      const long long base = fx_off_stats(W, len, slot, my_rank);
-      for (int r = 0; r < W; ++r) {
-        double *dst = P->inbox[r] + base;
-        if (tid < DP) dst[(size_t)k * DP + tid] = ps.yb_s[tid];
-        if (tid == 64) dst[(size_t)KP * DP + k] = phi_hat;
-        if (tid == 65 && k == 0) dst[(size_t)KP * DP + KP] = Hloc;
+      const long long base = ll_off_stats(W, slot, my_rank, k);
+      if (tid < DP + 2) {
+        const double v = tid < DP ? ps.yb_s[tid] : (tid == DP ? phi_hat : Hloc);
+        for (int r = 0; r < W; ++r) ll_send(P->inbox[r], base + tid, v, ep);
+      }
+      // the W rows of cluster k, one message per thread and round; summed in rank order (identical on all ranks)
+      bool ok = true;
+      const int rowlen = DP + 2;
+      for (int i = tid; i < W * rowlen; i += kClusterThreads) {
+        const int r = i / rowlen, j = i - r * rowlen;
+        ps.xrow[r][j] = ll_recv(hs.inbox_self, ll_off_stats(W, slot, r, k) + j, ep, &ok);
+      }
+      if (!ok) {
+        atomicOr(pa.info, GPC_INFO_PEER_TIMEOUT);
+        atomicOr(&pa.loop->done, GPC_DONE_PEER_TIMEOUT);
       }
       psync<true>();
-      if (warp == 0) {
-        __threadfence_system();
-        if (lane < W) st_relaxed_sys(reinterpret_cast<unsigned long long *>(P->inbox[lane]) + fx_off_sflag(W, len, slot, my_rank, k), e_stats);
-        bool ok = true;
-        if (lane < W) ok = flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_sflag(W, len, slot, lane, k), e_stats);
-        ok = __all_sync(0xffffffffu, ok);
-        if (!ok && lane == 0) {
-          atomicOr(pa.info, GPC_INFO_PEER_TIMEOUT);
-          atomicOr(&pa.loop->done, GPC_DONE_PEER_TIMEOUT);
-        }
+      double tot = 0.0;
+      if (tid < DP) {
+        for (int r = 0; r < W; ++r) tot += ps.xrow[r][tid];
+        ps.yb_s[tid] = tot;
       }
+      phi_hat = 0.0;
+      for (int r = 0; r < W; ++r) phi_hat += ps.xrow[r][DP];
       psync<true>();
-      hparts = hs.inbox_self + fx_off_stats(W, len, slot, 0);
-      hnum = W;
-      phi_hat = post_reduce_row<true>(hparts, W, len, k, KP, DP, ps);  // sum over the ranks, in rank order
     }
     if (tid < DP) pa.stats[(size_t)k * DP + tid] = ps.yb_s[tid];
     if (tid == 0) pa.stats[(size_t)KP * DP + k] = phi_hat;
+    if (stamp) hs.pt[2] = globaltimer_ns();
     mbar_wait(&ps.stage_bar, 0);
-    post_cluster_math<true>(pa, k, phi_hat, ps, ws_s);
+    if (stamp) hs.pt[4] = globaltimer_ns();
+    post_cluster_math<true>(pa, k, phi_hat, ps, ws_s, stamp ? hs.dbg : nullptr);
+    if (stamp) {
+      hs.pt[5] = globaltimer_ns();
+      hs.dbg_acc[0] += hs.dbg[0] - hs.pt[4];
+      for (int q = 1; q < 5; ++q) hs.dbg_acc[q] += hs.dbg[q] - hs.dbg[q - 1];
+      hs.dbg_acc[5] += hs.pt[5] - hs.dbg[4];
+    }
     __threadfence();
     psync<true>();
     if (tid == 0) {
-      const unsigned int done = atomicAdd(pa.counter, 1u);
-      ps.is_last = (done == (unsigned)KP - 1) ? 1 : 0;
+      atomicAdd(pa.counter, 1u);  // ticket: the scalar CTA finishes the evaluation once all KP clusters are in
       mbar_inval(&ps.stage_bar);
     }
-    psync<true>();
-    if (ps.is_last) {
-      __threadfence();
-      if (P != nullptr && warp == 0) {
-        // the entropies travel with cluster 0's rows: make sure this CTA has observed those flags itself
-        const int slot = (int)(e_stats & 1);
-        if (lane < hs.W) flag_wait(reinterpret_cast<const unsigned long long *>(hs.inbox_self) + fx_off_sflag(hs.W, len, slot, lane, 0), e_stats);
+    if (stamp) hs.pt[3] = globaltimer_ns();
+  } else if (cid == KP && tid < kClusterThreads) {
+    // ---- the "scalar" CTA: everything of the evaluation's tail that needs the statistics only -- entropy, phi_hat of every cluster,
+    // the mixing-proportion terms (lgamma / digamma per cluster) -- runs HERE, concurrently with the cluster CTAs' algebra; then it
+    // waits for their ticket and assembles the bound, the bias and the accept / reject / termination decision.
+    PostSmem &ps = *reinterpret_cast<PostSmem *>(smem_raw);
+    if (P != nullptr) {
+      // phi_hat of every cluster and the entropy from the same messages the cluster CTAs consume, summed in the same (rank) order
+      const int W = hs.W, slot = (int)(e_stats & 1);
+      const unsigned int ep = (unsigned int)e_stats;
+      bool ok = true;
+      for (int k = tid; k < pa.K; k += kClusterThreads) {
+        double v = 0.0;
+        for (int r = 0; r < W; ++r) v += ll_recv(hs.inbox_self, ll_off_stats(W, slot, r, k) + DP, ep, &ok);
+        ps.phi_hat_sh[k] = v;
+      }
+      if (tid == kClusterThreads - 1) {
+        double v = 0.0;
+        for (int r = 0; r < W; ++r) v += ll_recv(hs.inbox_self, ll_off_stats(W, slot, r, 0) + DP + 1, ep, &ok);
+        ps.H_s = v;
+      }
+      if (!ok) atomicOr(&pa.loop->done, GPC_DONE_PEER_TIMEOUT);
+      psync<true>();
+      post_tail_mixing<true>(pa, ps);
+    } else {
+      for (int k = warp; k < pa.K; k += kClusterThreads / 32) {
+        const double v = reduce_phi_hat_warp(hs.spart, ncl, len, KP, DP, k);  // the same routine as cluster k's own CTA: the same bits
+        if (lane == 0) ps.phi_hat_sh[k] = v;
       }
       psync<true>();
-      post_tail<true>(pa, ps, hparts, hnum, len, phase);  // resets the ticket (pa.counter)
-      __threadfence();
+      post_tail_prepare<true>(pa, ps, hs.spart, ncl, len);
     }
+    if (tid == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      int spins = 0;
+      while (ld_acquire_gpu_u32(pa.counter) < (unsigned)KP) {
+        if (((++spins) & 1023) == 0 && (long long)(globaltimer_ns() - t0) > kSpinLimitNs) {
+          atomicOr(&pa.loop->done, GPC_DONE_PEER_TIMEOUT);
+          break;
+        }
+      }
+    }
+    psync<true>();
+    post_tail_finish<true>(pa, ps, phase);  // resets the ticket (pa.counter)
+    __threadfence();
   }
   // B3: the decision and the new weights are visible to every CTA
   if (!grid_barrier<0, kGThreads>(hs)) return false;
@@ -252,6 +321,13 @@ __device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem
       hs.t_acc[3] += t4 - hs.t[3];
       hs.n_eval += 1;
       hs.n_g += (phase == GPC_PHASE_RETRY) ? 0 : 1;
+      hs.p_acc[0] += hs.pt[0] - hs.t[3];
+      hs.p_acc[1] += hs.pt[1] - hs.pt[0];
+      hs.p_acc[2] += hs.pt[2] - hs.pt[1];
+      hs.p_acc[3] += hs.pt[3] - hs.pt[2];
+      hs.p_acc[4] += t4 - hs.pt[3];
+      hs.p_acc[5] += hs.pt[4] - hs.pt[2];  // of the algebra interval: waiting for the staged workspace
+      hs.p_acc[6] += hs.pt[5] - hs.pt[4];  // ... and the algebra itself
     }
   }
   return true;
@@ -374,6 +450,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_mohgp_loop(const __grid_consta
     hs.e_stats = P ? __ldcg(P->epochs + 0) : 0ull;
     hs.e_dots = P ? __ldcg(P->epochs + 1) : 0ull;
     for (int q = 0; q < 4; ++q) hs.t_acc[q] = 0ull;
+    for (int q = 0; q < 7; ++q) hs.p_acc[q] = 0ull;
+    for (int q = 0; q < 8; ++q) hs.dbg_acc[q] = 0ull;
     hs.n_eval = hs.n_g = 0ull;
   }
 
@@ -426,6 +504,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_mohgp_loop(const __grid_consta
       for (int q = 0; q < 4; ++q) a.timing[q] += hs.t_acc[q];
       a.timing[4] += hs.n_eval;
       a.timing[5] += hs.n_g;
+      for (int q = 0; q < 7; ++q) a.timing[6 + q] += hs.p_acc[q];
+      for (int q = 0; q < 6; ++q) a.timing[16 + q] += hs.dbg_acc[q];
     }
     __threadfence();
     const unsigned int left = atomicAdd(a.sync + 1, 1u);

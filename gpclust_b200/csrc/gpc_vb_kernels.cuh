@@ -491,6 +491,10 @@ struct StepStatsArgs {
   // wide mode (template CL): clusters of `csize` CTAs, see NatgradArgs.  K is the total cluster count; partials holds one
   // full [T KPtot x DP | phi_hat KPtot | H | pad] block PER CLUSTER (rank r fills rows / entries [64 r, 64 r + 64), rank 0 H).
   int csize;
+  // reverse != 0: this CTA walks its row groups from the last to the first.  The G pass walks them first to last, so the S pass that
+  // follows starts on the operands (F, x, natural gradient) the G pass touched LAST -- still in L2 -- and ends on the groups the next
+  // G pass starts with (its x_new is that pass's x).
+  int reverse;
 };
 
 __host__ __device__ inline int s_stage_doubles(int KP, int DP) { return kGroupRows * DP + 3 * kGroupRows * KP; }
@@ -605,8 +609,9 @@ __device__ __forceinline__ void s_producer(const StepStatsArgs &a, const SSmem &
   {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(FG + XG + (has_ng ? XG : 0) + (load_old ? XG : 0)) * 8u;
-      int j = 0;
-      for (int grp = cid; grp < a.num_groups; grp += ncl, ++j) {
+      const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;  // row groups of this CTA: cid + m * ncl
+      for (int j = 0; j < Mc; ++j) {
+        const int grp = cid + (a.reverse ? Mc - 1 - j : j) * ncl;
         const int s = j % S;
         if (j >= S) mbar_wait(&empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
         double *st = stages + (size_t)s * stage_doubles;
@@ -640,8 +645,10 @@ __device__ __forceinline__ void s_softmax(const StepStatsArgs &a, const SSmem &m
   {
     // ---------------- softmax warps: CG step + softmax statistics of one group each
     double Hpart = 0.0;
-    int j = warp, iw = 0;
-    for (int grp = cid + warp * ncl; grp < a.num_groups; grp += kSSoftmaxWarps * ncl, j += kSSoftmaxWarps, ++iw) {
+    const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;
+    int iw = 0;
+    for (int j = warp; j < Mc; j += kSSoftmaxWarps, ++iw) {
+      const int grp = cid + (a.reverse ? Mc - 1 - j : j) * ncl;
       const int s = j % S;
       double *st = stages + (size_t)s * stage_doubles;
       const int row = grp * kGroupRows + g;
@@ -852,8 +859,8 @@ __device__ __forceinline__ void s_stats(const StepStatsArgs &a, const SSmem &m, 
     double colsum[NT];  // sum over rows == t (mod 4) of phi[row][8*mt + g]
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt) colsum[mt] = 0.0;
-    int j = 0;
-    for (int grp = cid; grp < a.num_groups; grp += ncl, ++j) {
+    const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;
+    for (int j = 0; j < Mc; ++j) {
       const int s = j % S;
       const double *st = stages + (size_t)s * stage_doubles;
       mbar_wait(&phi_bar[s], (uint32_t)((j / S) & 1));

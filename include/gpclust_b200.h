@@ -173,12 +173,14 @@ int gpc_reduce_push(const double *partials, int num_parts, int len, const gpc_pe
  * termination tests of gpc_loop_t fire); the phases are separated by grid-wide barriers instead of kernel boundaries, the statistics
  * are reduced per cluster by the CTA that computes that cluster's posterior, and with rows sharded over GPUs each cluster's row goes
  * straight into every peer's inbox with its own flag.  Arguments as for the entry points it replaces.
- *   grid      = gpc_default_grid(device) (one CTA per SM, all co-resident: cooperative launch); must be >= KP
+ *   grid      = gpc_default_grid(device) (one CTA per SM, all co-resident: cooperative launch); must be > KP (CTA k: cluster k; CTA KP:
+ *             entropy, mixing-proportion terms, bound and the accept / reject decision)
  *   gpart     grid*4 doubles, spart grid*gpc_stats_len(KP,DP) doubles
  *   dots/beta device scalars [3] / [1] (read back by the host with the control block)
  *   sync      4 zero-initialised unsigned ints (the kernel leaves them zero)
- *   timing    nullable: 6 unsigned 64-bit accumulators -- ns in G rows / dots barrier + exchange / S rows / posterior incl. barriers,
- *             evaluations, G phases (measured by CTA 0 with %globaltimer)
+ *   timing    nullable: 16 unsigned 64-bit accumulators (measured by CTA 0 with %globaltimer) -- [0..3] ns in G rows / dots barrier +
+ *             exchange / S rows / posterior incl. barriers, [4] evaluations, [5] G phases, [6..10] the posterior phase in detail:
+ *             wait at the barrier / local row reduction / NVLink exchange / posterior algebra + ticket / tail + barrier
  *   peers     NULL on one GPU; otherwise the inbox must hold gpc_xchg_doubles_fused(world, stats_len) doubles:
  *             [2][W][L] statistics | [2][W][4] dots | [2][W][64] statistics flags (sender, cluster) | [2][W] dots flags
  * A peer that never arrives sets GPC_DONE_PEER_TIMEOUT in loop->done (bounded waits, 4 s).                                      */
