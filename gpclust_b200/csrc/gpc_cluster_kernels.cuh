@@ -763,12 +763,20 @@ __device__ __forceinline__ void post_stage_ws(const double *ws, int D, PostSmem 
 // phi_hat_k (the cluster's own CTA, the CTA that evaluates the mixing-proportion terms) uses this routine: bit-identical values.
 __device__ __forceinline__ double reduce_phi_hat_warp(const double *partials, int num_parts, int len, int KP, int DP, int k) {
   const int lane = threadIdx.x & 31;
-  double q0 = 0.0, q1 = 0.0;
-  for (int p = lane; p < num_parts; p += 64) {
-    q0 += __ldcg(partials + (size_t)p * len + (size_t)KP * DP + k);
-    if (p + 32 < num_parts) q1 += __ldcg(partials + (size_t)(p + 32) * len + (size_t)KP * DP + k);
+  const double *src = partials + (size_t)KP * DP + k;
+  const int last = num_parts - 1;
+  double tot = 0.0;
+  // lane takes the vectors lane, lane + 32, ...: eight loads in flight per round (one L2 round trip for up to 256 vectors), clamped
+  // addresses as in post_reduce_row
+  for (int p0 = lane; p0 < num_parts; p0 += 256) {
+    double w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldcg(src + min(p0 + 32 * u, last) * len);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = (p0 + 32 * u <= last) ? w[u] : 0.0;
+    tot += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   }
-  return warp_sum(q0 + q1);
+  return warp_sum(tot);
 }
 
 // this cluster's statistics: fixed-order sum over `num_parts` vectors of stride `len` -> sm.yb_s[0..DP); returns phi_hat_k on every

@@ -150,9 +150,7 @@ __device__ __noinline__ void loop_dots_phase(LoopShared &hs) {
   const gpc_peers_t *P = hs.peers;
   if (P == nullptr) {
     if (warp < 3) {
-      double v = 0.0;
-      for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
-      v = warp_sum(v);  // fixed lane -> CTA assignment and fixed shuffle tree: identical on every CTA, run to run
+      const double v = reduce_dot_warp(hs.gpart, ncl, warp);
       if (lane == 0) {
         hs.dots[warp] = v;
         if (cid == 0) hs.dots_out[warp] = v;
@@ -164,9 +162,7 @@ __device__ __noinline__ void loop_dots_phase(LoopShared &hs) {
     const int slot = (int)(e_dots & 1);
     const unsigned int ep = (unsigned int)e_dots;
     if (cid == 0 && warp < 3) {
-      double v = 0.0;
-      for (int c = lane; c < ncl; c += 32) v += __ldcg(hs.gpart + (size_t)c * 4 + warp);
-      v = warp_sum(v);
+      const double v = reduce_dot_warp(hs.gpart, ncl, warp);
       if (lane < W) ll_send(P->inbox[lane], ll_off_dots(W, slot, my_rank) + warp, v, ep);  // lane r -> peer r, over NVLink
     }
     if (warp == 0) {

@@ -395,6 +395,17 @@ __device__ __forceinline__ void g_cta_partial(const GSmem &m, double *partials) 
   }
 }
 
+// dot `q` summed over the per-CTA partials by ONE WARP: all loads in flight at once (up to 256 CTAs), fixed order
+__device__ __forceinline__ double reduce_dot_warp(const double *gpart, int ncl, int q) {
+  const int lane = threadIdx.x & 31;
+  double w[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) w[u] = __ldcg(gpart + (size_t)min(lane + 32 * u, ncl - 1) * 4 + q);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) w[u] = (lane + 32 * u < ncl) ? w[u] : 0.0;
+  return warp_sum(((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7])));  // identical on every CTA, run to run
+}
+
 template <int KP, bool FULLK, bool CL = false>
 __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -426,10 +437,13 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
   if (is_last) {
     __threadfence();
     if (warp < 3) {
+      // fixed lane->CTA assignment and fixed shuffle tree => run-to-run deterministic (the same routine as the fused loop kernel)
       double v = 0.0;
-      for (int c = lane; c < (int)gridDim.x; c += 32) v += __ldcg(a.partials + (size_t)c * 4 + warp);
-      // fixed lane->CTA assignment and fixed shuffle tree => run-to-run deterministic
-      v = warp_sum(v);
+      if ((int)gridDim.x <= 256) v = reduce_dot_warp(a.partials, (int)gridDim.x, warp);
+      else {
+        for (int c = lane; c < (int)gridDim.x; c += 32) v += __ldcg(a.partials + (size_t)c * 4 + warp);
+        v = warp_sum(v);
+      }
       if (lane == 0) {
         a.dots_out[warp] = v;
         if (a.peers != nullptr) {  // this rank's contribution -> slot of the NEXT dots exchange in every inbox
