@@ -37,16 +37,16 @@ class MOHGP(CollapsedMixture):
 
         # features: F = Y, fragment-major, Npad x DP
         DP = _cabi.padded_d(self.D)
+        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major (include/gpclust_b200.h "Layout")
         if isinstance(Y, torch.Tensor):
             Yd = Y.to(device=self.device, dtype=torch.float64).contiguous()
             self._Y_host = None
+            check(lib.gpc_pack_rows(ptr(Yd), N, self.D, DP, _cabi.LAYOUT["features"], ptr(F), self._stream()), "gpc_pack_rows")
+            self.kernel_launches += 1
+            del Yd
         else:
             self._Y_host = _cabi.f64(Y)
-            Yd = torch.from_numpy(self._Y_host).to(self.device)
-        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major (include/gpclust_b200.h "Layout")
-        check(lib.gpc_pack_rows(ptr(Yd), N, self.D, DP, _cabi.LAYOUT["features"], ptr(F), self._stream()), "gpc_pack_rows")
-        self.kernel_launches += 1
-        del Yd
+            self.kernel_launches += _cabi.upload_pack(self._Y_host, self.D, DP, _cabi.LAYOUT["features"], F, self.device, self._stream())
         self._set_features(F, DP)
 
         # Computations that can be done outside the optimisation loop (MOHGP.py:52-53)

@@ -205,3 +205,64 @@ def to_host(t):
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return h.numpy()
+
+
+# ---------------------------------------------------------------------------------------------- host -> device ingest
+class _Ingest(object):
+    """Pipelined upload of a (pageable) numpy matrix into the fragment-major device layout.
+
+    A plain cudaMemcpy from pageable memory is staged by the driver through one bounce buffer on one thread (a few GB/s).  Here the
+    rows are cut into chunks; several host threads copy chunk i+1 into a pinned staging buffer while the DMA engine moves chunk i
+    over PCIe and gpc_pack_rows re-orders chunk i-1 into the fragment-major layout -- three stages in flight, all device work
+    in order on the caller's stream.  Staging buffers and the thread pool are created once per process."""
+    CHUNK_BYTES = int(os.environ.get("GPCLUST_B200_INGEST_CHUNK_MB", "32")) << 20
+    NBUF = 3
+
+    def __init__(self):
+        self.pinned, self.dev, self.events, self.pool, self.threads = None, {}, None, None, 0
+
+    def _setup(self, torch, device):
+        if self.pinned is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self.threads = max(1, min(int(os.environ.get("GPCLUST_B200_INGEST_THREADS", "8")), (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+            self.pool = ThreadPoolExecutor(self.threads)
+            self.pinned = [torch.empty(self.CHUNK_BYTES // 8, dtype=torch.float64, pin_memory=True) for _ in range(self.NBUF)]
+            self.events = [torch.cuda.Event() for _ in range(self.NBUF)]
+        key = (device.type, device.index)
+        if key not in self.dev:
+            self.dev[key] = [torch.empty(self.CHUNK_BYTES // 8, dtype=torch.float64, device=device) for _ in range(self.NBUF)]
+        return self.dev[key]
+
+    def upload_pack(self, src, C, CP, layout, dst, device, stream_ptr):
+        """src: C-contiguous float64 numpy (N, C).  dst: device tensor, fragment-major (padded_rows(N) x CP).  Returns launches."""
+        import torch
+        N = src.shape[0]
+        dev = self._setup(torch, device)
+        rows = max(GPC_ROW_TILE, (self.CHUNK_BYTES // (8 * C)) // GPC_ROW_TILE * GPC_ROW_TILE)  # whole 64-row tiles: only the last chunk pads
+        launches = 0
+        for i, lo in enumerate(range(0, N, rows)):
+            hi = min(N, lo + rows)
+            b = i % self.NBUF
+            if i >= self.NBUF:
+                self.events[b].synchronize()  # the DMA that last read this staging buffer has finished
+            stage = self.pinned[b][:(hi - lo) * C].view(hi - lo, C).numpy()
+            n = hi - lo
+            if self.threads > 1 and n * C >= (1 << 18):
+                cuts = [lo + n * t // self.threads for t in range(self.threads + 1)]
+                list(self.pool.map(lambda ab: np.copyto(stage[ab[0] - lo:ab[1] - lo], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+            else:
+                np.copyto(stage, src[lo:hi])
+            d = dev[b][:n * C]
+            d.copy_(self.pinned[b][:n * C], non_blocking=True)
+            self.events[b].record()
+            check(lib.gpc_pack_rows(ctypes.c_void_p(d.data_ptr()), n, C, CP, layout, ctypes.c_void_p(dst.data_ptr() + 8 * lo * CP), stream_ptr),
+                  "gpc_pack_rows")
+            launches += 1
+        return launches
+
+
+_ingest = _Ingest()
+
+
+def upload_pack(src, C, CP, layout, dst, device, stream_ptr):
+    return _ingest.upload_pack(src, C, CP, layout, dst, device, stream_ptr)

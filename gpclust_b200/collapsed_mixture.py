@@ -202,13 +202,15 @@ class CollapsedMixture(CollapsedVB):
         K = self.K
         if K != self._kbuf_K:
             self._alloc_k(K)
+        cur = self._xbuf[self._xi]
         if isinstance(x, torch.Tensor):
             src = x.to(device=self.device, dtype=torch.float64).reshape(self.N, K).contiguous()
+            check(lib.gpc_pack_rows(ptr(src), self.N, K, self._KP, _cabi.LAYOUT["logits"], ptr(cur), self._stream()), "gpc_pack_rows")
+            self.kernel_launches += 1
         else:
-            src = torch.from_numpy(_cabi.f64(np.asarray(x).reshape(self.N, K))).to(self.device)
-        cur = self._xbuf[self._xi]
-        check(lib.gpc_pack_rows(ptr(src), self.N, K, self._KP, _cabi.LAYOUT["logits"], ptr(cur), self._stream()), "gpc_pack_rows")
-        self.kernel_launches += 1
+            # host array: chunked, pipelined staging -> PCIe -> layout conversion (see _cabi._Ingest)
+            self.kernel_launches += _cabi.upload_pack(_cabi.f64(np.asarray(x).reshape(self.N, K)), K, self._KP, _cabi.LAYOUT["logits"], cur,
+                                                      self.device, self._stream())
         self._xprev = None
         self._xtrial = (self._xi + 1) % 3
         self._state_valid = False

@@ -1,4 +1,5 @@
-"""Wall-clock breakdown of the end-to-end call sequence of bench.py (construct from pinned host arrays, optimize, read back)."""
+"""Wall-clock breakdown of the end-to-end call sequence of bench.py (construct from plain numpy arrays -- or pinned ones with --pin --,
+optimize, read back)."""
 import os
 import sys
 import time
@@ -12,8 +13,9 @@ import bench
 from gpclust_b200 import MOHGP, kern
 
 X, Y, phi0 = bench.synth(1000000, bench.D, bench.K)
-pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-Y, phi0 = pin(Y), pin(phi0)
+if "--pin" in sys.argv:
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    Y, phi0 = pin(Y), pin(phi0)
 
 
 def T(label, t0):
@@ -23,13 +25,13 @@ def T(label, t0):
     return t1
 
 
-for rep in range(2):
+for rep in range(3):
     print("rep", rep)
     t = time.perf_counter()
     m = MOHGP(X, kern.RBF(1, 1.0, 2.0).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=bench.K, phi_init=phi0)
     t = T("construct", t)
-    m.optimize(method="HS", maxiter=30, ftol=-1.0, gtol=-1.0, verbose=False)
-    t = T("optimize(30)", t)
+    m.optimize(method="HS", maxiter=20, ftol=-1.0, gtol=-1.0, verbose=False)
+    t = T("optimize(20)", t)
     phi = m.phi
     t = T("m.phi", t)
     b = m.bound()
