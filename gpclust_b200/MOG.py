@@ -71,7 +71,7 @@ class MOG(CollapsedMixture):
     def _alloc_model(self):
         torch = self.torch
         D, K = self.D, self._KP
-        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        z = lambda *shape: _cabi.dzeros(self.device, *shape)
         self._mun_c = z(K, D)
         self._Sns = z(K, D, D)
         self._Sns_inv = z(K, D, D)

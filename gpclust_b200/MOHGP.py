@@ -37,7 +37,7 @@ class MOHGP(CollapsedMixture):
 
         # features: F = Y, fragment-major, Npad x DP
         DP = _cabi.padded_d(self.D)
-        F = torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major (include/gpclust_b200.h "Layout")
+        F = _cabi.dzeros(self.device, self._Npad, DP) if _cabi.GUARD else torch.empty((self._Npad, DP), dtype=torch.float64, device=self.device)  # fragment-major (include/gpclust_b200.h "Layout")
         if isinstance(Y, torch.Tensor):
             Yd = Y.to(device=self.device, dtype=torch.float64).contiguous()
             self._Y_host = None
@@ -61,7 +61,7 @@ class MOHGP(CollapsedMixture):
         torch = self.torch
         self._X_dev = torch.from_numpy(self.X).to(self.device)
         D = self.D
-        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        z = lambda *shape: _cabi.dzeros(self.device, *shape)
         self._Sf, self._Sy = z(D, D), z(D, D)
         self._Ly, self._Ly_inv, self._Sy_inv, self._A = z(D, D), z(D, D), z(D, D), z(D, D)
         self._Sy_logdet, self._const = z(1), z(1)
@@ -96,7 +96,7 @@ class MOHGP(CollapsedMixture):
     def _alloc_model(self):
         torch = self.torch
         D, K = self.D, self._KP
-        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        z = lambda *shape: _cabi.dzeros(self.device, *shape)
         self._muk_t = z(K, D)
         self._Syi_ybark_t = z(K, D)
         self._Lambda_inv = None  # K x D x D attributes: allocated and filled on first read (_dense_posterior)
@@ -244,7 +244,7 @@ class MOHGP(CollapsedMixture):
         if "dense" not in self._cache:
             torch = self.torch
             D, KP = self.D, self._KP
-            z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+            z = lambda *shape: _cabi.dzeros(self.device, *shape)
             self._Lambda_inv, self._C_chols_dev = z(KP, D, D), z(KP, D, D)
             scratch = {"Wt": z(KP, self._DP), "muk_t": z(KP, D), "per_k": z(KP, 4), "s": z(KP, D), "info": torch.zeros(1, dtype=torch.int32, device=self.device)}
             check(lib.gpc_mohgp_cluster(ptr(self._stats), ptr(self._A), ptr(self._Ly), ptr(self._Ly_inv), ptr(self._Sy), ptr(self._Sy_inv), ptr(self._Sf),

@@ -95,10 +95,10 @@ class CollapsedMixture(CollapsedVB):
         self._F = None          # Npad x DP features, set by the subclass
         self._DP = None
         self._kbuf_K = None
-        self._ctrl = torch.zeros(_CTRL_LEN, dtype=torch.float64, device=self.device)
+        self._ctrl = _cabi.dzeros(self.device, _CTRL_LEN)
         self._ctrl_host = torch.zeros(_CTRL_LEN, dtype=torch.float64).pin_memory()
         self._counter = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self._gpart = torch.zeros(self._grid * 16, dtype=torch.float64, device=self.device)  # 4 doubles per CTA, up to 4 CTAs per SM
+        self._gpart = _cabi.dzeros(self.device, self._grid * 16)  # 4 doubles per CTA, up to 4 CTAs per SM
         self._state_valid = False
         self._bound_value = None
         self._peers = None      # peer-memory exchange descriptor (rows sharded over the GPUs of one box), see sharding.py
@@ -144,7 +144,7 @@ class CollapsedMixture(CollapsedVB):
         self._KP = KP
         self._kbuf_K = K
         self._graphs = {}
-        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.device)
+        z = lambda *shape: _cabi.dzeros(self.device, *shape)
         self._xbuf = [z(self._Npad, KP) for _ in range(3)]
         self._lsebuf = [z(self._Npad) for _ in range(3)]  # row logsumexp of the matching logits buffer
         self._xi, self._xprev, self._xtrial = 0, None, 1
@@ -169,8 +169,8 @@ class CollapsedMixture(CollapsedVB):
         KP, DP = self._KP, self._DP
         self._graphs = {}
         self._stats_len = lib.gpc_stats_len(KP, DP)
-        self._stats = torch.zeros(self._stats_len, dtype=torch.float64, device=self.device)
-        self._spart = torch.zeros(self._grid * self._stats_len, dtype=torch.float64, device=self.device)
+        self._stats = _cabi.dzeros(self.device, self._stats_len)
+        self._spart = _cabi.dzeros(self.device, self._grid * self._stats_len)
         # K > 64: one launch per pass by thread-block clusters of KP/64 CTAs (gpc_*_wide); GPCLUST_B200_WIDE=0 keeps the
         # per-chunk launches (gpc_*_chunk) for comparison
         self._wide = self._chunks > 1 and os.environ.get("GPCLUST_B200_WIDE", "1") != "0"
@@ -181,7 +181,7 @@ class CollapsedMixture(CollapsedVB):
                 check(self._ncl or -1, "gpc_wide_clusters")
             self._nparts = self._ncl
         self._peers = self._shards.setup_peers(self._stats_len, self.device) if (self._use_peer_exchange() and (self._chunks == 1 or self._wide)) else None
-        self._Wt = torch.zeros((KP, DP), dtype=torch.float64, device=self.device)
+        self._Wt = _cabi.dzeros(self.device, KP, DP)
 
         self._alloc_model()
 
@@ -248,17 +248,21 @@ class CollapsedMixture(CollapsedVB):
 
     def _softmax_readout(self):
         if "softmax" not in self._cache:
-            torch = self.torch
-            phi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
-            logphi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
-            grid = min(self._grid * 4, (self.N + 7) // 8)
-            hpart = torch.zeros(grid, dtype=torch.float64, device=self.device)
-            x = self._unpad(self._xbuf[self._xi])
-            check(lib.gpc_softmax_rows(ptr(x), self.N, self.K, self.K, ptr(phi), ptr(logphi), self.K, ptr(hpart), grid,
-                                       self._stream()), "gpc_softmax_rows")
-            self.kernel_launches += 1
-            self._cache["softmax"] = (phi, logphi, hpart)
+            with _cabi.nvtx_range("gpclust.phi_readout"):
+                self._cache["softmax"] = self._softmax_readout_now()
         return self._cache["softmax"]
+
+    def _softmax_readout_now(self):
+        torch = self.torch
+        phi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
+        logphi = torch.empty((self.N, self.K), dtype=torch.float64, device=self.device)
+        grid = min(self._grid * 4, (self.N + 7) // 8)
+        hpart = torch.zeros(grid, dtype=torch.float64, device=self.device)
+        x = self._unpad(self._xbuf[self._xi])
+        check(lib.gpc_softmax_rows(ptr(x), self.N, self.K, self.K, ptr(phi), ptr(logphi), self.K, ptr(hpart), grid,
+                                   self._stream()), "gpc_softmax_rows")
+        self.kernel_launches += 1
+        return (phi, logphi, hpart)
 
     @property
     def phi(self):
@@ -399,6 +403,10 @@ class CollapsedMixture(CollapsedVB):
     def do_computations(self):
         """Statistics, per-cluster posterior and bound at the current logits (MOHGP.py:70-90 / MOG.py:52-61).
         Raises numpy.linalg.LinAlgError when a per-cluster factorisation fails (GPy jitchol semantics)."""
+        with _cabi.nvtx_range("gpclust.do_computations"):
+            return self._do_computations()
+
+    def _do_computations(self):
         self._s_pass(self._xbuf[self._xi], None, None, None, None, self._lsebuf[self._xi], "zero", 0.0, 0.0)
         bound, _, _, failed = self._readback()
         self._cache = {}
@@ -635,7 +643,8 @@ class CollapsedMixture(CollapsedVB):
             ev = self._launch_events
             if ev is not None and not rows_all:
                 ev[0].record()  # bench.py: the timed region starts when the first launch is enqueued (loop-state set-up is not a step)
-            self._enqueue_passes(bufs, n)
+            with _cabi.nvtx_range("gpclust.vb_loop[%d evaluations]" % n):
+                self._enqueue_passes(bufs, n)
             if ev is not None:
                 ev[1].record()  # ... and ends behind the last one (re-recorded should a second batch be needed)
             L, rows = self._loop_download()
