@@ -13,6 +13,14 @@ import bench
 from gpclust_b200 import MOHGP, kern
 
 X, Y, phi0 = bench.synth(1000000, bench.D, bench.K)
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lo, hi = rank * 1000000 // world, (rank + 1) * 1000000 // world
+    Y, phi0 = np.ascontiguousarray(Y[lo:hi]), np.ascontiguousarray(phi0[lo:hi])
 if "--pin" in sys.argv:
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     Y, phi0 = pin(Y), pin(phi0)
@@ -21,12 +29,16 @@ if "--pin" in sys.argv:
 def T(label, t0):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    print("  %-28s %8.1f ms" % (label, (t1 - t0) * 1e3))
+    if rank == 0:
+        print("  %-28s %8.1f ms" % (label, (t1 - t0) * 1e3), flush=True)
     return t1
 
 
 for rep in range(3):
-    print("rep", rep)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print("rep", rep, flush=True)
     t = time.perf_counter()
     m = MOHGP(X, kern.RBF(1, 1.0, 2.0).fix(), (kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05)).fix(), Y, K=bench.K, phi_init=phi0)
     t = T("construct", t)
@@ -37,3 +49,5 @@ for rep in range(3):
     b = m.bound()
     t = T("m.bound()", t)
     del m
+if world > 1:
+    dist.destroy_process_group()
