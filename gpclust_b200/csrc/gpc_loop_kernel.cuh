@@ -350,9 +350,12 @@ template <int KP, bool FULLK>
 __device__ GPC_G_ATTR void loop_g_phase(const NatgradArgs &ga, LoopShared &hs, unsigned char *smem_raw) {
   const GSmem gm = g_carve(smem_raw, ga.stages, KP, ga.DP);
   const GPtrs gp = g_resolve(ga, KP, 0, &hs.L);
-  g_setup<KP, false>(ga, gm, gp);
+  g_setup_bars<KP, false>(ga, gm);
   __syncthreads();
-  g_rows<KP, FULLK, false>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x, 0, 1);
+  g_prefeed<KP>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x);  // first HBM round trip under the weight loads
+  g_setup_w<KP>(ga, gm, gp);
+  __syncthreads();
+  g_rows<KP, FULLK, false>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x, 0, 1, true);
   fence_proxy_async();  // this CTA's natural gradient is staged by its own bulk copies in the S phase
   __syncthreads();
 }

@@ -141,16 +141,27 @@ __device__ __forceinline__ GPtrs g_resolve(const NatgradArgs &a, int KP, int cra
 }
 // barriers, resident weights (B-fragment order) and bias; the caller synchronises the block (cluster) afterwards
 template <int KP, bool CL>
-__device__ __forceinline__ void g_setup(const NatgradArgs &a, const GSmem &m, const GPtrs &p) {
+__device__ __forceinline__ void g_setup_bars(const NatgradArgs &a, const GSmem &m) {
   constexpr int NT = KP / 8;
   constexpr int UNITS = kGConsumers / ((NT >= 2) ? 2 : 1);
-  const int DP = a.DP;
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) mbar_init(&m.full_bar[s], 1);
     if (CL)
       for (int s = 0; s < 2 * UNITS; ++s) mbar_init(&m.mb_bar[s], 1);
     mbar_fence_init();
   }
+}
+template <int KP>
+__device__ __forceinline__ void g_setup_w(const NatgradArgs &a, const GSmem &m, const GPtrs &p);
+template <int KP, bool CL>
+__device__ __forceinline__ void g_setup(const NatgradArgs &a, const GSmem &m, const GPtrs &p) {
+  g_setup_bars<KP, CL>(a, m);
+  g_setup_w<KP>(a, m, p);
+}
+template <int KP>
+__device__ __forceinline__ void g_setup_w(const NatgradArgs &a, const GSmem &m, const GPtrs &p) {
+  constexpr int NT = KP / 8;
+  const int DP = a.DP;
   for (int i = threadIdx.x; i < KP * DP; i += blockDim.x) {
     const int ln = i & 31, f = i >> 5;  // f = ks*NT + nt
     const int nt = f % NT, ks = f / NT;
@@ -169,8 +180,37 @@ __device__ __forceinline__ void g_setup(const NatgradArgs &a, const GSmem &m, co
 // the refill), and the four schedulers carry three compute warps each.
 // The row loop of one CTA: on return red_s[warp*4 + {0,1,2}] hold the warp's partial dots (the caller synchronises).
 // `cid` / `ncl`: index of this CTA (cluster of CTAs in wide mode) among those that share the row groups.
+// the first R ring slots of every unit, armed by the unit's leader lane (what g_rows does on entry unless told `prefed`): the fused
+// loop kernel issues them BEFORE it loads the weights, so that the first HBM round trip overlaps the L2 reads of W
+template <int KP>
+__device__ __forceinline__ void g_prefeed(const NatgradArgs &a, const GSmem &m, const GPtrs &p, int cid, int ncl) {
+  constexpr int NT = KP / 8;
+  constexpr int NSPLIT = (NT >= 2) ? 2 : 1;
+  constexpr int UNITS = kGConsumers / NSPLIT;
+  constexpr int XG = kGroupRows * KP;
+  const int DP = a.DP, FG = kGroupRows * DP, R = a.stages / UNITS, stage_doubles = g_stage_doubles(KP, DP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, unit = warp / NSPLIT, h = warp % NSPLIT;
+  if (h != 0 || lane != 0) return;
+  const bool has_old = (p.ng_old != nullptr);
+  const size_t GS = a.xg_stride ? (size_t)a.xg_stride : (size_t)XG;
+  const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? kGroupRows : 0)) * 8u;
+  double *ustages = m.stages + (size_t)unit * R * stage_doubles;
+  uint64_t *ubar = m.full_bar + unit * R;
+  for (int i = 0; i < R; ++i) {
+    const long long grp = (long long)cid + (long long)unit * ncl + (long long)i * UNITS * ncl;
+    if (grp >= a.num_groups) break;
+    double *st = ustages + (size_t)i * stage_doubles;
+    mbar_arrive_expect_tx(&ubar[i], bytes);
+    bulk_g2s(st, a.F + (size_t)grp * FG, FG * 8u, &ubar[i]);
+    bulk_g2s(st + FG, p.x + (size_t)grp * GS, XG * 8u, &ubar[i]);
+    bulk_g2s(st + FG + XG, p.lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[i]);
+    if (has_old) bulk_g2s(st + FG + XG + kGroupRows, p.lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[i]);
+  }
+}
+
 template <int KP, bool FULLK, bool CL>
-__device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, const GPtrs &p, int cid, int ncl, int crank, int csize) {
+__device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, const GPtrs &p, int cid, int ncl, int crank, int csize,
+                                       bool prefed = false) {
   constexpr int NT = KP / 8;
   constexpr int NSPLIT = (NT >= 2) ? 2 : 1;
   constexpr int NTW = NT / NSPLIT;           // n-tiles per warp
@@ -207,7 +247,7 @@ __device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, con
       bulk_g2s(st + FG + XG, p_lse + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
       if (has_old) bulk_g2s(st + FG + XG + kGroupRows, p_lse_old + (size_t)grp * kGroupRows, kGroupRows * 8u, &ubar[slot]);
     };
-    if (h == 0 && lane == 0)
+    if (!prefed && h == 0 && lane == 0)
       for (int i = 0; i < R; ++i) {
         const long long grp = (long long)grp0 + (long long)i * gstride;
         if (grp < a.num_groups) feed(i, (int)grp);
