@@ -228,6 +228,7 @@ class _Ingest(object):
             self.pool = ThreadPoolExecutor(self.threads)
             self.pinned = [torch.empty(self.CHUNK_BYTES // 8, dtype=torch.float64, pin_memory=True) for _ in range(self.NBUF)]
             self.events = [torch.cuda.Event() for _ in range(self.NBUF)]
+            self.busy = [False] * self.NBUF
         key = (device.type, device.index)
         if key not in self.dev:
             self.dev[key] = [torch.empty(self.CHUNK_BYTES // 8, dtype=torch.float64, device=device) for _ in range(self.NBUF)]
@@ -247,8 +248,8 @@ class _Ingest(object):
         for i, lo in enumerate(range(0, N, rows)):
             hi = min(N, lo + rows)
             b = i % self.NBUF
-            if i >= self.NBUF:
-                self.events[b].synchronize()  # the DMA that last read this staging buffer has finished
+            if self.busy[b]:
+                self.events[b].synchronize()  # the DMA that last read this staging buffer (this upload's or an earlier one's) has finished
             stage = self.pinned[b][:(hi - lo) * C].view(hi - lo, C).numpy()
             n = hi - lo
             if self.threads > 1 and n * C >= (1 << 18):
@@ -259,6 +260,7 @@ class _Ingest(object):
             d = dev[b][:n * C]
             d.copy_(self.pinned[b][:n * C], non_blocking=True)
             self.events[b].record()
+            self.busy[b] = True
             check(lib.gpc_pack_rows(ctypes.c_void_p(d.data_ptr()), n, C, CP, layout, ctypes.c_void_p(dst.data_ptr() + 8 * lo * CP), stream_ptr),
                   "gpc_pack_rows")
             launches += 1

@@ -1,4 +1,5 @@
 """Ingest helpers: loaders for the reference's data files and the notebook's preparation steps."""
+import ctypes
 import os
 
 import numpy as np
@@ -40,3 +41,29 @@ def test_normalisation_and_replicate_scores_match_numpy():
     assert np.max(np.abs(got - scores) / scores) < 1e-12
     top, index = io.select_top_series(e, times, n=500)
     assert np.array_equal(index, np.argsort(scores)[::-1][:500]) and top.shape == (500, times.size)
+
+
+@pytest.mark.gpu
+def test_pipelined_ingest_many_chunks_back_to_back(monkeypatch):
+    """Host -> device ingest (_cabi._Ingest): chunked staging / DMA / layout conversion.  Two uploads back to back through the same
+    staging ring with many small chunks each (the second must not overwrite staging buffers the first one's DMA is still reading),
+    ragged last chunk, both layouts; the device content must equal the host arrays exactly."""
+    import torch
+    from gpclust_b200 import _cabi
+    from gpclust_b200._cabi import lib, check, ptr
+    ing = _cabi._Ingest()
+    monkeypatch.setattr(ing, "CHUNK_BYTES", 1 << 16)  # 64 KB chunks: 128 rows of 64 doubles
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.RandomState(0)
+    for rep in range(3):
+        outs = []
+        for (N, C, CP, layout) in [(5000 + 37 * rep, 64, 64, "features"), (5000 + 37 * rep, 64, 64, "logits"), (3001, 24, 24, "features"), (3001, 7, 8, "logits")]:
+            src = rng.randn(N, C)
+            dst = torch.full((_cabi.padded_rows(N), CP), 7.0, dtype=torch.float64, device=dev)
+            ing.upload_pack(src, C, CP, _cabi.LAYOUT[layout], dst, dev, st)
+            outs.append((src, dst, N, C, CP, layout))
+        for src, dst, N, C, CP, layout in outs:  # verified only after ALL uploads were enqueued
+            back = torch.empty((N, C), dtype=torch.float64, device=dev)
+            check(lib.gpc_unpack_rows(ptr(dst), N, C, CP, _cabi.LAYOUT[layout], ptr(back), st), "gpc_unpack_rows")
+            assert np.array_equal(back.cpu().numpy(), src), (N, C, layout, rep)
