@@ -145,26 +145,25 @@ class MOHGP(CollapsedMixture):
         return CollapsedMixture._kernel_gradients(self)
 
     def update_kern_grads(self):
-        """MOHGP.py:92-122: derivative of the bound w.r.t. the kernel parameters through dL/dSf and dL/dSy.  K x D x D
-        host algebra on the device-computed posterior (C_chols from the literal Cholesky route), once per hyper-parameter
-        objective evaluation -- not part of the VB iteration."""
-        from scipy.linalg import solve_triangular
+        """MOHGP.py:92-122: derivative of the bound w.r.t. the kernel parameters through dL/dSf and dL/dSy.  The two D x D matrices
+        come from the device (gpc_mohgp_kern_grads: eigenbasis form, O(K D^2) instead of K triangular solves and K D^3 products on
+        the host); the contraction with dK/dtheta (GPy update_gradients_full) is D x D host algebra."""
+        self._ensure_state()
+        torch = self.torch
         D = self.D
-        Sy_chol_inv, Sf, Sy_inv, phi_hat = self.Sy_chol_inv, self.Sf, self.Sy_inv, self.phi_hat
-        Syi_ybark, ybark, YTY = self.Syi_ybark, self.ybark, self.YTY
-        tmp = [solve_triangular(L, Sy_chol_inv, lower=True) for L in self._C_chols]
-        B_invs = [ph * np.dot(t.T, t) for ph, t in zip(phi_hat, tmp)]
-        LiSfi = [np.eye(D) - np.dot(Sf, Bi) for Bi in B_invs]
-        tmp1 = [np.dot(L.T, s) for L, s in zip(LiSfi, Syi_ybark.T)]
-        dL_dSf = 0.5 * sum([np.dot(t[:, None], t[None, :]) for t in tmp1]) - 0.5 * sum(B_invs)
+        work = torch.empty(int(lib.gpc_mohgp_kern_grads_work(self.K, D)), dtype=torch.float64, device=self.device)
+        out = torch.empty((2, D, D), dtype=torch.float64, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with _cabi.nvtx_range("gpclust.kern_grads"):
+            check(lib.gpc_mohgp_kern_grads(ptr(self._stats), ptr(self._eig_ws), ptr(self._Sf), ptr(self._Sy_inv), ptr(self._YTY), ptr(self._Syi_ybark_t),
+                                           float(self.N_total), self.K, D, self._KP, self._DP, ptr(work), ptr(out[0]), ptr(out[1]), ptr(info),
+                                           self._stream()), "gpc_mohgp_kern_grads")
+        self.kernel_launches += 2
+        host = out.cpu().numpy()
+        if int(info.item()):
+            raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+        dL_dSf, dL_dSy = host[0], host[1]
         self.kernF.update_gradients_full(dL_dK=dL_dSf, X=self.X)
-        Byks = [np.dot(Bi, yk) for Bi, yk in zip(B_invs, ybark.T)]
-        SyyS = self.Syi_ybarkybarkT_Syi
-        dL_dSy = sum([np.dot(Byk[:, None], Byk[None, :]) / np.power(ph, 3) - S_k / ph - Bi / ph
-                      for Bi, Byk, ph, S_k in zip(B_invs, Byks, phi_hat, SyyS) if ph > 1e-6])
-        dL_dSy = dL_dSy + (self.K - self.N_total) * Sy_inv
-        dL_dSy = dL_dSy + Sy_inv.dot(YTY).dot(Sy_inv)
-        dL_dSy = dL_dSy / 2.0
         self.kernY.update_gradients_full(dL_dK=dL_dSy, X=self.X)
         self._dL_dSf, self._dL_dSy = dL_dSf, dL_dSy
         self._kern_grads_valid = True

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "gpc_mohgp_cluster": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "gpc_mohgp_eig_ws_len": [_i],
     "gpc_mohgp_eig": [_p, _p, _p, _p, _p, _i, _p, _p],
+    "gpc_mohgp_kern_grads_work": [_i, _i],
+    "gpc_mohgp_kern_grads": [_p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "gpc_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p],
     "gpc_loop_mohgp_post": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "gpc_loop_mohgp_post_px": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
@@ -96,7 +98,7 @@ PROTOTYPES = {
     "gpc_graph_launch": [_p, _p],
     "gpc_graph_destroy": [_p],
 }
-_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_omgp_kgrad_tiles": _ll, "gpc_xchg_doubles": _ll, "gpc_xchg_doubles_fused": _ll}
+_RESTYPE = {"gpc_padded_rows": _ll, "gpc_omgp_padded_n": _ll, "gpc_omgp_kgrad_tiles": _ll, "gpc_xchg_doubles": _ll, "gpc_xchg_doubles_fused": _ll, "gpc_mohgp_kern_grads_work": _ll}
 
 
 class GpcBufs(ctypes.Structure):

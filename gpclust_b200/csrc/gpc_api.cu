@@ -632,6 +632,24 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
   return launch_rc();
 }
 
+int gpc_mohgp_kern_grads(const double *stats, const double *eig_ws, const double *Sf, const double *Sy_inv, const double *YTY, const double *Syi_ybark_t,
+                         double n_total, int K, int D, int KP, int DP, double *work, double *dL_dSf, double *dL_dSy, int *info, void *stream) {
+  if (!stats || !eig_ws || !Sf || !Sy_inv || !YTY || !Syi_ybark_t || !work || !dL_dSf || !dL_dSy || !info) return GPC_EINVAL;
+  if (K < 1 || K > KP || KP > GPC_MAX_KTOT || D < 1 || D > DP || DP > GPC_MAX_DP) return GPC_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (rc) return rc;
+  const size_t KD = (size_t)K * D;
+  double *t1 = work, *by = work + KD, *w1 = work + 2 * KD, *w2 = work + 3 * KD, *cw = work + 4 * KD, *scratch = cw + 2 * (size_t)K;
+  MohgpKgradArgs a{stats, eig_ws, Sf, Syi_ybark_t, t1, by, w1, w2, cw, info, K, D, KP, DP};
+  k_mohgp_kgrad_cluster<<<K, kClusterThreads, 0, st>>>(a);
+  if ((rc = launch_rc())) return rc;
+  MohgpKgradFinalArgs f{t1, by, Syi_ybark_t, w1, w2, cw, eig_ws, Sy_inv, YTY, dL_dSf, dL_dSy, scratch, n_total, K, D};
+  k_mohgp_kgrad_final<<<1, kKgradThreads, 0, st>>>(f);
+  return launch_rc();
+}
+long long gpc_mohgp_kern_grads_work(int K, int D) { return (K < 1 || D < 1) ? -1 : 4LL * K * D + 2LL * K + (long long)D * D; }
+
 int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
                         const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
                         double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP,

@@ -1052,6 +1052,140 @@ __global__ void __launch_bounds__(kClusterThreads) k_mohgp_post(const MohgpPostA
 }
 
 // ------------------------------------------------------------------------------------------------
+// dL/dSf and dL/dSy of the MOHGP bound (MOHGP.update_kern_grads, MOHGP.py:92-122) in the eigenbasis of A.
+//
+// The reference forms, per cluster, tmp = L_k^-1 Ly^-1, B_inv_k = phi_hat_k tmp^T tmp (a triangular solve and a D^3 product each) and
+// sums K dense D x D matrices.  With C_k = Q diag(den_k) Q^T, den_ki = 1 + jitter_k + phi_hat_k lam_i and U = Ly^-T Q:
+//     B_inv_k              = phi_hat_k U diag(1/den_k) U^T
+//     sum_k B_inv_k        = U diag(sum_k phi_hat_k/den_ki) U^T                 ONE D x D product instead of K
+//     sum_k B_inv_k/ph_k   = U diag(sum_{k: ph_k > 1e-6} 1/den_ki) U^T
+//     tmp1_k = (I - Sf B_inv_k)^T s_k = s_k - B_inv_k (Sf s_k)       (Sf symmetric)   MOHGP.py:100-101
+//     Byk    = B_inv_k ybark_k                                                        MOHGP.py:111
+//   dL_dSf = 1/2 sum_k tmp1_k tmp1_k^T - 1/2 sum_k B_inv_k                            MOHGP.py:104-106
+//   dL_dSy = 1/2 [ sum_{k: ph_k > 1e-6} (Byk Byk^T / ph_k^3 - s_k s_k^T / ph_k - B_inv_k / ph_k) + (K - N) Sy_inv + Sy_inv YTY Sy_inv ]   :112-118
+// Kernel 1 (one CTA per cluster): the per-cluster vectors and weights, four matrix-vector products each.
+// Kernel 2 (one CTA): the two D x D matrices.
+struct MohgpKgradArgs {
+  const double *stats;    // [ybark KP x DP | phi_hat KP | ...] at the current point
+  const double *ws;       // k_mohgp_eig workspace
+  const double *Sf;       // D x D
+  const double *s_t;      // K x D : rows s_k = Sy^-1 ybark_k (Syi_ybark_t of the posterior kernel)
+  double *t1, *by;        // out K x D : tmp1_k, Byk
+  double *w1, *w2;        // out K x D : phi_hat_k / den_ki ; 1 / den_ki (zero row when phi_hat_k <= 1e-6)
+  double *cw;             // out K x 2 : 1/phi_hat_k^3, 1/phi_hat_k (zeros when phi_hat_k <= 1e-6)
+  int *info;
+  int K, D, KP, DP;
+};
+__global__ void __launch_bounds__(kClusterThreads) k_mohgp_kgrad_cluster(const MohgpKgradArgs a) {
+  __shared__ double red[4][GPC_MAX_DP];
+  __shared__ double yb_s[GPC_MAX_DP], s_s[GPC_MAX_DP], v_s[GPC_MAX_DP], u_s[GPC_MAX_DP], q_s[GPC_MAX_DP];
+  const int D = a.D, DP = a.DP, KP = a.KP, k = blockIdx.x, tid = threadIdx.x, r = tid & 63, pg = tid >> 6;
+  const double *lam = a.ws, *U = a.ws + GPC_MAX_DP, *Ut = U + D * D, *scal = Ut + 3 * D * D;
+  const double phi_hat = a.stats[(size_t)KP * DP + k];
+  auto sum4 = [&](int i) { return (red[0][i] + red[1][i]) + (red[2][i] + red[3][i]); };
+  if (tid < D) {
+    yb_s[tid] = a.stats[(size_t)k * DP + tid];
+    s_s[tid] = a.s_t[(size_t)k * D + tid];
+  }
+  // jitter exactly as the posterior (GPy jitchol emulation)
+  double jitter = 0.0;
+  bool ok = (1.0 + phi_hat * scal[4] > 0.0) && isfinite(phi_hat);
+  if (!ok && isfinite(phi_hat)) {
+    const double diag_mean = 1.0 + phi_hat * scal[5] / D;
+    for (int attempt = 1; attempt < 6 && !ok; ++attempt) {
+      if (attempt == 1) jitter = diag_mean * 1e-6;
+      else jitter *= 10.0;
+      if (!isfinite(jitter)) break;
+      ok = (1.0 + jitter + phi_hat * scal[4] > 0.0);
+    }
+  }
+  if (!ok && tid == 0) atomicOr(a.info, GPC_INFO_NOT_PD);
+  const bool big = phi_hat > 1e-6;
+  __syncthreads();
+  // v = Sf s  (global Sf, symmetric)
+  red[pg][r] = matvec_t_part(a.Sf, s_s, D, r, pg);
+  __syncthreads();
+  if (tid < D) v_s[tid] = sum4(tid);
+  __syncthreads();
+  // u = U^T v ; q = U^T ybark   -> scaled by phi_hat / den
+  red[pg][r] = matvec_t_part(U, v_s, D, r, pg);
+  __syncthreads();
+  double den = 1.0;
+  if (tid < D) {
+    den = (1.0 + jitter) + phi_hat * lam[tid];
+    u_s[tid] = sum4(tid) * (phi_hat / den);
+    a.w1[(size_t)k * D + tid] = ok ? phi_hat / den : 0.0;
+    a.w2[(size_t)k * D + tid] = (ok && big) ? 1.0 / den : 0.0;
+  }
+  __syncthreads();
+  red[pg][r] = matvec_t_part(U, yb_s, D, r, pg);
+  __syncthreads();
+  if (tid < D) q_s[tid] = sum4(tid) * (phi_hat / den);
+  __syncthreads();
+  // tmp1 = s - U u ; Byk = U q
+  red[pg][r] = matvec_t_part(Ut, u_s, D, r, pg);
+  __syncthreads();
+  if (tid < D) a.t1[(size_t)k * D + tid] = ok ? s_s[tid] - sum4(tid) : 0.0;
+  __syncthreads();
+  red[pg][r] = matvec_t_part(Ut, q_s, D, r, pg);
+  __syncthreads();
+  if (tid < D) a.by[(size_t)k * D + tid] = ok ? sum4(tid) : 0.0;
+  if (tid == 0) {
+    a.cw[2 * k + 0] = (ok && big) ? 1.0 / (phi_hat * phi_hat * phi_hat) : 0.0;
+    a.cw[2 * k + 1] = (ok && big) ? 1.0 / phi_hat : 0.0;
+  }
+}
+
+struct MohgpKgradFinalArgs {
+  const double *t1, *by, *s_t, *w1, *w2, *cw;  // K x D (cw: K x 2)
+  const double *ws, *Sy_inv, *YTY;
+  double *dL_dSf, *dL_dSy;                     // out D x D
+  double *scratch;                             // D x D : Sy_inv YTY
+  double n_total;
+  int K, D;
+};
+constexpr int kKgradThreads = 1024;
+__global__ void __launch_bounds__(kKgradThreads) k_mohgp_kgrad_final(const MohgpKgradFinalArgs a) {
+  __shared__ double a1[GPC_MAX_DP], a2[GPC_MAX_DP];
+  const int D = a.D, K = a.K, tid = threadIdx.x, nth = blockDim.x;
+  const double *U = a.ws + GPC_MAX_DP;
+  for (int i = tid; i < D; i += nth) {
+    double x = 0.0, y = 0.0;
+    for (int k = 0; k < K; ++k) {
+      x += a.w1[(size_t)k * D + i];
+      y += a.w2[(size_t)k * D + i];
+    }
+    a1[i] = x;
+    a2[i] = y;
+  }
+  for (int e = tid; e < D * D; e += nth) {  // M = Sy_inv YTY
+    const int i = e / D, j = e % D;
+    double v = 0.0;
+    for (int m = 0; m < D; ++m) v += a.Sy_inv[i * D + m] * a.YTY[m * D + j];
+    a.scratch[e] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < D * D; e += nth) {
+    const int i = e / D, j = e % D;
+    double tt = 0.0, bb = 0.0, ss = 0.0;
+    for (int k = 0; k < K; ++k) {
+      tt += a.t1[(size_t)k * D + i] * a.t1[(size_t)k * D + j];
+      bb += a.by[(size_t)k * D + i] * a.by[(size_t)k * D + j] * a.cw[2 * k];
+      ss += a.s_t[(size_t)k * D + i] * a.s_t[(size_t)k * D + j] * a.cw[2 * k + 1];
+    }
+    double u1 = 0.0, u2 = 0.0, sys = 0.0;
+    for (int m = 0; m < D; ++m) {
+      const double uu = U[i * D + m] * U[j * D + m];
+      u1 += uu * a1[m];
+      u2 += uu * a2[m];
+      sys += a.scratch[i * D + m] * a.Sy_inv[m * D + j];
+    }
+    a.dL_dSf[e] = 0.5 * tt - 0.5 * u1;
+    a.dL_dSy[e] = 0.5 * (((bb - ss) - u2) + ((double)K - a.n_total) * a.Sy_inv[e] + sys);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MOG: features f = [x_i x_j (i <= j, row-major upper) | x_i], NF = D(D+1)/2 + D, computed from data
 // centred at `centre` (the posterior is translation invariant; centring limits cancellation).
 struct MogClusterArgs {

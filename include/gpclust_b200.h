@@ -264,6 +264,14 @@ int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const
 int gpc_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
                    const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,
                    double *mixgrad_out, unsigned int *counter, int *info, double alpha, int prior, int K, int D, int KP, int DP, void *stream);
+/* ---- kernel hyper-parameter gradients of MOHGP (MOHGP.update_kern_grads, MOHGP.py:92-122) on the device, in the eigenbasis of A:
+ * dL_dSf and dL_dSy (D x D each) from the statistics and the posterior of the current point -- O(K D^2) + two D x K x D products
+ * instead of the reference's K triangular solves and K dense D^3 products.  stats / Syi_ybark_t as left by gpc_mohgp_post;
+ * work: gpc_mohgp_kern_grads_work(K, D) doubles.  *info is cleared first (GPC_INFO_NOT_PD as in gpc_mohgp_post).
+ * The host applies GPy's update_gradients_full (D x D contractions with dK/dtheta) to the two matrices.                     */
+long long gpc_mohgp_kern_grads_work(int K, int D);
+int gpc_mohgp_kern_grads(const double *stats, const double *eig_ws, const double *Sf, const double *Sy_inv, const double *YTY, const double *Syi_ybark_t,
+                         double n_total, int K, int D, int KP, int DP, double *work, double *dL_dSf, double *dL_dSy, int *info, void *stream);
 /* gpc_mohgp_post + the device-side accept / reject / termination step (dots, beta: as written by the two passes) */
 int gpc_loop_mohgp_post(const double *partials, int num_parts, double *stats, const double *eig_ws, const double *Sy_inv, const double *Sf,
                         const double *const_term, double *Wt, double *muk_t, double *Syi_ybark_t, double *per_k, double *bias, double *scalars,

@@ -103,3 +103,34 @@ def test_gpu_optimize_interleaves_hyperparameter_steps_like_the_reference():
     pp = np.array([getattr(k, n) for k, n in mp._kernel_param_list()])
     assert np.allclose(pp, po, rtol=1e-4)
     assert not np.allclose(pp, [1.0, 2.0, 0.1, 1.0, 0.05])  # the kernels did move
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,D,K", [(3000, 64, 20), (800, 33, 7), (400, 8, 3)])
+def test_gpu_device_kernel_gradient_matrices(N, D, K):
+    """dL/dSf and dL/dSy from the device (gpc_mohgp_kern_grads: eigenbasis form of MOHGP.py:92-122, no per-cluster factorisation)
+    against the oracle's literal restatement (K triangular solves and dense products), including a cluster with phi_hat <= 1e-6
+    (excluded from the dL/dSy sum, MOHGP.py:113) and after some optimisation."""
+    from gpclust_b200 import MOHGP, kern
+    X, Y, _ = mohgp_problem(N, D, K, 5)
+    np.random.seed(6)
+    phi0 = np.random.randn(N, K)
+    phi0[:, K - 1] = -60.0  # an (almost) empty cluster
+    mo = MOHGPOracle(X, G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05), Y, K=K)
+    mo.set_vb_param(phi0.flatten())
+    mo.out = io.StringIO()
+    mp = MOHGP(X, kern.RBF(1, 1.0, 2.0), kern.RBF(1, 0.1, 1.0) + kern.White(1, 0.05), Y, K=K, phi_init=phi0)
+    assert mo.phi_hat[K - 1] < 1e-6
+    for it in range(2):
+        mo.update_kern_grads()
+        mp.update_kern_grads()
+        assert relerr(mp._dL_dSf, mo.dL_dSf) < 1e-7, it
+        assert relerr(mp._dL_dSy, mo.dL_dSy) < 1e-7, it
+        assert relerr(mp._kernel_gradients(), mo.kernel_gradients()) < 1e-7, it
+        # a few VB steps with the kernels held fixed, then again
+        for k in (mp.kernF, mp.kernY):
+            k.fix()
+        mo.optimize(maxiter=6, verbose=False)
+        mp.optimize(maxiter=6, verbose=False)
+        for k in (mp.kernF, mp.kernY):
+            k.unfix()
