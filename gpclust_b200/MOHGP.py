@@ -195,11 +195,6 @@ class MOHGP(CollapsedMixture):
     def _launch_fused(self, bufs, n):
         import ctypes
         px = ptr(self._peers["desc"]) if self._peers is not None else None
-        per = int(os.environ.get("GPCLUST_B200_FUSED_EVALS", "0"))  # experiment: split the n evaluations over launches of `per` each
-        if per > 0 and n > per:
-            for i in range(0, n, per):
-                self._launch_fused(bufs, min(per, n - i))
-            return
         check(lib.gpc_mohgp_loop(ptr(self._F), ctypes.byref(bufs), ptr(self._Wt), ptr(self._bias), ptr(self._gpart), ptr(self._spart),
                                  ptr(self._ctrl[3:]), ptr(self._ctrl[6:]), ptr(self._stats), ptr(self._eig_ws), ptr(self._Sy_inv), ptr(self._Sf),
                                  ptr(self._const), ptr(self._muk_t), ptr(self._Syi_ybark_t), ptr(self._per_k), ptr(self._ctrl), ptr(self._mixgrad),

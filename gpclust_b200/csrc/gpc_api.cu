@@ -4,7 +4,6 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
-#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -79,14 +78,12 @@ int launch_vb(Kern kern, const Args &a, size_t smem, int grid, int threads, cuda
 template <int KP>
 int launch_natgrad(NatgradArgs &a, int grid, cudaStream_t st) {
   a.stages = natgrad_stages(KP, a.DP);
-  size_t smem = natgrad_smem(KP, a.DP, a.stages);
-  if (const char *e = getenv("GPC_DEBUG_G_SMEM")) smem = (size_t)atoi(e);  // experiment: L1 carve-out sensitivity of the G pass
+  const size_t smem = natgrad_smem(KP, a.DP, a.stages);
   return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, kGThreads, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, kGThreads, st);
 }
 template <int KP>
 int launch_step_stats(StepStatsArgs &a, int grid, cudaStream_t st) {
   a.stages = step_stats_stages(KP, a.DP);
-  if (const char *e = getenv("GPC_DEBUG_S_STAGES")) a.stages = atoi(e);  // experiment: ring depth / L1 carve-out of the S pass
   const size_t smem = step_stats_smem(KP, a.DP, a.stages);
   return a.K == KP ? launch_vb(k_step_stats<KP, true>, a, smem, grid, kSThreads, st)
                    : launch_vb(k_step_stats<KP, false>, a, smem, grid, kSThreads, st);
@@ -1049,8 +1046,7 @@ LoopGeom loop_geometry(int KP, int DP, int D) {
   // L1, and the carve-out is per launch -- with the 228 KB configuration (what a full-depth S ring would ask for) the G phase
   // loses 8 % (measured: 580 vs 539 us at 1M rows), while the S ring is insensitive to its depth from 8 stages up.  180 KB of rings
   // (+ header) selects the 196 KB configuration: two ring slots per G unit, ten S stages.
-  size_t budget = kLoopRingBudget;
-  if (const char *e = getenv("GPC_DEBUG_LOOP_BUDGET")) budget = (size_t)atoi(e);  // experiments (tools/scratch)
+  const size_t budget = kLoopRingBudget;
   {
     const int units = kGConsumers / ((KP / 8 >= 2) ? 2 : 1);
     const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;
@@ -1130,7 +1126,6 @@ int gpc_mohgp_loop(const double *F, const gpc_bufs_t *bufs, double *Wt, double *
   a.s.num_groups = a.g.num_groups;
   a.s.bufs = *bufs;
   a.s.reverse = 0;  // no measurable gain from the reverse sweep at 125k .. 1M rows per GPU (and it changes the summation order)
-  if (const char *e = getenv("GPC_DEBUG_S_REVERSE")) a.s.reverse = atoi(e);  // experiment
   a.p = MohgpPostArgs{spart, grid, stats, eig_ws, Sy_inv, Sf, const_term, Wt, muk_t, Syi_ybark_t, per_k, bias, scalars, mixgrad_out,
                       sync + 2, info, alpha, prior, K, D, KP, DP, dots, beta, loop, GPC_PHASE_CONJ, nullptr};
   a.peers = peers;
