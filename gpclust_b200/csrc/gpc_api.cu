@@ -864,53 +864,71 @@ int gpc_omgp_build(const double *X, long long N, int q, int nparts, const int *k
   return launch_rc();
 }
 
+namespace {
+constexpr size_t kDiagSmem = sizeof(double) * 2 * kOB * (kOB + 1);
+int omgp_attrs() {
+  int rc;
+  if ((rc = cuda_rc(ensure_dyn_smem(k_omgp_chol_diag, kDiagSmem)))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_within))) return rc;
+  if ((rc = tile_attr(k_omgp_chol_big))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_row))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_within))) return rc;
+  if ((rc = tile_attr(k_omgp_inv_big))) return rc;
+  return 0;
+}
+// factorisation of the block-column group [p0, p1): diagonal tile, panel and the group's own remaining columns, tile column by tile column
+void chol_group(double *A, int ld, int nb, int p0, int p1, double *dinv, double *ldsum, int *info, cudaStream_t st) {
+  for (int jb = p0; jb < p1; ++jb) {
+    k_omgp_chol_diag<<<1, kClusterThreads, kDiagSmem, st>>>(A, ld, jb, dinv, ldsum, info);
+    const int m = nb - jb - 1;
+    if (m > 0) k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
+    if (m > 0 && p1 - jb - 1 > 0) k_omgp_chol_within<<<dim3(m, p1 - jb - 1), 256, kTileSmem, st>>>(A, ld, jb);
+  }
+}
+void chol_big(double *A, int ld, int nb, int p0, int p1, cudaStream_t st) {
+  const int m = nb - p1;
+  if (m > 0) k_omgp_chol_big<<<m * (m + 1) / 2, 256, kTileSmem, st>>>(A, ld, p0, p1);
+}
+// inverse steps of the group [p0, p1) (W's diagonal tiles of the group must be in place) and the push to the rows below it
+void inv_group(double *W, int ld, const double *L, int nb, int p0, int p1, const double *dinv, cudaStream_t st) {
+  for (int ib = p0; ib < p1; ++ib) {
+    if (ib > 0) k_omgp_inv_row<<<ib, 256, kTileSmem, st>>>(W, ld, ib, dinv);
+    if (p1 - ib - 1 > 0) k_omgp_inv_within<<<dim3(ib + 1, p1 - ib - 1), 256, kTileSmem, st>>>(W, ld, L, ld, ib);
+  }
+  if (nb - p1 > 0) k_omgp_inv_big<<<dim3(p1, nb - p1), 256, kTileSmem, st>>>(W, ld, L, ld, p0, p1);
+}
+}  // namespace
+
 int gpc_chol_blocked(double *A, long long Npad, double *dinv, double *ldsum, int *info, void *stream) {
   if (!A || !dinv || !ldsum || !info || Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
   int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (rc) return rc;
-  constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
-  if ((rc = cuda_rc(ensure_dyn_smem(k_omgp_chol_diag, diag_smem)))) return rc;
-  if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
-  if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
+  if ((rc = omgp_attrs())) return rc;
   const int nb = (int)(Npad / kOB), ld = (int)Npad;
-  for (int jb = 0; jb < nb; ++jb) {
-    k_omgp_chol_diag<<<1, kClusterThreads, diag_smem, st>>>(A, ld, jb, dinv, ldsum, info);
-    const int m = nb - jb - 1;
-    if (m > 0) {
-      k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
-      k_omgp_chol_trail<<<m * (m + 1) / 2, 256, kTileSmem, st>>>(A, ld, jb, 0);
-    }
+  for (int p0 = 0; p0 < nb; p0 += kOGroup) {
+    const int p1 = p0 + kOGroup < nb ? p0 + kOGroup : nb;
+    chol_group(A, ld, nb, p0, p1, dinv, ldsum, info, st);
+    chol_big(A, ld, nb, p0, p1, st);
   }
   return launch_rc();
 }
 
-// Factorisation and triangular inverse pipelined over two streams: step jb of the inverse needs only the diagonal-tile inverse
-// and column jb of L, both final once the panel of step jb is done, so the inverse chain (aux stream) runs underneath the
-// trailing updates of the factorisation (main stream) instead of after them.  Capturable (the events become graph edges).
+// Factorisation and triangular inverse pipelined over two streams.  The inverse steps of a group need only that group's block columns of
+// L and its diagonal-tile inverses, final once the group is factorised: the aux stream runs inverse group g underneath the main
+// stream's trailing update of group g and the factorisation of group g+1.  Capturable (the events become graph edges).
 int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int *info, double *W, void *stream, void *aux_stream) {
   if (!A || !dinv || !ldsum || !info || !W || !aux_stream || stream == aux_stream) return GPC_EINVAL;
   if (Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream), ax = as_stream(aux_stream);
   int rc = cuda_rc(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (rc) return rc;
-  constexpr size_t diag_smem = sizeof(double) * 2 * kOB * (kOB + 1);
-  if ((rc = cuda_rc(ensure_dyn_smem(k_omgp_chol_diag, diag_smem)))) return rc;
-  if ((rc = tile_attr(k_omgp_chol_panel))) return rc;
-  if ((rc = tile_attr(k_omgp_chol_trail))) return rc;
-  if ((rc = tile_attr(k_omgp_inv_row))) return rc;
-  if ((rc = tile_attr(k_omgp_inv_trail))) return rc;
+  if ((rc = omgp_attrs())) return rc;
   const int nb = (int)(Npad / kOB), ld = (int)Npad;
   const long long total = Npad * Npad;
-  // Main stream = the critical chain  diag(j) -> panel(j) -> trailing update of block column j+1 (look-ahead) -> diag(j+1) ...;
-  // aux stream = the bulk work: inverse step j and the rest of trailing update j, both released by panel(j).
-  // Two event objects re-recorded per step (a wait captures the record that precedes it).
-  cudaEvent_t ev, rest;
+  cudaEvent_t ev;
   if ((rc = cuda_rc(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)))) return rc;
-  if ((rc = cuda_rc(cudaEventCreateWithFlags(&rest, cudaEventDisableTiming)))) {
-    cudaEventDestroy(ev);
-    return rc;
-  }
   // every event call is an edge of the two-stream pipeline: the first failure is kept and returned (a lost edge would silently
   // drop a dependency between the factorisation and the inverse)
   auto edge = [&rc](cudaError_t e) {
@@ -919,26 +937,18 @@ int gpc_chol_inverse(double *A, long long Npad, double *dinv, double *ldsum, int
   edge(cudaEventRecord(ev, st));  // fork: the aux stream starts after everything enqueued on the main stream so far
   edge(cudaStreamWaitEvent(ax, ev, 0));
   k_omgp_inv_zero<<<(unsigned)((total / 2 + 255) / 256), 256, 0, ax>>>(W, total);
-  for (int jb = 0; jb < nb && rc == 0; ++jb) {
-    k_omgp_chol_diag<<<1, kClusterThreads, diag_smem, st>>>(A, ld, jb, dinv, ldsum, info);
-    const int m = nb - jb - 1;
-    if (m > 0) k_omgp_chol_panel<<<m, 256, kTileSmem, st>>>(A, ld, jb, dinv);
-    edge(cudaEventRecord(ev, st));
-    edge(cudaStreamWaitEvent(ax, ev, 0));
-    if (m > 0) {
-      if (jb > 0) edge(cudaStreamWaitEvent(st, rest, 0));  // block column jb+1 was last written by the rest-update of step jb-1
-      k_omgp_chol_trail<<<m, 256, kTileSmem, st>>>(A, ld, jb, 1);
-    }
-    k_omgp_inv_diag<<<1, 256, 0, ax>>>(W, ld, jb, dinv);
-    if (jb > 0) k_omgp_inv_row<<<jb, 256, kTileSmem, ax>>>(W, ld, jb, dinv);
-    if (m > 0) k_omgp_inv_trail<<<dim3(jb + 1, m), 256, kTileSmem, ax>>>(W, ld, A, ld, jb);
-    if (m > 1) k_omgp_chol_trail<<<m * (m + 1) / 2 - m, 256, kTileSmem, ax>>>(A, ld, jb, 2);
-    edge(cudaEventRecord(rest, ax));
+  for (int p0 = 0; p0 < nb && rc == 0; p0 += kOGroup) {
+    const int p1 = p0 + kOGroup < nb ? p0 + kOGroup : nb;
+    chol_group(A, ld, nb, p0, p1, dinv, ldsum, info, st);
+    edge(cudaEventRecord(ev, st));  // the group's block columns of L are final (one event object, re-recorded per group:
+    edge(cudaStreamWaitEvent(ax, ev, 0));  // a wait captures the record that precedes it)
+    chol_big(A, ld, nb, p0, p1, st);
+    for (int ib = p0; ib < p1; ++ib) k_omgp_inv_diag<<<1, 256, 0, ax>>>(W, ld, ib, dinv);
+    inv_group(W, ld, A, nb, p0, p1, dinv, ax);
   }
   edge(cudaEventRecord(ev, ax));  // join (always attempted: a forked capture must be joined back)
   edge(cudaStreamWaitEvent(st, ev, 0));
   cudaEventDestroy(ev);
-  cudaEventDestroy(rest);
   return rc ? rc : launch_rc();
 }
 
@@ -946,14 +956,13 @@ int gpc_tri_inverse_blocked(const double *L, long long Npad, const double *dinv,
   if (!L || !dinv || !W || Npad < kOB || (Npad % kOB) || Npad > 0x3fffffffLL) return GPC_EINVAL;
   cudaStream_t st = as_stream(stream);
   int rc;
-  if ((rc = tile_attr(k_omgp_inv_row))) return rc;
-  if ((rc = tile_attr(k_omgp_inv_trail))) return rc;
+  if ((rc = omgp_attrs())) return rc;
   const int nb = (int)(Npad / kOB), ld = (int)Npad;
   const long long total = Npad * Npad;
   k_omgp_inv_init<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ld, dinv);
-  for (int ib = 0; ib < nb; ++ib) {
-    if (ib > 0) k_omgp_inv_row<<<ib, 256, kTileSmem, st>>>(W, ld, ib, dinv);
-    if (ib + 1 < nb) k_omgp_inv_trail<<<dim3(ib + 1, nb - ib - 1), 256, kTileSmem, st>>>(W, ld, L, ld, ib);
+  for (int p0 = 0; p0 < nb; p0 += kOGroup) {
+    const int p1 = p0 + kOGroup < nb ? p0 + kOGroup : nb;
+    inv_group(W, ld, L, nb, p0, p1, dinv, st);
   }
   return launch_rc();
 }

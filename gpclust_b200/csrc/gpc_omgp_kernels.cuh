@@ -48,17 +48,24 @@ __global__ void k_omgp_build(const double *__restrict__ X, int N, int Npad, int 
 // three, which is what overlaps one CTA's global loads / read-modify-write epilogue with the DMMAs of the others.
 constexpr int kOKH = 32;          // k columns staged at a time
 constexpr int kOStrideH = 36;     // row stride of a 32-wide half read along k (bank skew 4)
+// nk > 1: C -= sum over nk consecutive 64-wide k tiles (P advances by 64 columns per tile; Q by 64 columns when QT, by 64 rows otherwise):
+// ONE read-modify-write of C for nk * 64 of k -- the arithmetic intensity of the blocked updates grows with nk (section 6 of DESIGN.md).
 template <bool QT, bool SUB>
 __device__ __forceinline__ void tile_product_64(const double *__restrict__ P, int ldp, const double *__restrict__ Q, int ldq, double *C, int ldc,
-                                                double *Ps, double *Qs) {
+                                                double *Ps, double *Qs, int nk = 1) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  double acc[8][2];
+  // warp w owns the 16 x 32 block (rows 16 (w/2) .., columns 32 (w%2) ..): per k-step 2 A fragments + 4 B fragments feed 8 DMMAs
+  // (an 8 x 64 strip per warp needs 1 + 8)
+  const int r0 = (warp >> 1) * 16, c0 = (warp & 1) * 32;
+  double acc[2][4][2];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-  const double *pa = Ps + (warp * 8 + g) * kOStrideH + t;
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const double *pa = Ps + (r0 + g) * kOStrideH + t;
 #pragma unroll 1
-  for (int kh = 0; kh < kOB / kOKH; ++kh) {
+  for (int kh = 0; kh < nk * (kOB / kOKH); ++kh) {
     __syncthreads();  // previous user of the staging buffers is done
     for (int e = tid; e < kOB * kOKH / 2; e += blockDim.x) {  // P rows x 32 columns of this half
       const int r = e >> 4, c2 = (e & 15) * 2;
@@ -78,22 +85,26 @@ __device__ __forceinline__ void tile_product_64(const double *__restrict__ P, in
     __syncthreads();
 #pragma unroll 4
     for (int ks = 0; ks < kOKH / 4; ++ks) {
-      const double af = pa[4 * ks];
+      const double af0 = pa[4 * ks], af1 = pa[8 * kOStrideH + 4 * ks];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const double bf = QT ? Qs[(8 * nt + g) * kOStrideH + 4 * ks + t] : Qs[(4 * ks + t) * kOStrideN + 8 * nt + g];
-        dmma884(acc[nt][0], acc[nt][1], af, bf);
+      for (int nt = 0; nt < 4; ++nt) {
+        const double bf = QT ? Qs[(c0 + 8 * nt + g) * kOStrideH + 4 * ks + t] : Qs[(4 * ks + t) * kOStrideN + c0 + 8 * nt + g];
+        dmma884(acc[0][nt][0], acc[0][nt][1], af0, bf);
+        dmma884(acc[1][nt][0], acc[1][nt][1], af1, bf);
       }
     }
   }
-  double *crow = C + (size_t)(warp * 8 + g) * ldc + 2 * t;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    if (SUB) {
-      const double2 c = *reinterpret_cast<const double2 *>(crow + 8 * nt);
-      stg2(crow + 8 * nt, c.x - acc[nt][0], c.y - acc[nt][1]);
-    } else {
-      stg2(crow + 8 * nt, acc[nt][0], acc[nt][1]);
+  for (int mt = 0; mt < 2; ++mt) {
+    double *crow = C + (size_t)(r0 + 8 * mt + g) * ldc + c0 + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (SUB) {
+        const double2 c = *reinterpret_cast<const double2 *>(crow + 8 * nt);
+        stg2(crow + 8 * nt, c.x - acc[mt][nt][0], c.y - acc[mt][nt][1]);
+      } else {
+        stg2(crow + 8 * nt, acc[mt][nt][0], acc[mt][nt][1]);
+      }
     }
   }
 }
@@ -170,29 +181,29 @@ __global__ void __launch_bounds__(256) k_omgp_chol_panel(double *A, int ld, int 
   tile_product_64<true, false>(T, ld, dinv + (size_t)jb * kOB * kOB, kOB, T, ld, sm, sm + kOB * kOStrideH);
 }
 
-// Trailing update after panel jb: A[i][k] -= A[i][jb] A[k][jb]^T for jb < k <= i (lower tiles only).
-// part: 0 = all lower tiles; 1 = only block column jb+1 (what the NEXT diagonal tile and panel need -- look-ahead);
-//       2 = everything but block column jb+1.
-__global__ void __launch_bounds__(256, 4) k_omgp_chol_trail(double *A, int ld, int jb, int part) {
+// ---- two-level blocking: block columns are factorised in GROUPS of kOGroup tiles.  Inside a group the right-looking update touches
+// only the group's own remaining columns (k = 64, thin); everything to the right of the group is updated ONCE per group with
+// k = 64 * (group width).  The 64-wide update reads two 32 KB panels and read-modify-writes a 32 KB tile per 0.5 MFLOP (4 flop/B: bound
+// by HBM at ~26 TFLOP/s, measured 20-22); with four tiles of k per pass over C it is 6.5 flop/B -- above the DMMA ridge.
+constexpr int kOGroup = 4;
+// within the group: A[ib][kb] -= A[ib][jb] A[kb][jb]^T for jb < kb < p1, ib >= kb   (grid: x = ib - jb - 1, y = kb - jb - 1)
+__global__ void __launch_bounds__(256, 4) k_omgp_chol_within(double *A, int ld, int jb) {
   extern __shared__ __align__(16) double sm[];
-  int a, b;
-  if (part == 1) {
-    a = blockIdx.x;
-    b = 0;
-  } else {
-    // decode the triangular tile index: blockIdx.x = a(a+1)/2 + b, 0 <= b <= a
-    a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-    while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
-    while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
-    b = blockIdx.x - a * (a + 1) / 2;
-    if (part == 2) {  // the triangle without its first column: shift by one block row / column
-      a += 1;
-      b += 1;
-    }
-  }
-  const int ib = jb + 1 + a, kb = jb + 1 + b;
+  const int ib = jb + 1 + blockIdx.x, kb = jb + 1 + blockIdx.y;
+  if (ib < kb) return;
   tile_product_64<true, true>(A + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld, A + (size_t)kb * kOB * ld + (size_t)jb * kOB, ld,
                               A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideH);
+}
+// right of the group [p0, p1): A[ib][kb] -= sum_{t in group} A[ib][t] A[kb][t]^T for p1 <= kb <= ib   (triangular tile index)
+__global__ void __launch_bounds__(256, 4) k_omgp_chol_big(double *A, int ld, int p0, int p1) {
+  extern __shared__ __align__(16) double sm[];
+  int a = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= (int)blockIdx.x) ++a;
+  while (a * (a + 1) / 2 > (int)blockIdx.x) --a;
+  const int b = blockIdx.x - a * (a + 1) / 2;
+  const int ib = p1 + a, kb = p1 + b;
+  tile_product_64<true, true>(A + (size_t)ib * kOB * ld + (size_t)p0 * kOB, ld, A + (size_t)kb * kOB * ld + (size_t)p0 * kOB, ld,
+                              A + (size_t)ib * kOB * ld + (size_t)kb * kOB, ld, sm, sm + kOB * kOStrideH, p1 - p0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -219,12 +230,23 @@ __global__ void __launch_bounds__(256) k_omgp_inv_row(double *W, int ld, int ib,
   double *T = W + (size_t)ib * kOB * ld + (size_t)blockIdx.x * kOB;
   tile_product_64<false, false>(dinv + (size_t)ib * kOB * kOB, kOB, T, ld, T, ld, sm, sm + kOB * kOStrideH);
 }
-// step ib, part (b): W[m][j] -= L[m][ib] * W[ib][j]  for m > ib, j <= ib   (grid: x = j, y = m - ib - 1)
-__global__ void __launch_bounds__(256, 4) k_omgp_inv_trail(double *W, int ld, const double *__restrict__ L, int ldl, int ib) {
+// two-level blocking of the inverse (as for the factorisation): inside the group [p0, p1) step ib pushes row ib only to the rows of
+// the group below it; the rows below the group receive the whole group at once with k = 64 * (group width).
+//   within: W[m][j] -= L[m][ib] W[ib][j]  for ib < m < p1, j <= ib        (grid: x = j, y = m - ib - 1)
+__global__ void __launch_bounds__(256, 4) k_omgp_inv_within(double *W, int ld, const double *__restrict__ L, int ldl, int ib) {
   extern __shared__ __align__(16) double sm[];
   const int jb = blockIdx.x, mb = ib + 1 + blockIdx.y;
   tile_product_64<false, true>(L + (size_t)mb * kOB * ldl + (size_t)ib * kOB, ldl, W + (size_t)ib * kOB * ld + (size_t)jb * kOB, ld,
                                W + (size_t)mb * kOB * ld + (size_t)jb * kOB, ld, sm, sm + kOB * kOStrideH);
+}
+//   big:    W[m][j] -= sum_{t in group} L[m][t] W[t][j]  for m >= p1, j < p1   (grid: x = j, y = m - p1); W[t][j] = 0 for t < j
+__global__ void __launch_bounds__(256, 4) k_omgp_inv_big(double *W, int ld, const double *__restrict__ L, int ldl, int p0, int p1) {
+  extern __shared__ __align__(16) double sm[];
+  const int jb = blockIdx.x, mb = p1 + blockIdx.y;
+  // columns right of the group's first tile: the rows t < j of the group hold zeros -- start the k loop at max(p0, j)
+  const int t0 = jb > p0 ? jb : p0;
+  tile_product_64<false, true>(L + (size_t)mb * kOB * ldl + (size_t)t0 * kOB, ldl, W + (size_t)t0 * kOB * ld + (size_t)jb * kOB, ld,
+                               W + (size_t)mb * kOB * ld + (size_t)jb * kOB, ld, sm, sm + kOB * kOStrideH, p1 - t0);
 }
 
 // ------------------------------------------------------------------------------------------------
