@@ -621,7 +621,7 @@ int gpc_mohgp_eig_ws_len(int D) { return (D < 1 || D > GPC_MAX_DP) ? -1 : eig_ws
 int gpc_mohgp_eig(const double *A, const double *Ly, const double *Ly_inv, const double *Sy_inv, const double *Sf, int D, double *ws,
                   void *stream) {
   if (!A || !Ly || !Ly_inv || !Sy_inv || !Sf || !ws || D < 1 || D > GPC_MAX_DP) return GPC_EINVAL;
-  const size_t smem = sizeof(double) * (2 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + GPC_MAX_DP + 32);
+  const size_t smem = sizeof(double) * (3 * (size_t)GPC_MAX_DP * (GPC_MAX_DP + 1) + GPC_MAX_DP + 32);  // A, V, G = A V + rotation scratch
   cudaError_t e = ensure_dyn_smem(k_mohgp_eig, smem);
   if (e != cudaSuccess) return cuda_rc(e);
   MohgpEigArgs a{A, Ly, Ly_inv, Sy_inv, Sf, ws, D};

@@ -544,8 +544,9 @@ struct MohgpEigArgs {
   int D;
 };
 
-// One CTA of 1024 threads (every round is three barrier-separated phases of n^2/2 .. n^2 independent element updates: latency,
-// not throughput).  Two-sided cyclic Jacobi with the round-robin parallel ordering: n/2 disjoint rotations per round.
+// One CTA of 1024 threads; round-robin parallel ordering: n/2 disjoint rotations per round.  Stage 1: one-sided (Hestenes) Jacobi, one
+// warp per column pair and one barrier per round (4.07 -> 2.7 ms at D = 64); stage 2 (fall-back): two-sided cyclic Jacobi, three
+// barrier-separated phases per round.  Latency, not throughput, bounds both.
 constexpr int kEigThreads = 1024;
 __global__ void __launch_bounds__(kEigThreads) k_mohgp_eig(const MohgpEigArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -568,14 +569,90 @@ __global__ void __launch_bounds__(kEigThreads) k_mohgp_eig(const MohgpEigArgs a)
   fro = block_sum(fro, red_s);
   int sweeps = 0;
   double off = 0.0;
-  for (; sweeps < 30; ++sweeps) {
+  // ---- stage 1: ONE-SIDED Jacobi (Hestenes) on G = A V, V = I: a rotation of the column pair (p, q) makes G_p and G_q orthogonal and
+  // touches nothing else, so the n/2 pairs of a round are fully independent -- one warp per pair (three warp-wide dot products, one
+  // rotation of two columns of G and of V), ONE block barrier per round instead of three.  At convergence the columns of G are
+  // lam_j v_j.  Valid whenever no two eigenvalues are +lam / -lam (always for positive semi-definite A = Ly^-1 Sf Ly^-T); the result is
+  // verified by its residual and the two-sided iteration below is the fall-back.
+  bool have = false;
+  {
+    double *Gs = red_s + 32;  // n x ld, behind the reduction scratch
+    __shared__ int rotated;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < n * n; e += nth) Gs[(e / n) * ld + (e % n)] = As[(e / n) * ld + (e % n)];
+    __syncthreads();
+    int sw = 0;
+    for (; sw < 30; ++sw) {
+      if (tid == 0) rotated = 0;
+      __syncthreads();
+      for (int round = 0; round < n - 1; ++round) {
+        if (warp < n / 2) {
+          int p, q;
+          if (warp == 0) {
+            p = n - 1;
+            q = round;
+          } else {
+            p = (round + warp) % (n - 1);
+            q = (round - warp + (n - 1)) % (n - 1);
+          }
+          const int i0 = lane, i1 = lane + 32;
+          const double gp0 = Gs[i0 * ld + p], gq0 = Gs[i0 * ld + q];
+          const double gp1 = i1 < n ? Gs[i1 * ld + p] : 0.0, gq1 = i1 < n ? Gs[i1 * ld + q] : 0.0;
+          const double al = warp_sum(gp0 * gp0 + gp1 * gp1), be = warp_sum(gq0 * gq0 + gq1 * gq1), ga = warp_sum(gp0 * gq0 + gp1 * gq1);
+          if (al > 0.0 && be > 0.0 && fabs(ga) > 1e-15 * sqrt(al * be)) {
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), sn_ = c * t;
+            Gs[i0 * ld + p] = c * gp0 - sn_ * gq0;
+            Gs[i0 * ld + q] = sn_ * gp0 + c * gq0;
+            const double vp0 = Qs[i0 * ld + p], vq0 = Qs[i0 * ld + q];
+            Qs[i0 * ld + p] = c * vp0 - sn_ * vq0;
+            Qs[i0 * ld + q] = sn_ * vp0 + c * vq0;
+            if (i1 < n) {
+              Gs[i1 * ld + p] = c * gp1 - sn_ * gq1;
+              Gs[i1 * ld + q] = sn_ * gp1 + c * gq1;
+              const double vp1 = Qs[i1 * ld + p], vq1 = Qs[i1 * ld + q];
+              Qs[i1 * ld + p] = c * vp1 - sn_ * vq1;
+              Qs[i1 * ld + q] = sn_ * vp1 + c * vq1;
+            }
+            if (lane == 0) rotated = 1;
+          }
+        }
+        __syncthreads();
+      }
+      if (rotated == 0) break;
+      __syncthreads();
+    }
+    // eigenvalues as Rayleigh quotients v_j . (A v_j) = v_j . G_j, and the residual |G_j - lam_j v_j|^2 summed over j
+    double res = 0.0;
+    for (int j = warp; j < n; j += nth / 32) {
+      const int i0 = lane, i1 = lane + 32;
+      const double g0 = Gs[i0 * ld + j], v0 = Qs[i0 * ld + j], g1 = i1 < n ? Gs[i1 * ld + j] : 0.0, v1 = i1 < n ? Qs[i1 * ld + j] : 0.0;
+      const double lj = warp_sum(g0 * v0 + g1 * v1);
+      const double d0 = g0 - lj * v0, d1 = g1 - lj * v1;
+      res += d0 * d0 + d1 * d1;  // summed over lanes below
+      if (lane == 0) Gs[j * ld + j] = lj;               // the diagonal of Gs now carries lam_j (G itself is no longer needed on it)
+    }
+    res = block_sum(res, red_s);
+    have = (sw < 30) && (res <= 1e-24 * fro);
+    if (have) {
+      for (int j = tid; j < n; j += nth) As[j * ld + j] = Gs[j * ld + j];
+      sweeps = sw;
+      off = res;
+    } else {
+      for (int e = tid; e < n * n; e += nth) Qs[(e / n) * ld + (e % n)] = ((e / n) == (e % n)) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+  }
+  // ---- stage 2 (fall-back): two-sided cyclic Jacobi
+  for (; !have && sweeps < 30; ++sweeps) {
     off = 0.0;
     for (int e = tid; e < n * n; e += nth) {
       const int i = e / n, j = e % n;
       if (i != j) off += As[i * ld + j] * As[i * ld + j];
     }
     off = block_sum(off, red_s);
-    if (!(off > 1e-34 * fro)) break;
+    if (!(off > 1e-30 * fro)) break;  // off-diagonal norm below 1e-15 of the matrix norm
     for (int round = 0; round < n - 1; ++round) {
       if (tid < n / 2) {
         int p, q;
