@@ -49,23 +49,32 @@ def config_of(method):
             "l2": "inputs larger than L2: every step streams 11 N x K / N x D arrays (5.6 GB over all GPUs, >= 700 MB per GPU at 8 GPUs) "
                   "against 126 MB of L2; no flush between steps"}
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.json)
+def source_sha16():
+    """sha16 over the CUDA sources and the C-ABI header, in name order: identifies what libgpclust_b200.so is built from."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "gpclust_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "gpclust_b200.h")]:
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(kernel, n_loc, n_evals, n_g):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture of the shipped
     binary (profiles/ncu_traffic_r02.json, written by tools/ncu_traffic.py next to the capture: bytes per G phase and per S phase at
-    1M rows, and the sha16 of the .so it was taken from), scaled to this launch.  None when there is no capture for this binary."""
+    1M rows, and the sha16 of the CUDA sources the captured library was built from), scaled to this launch.  None when there is no capture for this binary."""
     try:
-        import hashlib
         with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
             rec = json.load(f)
-        so = os.path.join(ROOT, "gpclust_b200", "_lib", "libgpclust_b200.so")
-        sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16]
+        sha = source_sha16()
         per = rec["kernels"].get(kernel)
         if per is None:
             return None, "no capture of %s in profiles/ncu_traffic_r02.json" % kernel
         scale = n_loc / float(rec["rows"])
         val = (per["dram_bytes_per_g_phase"] * n_g + per["dram_bytes_per_s_phase"] * n_evals) * scale
-        src = "%s (ncu --set full at %d rows, scaled by rows per GPU and evaluations per launch; capture of lib %s, this run %s)" % (
-            rec["source"], rec["rows"], rec["lib_sha16"], "the same binary" if rec["lib_sha16"] == sha else "a DIFFERENT binary " + sha)
+        src = "%s (ncu --set full at %d rows, scaled by rows per GPU and evaluations per launch; captured library built from sources %s, this run %s)" % (
+            rec["source"], rec["rows"], rec["src_sha16"], "the same sources" if rec["src_sha16"] == sha else "DIFFERENT sources " + sha)
         return val, src
     except (OSError, KeyError, ValueError) as e:
         return None, "unavailable (%s)" % type(e).__name__

@@ -1,6 +1,6 @@
 """profiles/ncu_traffic_r02.json from an `ncu --page raw --csv` export of the shipped binary: DRAM bytes (read + write) per G phase and per
-S phase of the dominant kernel, and the sha16 of the .so the capture was taken from (bench.py reports `roofline.traffic` from it and says
-whether the running binary is the captured one).
+S phase of the dominant kernel, and the sha16 of the CUDA sources the captured library was built from (bench.py reports `roofline.traffic` from it and
+says whether the running library is built from the same sources).
 Usage: python tools/ncu_traffic.py raw.csv ROWS EVALS G_PHASES source-name"""
 import csv
 import hashlib
@@ -13,8 +13,9 @@ raw, rows, evals, g_phases, source = sys.argv[1], int(sys.argv[2]), int(sys.argv
 table = list(csv.reader(open(raw)))
 hdr, units = table[0], table[1]
 out = {"rows": rows, "source": source, "kernels": {}}
-so = os.path.join(ROOT, "gpclust_b200", "_lib", "libgpclust_b200.so")
-out["lib_sha16"] = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16]
+sys.path.insert(0, ROOT)
+from bench import source_sha16  # noqa: E402  (hash of the CUDA sources + the C-ABI header: what the library is built from)
+out["src_sha16"] = source_sha16()
 
 
 def to_bytes(v, u):
