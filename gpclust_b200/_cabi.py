@@ -245,24 +245,36 @@ class _Ingest(object):
             return self._upload_pack(src, N, C, CP, layout, dst, dev, stream_ptr)
 
     def _upload_pack(self, src, N, C, CP, layout, dst, dev, stream_ptr):
+        import torch
+        try:
+            pinned_src = torch.from_numpy(src)
+            if not pinned_src.is_pinned():
+                pinned_src = None
+        except Exception:
+            pinned_src = None
         rows = max(GPC_ROW_TILE, (self.CHUNK_BYTES // (8 * C)) // GPC_ROW_TILE * GPC_ROW_TILE)  # whole 64-row tiles: only the last chunk pads
         launches = 0
         for i, lo in enumerate(range(0, N, rows)):
             hi = min(N, lo + rows)
             b = i % self.NBUF
-            if self.busy[b]:
-                self.events[b].synchronize()  # the DMA that last read this staging buffer (this upload's or an earlier one's) has finished
-            stage = self.pinned[b][:(hi - lo) * C].view(hi - lo, C).numpy()
             n = hi - lo
-            if self.threads > 1 and n * C >= (1 << 18):
-                cuts = [lo + n * t // self.threads for t in range(self.threads + 1)]
-                list(self.pool.map(lambda ab: np.copyto(stage[ab[0] - lo:ab[1] - lo], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
-            else:
-                np.copyto(stage, src[lo:hi])
             d = dev[b][:n * C]
-            d.copy_(self.pinned[b][:n * C], non_blocking=True)
-            self.events[b].record()
-            self.busy[b] = True
+            if pinned_src is not None:
+                # the caller's array is page-locked already: DMA straight out of it, no staging copy (device chunk buffers are
+                # recycled in stream order)
+                d.copy_(pinned_src[lo:hi].reshape(-1), non_blocking=True)
+            else:
+                if self.busy[b]:
+                    self.events[b].synchronize()  # the DMA that last read this staging buffer (this upload's or an earlier one's) has finished
+                stage = self.pinned[b][:n * C].view(n, C).numpy()
+                if self.threads > 1 and n * C >= (1 << 18):
+                    cuts = [lo + n * t // self.threads for t in range(self.threads + 1)]
+                    list(self.pool.map(lambda ab: np.copyto(stage[ab[0] - lo:ab[1] - lo], src[ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+                else:
+                    np.copyto(stage, src[lo:hi])
+                d.copy_(self.pinned[b][:n * C], non_blocking=True)
+                self.events[b].record()
+                self.busy[b] = True
             check(lib.gpc_pack_rows(ctypes.c_void_p(d.data_ptr()), n, C, CP, layout, ctypes.c_void_p(dst.data_ptr() + 8 * lo * CP), stream_ptr),
                   "gpc_pack_rows")
             launches += 1

@@ -60,6 +60,8 @@ def test_pipelined_ingest_many_chunks_back_to_back(monkeypatch):
         outs = []
         for (N, C, CP, layout) in [(5000 + 37 * rep, 64, 64, "features"), (5000 + 37 * rep, 64, 64, "logits"), (3001, 24, 24, "features"), (3001, 7, 8, "logits")]:
             src = rng.randn(N, C)
+            if rep == 2:
+                src = torch.from_numpy(src).pin_memory().numpy()  # page-locked input: DMA straight out of it (no staging copy)
             dst = torch.full((_cabi.padded_rows(N), CP), 7.0, dtype=torch.float64, device=dev)
             ing.upload_pack(src, C, CP, _cabi.LAYOUT[layout], dst, dev, st)
             outs.append((src, dst, N, C, CP, layout))
