@@ -305,6 +305,9 @@ __device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem
     post_tail_finish<true>(pa, ps, phase);  // resets the ticket (pa.counter)
     __threadfence();
   }
+  // the posterior's scratch and the staged workspace live in the ring memory: generic-proxy accesses ordered before the next phase's
+  // bulk copies into the same bytes
+  fence_proxy_async();
   // B3: the decision and the new weights are visible to every CTA
   if (!grid_barrier<0, kGThreads>(hs)) return false;
   if (tid == 0) {
