@@ -75,8 +75,24 @@ int launch_vb(Kern kern, const Args &a, size_t smem, int grid, int threads, cuda
   kern<<<grid, threads, smem, st>>>(a);
   return launch_rc();
 }
+// the warp-specialised G pass (one chunk of K <= 64 clusters): ring depth and shared memory
+int natgrad2_stages(int KP, int DP, size_t budget) {
+  const size_t fixed = sizeof(double) * (size_t)kG2FixedDoubles + 64;
+  const size_t per = sizeof(double) * (size_t)g2_stage_doubles(KP, DP) + 3 * sizeof(uint64_t);
+  const int s = (int)((budget - fixed) / per);
+  return s > kMaxStages ? kMaxStages : s;
+}
+size_t natgrad2_smem(int KP, int DP, int S) {
+  return sizeof(double) * ((size_t)S * g2_stage_doubles(KP, DP) + kG2FixedDoubles) + sizeof(uint64_t) * 3 * S;
+}
 template <int KP>
 int launch_natgrad(NatgradArgs &a, int grid, cudaStream_t st) {
+  if (a.sa_vec == nullptr && a.xg_stride == 0) {
+    a.stages = natgrad2_stages(KP, a.DP, kSmemBudget);
+    const size_t smem = natgrad2_smem(KP, a.DP, a.stages);
+    return a.K == KP ? launch_vb(k_natgrad2<KP, true>, a, smem, grid, kGThreads, st) : launch_vb(k_natgrad2<KP, false>, a, smem, grid, kGThreads, st);
+  }
+  // sweep 1 of the per-chunk launches (K > 64 without thread-block clusters): the unit design
   a.stages = natgrad_stages(KP, a.DP);
   const size_t smem = natgrad_smem(KP, a.DP, a.stages);
   return a.K == KP ? launch_vb(k_natgrad<KP, true>, a, smem, grid, kGThreads, st) : launch_vb(k_natgrad<KP, false>, a, smem, grid, kGThreads, st);
@@ -1051,19 +1067,11 @@ struct LoopGeom {
 };
 LoopGeom loop_geometry(int KP, int DP, int D) {
   LoopGeom q;
-  // Shared memory deliberately NOT maxed out: the G rows read the previous-point operands and write the natural gradient through
-  // L1, and the carve-out is per launch -- with the 228 KB configuration (what a full-depth S ring would ask for) the G phase
-  // loses 8 % (measured: 580 vs 539 us at 1M rows), while the S ring is insensitive to its depth from 8 stages up.  180 KB of rings
-  // (+ header) selects the 196 KB configuration: two ring slots per G unit, ten S stages.
+  // Shared memory deliberately NOT maxed out: neither ring gains anything beyond nine stages (measured: G rows 520-521 us with
+  // 10 .. 13 stages, 525 with 9; S rows flat from 8 up), while the posterior phase between them loses 5 us per evaluation when the
+  // launch's carve-out leaves L1 only 28 KB.  180 KB of rings (+ header) selects the 196 KB configuration: ten stages each.
   const size_t budget = kLoopRingBudget;
-  {
-    const int units = kGConsumers / ((KP / 8 >= 2) ? 2 : 1);
-    const size_t fixed = sizeof(double) * (size_t)g_fixed_doubles(KP, DP) + 64;
-    const size_t per = sizeof(double) * (size_t)g_stage_doubles(KP, DP) + sizeof(uint64_t);
-    int r = (int)((budget - fixed) / per) / units;
-    if (r > kMaxUnitSlots) r = kMaxUnitSlots;
-    q.g_stages = r * units;
-  }
+  q.g_stages = natgrad2_stages(KP, DP, budget);
   {
     const size_t fixed = sizeof(double) * kSSoftmaxWarps + 64;
     const size_t per = sizeof(double) * (size_t)s_stage_doubles(KP, DP) + 3 * sizeof(uint64_t);
@@ -1071,7 +1079,7 @@ LoopGeom loop_geometry(int KP, int DP, int D) {
     q.s_stages = st > kMaxStages ? kMaxStages : st;
   }
   const size_t post = (((size_t)eig_ws_len(D) * 8 + 127) & ~(size_t)127) + sizeof(PostSmem);
-  size_t m = natgrad_smem(KP, DP, q.g_stages);
+  size_t m = natgrad2_smem(KP, DP, q.g_stages);
   if (step_stats_smem(KP, DP, q.s_stages) > m) m = step_stats_smem(KP, DP, q.s_stages);
   if (post > m) m = post;
   q.smem = kLoopHeaderBytes + ((m + 127) & ~(size_t)127);

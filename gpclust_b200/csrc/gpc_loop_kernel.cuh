@@ -351,14 +351,11 @@ __device__ __noinline__ bool loop_post_phase(LoopShared &hs, unsigned char *smem
 // the row phases as callable units (kernel parameters are __grid_constant__: their address can be passed on without a local copy)
 template <int KP, bool FULLK>
 __device__ GPC_G_ATTR void loop_g_phase(const NatgradArgs &ga, LoopShared &hs, unsigned char *smem_raw) {
-  const GSmem gm = g_carve(smem_raw, ga.stages, KP, ga.DP);
+  const G2Smem gm = g2_carve(smem_raw, ga.stages, KP, ga.DP);
   const GPtrs gp = g_resolve(ga, KP, 0, &hs.L);
-  g_setup_bars<KP, false>(ga, gm);
+  g2_setup(gm, ga.stages);
   __syncthreads();
-  g_prefeed<KP>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x);  // first HBM round trip under the weight loads
-  g_setup_w<KP>(ga, gm, gp);
-  __syncthreads();
-  g_rows<KP, FULLK, false>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x, 0, 1, true);
+  g2_rows<KP, FULLK>(ga, gm, gp, (int)blockIdx.x, (int)gridDim.x);  // the producer warp starts the HBM traffic while the product warps load W
   fence_proxy_async();  // this CTA's natural gradient is staged by its own bulk copies in the S phase
   __syncthreads();
 }
@@ -392,10 +389,14 @@ __device__ __noinline__ bool loop_begin_eval(LoopShared &hs) {
 }
 // end of the G rows: per-CTA partial dots, ring barriers invalidated (the memory is re-carved by the S phase)
 __device__ __noinline__ void loop_after_g(LoopShared &hs, unsigned char *smem_raw) {
-  const GSmem gm = g_carve(smem_raw, hs.g_stages, hs.KP, hs.DP);
-  g_cta_partial(gm, const_cast<double *>(hs.gpart));
+  const G2Smem gm = g2_carve(smem_raw, hs.g_stages, hs.KP, hs.DP);
+  g_cta_partial(gm.red_s, const_cast<double *>(hs.gpart));
   if (threadIdx.x == 0) {
-    for (int s = 0; s < hs.g_stages; ++s) mbar_inval(&gm.full_bar[s]);
+    for (int s = 0; s < hs.g_stages; ++s) {
+      mbar_inval(&gm.full_bar[s]);
+      mbar_inval(&gm.a_bar[s]);
+      mbar_inval(&gm.empty_bar[s]);
+    }
     if (hs.timing != nullptr && blockIdx.x == 0) hs.t[1] = hs.t[2] = globaltimer_ns();
   }
 }

@@ -427,10 +427,10 @@ __device__ __forceinline__ void g_rows(const NatgradArgs &a, const GSmem &m, con
 }
 
 // per-CTA partial of the three dots (fixed order over the warps); call after the block-wide barrier that follows g_rows
-__device__ __forceinline__ void g_cta_partial(const GSmem &m, double *partials) {
+__device__ __forceinline__ void g_cta_partial(const double *red_s, double *partials) {
   if (threadIdx.x < 3) {
     double v = 0.0;
-    for (int w = 0; w < kGConsumers; ++w) v += m.red_s[w * 4 + threadIdx.x];
+    for (int w = 0; w < kGConsumers; ++w) v += red_s[w * 4 + threadIdx.x];
     partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
   }
 }
@@ -446,27 +446,300 @@ __device__ __forceinline__ double reduce_dot_warp(const double *gpart, int ncl, 
   return warp_sum(((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7])));  // identical on every CTA, run to run
 }
 
-template <int KP, bool FULLK, bool CL = false>
-__global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// ------------------------------------------------------------------------------------------------
+// G pass, K <= 64: warp-specialised row loop (the shape of the S pass)
+// ------------------------------------------------------------------------------------------------
+// 1 producer warp + 4 PRODUCT warps (tensor pipe) + 7 ELEMENT warps (exp / row sums / dots), around ONE ring of group-sized stages
+//   [ F group, later a = F.W + bias - x | x | x_old | ng_old | lse (8) | lse_old (8) ]
+// filled by the producer with cp.async.bulk -- the previous-point operands included, so that nobody waits on an HBM load with
+// registers as the landing zone.  Every stage is visited by all four product warps (warp p: n-tiles p, p + 4; its B fragments of W
+// live in REGISTERS for the whole pass, the accumulators start at bias - x) -- they take the A fragments of F into registers, meet on
+// a named barrier and overwrite the head of the stage with a -- and then by ONE element warp (stage j -> warp j mod 7: the whole row
+// of 8*KP/32 elements per lane, so the row sum sum_k phi*a needs the quad shuffle only).  exp(x - lse) is evaluated by the element
+// warp while the product warps still work on the stage.
+// Why: in the unit design (g_rows) every warp alternates between a DMMA chain and the elementwise work and waits ~3 000 cycles per
+// visit for the previous-point loads; three such warps per scheduler keep the shared FP64 / DMMA pipe 55-62 % busy.  Specialised
+// roles overlap the two kinds of pipe work and the memory latency the way the S pass does (0.94-0.96 of HBM).
+__host__ __device__ inline int g2_head_doubles(int KP, int DP) { return kGroupRows * (DP > KP ? DP : KP); }
+__host__ __device__ inline int g2_stage_doubles(int KP, int DP) { return g2_head_doubles(KP, DP) + 3 * kGroupRows * KP + 2 * kGroupRows; }
+constexpr int kG2ProductBar = 7;  // named barrier of the four product warps
+
+struct G2Smem {
+  double *stages, *red_s;
+  uint64_t *full_bar, *a_bar, *empty_bar;
+};
+constexpr int kG2FixedDoubles = kGConsumers * 4;  // dot partials
+__device__ __forceinline__ G2Smem g2_carve(unsigned char *smem_raw, int S, int KP, int DP) {
+  G2Smem m;
+  m.stages = reinterpret_cast<double *>(smem_raw);
+  m.red_s = m.stages + (size_t)S * g2_stage_doubles(KP, DP);  // kGConsumers * 4
+  m.full_bar = reinterpret_cast<uint64_t *>(m.red_s + kGConsumers * 4);
+  m.a_bar = m.full_bar + S;
+  m.empty_bar = m.a_bar + S;
+  return m;
+}
+// barriers + zeroed dot partials; the caller synchronises the block afterwards
+__device__ __forceinline__ void g2_setup(const G2Smem &m, int S) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&m.full_bar[s], 1);
+      mbar_init(&m.a_bar[s], kSStatWarps);
+      mbar_init(&m.empty_bar[s], 1);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < kGConsumers * 4; i += blockDim.x) m.red_s[i] = 0.0;
+}
+
+// ---------------- producer (one lane): bulk copies of the stage operands
+template <int KP>
+__device__ __forceinline__ void g2_producer(const NatgradArgs &a, const G2Smem &m, const GPtrs &p, int cid, int ncl) {
+  constexpr int XG = kGroupRows * KP;
+  const int DP = a.DP, FG = kGroupRows * DP, S = a.stages, HD = g2_head_doubles(KP, DP), SD = g2_stage_doubles(KP, DP);
+  if ((threadIdx.x & 31) != 0) return;
+  const bool has_old = (p.ng_old != nullptr);
+  const uint32_t bytes = (uint32_t)(FG + XG + kGroupRows + (has_old ? 2 * XG + kGroupRows : 0)) * 8u;
+  const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;  // row groups of this CTA: cid + j * ncl
+  for (int j = 0; j < Mc; ++j) {
+    const size_t grp = (size_t)cid + (size_t)j * ncl;
+    const int s = j % S;
+    if (j >= S) mbar_wait(&m.empty_bar[s], (uint32_t)(((j / S) & 1) ^ 1));
+    double *st = m.stages + (size_t)s * SD;
+    mbar_arrive_expect_tx(&m.full_bar[s], bytes);
+    bulk_g2s(st, a.F + grp * FG, FG * 8u, &m.full_bar[s]);
+    bulk_g2s(st + HD, p.x + grp * XG, XG * 8u, &m.full_bar[s]);
+    bulk_g2s(st + HD + 3 * XG, p.lse + grp * kGroupRows, kGroupRows * 8u, &m.full_bar[s]);
+    if (has_old) {
+      bulk_g2s(st + HD + XG, p.x_old + grp * XG, XG * 8u, &m.full_bar[s]);
+      bulk_g2s(st + HD + 2 * XG, p.ng_old + grp * XG, XG * 8u, &m.full_bar[s]);
+      bulk_g2s(st + HD + 3 * XG + kGroupRows, p.lse_old + grp * kGroupRows, kGroupRows * 8u, &m.full_bar[s]);
+    }
+  }
+}
+
+// ---------------- product warps: a = F.W + bias - x for the n-tiles pw, pw + 4 of every stage, left in the head of the stage.
+// A DMMA m8n8k4 occupies the scheduler's FP64 pipe for 16 cycles and has 26 cycles of dependent-issue latency
+// (tools/microbench/dmma_latency.cu: 26.0 cycles per DMMA with one accumulator chain, 16.2 with two): two chains keep one warp at the
+// peak rate, provided it issues DMMAs and next to nothing else.  Hence: all A fragments of the stage into registers first, then the
+// 2 x 16 DMMAs back to back as kG2Split chains per n-tile (k-step ks -> chain ks mod kG2Split; chain 0 starts at -x, chain 1 at the
+// bias, so that a = F.W + bias - x costs one addition per element).
+#ifndef GPC_G2_SPLIT
+#define GPC_G2_SPLIT 2
+#endif
+constexpr int kG2Split = GPC_G2_SPLIT;
+template <int KP, bool FULLK, bool FULLD>
+__device__ __forceinline__ void g2_product_loop(const NatgradArgs &a, const G2Smem &m, const GPtrs &p, int cid, int ncl) {
+  constexpr int NT = KP / 8;
+  constexpr int NTP = (NT + kSStatWarps - 1) / kSStatWarps;  // n-tiles per product warp
+  constexpr int KS = GPC_MAX_DP / 4;                         // k-steps at the widest feature block
+  const int DP = a.DP, S = a.stages, HD = g2_head_doubles(KP, DP), SD = g2_stage_doubles(KP, DP), ksteps = FULLD ? KS : DP / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int pw = warp - kSSoftmaxWarps;
+  const int Kc = FULLK ? KP : a.K;
+  // B fragments of this warp's n-tiles (lane (g, t): W[4 ks + t][8 nt + g]) and its bias entries in registers for the whole pass
+  double wr[KS][NTP], b0[NTP], b1[NTP];
+#pragma unroll
+  for (int q = 0; q < NTP; ++q) {
+    const int nt = pw + kSStatWarps * q;
+    const bool has = nt < NT;
+    const double *wrow = p.Wt + (size_t)(8 * (has ? nt : 0) + g) * DP + t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) wr[ks][q] = (has && (FULLD || ks < ksteps)) ? __ldcg(wrow + 4 * ks) : 0.0;  // L2: rewritten by other CTAs inside the fused loop kernel
+    const int c = 8 * (has ? nt : 0) + 2 * t;
+    b0[q] = (has && (FULLK || c < Kc)) ? __ldcg(p.bias + c) : 0.0;
+    b1[q] = (has && (FULLK || c + 1 < Kc)) ? __ldcg(p.bias + c + 1) : 0.0;
+  }
+  const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;
+  for (int j = 0; j < Mc; ++j) {
+    const int s = j % S;
+    double *st = m.stages + (size_t)s * SD;
+    mbar_wait(&m.full_bar[s], (uint32_t)((j / S) & 1));
+    double af[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) af[ks] = (FULLD || ks < ksteps) ? st[ks * 32 + lane] : 0.0;
+    // chain 0 starts at -x, chain 1 at the bias, the others at 0
+    double acc[NTP][kG2Split][2];
+#pragma unroll
+    for (int q = 0; q < NTP; ++q) {
+      const int nt = pw + kSStatWarps * q;
+      double2 xv = make_double2(0.0, 0.0);
+      if (nt < NT) xv = *reinterpret_cast<const double2 *>(st + HD + nt * 64 + 2 * lane);
+      acc[q][0][0] = -xv.x;
+      acc[q][0][1] = -xv.y;
+      acc[q][1][0] = b0[q];
+      acc[q][1][1] = b1[q];
+#pragma unroll
+      for (int c = 2; c < kG2Split; ++c) acc[q][c][0] = acc[q][c][1] = 0.0;
+    }
+    if (FULLD) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int q = 0; q < NTP; ++q) dmma884(acc[q][ks % kG2Split][0], acc[q][ks % kG2Split][1], af[ks], wr[ks][q]);
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        if (ks < ksteps) {
+#pragma unroll
+          for (int q = 0; q < NTP; ++q) dmma884(acc[q][ks % kG2Split][0], acc[q][ks % kG2Split][1], af[ks], wr[ks][q]);
+        }
+    }
+    // every product warp holds its A fragments of the stage in registers: the head may be overwritten
+    asm volatile("bar.sync %0, %1;\n" ::"n"(kG2ProductBar), "n"(kSStatWarps * 32) : "memory");
+#pragma unroll
+    for (int q = 0; q < NTP; ++q) {
+      const int nt = pw + kSStatWarps * q;
+      if (nt < NT) {
+        const int c = 8 * nt + 2 * t;
+        double a0 = acc[q][0][0] + acc[q][1][0], a1 = acc[q][0][1] + acc[q][1][1];
+#pragma unroll
+        for (int cc = 2; cc < kG2Split; ++cc) {
+          a0 += acc[q][cc][0];
+          a1 += acc[q][cc][1];
+        }
+        if (!(FULLK || c < Kc)) a0 = 0.0;
+        if (!(FULLK || c + 1 < Kc)) a1 = 0.0;
+        *reinterpret_cast<double2 *>(st + nt * 64 + 2 * lane) = make_double2(a0, a1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&m.a_bar[s]);
+  }
+}
+template <int KP, bool FULLK>
+__device__ __forceinline__ void g2_product(const NatgradArgs &a, const G2Smem &m, const GPtrs &p, int cid, int ncl) {
+  static_assert(kG2Split >= 2, "chain 0 carries -x, chain 1 the bias");
+  if (a.DP == GPC_MAX_DP) g2_product_loop<KP, FULLK, true>(a, m, p, cid, ncl);  // no predicates around the DMMAs
+  else g2_product_loop<KP, FULLK, false>(a, m, p, cid, ncl);
+}
+
+// ---------------- element warps: natural gradient, gradient and the three dots of one group each; red_s[warp*4 + {0,1,2}] <- dots
+template <int KP, bool FULLK>
+__device__ __forceinline__ void g2_element(const NatgradArgs &a, const G2Smem &m, const GPtrs &p, int cid, int ncl) {
+  constexpr int NT = KP / 8;
+  constexpr int XG = kGroupRows * KP;
+  constexpr int EB = NT > 4 ? 4 : NT;  // n-tiles per exp batch at the current point
+  constexpr int HB = NT > 2 ? 2 : NT;  // ... at the previous point (evaluated and consumed batch by batch: register peak)
+  const int DP = a.DP, S = a.stages, HD = g2_head_doubles(KP, DP), SD = g2_stage_doubles(KP, DP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double exp_tab = kExpTab[lane];  // this lane's entry of the 2^(j/32) table (exp_batch_tab)
+  const int Kc = FULLK ? KP : a.K;
+  const bool has_old = (p.ng_old != nullptr);
+  double *p_ng_out = p.ng_out, *p_grad_out = p.grad_out;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d0b = 0.0, d1b = 0.0, d2b = 0.0;  // two chains per dot (even / odd column of the lane)
+  const int Mc = cid < a.num_groups ? (a.num_groups - cid + ncl - 1) / ncl : 0;
+  for (int j = warp; j < Mc; j += kSSoftmaxWarps) {
+    const size_t grp = (size_t)cid + (size_t)j * ncl;
+    const int s = j % S;
+    const uint32_t par = (uint32_t)((j / S) & 1);
+    const double *st = m.stages + (size_t)s * SD;
+    const bool row_ok = (long long)(grp * kGroupRows + g) < (long long)a.N;
+    mbar_wait(&m.full_bar[s], par);
+    const double lse = st[HD + 3 * XG + g];
+    const double lse_o = has_old ? st[HD + 3 * XG + kGroupRows + g] : 0.0;
+    // ---- phi = exp(x - lse): needs the stage only, runs while the product warps still work on it
+    double phi[2 * NT];
+    const double *xs = st + HD + 2 * lane;
+#pragma unroll
+    for (int q0 = 0; q0 < NT; q0 += EB) {
+      double eb[2 * EB];
+#pragma unroll
+      for (int q = 0; q < EB; ++q) {
+        const double2 xv = *reinterpret_cast<const double2 *>(xs + (q0 + q) * 64);
+        eb[2 * q] = xv.x - lse;
+        eb[2 * q + 1] = xv.y - lse;
+      }
+      exp_batch_tab<2 * EB>(eb, exp_tab);
+#pragma unroll
+      for (int q = 0; q < EB; ++q) {
+        const int c = 8 * (q0 + q) + 2 * t;
+        phi[2 * (q0 + q)] = (FULLK || c < Kc) ? eb[2 * q] : 0.0;
+        phi[2 * (q0 + q) + 1] = (FULLK || c + 1 < Kc) ? eb[2 * q + 1] : 0.0;
+      }
+    }
+    // ---- a from the product warps; row sum sa = sum_k phi*a (the quad holds the whole row)
+    mbar_wait(&m.a_bar[s], par);
+    double av[2 * NT];
+    double sa = 0.0, sa2 = 0.0;
+    const double *as = st + 2 * lane;
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const double2 v = *reinterpret_cast<const double2 *>(as + q * 64);
+      av[2 * q] = v.x;
+      av[2 * q + 1] = v.y;
+      sa = fma(phi[2 * q], v.x, sa);
+      sa2 = fma(phi[2 * q + 1], v.y, sa2);
+    }
+    sa = quad_sum(sa + sa2);
+    // ---- natural gradient, gradient, dots (MOHGP.py:150-153, collapsed_vb.py:154,160-164)
+    const size_t goff = grp * XG + 2 * lane;
+    double *ngo_g = p_ng_out + goff;
+    double *gro_g = p_grad_out ? p_grad_out + goff : nullptr;
+    const double *xos = st + HD + XG + 2 * lane, *ngs = st + HD + 2 * XG + 2 * lane;
+#pragma unroll
+    for (int q0 = 0; q0 < NT; q0 += HB) {
+      double pb[2 * HB];
+      if (has_old) {
+#pragma unroll
+        for (int q = 0; q < HB; ++q) {
+          const double2 xo = *reinterpret_cast<const double2 *>(xos + (q0 + q) * 64);
+          pb[2 * q] = xo.x - lse_o;
+          pb[2 * q + 1] = xo.y - lse_o;
+        }
+        exp_batch_tab<2 * HB>(pb, exp_tab);
+      }
+#pragma unroll
+      for (int qq = 0; qq < HB; ++qq) {
+        const int q = q0 + qq;
+        const int c = 8 * q + 2 * t;
+        const bool ok0 = (FULLK || c < Kc) && row_ok, ok1 = (FULLK || c + 1 < Kc) && row_ok;
+        const double n0 = ok0 ? av[2 * q] - sa : 0.0;
+        const double n1 = ok1 ? av[2 * q + 1] - sa : 0.0;
+        const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
+        stg2(ngo_g + q * 64, n0, n1);
+        if (gro_g) stg2(gro_g + q * 64, g0, g1);
+        d0 = fma(n0, g0, d0);
+        d0b = fma(n1, g1, d0b);
+        if (has_old) {
+          const double2 ngo = *reinterpret_cast<const double2 *>(ngs + q * 64);
+          const double po0 = ok0 ? pb[2 * qq] : 0.0, po1 = ok1 ? pb[2 * qq + 1] : 0.0;
+          const double e0 = n0 - ngo.x, e1 = n1 - ngo.y;
+          d1 = fma(e0, g0, d1);
+          d1b = fma(e1, g1, d1b);
+          d2 = fma(e0, ngo.x * po0, d2);
+          d2b = fma(e1, ngo.y * po1, d2b);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&m.empty_bar[s]);  // the stage goes back to the producer
+  }
+  d0 = warp_sum(d0 + d0b);
+  d1 = warp_sum(d1 + d1b);
+  d2 = warp_sum(d2 + d2b);
+  if (lane == 0) {
+    m.red_s[warp * 4 + 0] = d0;
+    m.red_s[warp * 4 + 1] = d1;
+    m.red_s[warp * 4 + 2] = d2;
+  }
+}
+// the three roles; the caller has run g2_setup + a block barrier and synchronises the block afterwards
+template <int KP, bool FULLK>
+__device__ __forceinline__ void g2_rows(const NatgradArgs &a, const G2Smem &m, const GPtrs &p, int cid, int ncl) {
+  static_assert(kGThreads == kSThreads, "the specialised G pass uses the warp roles of the S pass");
+  const int warp = threadIdx.x >> 5;
+  if (warp == kSSoftmaxWarps + kSStatWarps) g2_producer<KP>(a, m, p, cid, ncl);
+  else if (warp < kSSoftmaxWarps) g2_element<KP, FULLK>(a, m, p, cid, ncl);
+  else g2_product<KP, FULLK>(a, m, p, cid, ncl);
+}
+
+// end of a stand-alone G pass: deterministic two-level reduction of the three dots (per-CTA partial, the last CTA sums all partials
+// in index order) and, with rows sharded over GPUs, the push of this rank's dots into every peer's inbox
+__device__ __forceinline__ void g_finish(const NatgradArgs &a, const double *red_s) {
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
-  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
-  if (a.loop != nullptr) {
-    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
-    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
-  }
-  const GSmem m = g_carve(smem_raw, a.stages, KP, a.DP);
-  const GPtrs p = g_resolve(a, KP, crank, a.loop);
-  g_setup<KP, CL>(a, m, p);
-  if (CL) cluster_sync_all();  // every peer's mailbox barriers exist before the first remote arrive
-  else __syncthreads();
-  g_rows<KP, FULLK, CL>(a, m, p, cid, ncl, crank, csize);
-  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
-  else __syncthreads();
   // deterministic two-level reduction: per-CTA partial, last CTA sums all partials in index order
-  g_cta_partial(m, a.partials);
+  g_cta_partial(red_s, a.partials);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -505,6 +778,43 @@ __global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
       if (lane == 0) *a.counter = 0u;
     }
   }
+}
+
+template <int KP, bool FULLK, bool CL = false>
+__global__ void __launch_bounds__(kGThreads, 1) k_natgrad(const NatgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? a.csize : 1;
+  const int cid = CL ? (int)cluster_id_x() : (int)blockIdx.x, ncl = CL ? (int)cluster_count_x() : (int)gridDim.x;
+  if (a.loop != nullptr) {
+    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
+    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
+  }
+  const GSmem m = g_carve(smem_raw, a.stages, KP, a.DP);
+  const GPtrs p = g_resolve(a, KP, crank, a.loop);
+  g_setup<KP, CL>(a, m, p);
+  if (CL) cluster_sync_all();  // every peer's mailbox barriers exist before the first remote arrive
+  else __syncthreads();
+  g_rows<KP, FULLK, CL>(a, m, p, cid, ncl, crank, csize);
+  if (CL) cluster_sync_all();  // no CTA leaves while a peer may still store into its mailbox
+  else __syncthreads();
+  g_finish(a, m.red_s);
+}
+
+// K <= 64, one chunk: the warp-specialised row loop
+template <int KP, bool FULLK>
+__global__ void __launch_bounds__(kGThreads, 1) k_natgrad2(const NatgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (a.loop != nullptr) {
+    if (loop_skip(a.loop, GPC_PHASE_CONJ)) return;
+    if (a.loop->slot_mode != 0 && a.loop->need_retry != 0) return;  // retry slot: same point, the gradient and its dots stand
+  }
+  const G2Smem m = g2_carve(smem_raw, a.stages, KP, a.DP);
+  const GPtrs p = g_resolve(a, KP, 0, a.loop);
+  g2_setup(m, a.stages);
+  __syncthreads();
+  g2_rows<KP, FULLK>(a, m, p, (int)blockIdx.x, (int)gridDim.x);
+  __syncthreads();
+  g_finish(a, m.red_s);
 }
 
 // ------------------------------------------------------------------------------------------------
