@@ -619,7 +619,7 @@ __device__ __forceinline__ void g2_element(const NatgradArgs &a, const G2Smem &m
   constexpr int NT = KP / 8;
   constexpr int XG = kGroupRows * KP;
   constexpr int EB = NT > 4 ? 4 : NT;  // n-tiles per exp batch at the current point
-  constexpr int HB = NT > 2 ? 2 : NT;  // ... at the previous point (evaluated and consumed batch by batch: register peak)
+  constexpr int HB = NT > 4 ? 4 : NT;  // ... at the previous point (evaluated and consumed batch by batch: register peak)
   const int DP = a.DP, S = a.stages, HD = g2_head_doubles(KP, DP), SD = g2_stage_doubles(KP, DP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const double exp_tab = kExpTab[lane];  // this lane's entry of the 2^(j/32) table (exp_batch_tab)
@@ -659,14 +659,11 @@ __device__ __forceinline__ void g2_element(const NatgradArgs &a, const G2Smem &m
     }
     // ---- a from the product warps; row sum sa = sum_k phi*a (the quad holds the whole row)
     mbar_wait(&m.a_bar[s], par);
-    double av[2 * NT];
     double sa = 0.0, sa2 = 0.0;
     const double *as = st + 2 * lane;
 #pragma unroll
     for (int q = 0; q < NT; ++q) {
       const double2 v = *reinterpret_cast<const double2 *>(as + q * 64);
-      av[2 * q] = v.x;
-      av[2 * q + 1] = v.y;
       sa = fma(phi[2 * q], v.x, sa);
       sa2 = fma(phi[2 * q + 1], v.y, sa2);
     }
@@ -693,8 +690,10 @@ __device__ __forceinline__ void g2_element(const NatgradArgs &a, const G2Smem &m
         const int q = q0 + qq;
         const int c = 8 * q + 2 * t;
         const bool ok0 = (FULLK || c < Kc) && row_ok, ok1 = (FULLK || c + 1 < Kc) && row_ok;
-        const double n0 = ok0 ? av[2 * q] - sa : 0.0;
-        const double n1 = ok1 ? av[2 * q + 1] - sa : 0.0;
+        // a is re-read from the stage rather than kept across the row sum: 32 registers that the exp batches of 8 need more
+        const double2 av = *reinterpret_cast<const double2 *>(as + q * 64);
+        const double n0 = ok0 ? av.x - sa : 0.0;
+        const double n1 = ok1 ? av.y - sa : 0.0;
         const double g0 = n0 * phi[2 * q], g1 = n1 * phi[2 * q + 1];
         stg2(ngo_g + q * 64, n0, n1);
         if (gro_g) stg2(gro_g + q * 64, g0, g1);

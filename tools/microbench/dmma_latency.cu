@@ -1,5 +1,5 @@
-// DMMA (mma.sync m8n8k4 f64) issue interval and dependent-issue latency on sm_100a: ONE warp per SM, NACC independent accumulator
-// chains issued round-robin.  cycles per DMMA = max(issue interval, latency / NACC).  Not product code.
+// DMMA (mma.sync m8n8k4 f64) and DFMA issue interval and dependent-issue latency on sm_100a: `warps_per_sm` warps per SM, NACC
+// independent accumulator chains issued round-robin.  cycles per DMMA = max(issue interval, latency / NACC).  Not product code.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dmma_latency dmma_latency.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -25,6 +25,34 @@ __global__ void k(double *out, long long *cyc, int iters) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 template <int NACC>
+__global__ void kf(double *out, long long *cyc, int iters) {
+  double c[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) c[i] = i * 1e-3;
+  const double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9 * threadIdx.x;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c[i] = fma(c[i], a, b);
+  }
+  const long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; i++) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+template <int NACC>
+void runf(double *out, long long *cyc, int warps) {
+  const int iters = 20000;
+  kf<NACC><<<148, 32 * warps>>>(out, cyc, iters);
+  cudaDeviceSynchronize();
+  long long h;
+  cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+  printf("{\"probe\": \"dfma_chains\", \"warps_per_sm\": %d, \"chains_per_warp\": %d, \"cycles_per_dfma_per_warp\": %.2f}\n", warps, NACC,
+         (double)h / ((double)iters * NACC));
+}
+template <int NACC>
 void run(double *out, long long *cyc, int warps) {
   const int iters = 20000;
   k<NACC><<<148, 32 * warps>>>(out, cyc, iters);
@@ -48,6 +76,13 @@ int main() {
     run<8>(out, cyc, warps);
     run<12>(out, cyc, warps);
     run<16>(out, cyc, warps);
+  }
+  for (int warps : {1, 4, 8}) {
+    runf<1>(out, cyc, warps);
+    runf<2>(out, cyc, warps);
+    runf<4>(out, cyc, warps);
+    runf<8>(out, cyc, warps);
+    runf<16>(out, cyc, warps);
   }
   return 0;
 }
