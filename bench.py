@@ -5,14 +5,16 @@ K=64 clusters, FP64, method='HS', synthetic data (SURVEY.md section 8d recipe).
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one pass of the collapsed-VB loop body (collapsed_vb.py:147-303): G pass (natural gradient +
-CG dots), S pass (search direction, trial point, softmax, statistics), per-cluster posterior, bound, and
-the host accept/reject decision on the bound read back from the device.  Rows are sharded over the ranks
-(strong scaling: N_total is fixed at 1M), statistics and dots are all-reduced over NCCL.
+A "step" is one pass of the collapsed-VB loop body (collapsed_vb.py:147-303): G rows (natural gradient + CG dots), S rows (search
+direction, trial point, softmax, statistics), per-cluster posterior, bound and the accept / reject / termination decision -- all
+phases of ONE persistent cooperative kernel (k_mohgp_loop); the trace is read back once after the K steps.  Rows are
+sharded over the ranks (strong scaling: N_total is fixed at 1M); statistics and dots cross NVLink inside that kernel (no NCCL call
+per pass; NCCL carries the set-up, the barriers and the gather of the parity record).
 
 The JSON line carries, besides the contract keys:
-  roofline      the dominant N-sized kernel (largest share of the step), HBM-bound: algorithmic bytes per
-                launch / mean CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  roofline      the kernel of the timed region, HBM-bound: algorithmic bytes of everything the launch did / its CUDA-event
+                duration, against MEASURED_PEAKS.json hbm_gbs; roofline_by_kernel = the two row phases from in-kernel timers
+  parity        the oracle evaluated at N=1M on the bench inputs, outside every timed region, on this rank count
   fp64_tensor   4*N*K*D flop per step / step time against the measured DMMA peak (profiles/fp64_peaks_r01.json)
   cpu_baseline  the oracle port of the reference's native path (weave C kernels + numpy/LAPACK) on the
                 host cores, on a bounded row sample, scaled linearly in N
@@ -561,7 +563,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", default="HS", choices=["HS", "PR", "FR", "steepest"])
