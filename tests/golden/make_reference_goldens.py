@@ -56,6 +56,10 @@ def install_gpy_stub():
         def optimizer_array(self):
             return np.zeros(0)
 
+        @optimizer_array.setter
+        def optimizer_array(self, value):  # collapsed_mixture.py:174 restores it after a failed split: nothing is free here
+            assert np.asarray(value).size == 0
+
         def randomize(self):
             pass
 
@@ -182,6 +186,39 @@ def mog_case(GPclust, name, N, D, K, prior_Z, alpha, seed, maxiter=30):
     print("mog", name, "bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
 
 
+def splits_case(GPclust, name, N, D, K0, K_true, prior_Z, alpha, seed, kernF, kernY):
+    """The reference's own merge-split search on MOHGP (collapsed_mixture.py:96-205): optimize with the steepest method (VBEM),
+    then systematic_splits() from K0 < K_true clusters.  The stdout of the whole search is kept: which splits were attempted,
+    which succeeded and by how much the bound changed.  (Used by the CPU oracle test only -- the file name keeps it out of the
+    `reference_mohgp_*` parametrisations.)"""
+    rng = np.random.RandomState(seed)
+    X = np.linspace(0, 10, D)[:, None]
+    Sf, Sy = kernF.K(X), kernY.K(X)
+    z = rng.randint(0, K_true, N)
+    means = (np.linalg.cholesky(Sf + 1e-8 * np.eye(D)).dot(rng.randn(D, K_true))).T * 2.0
+    Y = means[z] + (np.linalg.cholesky(Sy + 1e-8 * np.eye(D)).dot(rng.randn(D, N))).T
+    np.random.seed(seed + 1)
+    m = GPclust.MOHGP(X, kernF, kernY, Y, K=K0, alpha=alpha, prior_Z=prior_Z)
+    out = {"X": X, "Y": Y, "phi0": m.phi_.copy(), "K": K0, "alpha": alpha, "prior_Z": prior_Z,
+           "kernF": json.dumps(kernF.spec()), "kernY": json.dumps(kernY.spec()), "bound0": m.bound()}
+    out["trace_steepest"] = run_optimize(m, method="steepest", maxiter=40)
+    out.update(bound1=m.bound(), phi1=m.phi.copy())
+    np.random.seed(seed + 2)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        m.systematic_splits(verbose=True)
+    text = buf.getvalue().replace("\r", "\n")
+    events = re.findall(r"attempting to split cluster\s+(\d+)|split (failed|suceeded), bound changed by:\s+(\S+)", text)
+    attempts = [int(a) for a, _, _ in events if a]
+    results = [(1.0 if r == "suceeded" else 0.0, float(v)) for a, r, v in events if r]
+    out.update(split_attempts=np.array(attempts, dtype=np.int64), split_results=np.array(results, dtype=np.float64).reshape(-1, 2),
+               K2=m.K, bound2=m.bound(), phi2=m.phi.copy(), phi_hat2=m.phi_hat.copy(),
+               rng_after=np.random.randn(3))  # the legacy global stream must have been consumed identically
+    np.savez_compressed(os.path.join(HERE, "reference_splits_%s.npz" % name), **out)
+    print("splits", name, "K %d -> %d, bound %.12g -> %.12g -> %.12g, %d attempts, %d succeeded" % (
+        K0, m.K, out["bound0"], out["bound1"], out["bound2"], len(attempts), int(sum(r[0] for r in results))))
+
+
 def main():
     install_gpy_stub()
     sys.path.insert(0, REF)
@@ -201,6 +238,10 @@ def main():
     omgp_case(GPclust, "k3", N=30, Dy=2, K=3, prior_Z="DP", alpha=2.0, seed=4, variance=0.05, kernels=None)
     mog_case(GPclust, "d3", N=80, D=3, K=4, prior_Z="symmetric", alpha=1.0, seed=5)
     mog_case(GPclust, "dp", N=70, D=2, K=5, prior_Z="DP", alpha=4.0, seed=6)
+    splits_case(GPclust, "mohgp", N=90, D=10, K0=2, K_true=4, prior_Z="symmetric", alpha=1.0, seed=7,
+                kernF=G.RBF(1, 1.0, 2.0), kernY=G.RBF(1, 0.1, 1.0) + G.White(1, 0.05))
+    splits_case(GPclust, "mohgp_dp", N=70, D=8, K0=3, K_true=5, prior_Z="DP", alpha=2.0, seed=8,
+                kernF=G.Matern52(1, 1.0, 3.0), kernY=G.Matern32(1, 0.1, 2.0) + G.White(1, 0.05))
 
 
 if __name__ == "__main__":

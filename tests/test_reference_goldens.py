@@ -141,6 +141,40 @@ def test_oracle_mog_matches_reference(path):
     _check_model(m, d, m.trace)
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "reference_splits_*.npz"))))
+def test_oracle_merge_split_search_matches_reference(path):
+    """collapsed_mixture.py:96-205 through the reference's own code (MOHGP, steepest optimisation, then systematic_splits()):
+    the oracle must attempt the same clusters in the same order, take the same accept / reject decision for every split with the
+    same change of the bound, end with the same K and assignments, and leave the legacy numpy stream in the same state."""
+    import re
+    d = _load(path)
+    m = MOHGPOracle(d["X"], _kern(json.loads(str(d["kernF"])), G), _kern(json.loads(str(d["kernY"])), G), d["Y"], K=int(d["K"]),
+                    alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]), mahalanobis=mahalanobis_pairs_solve)
+    m.set_vb_param(d["phi0"].flatten())
+    assert abs(m.bound() - _scalar(d["bound0"])) < TOL * abs(_scalar(d["bound0"]))
+    m.out = io.StringIO()
+    m.optimize(method="steepest", maxiter=40, verbose=False)
+    _check_trace(m.trace, d["trace_steepest"])
+    assert abs(m.bound() - _scalar(d["bound1"])) < TOL * abs(_scalar(d["bound1"]))
+    seed = {"reference_splits_mohgp.npz": 7, "reference_splits_mohgp_dp.npz": 8}[os.path.basename(path)]
+    np.random.seed(seed + 2)
+    m.out = io.StringIO()
+    m.systematic_splits(verbose=True)
+    text = m.out.getvalue()
+    events = re.findall(r"attempting to split cluster\s+(\d+)|split (failed|suceeded), bound changed by:\s+(\S+)", text)
+    attempts = [int(a) for a, _, _ in events if a]
+    results = np.array([(1.0 if r == "suceeded" else 0.0, float(v)) for a, r, v in events if r]).reshape(-1, 2)
+    assert attempts == list(d["split_attempts"])
+    assert np.array_equal(results[:, 0], d["split_results"][:, 0])
+    # bound increments of whole optimisations (up to 100 + 5000 evaluations each): rounding of the loop amplified
+    assert np.allclose(results[:, 1], d["split_results"][:, 1], rtol=1e-6, atol=1e-6)
+    assert m.K == int(d["K2"])
+    assert abs(m.bound() - _scalar(d["bound2"])) < 1e-8 * abs(_scalar(d["bound2"]))
+    assert np.array_equal(np.argmax(m.phi, 1), np.argmax(d["phi2"], 1))
+    assert relerr(m.phi_hat, d["phi_hat2"]) < 1e-6
+    assert np.array_equal(np.random.randn(3), d["rng_after"])
+
+
 # ------------------------------------------------------------------------------------------------ product (GPU)
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", _cases("mohgp"))
