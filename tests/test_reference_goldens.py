@@ -237,3 +237,16 @@ def test_gpu_omgp_matches_reference(path):
     assert relerr(kgrads(), d["kgrad1"]) < 1e-7
     mu, va = m.predict(d["Xnew"], 0)
     assert relerr(mu, d["pred_mu0"]) < 1e-7 and relerr(va, d["pred_va0"]) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "reference_splits_*.npz"))))
+def test_gpu_merge_split_search_matches_reference(path):
+    """The reference's own MOHGP merge-split search (optimize(method='steepest') + systematic_splits(), K 2 -> 4 and 3 -> 5) replayed
+    through the GPU path: same attempted clusters, same accept / reject per split, bound increments, final K, assignments and
+    legacy-RNG state (tools/check_split_fixture.py; measured on B200: profiles/split_fixture_r02.jsonl, bounds to 2e-14)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from check_split_fixture import replay
+    rec = replay(path)
+    assert rec["ok"], rec
