@@ -17,7 +17,11 @@ Parity pins:
   * MOHGP, OMGP (and MOG again): PINNED against outputs of the reference's own modules -- /root/reference/GPclust
     imported unmodified in the build container with a stub `GPy` (tests/golden/make_reference_goldens.py) --
     stored in tests/golden/reference_*.npz and checked by tests/test_reference_goldens.py: start bound, gradient,
-    natural gradient, posterior means, full optimisation trace (iteration numbering, bounds, betas), final phi.
+    natural gradient, posterior means, full optimisation trace (iteration numbering, bounds, betas), final phi,
+    MOHGP.predict_components, OMGP.update_kern_grads, and the merge-split search on MOHGP (reference_splits_*.npz:
+    attempts, decisions, bound increments, final K / assignments, state of the legacy numpy stream).
+  * Oracle-independent identities (tests/test_oracle_identities.py): gradient = derivative of the bound, product-of-
+    Gaussians posterior, equality of the Mahalanobis / softmax forms incl. the C port, monotone bound.
     What remains the shim's (not the reference's) is the GPy layer itself (thin LAPACK wrappers, closed-form
     covariances): GPy is a third-party dependency absent from /root/reference (`GPy>=0.6`, setup.py:14).
 """
