@@ -124,9 +124,16 @@ def mohgp_case(GPclust, name, N, D, K, prior_Z, alpha, seed, kernF, kernY, X=Non
     out.update(bound0=m.bound(), grad0=g, natgrad0=ng, phi_init=m.phi.copy(), phi_hat0=m.phi_hat.copy(), H0=m.H, muk0=m.muk.copy(),
                Lambda_inv0=m.Lambda_inv.copy(), log_det_diff0=m.log_det_diff.copy(), ybark0=m.ybark.copy(),
                Sy_chol=m.Sy_chol.copy(), Sy_logdet=m.Sy_logdet, mix0=m.mixing_prop_bound(), mixgrad0=m.mixing_prop_bound_grad().copy())
+
+    def kgrads():
+        # the reference's own update_kern_grads (MOHGP.py:92-122): d bound / d (kernel parameter), kernF's then kernY's
+        m.update_kern_grads()
+        return np.array([getattr(o, n + "_gradient") for o, n in m.kernF.param_list() + m.kernY.param_list()])
+
+    out.update(kgrad0=kgrads())
     out["trace"] = run_optimize(m, method=method, maxiter=maxiter)
     g, ng = m.vb_grad_natgrad()
-    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy(), muk1=m.muk.copy())
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy(), phi_1=m.phi_.copy(), muk1=m.muk.copy(), kgrad1=kgrads())
     # the reference's own MOHGP.predict_components (MOHGP.py:156-174) at the optimised point, inside and outside the design range
     Xnew = np.linspace(X.min() - 1.0, X.max() + 1.0, 9)[:, None]
     mu, var = m.predict_components(Xnew)

@@ -98,10 +98,12 @@ def test_oracle_mohgp_matches_reference(path):
     assert relerr(m.phi, d["phi_init"]) < 1e-14 and abs(m.H - _scalar(d["H0"])) < 1e-12 * abs(_scalar(d["H0"]))
     assert abs(m.mixing_prop_bound() - _scalar(d["mix0"])) < 1e-12 * max(1.0, abs(_scalar(d["mix0"])))
     assert relerr(m.mixing_prop_bound_grad(), d["mixgrad0"]) < 1e-14
+    assert relerr(m.kernel_gradients(), d["kgrad0"]) < TOL  # MOHGP.update_kern_grads (MOHGP.py:92-122) at the initial point
     m.out = io.StringIO()
     m.optimize(method=str(d["method"]), maxiter=int(d["trace"][-1, 0]) if len(d["trace"]) else 25, verbose=False)
     _check_model(m, d, m.trace)
     _check_predict(m, d)
+    assert relerr(m.kernel_gradients(), d["kgrad1"]) < 1e-7  # at the optimised point (rounding of the loop amplified)
 
 
 def _check_predict(m, d, tol=1e-7):
