@@ -85,3 +85,37 @@ def test_eigenbasis_kernel_gradient_matrices():
         assert relerr(Bk, B_invs[k]) < 1e-10
     dsum = np.sum([m.phi_hat[k] / (1.0 + m.phi_hat[k] * lam) for k in range(m.K)], 0)
     assert relerr((U * dsum).dot(U.T), sum(B_invs)) < 1e-10
+
+
+def test_mog_feature_expansion_identities():
+    """gpclust_b200/MOG.py: with f(x) = [x_i x_j (i <= j) | x_i] of the CENTRED data, phi^T F holds Ck and Xsumk, the quadratic form of
+    MOG.py:74-77 is linear in f(x), and centring changes nothing but a shift of `mun` (MOG.py:52-61) -- numpy, against the oracle."""
+    from helpers import load_mog_data
+    from oracle.vb_oracle import MOGOracle
+    rng = np.random.RandomState(0)
+    X = np.hstack([load_mog_data()[:120], rng.randn(120, 1) * 3 + 5.0])   # D = 3, far from the origin in one coordinate
+    np.random.seed(1)
+    m = MOGOracle(X, K=4)
+    N, D, K = X.shape[0], X.shape[1], m.K
+    mean = X.mean(0)
+    Xc = X - mean
+    iu = np.triu_indices(D)
+    F = np.hstack([Xc[:, iu[0]] * Xc[:, iu[1]], Xc])                      # N x (D(D+1)/2 + D)
+    T = m.phi.T.dot(F)                                                    # the S pass's statistics
+    # posterior from the statistics of the centred data (m0 shifted too)
+    m0c = m.m0 - mean
+    for k in range(K):
+        Ck = np.zeros((D, D))
+        Ck[iu] = T[k, :len(iu[0])]
+        Ck = Ck + Ck.T - np.diag(np.diag(Ck))
+        Xsum = T[k, len(iu[0]):]
+        mun_c = (m.k0 * m0c + Xsum) / m.kNs[k]
+        Sn = m.S0 + Ck + m.k0 * np.outer(m0c, m0c) - m.kNs[k] * np.outer(mun_c, mun_c)
+        assert relerr(mun_c + mean, m.mun[:, k]) < 1e-12
+        assert relerr(Sn, m.Sns[:, :, k]) < 1e-10
+        # (x - mu)^T S (x - mu) = sum_{i<=j} (2 - delta_ij) S_ij x_i x_j - 2 (S mu)^T x + mu^T S mu: one row of W plus a bias
+        S = m.Sns_inv[:, :, k]
+        w = np.concatenate([np.where(iu[0] == iu[1], 1.0, 2.0) * S[iu], -2.0 * S.dot(mun_c)])
+        q = F.dot(w) + mun_c.dot(S).dot(mun_c)
+        x_m = X - m.mun[:, k]
+        assert relerr(q, np.einsum("ni,ij,nj->n", x_m, S, x_m)) < 1e-10
