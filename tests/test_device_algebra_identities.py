@@ -119,3 +119,42 @@ def test_mog_feature_expansion_identities():
         q = F.dot(w) + mun_c.dot(S).dot(mun_c)
         x_m = X - m.mun[:, k]
         assert relerr(q, np.einsum("ni,ij,nj->n", x_m, S, x_m)) < 1e-10
+
+
+def test_omgp_triangular_inverse_identities():
+    """with B = L L^T and W = L^-1, everything OMGP.py:96-147 and :55-94 need comes from W and alpha = W^T (W Y):
+    tr(B^-1 Y Y^T) = sum Y o alpha (the reference solves against the N x N YYT), logdet B = -2 sum log diag W, diag(B^-1) = squared
+    column norms of W, and dL_dB = B^-1 (Y Y^T - B) B^-1 = alpha alpha^T - B^-1 contracts with any dK/dtheta tile by tile."""
+    rng = np.random.RandomState(0)
+    N, D = 50, 2
+    X = np.sort(rng.uniform(0, 10, N))[:, None]
+    Y = np.hstack([np.sin(X), np.cos(X)]) + 0.1 * rng.randn(N, D)
+    phi = rng.dirichlet([1.0, 1.0, 1.0], N)[:, 0]
+    kern, variance = G.RBF(1, 1.3, 0.9), 0.05
+    B = kern.K(X) + np.diag(variance / (phi + 1e-6))
+    L = np.linalg.cholesky(B)
+    W = np.linalg.inv(L)
+    alpha = W.T.dot(W.dot(Y))
+    Bi, LB, _, logdet = G.pdinv(B)
+    assert abs(np.sum(Y * alpha) - G.dpotrs(LB, Y.dot(Y.T))[0].trace()) < 1e-10 * abs(np.sum(Y * alpha))   # OMGP.py:113
+    assert abs(-2.0 * np.sum(np.log(np.diag(W))) - logdet) < 1e-12 * abs(logdet)                            # OMGP.py:114
+    assert relerr(np.sum(W * W, 0), np.diag(Bi)) < 1e-10                                                    # OMGP.py:137
+    assert relerr(alpha, G.dpotrs(LB, Y)[0]) < 1e-10                                                        # OMGP.py:136
+    # OMGP.py:71-77 (with the matrix the reference uses there: no 1e-6)
+    B0 = kern.K(X) + np.diag(variance / phi)
+    Bi0, LB0, _, _ = G.pdinv(B0)
+    tmp = G.dpotrs(LB0, Y.dot(Y.T))[0]
+    tmp[np.diag_indices(N)] -= 1.0
+    dL_dB = G.dpotrs(LB0, tmp.T)[0]
+    a0 = Bi0.dot(Y)
+    assert relerr(a0.dot(a0.T) - Bi0, dL_dB) < 1e-9
+    # contraction tile by tile (16 x 16 tiles of B^-1 = W^T W formed one at a time) == the dense contraction
+    W0 = np.linalg.inv(np.linalg.cholesky(B0))
+    dK = kern.K(X) / kern.variance                                        # dK / d variance
+    acc = 0.0
+    for i in range(0, N, 16):
+        for j in range(0, N, 16):
+            tile = W0[:, i:i + 16].T.dot(W0[:, j:j + 16])
+            acc += np.sum((a0[i:i + 16].dot(a0[j:j + 16].T) - tile) * dK[i:i + 16, j:j + 16])
+    kern.update_gradients_full(0.5 * dL_dB, X)
+    assert abs(0.5 * acc - kern.variance_gradient) < 1e-9 * abs(kern.variance_gradient)
