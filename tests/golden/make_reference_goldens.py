@@ -226,6 +226,34 @@ def splits_case(GPclust, name, N, D, K0, K_true, prior_Z, alpha, seed, kernF, ke
         K0, m.K, out["bound0"], out["bound1"], out["bound2"], len(attempts), int(sum(r[0] for r in results))))
 
 
+def config1_case(GPclust):
+    """BASELINE.json configs[0] stand-in (data/kalinka09.csv itself is not in the reference tree): the replicate /
+    time design of the melanogaster rows of data/kalinka09_pdata.csv (56 samples, 8 replicates per hour), Matern52 kernels and DP prior
+    as in drosophila.ipynb, N = 500 series drawn from the model and row-normalised, K = 20 -- the same problem as
+    tests/test_gpu_mohgp.py::test_matern_dp_drosophila_like, run here through the reference's own MOHGP / CollapsedVB."""
+    rows = [l.strip().split(",") for l in open(os.path.join(HERE, "kalinka09_pdata.csv")).read().strip().split("\n")]
+    hours = np.array([float(r[2]) for r in rows if r[0] == "me"])
+    X = hours[:56, None]
+    D = X.shape[0]
+    rng = np.random.RandomState(0)
+    kF, kY = G.Matern52(1, 1.0, 12.0), G.Matern52(1, 0.1, 12.0) + G.White(1, 0.05)
+    Sf, Sy = kF.K(X), kY.K(X)
+    K, N = 20, 500
+    means = np.linalg.cholesky(Sf + 1e-6 * np.eye(D)).dot(rng.randn(D, 6)).T
+    Y = means[rng.randint(0, 6, N)] + np.linalg.cholesky(Sy + 1e-8 * np.eye(D)).dot(rng.randn(D, N)).T
+    Y = (Y - Y.mean(1)[:, None]) / Y.std(1)[:, None]
+    np.random.seed(2)
+    m = GPclust.MOHGP(X, kF, kY, Y, K=K, prior_Z="DP", alpha=1.0)
+    out = {"X": X, "Y": Y, "phi0": m.phi_.copy(), "K": K, "alpha": 1.0, "prior_Z": "DP", "method": "HS",
+           "kernF": json.dumps(kF.spec()), "kernY": json.dumps(kY.spec())}
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound0=m.bound(), natgrad0=ng, phi_hat0=m.phi_hat.copy(), muk0=m.muk.copy(), log_det_diff0=m.log_det_diff.copy())
+    out["trace"] = run_optimize(m, method="HS", maxiter=30)
+    out.update(bound1=m.bound(), phi1=m.phi.copy(), muk1=m.muk.copy())
+    np.savez_compressed(os.path.join(HERE, "reference_config1_kalinka.npz"), **out)
+    print("config1 kalinka stand-in: bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
+
+
 def main():
     install_gpy_stub()
     sys.path.insert(0, REF)
@@ -245,6 +273,7 @@ def main():
     omgp_case(GPclust, "k3", N=30, Dy=2, K=3, prior_Z="DP", alpha=2.0, seed=4, variance=0.05, kernels=None)
     mog_case(GPclust, "d3", N=80, D=3, K=4, prior_Z="symmetric", alpha=1.0, seed=5)
     mog_case(GPclust, "dp", N=70, D=2, K=5, prior_Z="DP", alpha=4.0, seed=6)
+    config1_case(GPclust)
     splits_case(GPclust, "mohgp", N=90, D=10, K0=2, K_true=4, prior_Z="symmetric", alpha=1.0, seed=7,
                 kernF=G.RBF(1, 1.0, 2.0), kernY=G.RBF(1, 0.1, 1.0) + G.White(1, 0.05))
     splits_case(GPclust, "mohgp_dp", N=70, D=8, K0=3, K_true=5, prior_Z="DP", alpha=2.0, seed=8,

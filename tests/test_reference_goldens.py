@@ -143,6 +143,26 @@ def test_oracle_mog_matches_reference(path):
     _check_model(m, d, m.trace)
 
 
+def test_oracle_config1_standin_matches_reference():
+    """BASELINE.json configs[0] stand-in (kalinka replicate / time design, D = 56, Matern52, DP prior, N = 500, K = 20) through the
+    reference's own MOHGP / CollapsedVB.optimize: the oracle reproduces the start bound, natural gradient, posterior means, the
+    28-line optimisation trace and the final assignments.  (The GPU path runs the same problem against the oracle in
+    tests/test_gpu_mohgp.py::test_matern_dp_drosophila_like.)"""
+    d = _load(os.path.join(GOLDEN, "reference_config1_kalinka.npz"))
+    m = MOHGPOracle(d["X"], _kern(json.loads(str(d["kernF"])), G), _kern(json.loads(str(d["kernY"])), G), d["Y"], K=int(d["K"]),
+                    alpha=float(d["alpha"]), prior_Z=str(d["prior_Z"]))
+    m.set_vb_param(d["phi0"].flatten())
+    assert abs(m.bound() - _scalar(d["bound0"])) < TOL * abs(_scalar(d["bound0"]))
+    assert relerr(m.vb_grad_natgrad()[1], d["natgrad0"]) < TOL
+    assert relerr(m.muk, d["muk0"]) < TOL and relerr(m.log_det_diff, d["log_det_diff0"]) < TOL and relerr(m.phi_hat, d["phi_hat0"]) < 1e-13
+    m.out = io.StringIO()
+    m.optimize(method="HS", maxiter=30, verbose=False)
+    _check_trace(m.trace, d["trace"])
+    assert abs(m.bound() - _scalar(d["bound1"])) < TOL * abs(_scalar(d["bound1"]))
+    assert relerr(m.phi, d["phi1"]) < 1e-7 and np.array_equal(np.argmax(m.phi, 1), np.argmax(d["phi1"], 1))
+    assert relerr(m.muk, d["muk1"]) < 1e-7
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "reference_splits_*.npz"))))
 def test_oracle_merge_split_search_matches_reference(path):
     """collapsed_mixture.py:96-205 through the reference's own code (MOHGP, steepest optimisation, then systematic_splits()):
