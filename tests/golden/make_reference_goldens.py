@@ -254,6 +254,28 @@ def config1_case(GPclust):
     print("config1 kalinka stand-in: bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
 
 
+def omgp_demo_case(GPclust):
+    """The reference's own demo data for OMGP (data/split_data_test.csv, OMGP_demo.ipynb cells [2]-[12]: N = 250 points of two
+    overlapping curves, K = 2, variance 0.01, DP prior) -- the notebook's stored outputs are unseeded, so the run is repeated here with a
+    seed through the reference's own OMGP / CollapsedVB.  CPU oracle pin (the file name keeps it out of the `reference_omgp_*` cases)."""
+    raw = np.loadtxt(os.path.join(HERE, "split_data_test.csv"), delimiter=",", skiprows=1)
+    X, Y = raw[:, 1:2], raw[:, 2:3]
+    np.random.seed(11)
+    m = GPclust.OMGP(X, Y, K=2, variance=0.01, prior_Z="DP")
+    out = {"X": X, "Y": Y, "phi0": m.phi_.copy(), "K": 2, "alpha": 1.0, "prior_Z": "DP", "variance": 0.01,
+           "kernels": json.dumps([k.spec() for k in m.kern])}
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound0=m.bound(), grad0=g, natgrad0=ng, log_likelihood0=m.log_likelihood())
+    out["trace"] = run_optimize(m, method="HS", maxiter=15)
+    g, ng = m.vb_grad_natgrad()
+    out.update(bound1=m.bound(), grad1=g, natgrad1=ng, phi1=m.phi.copy())
+    Xnew = np.linspace(X.min(), X.max(), 11)[:, None]
+    mu, va = m.predict(Xnew, 1)
+    out.update(Xnew=Xnew, pred_mu1=mu, pred_va1=va)
+    np.savez_compressed(os.path.join(HERE, "reference_demo_omgp.npz"), **out)
+    print("omgp demo data: bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
+
+
 def main():
     install_gpy_stub()
     sys.path.insert(0, REF)
@@ -274,6 +296,7 @@ def main():
     mog_case(GPclust, "d3", N=80, D=3, K=4, prior_Z="symmetric", alpha=1.0, seed=5)
     mog_case(GPclust, "dp", N=70, D=2, K=5, prior_Z="DP", alpha=4.0, seed=6)
     config1_case(GPclust)
+    omgp_demo_case(GPclust)
     splits_case(GPclust, "mohgp", N=90, D=10, K0=2, K_true=4, prior_Z="symmetric", alpha=1.0, seed=7,
                 kernF=G.RBF(1, 1.0, 2.0), kernY=G.RBF(1, 0.1, 1.0) + G.White(1, 0.05))
     splits_case(GPclust, "mohgp_dp", N=70, D=8, K0=3, K_true=5, prior_Z="DP", alpha=2.0, seed=8,

@@ -143,6 +143,22 @@ def test_oracle_mog_matches_reference(path):
     _check_model(m, d, m.trace)
 
 
+def test_oracle_omgp_demo_data_matches_reference():
+    """The reference's own OMGP demo data (data/split_data_test.csv, N = 250, K = 2, variance 0.01, DP prior; OMGP_demo.ipynb) through
+    the reference's own code with a seed: start bound (the notebook's unseeded cell [6] prints 921.947; a seeded start gives 921.42),
+    gradients, trace, final responsibilities and predict()."""
+    d = _load(os.path.join(GOLDEN, "reference_demo_omgp.npz"))
+    kernels = [_kern(s, G) for s in json.loads(str(d["kernels"]))]
+    m = OMGPOracle(d["X"], d["Y"], K=int(d["K"]), kernels=kernels, variance=float(d["variance"]), alpha=float(d["alpha"]),
+                   prior_Z=str(d["prior_Z"]))
+    m.set_vb_param(d["phi0"].flatten())
+    _check_start(m, d)
+    assert 900.0 < m.bound() < 940.0 and abs(m.log_likelihood() - _scalar(d["log_likelihood0"])) < TOL * abs(m.bound())
+    m.out = io.StringIO()
+    m.optimize(method="HS", maxiter=15, verbose=False)
+    _check_model(m, d, m.trace)
+
+
 def test_oracle_config1_standin_matches_reference():
     """BASELINE.json configs[0] stand-in (kalinka replicate / time design, D = 56, Matern52, DP prior, N = 500, K = 20) through the
     reference's own MOHGP / CollapsedVB.optimize: the oracle reproduces the start bound, natural gradient, posterior means, the
