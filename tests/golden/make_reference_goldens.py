@@ -276,6 +276,57 @@ def omgp_demo_case(GPclust):
     print("omgp demo data: bound0 %.12g -> bound1 %.12g, %d trace rows" % (out["bound0"], out["bound1"], len(out["trace"])))
 
 
+def quirks_case(GPclust):
+    """Edge cases of SURVEY.md appendix A through the reference's own code (CPU oracle pin):
+      A.3   a cluster nobody belongs to (phi_hat <= 1e-6): Lambda_inv_k := Sf, the rest computed normally; remove_empty_clusters()
+      A.9   reorder() sorts the clusters under the DP prior and is a no-op under the symmetric one
+      A.6   maxiter may be a float; the iteration count at the exit
+      A.10  randomize() re-draws phi_ from the legacy global stream
+      A.11  OMGP.do_computations grows the kernel list by ONE per call: with one kernel given and K = 3 the first bound() sums over
+            two components only, the next set_vb_param() adds the third"""
+    out = {}
+    rng = np.random.RandomState(21)
+    D, N, K = 8, 50, 4
+    X = np.linspace(0, 10, D)[:, None]
+    kF, kY = G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+    Y = (np.linalg.cholesky(kF.K(X) + 1e-8 * np.eye(D)).dot(rng.randn(D, 3))).T[rng.randint(0, 3, N)] + 0.3 * rng.randn(N, D)
+    np.random.seed(22)
+    m = GPclust.MOHGP(X, kF, kY, Y, K=K, prior_Z="DP", alpha=2.0)
+    phi_ = m.phi_.copy()
+    phi_[:, 2] = -60.0                                   # nobody belongs to cluster 2: phi_hat[2] ~ 1e-25
+    m.set_vb_param(phi_.flatten())
+    g, ng = m.vb_grad_natgrad()
+    out.update(e_X=X, e_Y=Y, e_phi0=phi_, e_phi_hat=m.phi_hat.copy(), e_bound=m.bound(), e_grad=g, e_natgrad=ng, e_Lambda_inv=m.Lambda_inv.copy(),
+               e_muk=m.muk.copy(), e_log_det_diff=m.log_det_diff.copy(), e_Sf=m.Sf.copy())
+    m.reorder()                                          # DP: biggest first, the empty one last
+    out.update(r_phi_hat=m.phi_hat.copy(), r_bound=m.bound(), r_phi_=m.phi_.copy())
+    m.remove_empty_clusters()
+    out.update(x_K=m.K, x_bound=m.bound(), x_phi_hat=m.phi_hat.copy())
+    out["f_trace"] = run_optimize(m, method="HS", maxiter=3.5)
+    np.random.seed(23)
+    m.randomize()
+    out.update(z_phi_=m.phi_.copy(), z_bound=m.bound())
+    np.random.seed(22)
+    ms = GPclust.MOHGP(X, kF, kY, Y, K=K, prior_Z="symmetric", alpha=2.0)
+    before = ms.phi_.copy()
+    ms.reorder()
+    out.update(s_noop=np.array_equal(before, ms.phi_), s_bound=ms.bound())
+
+    Xo = np.sort(rng.uniform(0, 10, 30))[:, None]
+    Yo = np.sin(Xo) + 0.1 * rng.randn(30, 1)
+    np.random.seed(24)
+    mo = GPclust.OMGP(Xo, Yo, K=3, kernels=[G.RBF(1, 1.0, 1.5)], variance=0.05)
+    out.update(o_X=Xo, o_Y=Yo, o_phi0=mo.phi_.copy(), o_nkern0=len(mo.kern), o_bound0=mo.bound())
+    mo.set_vb_param(mo.get_vb_param())
+    out.update(o_nkern1=len(mo.kern), o_bound1=mo.bound())
+    mo.set_vb_param(mo.get_vb_param())
+    g, ng = mo.vb_grad_natgrad()
+    out.update(o_nkern2=len(mo.kern), o_bound2=mo.bound(), o_natgrad2=ng)
+    np.savez_compressed(os.path.join(HERE, "reference_quirks.npz"), **out)
+    print("quirks: empty-cluster bound %.12g, reordered %.12g, K after removal %d, float maxiter exit at iteration %d, OMGP kernels %d -> %d -> %d" % (
+        out["e_bound"], out["r_bound"], out["x_K"], int(out["f_trace"][-1, 0]), out["o_nkern0"], out["o_nkern1"], out["o_nkern2"]))
+
+
 def main():
     install_gpy_stub()
     sys.path.insert(0, REF)
@@ -296,6 +347,7 @@ def main():
     mog_case(GPclust, "d3", N=80, D=3, K=4, prior_Z="symmetric", alpha=1.0, seed=5)
     mog_case(GPclust, "dp", N=70, D=2, K=5, prior_Z="DP", alpha=4.0, seed=6)
     config1_case(GPclust)
+    quirks_case(GPclust)
     omgp_demo_case(GPclust)
     splits_case(GPclust, "mohgp", N=90, D=10, K0=2, K_true=4, prior_Z="symmetric", alpha=1.0, seed=7,
                 kernF=G.RBF(1, 1.0, 2.0), kernY=G.RBF(1, 0.1, 1.0) + G.White(1, 0.05))

@@ -143,6 +143,50 @@ def test_oracle_mog_matches_reference(path):
     _check_model(m, d, m.trace)
 
 
+def test_oracle_quirks_match_reference():
+    """SURVEY.md appendix A edge cases through the reference's own code (tests/golden/reference_quirks.npz): an empty cluster
+    (phi_hat <= 1e-6 -> Lambda_inv_k := Sf), reorder() under DP / symmetric priors, remove_empty_clusters(), a float maxiter,
+    randomize(), and OMGP's kernel list growing by one per do_computations()."""
+    d = _load(os.path.join(GOLDEN, "reference_quirks.npz"))
+    kF, kY = G.RBF(1, 1.0, 2.0), G.RBF(1, 0.1, 1.0) + G.White(1, 0.05)
+    np.random.seed(22)
+    m = MOHGPOracle(d["e_X"], kF, kY, d["e_Y"], K=4, prior_Z="DP", alpha=2.0, mahalanobis=mahalanobis_pairs_solve)
+    m.set_vb_param(d["e_phi0"].flatten())
+    assert m.phi_hat[2] < 1e-20 and relerr(m.phi_hat, d["e_phi_hat"]) < 1e-13
+    assert abs(m.bound() - _scalar(d["e_bound"])) < TOL * abs(_scalar(d["e_bound"]))
+    assert np.array_equal(m.Lambda_inv[2], d["e_Sf"]) and relerr(m.Lambda_inv, d["e_Lambda_inv"]) < TOL        # A.3
+    assert relerr(m.muk, d["e_muk"]) < TOL and relerr(m.log_det_diff, d["e_log_det_diff"]) < TOL
+    g, ng = m.vb_grad_natgrad()
+    assert relerr(ng, d["e_natgrad"]) < TOL and relerr(g, d["e_grad"]) < TOL
+    m.reorder()                                                                                               # A.9 (DP)
+    assert np.all(np.diff(m.phi_hat) <= 0) and np.array_equal(m.phi_, d["r_phi_"])
+    assert relerr(m.phi_hat, d["r_phi_hat"]) < 1e-13 and abs(m.bound() - _scalar(d["r_bound"])) < TOL * abs(_scalar(d["r_bound"]))
+    m.remove_empty_clusters()
+    assert m.K == int(d["x_K"]) == 3 and relerr(m.phi_hat, d["x_phi_hat"]) < 1e-13
+    assert abs(m.bound() - _scalar(d["x_bound"])) < TOL * abs(_scalar(d["x_bound"]))
+    m.out = io.StringIO()
+    m.optimize(method="HS", maxiter=3.5, verbose=False)                                                       # A.6: float maxiter
+    _check_trace(m.trace, d["f_trace"])
+    np.random.seed(23)
+    m.randomize()                                                                                             # A.10
+    assert np.array_equal(m.phi_, d["z_phi_"]) and abs(m.bound() - _scalar(d["z_bound"])) < TOL * abs(_scalar(d["z_bound"]))
+    np.random.seed(22)
+    ms = MOHGPOracle(d["e_X"], kF, kY, d["e_Y"], K=4, prior_Z="symmetric", alpha=2.0, mahalanobis=mahalanobis_pairs_solve)
+    before = ms.phi_.copy()
+    ms.reorder()                                                                                              # A.9 (symmetric: no-op)
+    assert bool(d["s_noop"]) and np.array_equal(before, ms.phi_) and abs(ms.bound() - _scalar(d["s_bound"])) < TOL * abs(_scalar(d["s_bound"]))
+
+    np.random.seed(24)
+    mo = OMGPOracle(d["o_X"], d["o_Y"], K=3, kernels=[G.RBF(1, 1.0, 1.5)], variance=0.05)                     # A.11
+    assert np.array_equal(mo.phi_, d["o_phi0"])
+    for tag in ("0", "1", "2"):
+        assert len(mo.kern) == int(d["o_nkern" + tag])
+        assert abs(mo.bound() - _scalar(d["o_bound" + tag])) < TOL * abs(_scalar(d["o_bound" + tag]))
+        if tag != "2":
+            mo.set_vb_param(mo.get_vb_param())
+    assert relerr(mo.vb_grad_natgrad()[1], d["o_natgrad2"]) < TOL
+
+
 def test_oracle_omgp_demo_data_matches_reference():
     """The reference's own OMGP demo data (data/split_data_test.csv, N = 250, K = 2, variance 0.01, DP prior; OMGP_demo.ipynb) through
     the reference's own code with a seed: start bound (the notebook's unseeded cell [6] prints 921.947; a seeded start gives 921.42),
