@@ -58,6 +58,12 @@ class OMGP(CollapsedMixture):
             self.kern = [_kern.RBF(input_dim=1) for _ in range(K)]
         else:
             self.kern = list(kernels)
+            if len(self.kern) < K:
+                # Known divergence, stated instead of half-reproduced: the reference loops over the kernels PRESENT (OMGP.py:102,130) and
+                # grows the list by one per set_vb_param (OMGP.py:45-47), so with fewer kernels than components its first bounds sum
+                # over some components only (pinned for the oracle in tests/golden/reference_quirks.npz).
+                raise ValueError("OMGP: %d kernels given for K=%d components; pass one kernel per component (or kernels=None). The "
+                                 "reference would silently sum its bound over the first %d components only." % (len(self.kern), K, len(self.kern)))
         self.variance = float(np.asarray(variance).reshape(-1)[0])
         self.variance_fixed = False  # GPy: m.variance.fix()
         self.variance_gradient = 0.0

@@ -182,3 +182,13 @@ def test_hyperparameter_step():
     mp.optimize(maxiter=40, verbose=False)
     assert [r[0] for r in mp.optimize_trace] == [r[0] for r in mo.trace]
     assert abs(mp.bound() - mo.bound()) < 1e-5 * abs(mo.bound())
+
+
+def test_fewer_kernels_than_components_is_rejected():
+    """The reference would sum its bound over the kernels present only (OMGP.py:102, appendix A.11); the device path states the
+    divergence with a ValueError at construction instead of reproducing a partial sum (no kernel is launched before the check)."""
+    from gpclust_b200 import OMGP, kern
+    rng = np.random.RandomState(0)
+    X, Y = rng.uniform(0, 10, (20, 1)), rng.randn(20, 1)
+    with pytest.raises(ValueError, match="one kernel per component"):
+        OMGP(X, Y, K=3, kernels=[kern.RBF(1, 1.0, 1.5)])
